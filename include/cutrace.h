@@ -1,0 +1,231 @@
+/*
+ * cutrace.h — C-ABI of the B200-native render path for cutrace scenes.
+ *
+ * This is the drop-in boundary for the reference's render operator.  The reference has no FFI
+ * layer; the path sits behind a header-only C++ template operator
+ *
+ *     cutrace::gpu::render<S, bounces, tpb>(scene, fudge, max, depth_map, color_map, normal_map,
+ *                                           render_ms, total_ms)          (inc/kernel.hpp:86-130)
+ *
+ * whose input is produced by cutrace::cpu::schema::default_to_gpu() (inc/default_schema.hpp:935-937,
+ * inc/cpu_to_gpu.hpp:188-198).  The three entry points below replace exactly those two calls plus
+ * the row-wise cudaMemcpy read-back (inc/kernel.hpp:110-114):
+ *
+ *     default_to_gpu(scene)                     ->  cutrace_upload_scene()
+ *     gpu::render<S,5,256>(scene, 1e-3, ...)     ->  cutrace_render()
+ *     the per-row D2H copies + max-depth scan   ->  cutrace_download()
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.  See INTEGRATION.md for
+ * the binding a cutrace maintainer would add in main.cu.
+ *
+ * Conventions
+ *   - every function returns CUTRACE_OK (0) or a negative cutrace_status; the library never
+ *     prints, never calls exit(); cutrace_last_error() returns a thread-local message.
+ *   - host pointers in cutrace_scene_desc are borrowed for the duration of the call only.
+ *   - one ctx = one scene on one device; calls on a ctx must be externally serialised, distinct
+ *     ctxs are independent.
+ *   - images are row-major, row 0 = top, pixel (x,y) at y*width+x (inc/kernel.hpp:44-54).
+ *   - miss sentinels follow the reference: depth +INF, normal {0,0,0}, colour {0,0,0}
+ *     (inc/kernel.hpp:47-56, inc/shading.hpp:119,153); hit_id on a miss is CUTRACE_NO_HIT.
+ */
+#ifndef CUTRACE_B200_CUTRACE_H
+#define CUTRACE_B200_CUTRACE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUTRACE_ABI_VERSION 1u
+#define CUTRACE_NO_HIT 0xFFFFFFFFu
+
+typedef enum cutrace_status {
+  CUTRACE_OK = 0,
+  CUTRACE_ERR_INVALID_ARG = -1,   /* NULL pointer, bad size, index out of range in the scene */
+  CUTRACE_ERR_CUDA = -2,          /* a CUDA runtime call failed; message has the CUDA error   */
+  CUTRACE_ERR_NO_DEVICE = -3,     /* no CUDA device / requested ordinal does not exist        */
+  CUTRACE_ERR_OUT_OF_MEMORY = -4, /* device or host allocation failed                         */
+  CUTRACE_ERR_STATE = -5,         /* e.g. download before any render                          */
+  CUTRACE_ERR_INTERNAL = -6       /* BVH validation failed, queue overflow after retry, ...   */
+} cutrace_status;
+
+/* object kinds: variant order of default_gpu_object (inc/default_schema.hpp:920) */
+#define CUTRACE_OBJ_TRIANGLE 0u
+#define CUTRACE_OBJ_MESH 1u
+#define CUTRACE_OBJ_PLANE 2u
+#define CUTRACE_OBJ_SPHERE 3u
+
+/* light kinds: variant order of default_gpu_light (inc/default_schema.hpp:921) */
+#define CUTRACE_LIGHT_SUN 0u
+#define CUTRACE_LIGHT_POINT 1u
+
+/*
+ * Flat structure-of-arrays scene.  Replaces gpu_scene_{gpu_array<gpu_variant<...>> x3, cam}
+ * (inc/gpu_types.hpp:263-287, inc/cpu_to_gpu.hpp:69-199).
+ *
+ * object ids: `n_objects` is the length of the reference's scene.objects array; every primitive
+ * carries the index of the object it belongs to (a mesh of 1000 triangles is ONE object, see
+ * inc/ray_cast.hpp:45).  Triangles of one mesh must keep file order (tie-break rule,
+ * inc/default_schema.hpp:133-141).
+ */
+typedef struct cutrace_scene_desc {
+  uint32_t abi_version;      /* must be CUTRACE_ABI_VERSION */
+
+  /* camera after look_at (inc/default_schema.hpp:370-374): unit forward/right/up */
+  float cam_pos[3];
+  float cam_up[3];
+  float cam_forward[3];
+  float cam_right[3];
+  float ambient;             /* cam.ambient, inc/default_schema.hpp:357 */
+  uint32_t width, height;
+
+  /* triangles (loose triangles and mesh triangles alike), xyz interleaved, n_triangles*3 floats */
+  uint64_t n_triangles;
+  const float *tri_p1;
+  const float *tri_p2;
+  const float *tri_p3;
+  const uint32_t *tri_object;    /* n_triangles */
+
+  uint64_t n_spheres;
+  const float *sph_center;       /* n_spheres*3 */
+  const float *sph_radius;       /* n_spheres   */
+  const uint32_t *sph_object;    /* n_spheres   */
+
+  uint64_t n_planes;
+  const float *pl_point;         /* n_planes*3 */
+  const float *pl_normal;        /* n_planes*3, NOT normalised (reference keeps the JSON vector) */
+  const uint32_t *pl_object;     /* n_planes   */
+
+  uint32_t n_objects;
+  const uint32_t *obj_material;  /* n_objects: material index of each object */
+  const uint32_t *obj_kind;      /* optional (may be NULL), n_objects: CUTRACE_OBJ_*; used by the
+                                    scene dump and by the oracle (a mesh gets the reference's AABB
+                                    pre-test, a loose triangle does not). NULL = infer: an object
+                                    with exactly one triangle is a loose triangle. */
+
+  /* phong_material, inc/default_schema.hpp:319-343 */
+  uint32_t n_materials;
+  const float *mat_color;        /* n_materials*3 */
+  const float *mat_specular;     /* n_materials */
+  const float *mat_reflect;      /* n_materials */
+  const float *mat_phong;        /* n_materials */
+  const float *mat_transparency; /* n_materials */
+
+  /* lights, inc/default_schema.hpp:267-311 */
+  uint32_t n_lights;
+  const uint32_t *light_kind;    /* CUTRACE_LIGHT_* */
+  const float *light_vec;        /* n_lights*3: sun direction or point position */
+  const float *light_color;      /* n_lights*3 */
+} cutrace_scene_desc;
+
+/* cutrace_opts.flags */
+#define CUTRACE_FLAG_NO_SMEM_TOP 1u    /* do not stage the top of the BVH in shared memory */
+#define CUTRACE_FLAG_VALIDATE_BVH 2u   /* run the device-side BVH validator after the build */
+#define CUTRACE_FLAG_BRUTE_FORCE 4u    /* debug: skip the BVH, test every primitive per ray */
+
+typedef struct cutrace_opts {
+  float fudge;          /* min hit distance; the reference passes 1e-3 (main.cu:30)            */
+  uint32_t bounces;     /* recursion budget; the reference passes 5 (main.cu:30); max 15       */
+  int32_t device;       /* CUDA ordinal, -1 = current device                                   */
+  uint32_t flags;
+  /* screen-space sharding (multi-GPU): this ctx renders tiles t with t % tile_world == tile_rank.
+   * tile_world = 0 or 1 means the whole frame. Tiles are CUTRACE_TILE x CUTRACE_TILE pixels in
+   * row-major tile order. */
+  uint32_t tile_rank, tile_world;
+  void *stream;         /* cudaStream_t to launch on; NULL = a stream owned by the ctx         */
+  uint32_t leaf_size;   /* max primitives per BVH leaf (1..8); 0 = default (4)                 */
+  uint32_t reserved[7];
+} cutrace_opts;
+
+#define CUTRACE_TILE 32u
+
+typedef struct cutrace_stats {
+  float build_ms;       /* LBVH build inside cutrace_upload_scene (device time)               */
+  float render_ms;      /* device time of the last cutrace_render                              */
+  float gather_ms;      /* device time of cutrace_gather_* in the last frame (0 if unused)     */
+  float max_depth;      /* largest finite depth of the local pixels, 0 if none (kernel.hpp:120-125) */
+  uint64_t rays_primary;
+  uint64_t rays_reflect;
+  uint64_t rays_transmit;
+  uint64_t rays_shadow;     /* one per light per shaded hit                                    */
+  uint64_t shadow_casts;    /* closest-hit casts issued by shadow marches (>= rays_shadow when
+                               translucent surfaces are crossed, inc/shading.hpp:32)           */
+  uint64_t local_pixels;    /* pixels rendered by this ctx                                     */
+  uint32_t kernel_launches; /* kernels launched by the last cutrace_render                     */
+  uint32_t bvh_nodes;       /* live internal nodes                                             */
+  uint32_t bvh_depth;       /* deepest leaf                                                    */
+  uint32_t smem_nodes;      /* BVH nodes staged in shared memory                               */
+  float trace_ms;           /* device time in closest-hit kernels (sum over bounce levels)     */
+  float shade_ms;           /* device time in shadow+phong kernels                             */
+  uint32_t reserved[6];
+} cutrace_stats;
+
+typedef struct cutrace_ctx cutrace_ctx;
+
+/* fills o with the reference's defaults: fudge 1e-3, bounces 5, device -1, whole frame */
+void cutrace_default_opts(cutrace_opts *o);
+
+/* Replaces default_to_gpu() (inc/default_schema.hpp:935, inc/cpu_to_gpu.hpp:188-198): copies the
+ * scene to the device as flat SoA and builds the LBVH.  `opts` may be NULL (defaults). */
+int cutrace_upload_scene(const cutrace_scene_desc *scene, const cutrace_opts *opts, cutrace_ctx **out);
+
+/* Replaces the launch+sync in gpu::render (inc/kernel.hpp:103-108).  Blocks until the frame is
+ * complete on the device.  `stats` may be NULL.  Re-runnable. */
+int cutrace_render(cutrace_ctx *ctx, cutrace_stats *stats);
+
+/* Replaces the D2H copies and the max-depth scan of gpu::render (inc/kernel.hpp:110-125).
+ * Caller-owned host buffers of width*height (depth, hit_id) and width*height*3 (normal, colour)
+ * elements; any of them may be NULL.  For a sharded ctx only the local tiles are written. */
+int cutrace_download(cutrace_ctx *ctx, float *depth, float *normal, float *color, uint32_t *hit_id,
+                     float *max_depth);
+
+void cutrace_free(cutrace_ctx *ctx);
+
+/* thread-local, never NULL */
+const char *cutrace_last_error(void);
+
+/* ---- helpers around the three calls above ------------------------------------------------- */
+
+/* new camera / resolution for an uploaded scene (no rebuild).  cam_* as in cutrace_scene_desc. */
+int cutrace_set_camera(cutrace_ctx *ctx, const float pos[3], const float up[3], const float forward[3],
+                       const float right[3], float ambient, uint32_t width, uint32_t height);
+
+/* stats of the last upload/render */
+int cutrace_get_stats(cutrace_ctx *ctx, cutrace_stats *stats);
+
+/* Device-resident results of the last render, tile-major local layout: pixel j of local tile i is
+ * at (i*CUTRACE_TILE*CUTRACE_TILE + j).  Pointers stay valid until the next set_camera/free.
+ * Used by the multi-GPU gather (NCCL over the caller's communicator, or peer copies). */
+int cutrace_device_buffers(cutrace_ctx *ctx, float **depth, float **normal, float **color,
+                           uint32_t **hit_id, uint64_t *n_local_px_padded);
+
+/* Un-tiles `world` gathered rank buffers (each laid out as cutrace_device_buffers describes, rank r
+ * at gathered + r*stride elements of the respective type) into row-major full-frame DEVICE images
+ * on the ctx's device.  Any of the pointers may be NULL. */
+int cutrace_untile_device(cutrace_ctx *ctx, uint32_t world,
+                          const float *g_depth, const float *g_normal, const float *g_color,
+                          const uint32_t *g_id, uint64_t stride_px,
+                          float *depth, float *normal, float *color, uint32_t *hit_id);
+
+/* Output stage on the device (inc/images.hpp:26-88): maps full-frame row-major device images to
+ * the three 8-bit RGB images the reference hands to stbi_write_jpg. Any output may be NULL. */
+int cutrace_encode_bytes_device(cutrace_ctx *ctx, const float *depth, const float *normal,
+                                const float *color, float max_depth, uint64_t n_px,
+                                uint8_t *depth_rgb, uint8_t *normal_rgb, uint8_t *color_rgb);
+
+/* pinned host memory for the download buffers (optional; any host memory works) */
+void *cutrace_host_alloc(size_t bytes);
+void cutrace_host_free(void *p);
+
+/* device-side BVH self check (parent boxes contain children, every primitive reachable exactly
+ * once); returns CUTRACE_OK or CUTRACE_ERR_INTERNAL with a message. */
+int cutrace_validate_bvh(cutrace_ctx *ctx);
+
+uint32_t cutrace_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUTRACE_B200_CUTRACE_H */
