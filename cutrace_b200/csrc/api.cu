@@ -1,0 +1,540 @@
+// api.cu — the C-ABI (include/cutrace.h): scene upload + LBVH build, frame render, download.
+//
+//   cutrace_upload_scene  replaces default_to_gpu / cpu_to_gpu::convert (inc/cpu_to_gpu.hpp:188-198):
+//                         instead of cudaMallocManaged arrays of tagged unions with a nested
+//                         allocation per mesh (inc/default_schema.hpp:592-594) the scene becomes
+//                         flat 16-byte aligned records in device memory plus an LBVH.
+//   cutrace_render        replaces gpu::render's launch + sync (inc/kernel.hpp:103-108).
+//   cutrace_download      replaces its 3*h row cudaMemcpy calls and host max-depth scan
+//                         (inc/kernel.hpp:110-125) with one device un-tile + one copy per image.
+// There is NO CPU fallback anywhere in this library: without a CUDA device every entry point
+// fails with CUTRACE_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "bvh.cuh"
+#include "render.cuh"
+
+using namespace ctb;
+
+static thread_local std::string g_err = "";
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      return fail(e_ == cudaErrorMemoryAllocation ? CUTRACE_ERR_OUT_OF_MEMORY                          \
+                  : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? CUTRACE_ERR_NO_DEVICE \
+                                                                                  : CUTRACE_ERR_CUDA, \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                \
+    }                                                                                                 \
+  } while (0)
+
+struct cutrace_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cutrace_opts opts{};
+  // scene
+  BvhResult bvh;
+  PlaneRec *planes = nullptr;
+  MaterialRec *materials = nullptr;
+  LightRec *lights = nullptr;
+  uint32_t *obj_material = nullptr;
+  SceneView sv{};
+  int max_children = 0;
+  // frame
+  TileMap tm{};
+  uint64_t n_local_px = 0;   // padded: n_local_tiles * 1024
+  FrameTargets fb{};
+  RayRec *rays[2] = {nullptr, nullptr};
+  ShadeRec *shade = nullptr;
+  uint64_t batch_px = 0, cap = 0;
+  uint32_t factor = 1;
+  FrameCounters *d_ctr = nullptr;
+  FrameCounters *h_ctr = nullptr;   // pinned
+  LaunchCfg cfg{};
+  // download staging (row-major full frame), lazily allocated
+  float *st_depth = nullptr, *st_normal = nullptr, *st_color = nullptr;
+  uint32_t *st_id = nullptr;
+  uint64_t st_px = 0;
+  cutrace_stats stats{};
+  bool rendered = false;
+  std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void free_frame(cutrace_ctx *c) {
+  cudaFree(c->fb.depth); cudaFree(c->fb.normal); cudaFree(c->fb.color); cudaFree(c->fb.hit_id);
+  cudaFree(c->rays[0]); cudaFree(c->rays[1]); cudaFree(c->shade);
+  cudaFree(c->st_depth); cudaFree(c->st_normal); cudaFree(c->st_color); cudaFree(c->st_id);
+  c->fb = FrameTargets{};
+  c->rays[0] = c->rays[1] = nullptr; c->shade = nullptr;
+  c->st_depth = c->st_normal = c->st_color = nullptr; c->st_id = nullptr;
+  c->st_px = 0;
+  c->rendered = false;
+}
+
+int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
+  if (width == 0 || height == 0) return fail(CUTRACE_ERR_INVALID_ARG, "camera width/height must be > 0");
+  if ((uint64_t)width * height >= (1ull << 31)) return fail(CUTRACE_ERR_INVALID_ARG, "frame too large (>= 2^31 pixels)");
+  free_frame(c);
+  TileMap tm{};
+  tm.width = width; tm.height = height;
+  tm.tiles_x = (width + CUTRACE_TILE - 1) / CUTRACE_TILE;
+  tm.tiles_y = (height + CUTRACE_TILE - 1) / CUTRACE_TILE;
+  tm.world = c->opts.tile_world > 1 ? c->opts.tile_world : 1;
+  tm.rank = tm.world > 1 ? c->opts.tile_rank : 0;
+  uint32_t total_tiles = tm.tiles_x * tm.tiles_y;
+  // every rank gets the same padded tile count so that gathered rank buffers have one stride
+  tm.n_local_tiles = (total_tiles + tm.world - 1) / tm.world;
+  c->tm = tm;
+  c->n_local_px = (uint64_t)tm.n_local_tiles * 1024ull;
+  c->sv.cam.w = width; c->sv.cam.h = height;
+
+  uint32_t b = c->opts.bounces;
+  c->factor = (c->max_children >= 2 && b > 0) ? (1u << b) : 1u;
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  uint64_t fb_bytes = c->n_local_px * 32ull;
+  double budget = (double)free_b * 0.6 - (double)fb_bytes;
+  if (const char *e = getenv("CUTRACE_QUEUE_BUDGET_MB")) budget = atof(e) * 1048576.0;
+  double per_px = (double)c->factor * (2.0 * sizeof(RayRec) + sizeof(ShadeRec));
+  uint64_t batch = budget > per_px * 1024.0 ? (uint64_t)(budget / per_px) : 1024ull;
+  batch = (batch / 1024ull) * 1024ull;
+  if (batch < 1024) batch = 1024;
+  if (batch > c->n_local_px) batch = c->n_local_px;
+  while (batch * c->factor >= (1ull << 31) && batch > 1024) batch = ((batch / 2) / 1024ull) * 1024ull;
+  c->batch_px = batch;
+  c->cap = batch * c->factor;
+
+  CU(cudaMalloc(&c->fb.depth, sizeof(float) * c->n_local_px));
+  CU(cudaMalloc(&c->fb.normal, sizeof(float) * 3 * c->n_local_px));
+  CU(cudaMalloc(&c->fb.color, sizeof(float) * 3 * c->n_local_px));
+  CU(cudaMalloc(&c->fb.hit_id, sizeof(uint32_t) * c->n_local_px));
+  if (c->max_children > 0 && b > 0) {
+    CU(cudaMalloc(&c->rays[0], sizeof(RayRec) * c->cap));
+    CU(cudaMalloc(&c->rays[1], sizeof(RayRec) * c->cap));
+  }
+  CU(cudaMalloc(&c->shade, sizeof(ShadeRec) * c->cap));
+  return CUTRACE_OK;
+}
+
+template <typename T>
+int upload(T **dst, const std::vector<T> &src, cudaStream_t st) {
+  *dst = nullptr;
+  if (src.empty()) return CUTRACE_OK;
+  CU(cudaMalloc(dst, sizeof(T) * src.size()));
+  CU(cudaMemcpyAsync(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, st));
+  return CUTRACE_OK;
+}
+
+bool all_finite(const float *p, uint64_t n) {
+  for (uint64_t i = 0; i < n; i++)
+    if (!std::isfinite(p[i])) return false;
+  return true;
+}
+
+int validate_desc(const cutrace_scene_desc *s) {
+  if (!s) return fail(CUTRACE_ERR_INVALID_ARG, "scene is NULL");
+  if (s->abi_version != CUTRACE_ABI_VERSION) return fail(CUTRACE_ERR_INVALID_ARG, "cutrace_scene_desc.abi_version mismatch");
+  if (s->width == 0 || s->height == 0) return fail(CUTRACE_ERR_INVALID_ARG, "camera width/height must be > 0");
+  if (s->n_triangles && !(s->tri_p1 && s->tri_p2 && s->tri_p3 && s->tri_object)) return fail(CUTRACE_ERR_INVALID_ARG, "triangle arrays are NULL");
+  if (s->n_spheres && !(s->sph_center && s->sph_radius && s->sph_object)) return fail(CUTRACE_ERR_INVALID_ARG, "sphere arrays are NULL");
+  if (s->n_planes && !(s->pl_point && s->pl_normal && s->pl_object)) return fail(CUTRACE_ERR_INVALID_ARG, "plane arrays are NULL");
+  if (s->n_objects && !s->obj_material) return fail(CUTRACE_ERR_INVALID_ARG, "obj_material is NULL");
+  if (s->n_materials && !(s->mat_color && s->mat_specular && s->mat_reflect && s->mat_phong && s->mat_transparency))
+    return fail(CUTRACE_ERR_INVALID_ARG, "material arrays are NULL");
+  if (s->n_lights && !(s->light_kind && s->light_vec && s->light_color)) return fail(CUTRACE_ERR_INVALID_ARG, "light arrays are NULL");
+  if (s->n_triangles + s->n_spheres >= (1ull << 28)) return fail(CUTRACE_ERR_INVALID_ARG, "too many primitives (max 2^28-1)");
+  for (uint32_t i = 0; i < s->n_objects; i++)
+    if (s->obj_material[i] >= s->n_materials) return fail(CUTRACE_ERR_INVALID_ARG, "object material index out of range");
+  for (uint64_t i = 0; i < s->n_triangles; i++)
+    if (s->tri_object[i] >= s->n_objects) return fail(CUTRACE_ERR_INVALID_ARG, "tri_object index out of range");
+  for (uint64_t i = 0; i < s->n_spheres; i++)
+    if (s->sph_object[i] >= s->n_objects) return fail(CUTRACE_ERR_INVALID_ARG, "sph_object index out of range");
+  for (uint64_t i = 0; i < s->n_planes; i++)
+    if (s->pl_object[i] >= s->n_objects) return fail(CUTRACE_ERR_INVALID_ARG, "pl_object index out of range");
+  for (uint32_t i = 0; i < s->n_lights; i++)
+    if (s->light_kind[i] > CUTRACE_LIGHT_POINT) return fail(CUTRACE_ERR_INVALID_ARG, "unknown light kind");
+  if (!all_finite(s->tri_p1, 3 * s->n_triangles) || !all_finite(s->tri_p2, 3 * s->n_triangles) ||
+      !all_finite(s->tri_p3, 3 * s->n_triangles) || !all_finite(s->sph_center, 3 * s->n_spheres) ||
+      !all_finite(s->sph_radius, s->n_spheres))
+    return fail(CUTRACE_ERR_INVALID_ARG, "non-finite vertex / sphere data");
+  return CUTRACE_OK;
+}
+
+void set_cam(cutrace_ctx *c, const float pos[3], const float up[3], const float fwd[3], const float right[3], float ambient) {
+  Camera &cam = c->sv.cam;
+  cam.pos = mk3(pos[0], pos[1], pos[2]);
+  cam.up = mk3(up[0], up[1], up[2]);
+  cam.forward = mk3(fwd[0], fwd[1], fwd[2]);
+  cam.right = mk3(right[0], right[1], right[2]);
+  cam.ambient = ambient;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t cutrace_abi_version(void) { return CUTRACE_ABI_VERSION; }
+
+const char *cutrace_last_error(void) { return g_err.c_str(); }
+
+void cutrace_default_opts(cutrace_opts *o) {
+  if (!o) return;
+  memset(o, 0, sizeof *o);
+  o->fudge = 1e-3f;   // main.cu:30 passes the double literal 1e-3 into a float parameter
+  o->bounces = 5;
+  o->device = -1;
+  o->tile_world = 1;
+  o->leaf_size = 4;
+}
+
+void cutrace_free(cutrace_ctx *c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_frame(c);
+  cudaFree(c->bvh.nodes); cudaFree(c->bvh.prims);
+  cudaFree(c->planes); cudaFree(c->materials); cudaFree(c->lights); cudaFree(c->obj_material);
+  cudaFree(c->d_ctr);
+  if (c->h_ctr) cudaFreeHost(c->h_ctr);
+  for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, cutrace_ctx **out) {
+  if (!out) return fail(CUTRACE_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int rc = validate_desc(s);
+  if (rc) return rc;
+  cutrace_opts o;
+  if (opts) o = *opts; else cutrace_default_opts(&o);
+  if (o.bounces > 15) return fail(CUTRACE_ERR_INVALID_ARG, "bounces must be <= 15");
+  if (o.tile_world > 1 && o.tile_rank >= o.tile_world) return fail(CUTRACE_ERR_INVALID_ARG, "tile_rank >= tile_world");
+  if (o.leaf_size == 0) o.leaf_size = 4;
+  if (o.leaf_size > CTB_MAX_LEAF) return fail(CUTRACE_ERR_INVALID_ARG, "leaf_size must be <= 8");
+
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(CUTRACE_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");
+  int dev = o.device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if (dev >= n_dev) return fail(CUTRACE_ERR_NO_DEVICE, "requested CUDA device ordinal does not exist");
+
+  cutrace_ctx *c = new (std::nothrow) cutrace_ctx();
+  if (!c) return fail(CUTRACE_ERR_OUT_OF_MEMORY, "host allocation failed");
+  c->device = dev;
+  c->opts = o;
+  DeviceGuard guard(dev);
+  if (!guard.ok) { delete c; return fail(CUTRACE_ERR_CUDA, "cudaSetDevice failed"); }
+
+#define UP(call) do { int rc_ = (call); if (rc_) { cutrace_free(c); return rc_; } } while (0)
+#define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); cutrace_free(c); \
+    return fail(e_ == cudaErrorMemoryAllocation ? CUTRACE_ERR_OUT_OF_MEMORY : CUTRACE_ERR_CUDA, m_); } } while (0)
+
+  if (o.stream) c->stream = (cudaStream_t)o.stream;
+  else { CUF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  for (int i = 0; i < 72; i++) { cudaEvent_t ev; CUF(cudaEventCreate(&ev)); c->events.push_back(ev); }
+
+  // ---- flat records ----
+  std::vector<PlaneRec> planes(s->n_planes);
+  for (uint64_t i = 0; i < s->n_planes; i++) {
+    PlaneRec &p = planes[i];
+    p.px = s->pl_point[3 * i]; p.py = s->pl_point[3 * i + 1]; p.pz = s->pl_point[3 * i + 2]; p.obj = s->pl_object[i];
+    p.nx = s->pl_normal[3 * i]; p.ny = s->pl_normal[3 * i + 1]; p.nz = s->pl_normal[3 * i + 2]; p.pad = 0;
+  }
+  std::vector<MaterialRec> mats(s->n_materials);
+  bool all_opaque = true, any_child = false, any_both = false;
+  for (uint32_t i = 0; i < s->n_materials; i++) {
+    MaterialRec &m = mats[i];
+    m.r = s->mat_color[3 * i]; m.g = s->mat_color[3 * i + 1]; m.b = s->mat_color[3 * i + 2]; m.specular = s->mat_specular[i];
+    m.reflect = s->mat_reflect[i]; m.phong = s->mat_phong[i]; m.transparency = s->mat_transparency[i]; m.pad = 0;
+    bool r = (double)m.reflect >= 1e-6, t = (double)m.transparency >= 1e-6;   // inc/shading.hpp:130,141
+    // intensity += 1 - trans saturates in one step only if 1 - trans >= 1 (inc/shading.hpp:36-39)
+    if (!(1.0f - m.transparency >= 1.0f)) all_opaque = false;
+    any_child = any_child || r || t;
+    any_both = any_both || (r && t);
+  }
+  c->max_children = any_both ? 2 : (any_child ? 1 : 0);
+  std::vector<LightRec> lights(s->n_lights);
+  for (uint32_t i = 0; i < s->n_lights; i++) {
+    LightRec &l = lights[i];
+    l.vx = s->light_vec[3 * i]; l.vy = s->light_vec[3 * i + 1]; l.vz = s->light_vec[3 * i + 2]; l.kind = s->light_kind[i];
+    l.r = s->light_color[3 * i]; l.g = s->light_color[3 * i + 1]; l.b = s->light_color[3 * i + 2]; l.pad = 0;
+  }
+  std::vector<uint32_t> omat(s->obj_material, s->obj_material + s->n_objects);
+  UP(upload(&c->planes, planes, c->stream));
+  UP(upload(&c->materials, mats, c->stream));
+  UP(upload(&c->lights, lights, c->stream));
+  UP(upload(&c->obj_material, omat, c->stream));
+
+  // ---- primitives + LBVH ----
+  float *d_p1 = nullptr, *d_p2 = nullptr, *d_p3 = nullptr, *d_sc = nullptr, *d_sr = nullptr;
+  uint32_t *d_to = nullptr, *d_so = nullptr;
+  auto free_tmp = [&]() { cudaFree(d_p1); cudaFree(d_p2); cudaFree(d_p3); cudaFree(d_sc); cudaFree(d_sr); cudaFree(d_to); cudaFree(d_so); };
+#define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); free_tmp(); cutrace_free(c); \
+    return fail(e_ == cudaErrorMemoryAllocation ? CUTRACE_ERR_OUT_OF_MEMORY : CUTRACE_ERR_CUDA, m_); } } while (0)
+  const uint64_t nt = s->n_triangles, ns = s->n_spheres;
+  if (nt) {
+    CUT(cudaMalloc(&d_p1, sizeof(float) * 3 * nt)); CUT(cudaMalloc(&d_p2, sizeof(float) * 3 * nt));
+    CUT(cudaMalloc(&d_p3, sizeof(float) * 3 * nt)); CUT(cudaMalloc(&d_to, sizeof(uint32_t) * nt));
+    CUT(cudaMemcpyAsync(d_p1, s->tri_p1, sizeof(float) * 3 * nt, cudaMemcpyHostToDevice, c->stream));
+    CUT(cudaMemcpyAsync(d_p2, s->tri_p2, sizeof(float) * 3 * nt, cudaMemcpyHostToDevice, c->stream));
+    CUT(cudaMemcpyAsync(d_p3, s->tri_p3, sizeof(float) * 3 * nt, cudaMemcpyHostToDevice, c->stream));
+    CUT(cudaMemcpyAsync(d_to, s->tri_object, sizeof(uint32_t) * nt, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (ns) {
+    CUT(cudaMalloc(&d_sc, sizeof(float) * 3 * ns)); CUT(cudaMalloc(&d_sr, sizeof(float) * ns)); CUT(cudaMalloc(&d_so, sizeof(uint32_t) * ns));
+    CUT(cudaMemcpyAsync(d_sc, s->sph_center, sizeof(float) * 3 * ns, cudaMemcpyHostToDevice, c->stream));
+    CUT(cudaMemcpyAsync(d_sr, s->sph_radius, sizeof(float) * ns, cudaMemcpyHostToDevice, c->stream));
+    CUT(cudaMemcpyAsync(d_so, s->sph_object, sizeof(uint32_t) * ns, cudaMemcpyHostToDevice, c->stream));
+  }
+  BvhInput bi;
+  bi.d_p1 = d_p1; bi.d_p2 = d_p2; bi.d_p3 = d_p3; bi.d_tri_obj = d_to; bi.n_tri = (uint32_t)nt;
+  bi.d_sph_center = d_sc; bi.d_sph_radius = d_sr; bi.d_sph_obj = d_so; bi.n_sph = (uint32_t)ns;
+  bi.leaf_size = o.leaf_size; bi.stream = c->stream;
+  CUT(cudaEventRecord(c->events[0], c->stream));
+  std::string berr;
+  rc = build_bvh(bi, c->bvh, berr);
+  if (rc) { free_tmp(); cutrace_free(c); return fail(rc, berr); }
+  CUT(cudaEventRecord(c->events[1], c->stream));
+  CUT(cudaStreamSynchronize(c->stream));
+  CUT(cudaEventElapsedTime(&c->stats.build_ms, c->events[0], c->events[1]));
+  free_tmp();
+  if (o.flags & CUTRACE_FLAG_VALIDATE_BVH) {
+    rc = validate_bvh(c->bvh, c->stream, berr);
+    if (rc) { cutrace_free(c); return fail(rc, berr); }
+  }
+
+  SceneView &sv = c->sv;
+  sv.nodes = c->bvh.nodes; sv.prims = c->bvh.prims; sv.planes = c->planes; sv.materials = c->materials;
+  sv.lights = c->lights; sv.obj_material = c->obj_material;
+  sv.n_prims = c->bvh.n_prims; sv.n_nodes = c->bvh.n_nodes; sv.n_planes = (uint32_t)s->n_planes;
+  sv.n_lights = s->n_lights; sv.n_materials = s->n_materials; sv.n_objects = s->n_objects;
+  sv.root = c->bvh.root;
+  sv.all_opaque = all_opaque ? 1u : 0u;
+  sv.brute_force = (o.flags & CUTRACE_FLAG_BRUTE_FORCE) ? 1u : 0u;
+  sv.fudge = o.fudge;
+  set_cam(c, s->cam_pos, s->cam_up, s->cam_forward, s->cam_right, s->ambient);
+
+  CUF(cudaMalloc(&c->d_ctr, sizeof(FrameCounters)));
+  CUF(cudaHostAlloc(&c->h_ctr, sizeof(FrameCounters), cudaHostAllocDefault));
+  CUF(plan_launch(sv, !(o.flags & CUTRACE_FLAG_NO_SMEM_TOP), &c->cfg));
+  sv.smem_nodes = c->cfg.mode == 1 ? sv.n_nodes : 0;
+  sv.smem_prims = c->cfg.mode == 1 ? sv.n_prims : 0;
+  UP(alloc_frame(c, s->width, s->height));
+  c->stats.bvh_nodes = c->bvh.n_nodes;
+  c->stats.bvh_depth = c->bvh.depth;
+  c->stats.smem_nodes = sv.smem_nodes;
+  *out = c;
+  return CUTRACE_OK;
+#undef UP
+#undef CUF
+#undef CUT
+}
+
+int cutrace_set_camera(cutrace_ctx *c, const float pos[3], const float up[3], const float forward[3], const float right[3],
+                       float ambient, uint32_t width, uint32_t height) {
+  if (!c || !pos || !up || !forward || !right) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(c->device);
+  CU(cudaStreamSynchronize(c->stream));
+  set_cam(c, pos, up, forward, right, ambient);
+  if (width != c->tm.width || height != c->tm.height) {
+    int rc = alloc_frame(c, width, height);
+    if (rc) return rc;
+  }
+  c->rendered = false;
+  return CUTRACE_OK;
+}
+
+int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(CUTRACE_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t st = c->stream;
+  const uint32_t bounces = c->opts.bounces;
+  const uint32_t levels = (c->max_children > 0) ? bounces + 1 : 1;
+  cutrace_stats &S = c->stats;
+  S.rays_primary = S.rays_reflect = S.rays_transmit = S.rays_shadow = S.shadow_casts = 0;
+  S.kernel_launches = 0; S.max_depth = 0.f; S.trace_ms = S.shade_ms = 0.f; S.gather_ms = 0.f;
+  S.local_pixels = 0;
+  // pixels of this ctx that are inside the image
+  {
+    const TileMap &tm = c->tm;
+    uint64_t px = 0;
+    for (uint32_t lt = 0; lt < tm.n_local_tiles; lt++) {
+      uint32_t gt = lt * tm.world + tm.rank;
+      if (gt >= tm.tiles_x * tm.tiles_y) continue;
+      uint32_t tx = gt % tm.tiles_x, ty = gt / tm.tiles_x;
+      uint32_t w = std::min(CUTRACE_TILE, tm.width - tx * CUTRACE_TILE), h = std::min(CUTRACE_TILE, tm.height - ty * CUTRACE_TILE);
+      px += (uint64_t)w * h;
+    }
+    S.local_pixels = px;
+    S.rays_primary = px;
+  }
+  cudaEvent_t ev_begin = c->events[0], ev_end = c->events[1];
+  CU(cudaEventRecord(ev_begin, st));
+  CU(cudaMemsetAsync(c->fb.color, 0, sizeof(float) * 3 * c->n_local_px, st));
+  float max_depth = 0.f;
+  const bool atomic_acc = c->max_children >= 2;
+  for (uint64_t base = 0; base < c->n_local_px; base += c->batch_px) {
+    const uint32_t n_px = (uint32_t)std::min<uint64_t>(c->batch_px, c->n_local_px - base);
+    CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(FrameCounters), st));
+    size_t ev = 2;
+    for (uint32_t L = 0; L < levels; L++) {
+      uint64_t bound = (uint64_t)n_px * (c->max_children >= 2 ? (1ull << L) : 1ull);
+      if (bound > c->cap) bound = c->cap;
+      RayRec *in = c->rays[L & 1], *outq = c->rays[(L + 1) & 1];
+      CU(cudaEventRecord(c->events[ev++], st));
+      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade, c->d_ctr, c->fb, (uint32_t)bound, st);
+      CU(cudaEventRecord(c->events[ev++], st));
+      launch_shade(c->cfg, c->sv, L, c->shade, c->d_ctr, c->fb, atomic_acc, (uint32_t)bound, st);
+      CU(cudaEventRecord(c->events[ev++], st));
+      S.kernel_launches += 2;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+    if (base + c->batch_px >= c->n_local_px) CU(cudaEventRecord(ev_end, st));
+    CU(cudaStreamSynchronize(st));
+    const FrameCounters &h = *c->h_ctr;
+    if (h.overflow) return fail(CUTRACE_ERR_INTERNAL, "internal: ray queue overflow");
+    S.rays_reflect += h.rays_reflect;
+    S.rays_transmit += h.rays_transmit;
+    S.shadow_casts += h.shadow_casts;
+    for (uint32_t L = 0; L < levels; L++) S.rays_shadow += (uint64_t)h.n_shade[L] * c->sv.n_lights;
+    float md;
+    memcpy(&md, &h.max_depth_bits, 4);
+    if (md > max_depth) max_depth = md;
+    for (uint32_t L = 0; L < levels; L++) {
+      float a = 0.f, b = 0.f;
+      CU(cudaEventElapsedTime(&a, c->events[2 + 3 * L], c->events[3 + 3 * L]));
+      CU(cudaEventElapsedTime(&b, c->events[3 + 3 * L], c->events[4 + 3 * L]));
+      S.trace_ms += a; S.shade_ms += b;
+    }
+  }
+  CU(cudaEventElapsedTime(&S.render_ms, ev_begin, ev_end));
+  S.max_depth = max_depth;
+  c->rendered = true;
+  if (stats) *stats = S;
+  return CUTRACE_OK;
+}
+
+int cutrace_get_stats(cutrace_ctx *c, cutrace_stats *stats) {
+  if (!c || !stats) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  *stats = c->stats;
+  return CUTRACE_OK;
+}
+
+int cutrace_download(cutrace_ctx *c, float *depth, float *normal, float *color, uint32_t *hit_id, float *max_depth) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!c->rendered) return fail(CUTRACE_ERR_STATE, "cutrace_download called before cutrace_render");
+  DeviceGuard g(c->device);
+  cudaStream_t st = c->stream;
+  const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
+  if (c->st_px != n) {
+    cudaFree(c->st_depth); cudaFree(c->st_normal); cudaFree(c->st_color); cudaFree(c->st_id);
+    c->st_depth = c->st_normal = c->st_color = nullptr; c->st_id = nullptr; c->st_px = 0;
+    CU(cudaMalloc(&c->st_depth, sizeof(float) * n));
+    CU(cudaMalloc(&c->st_normal, sizeof(float) * 3 * n));
+    CU(cudaMalloc(&c->st_color, sizeof(float) * 3 * n));
+    CU(cudaMalloc(&c->st_id, sizeof(uint32_t) * n));
+    c->st_px = n;
+  }
+  if (c->tm.world > 1) {
+    // sharded ctx: foreign tiles read as misses; the real multi-GPU path gathers device buffers instead
+    launch_fill_sentinels(c->st_depth, c->st_normal, c->st_color, c->st_id, n, st);
+    launch_untile(c->tm, c->tm.world, c->fb.depth, c->fb.normal, c->fb.color, c->fb.hit_id, 0, (int)c->tm.rank, c->st_depth,
+                  c->st_normal, c->st_color, c->st_id, st);
+  } else {
+    launch_untile(c->tm, 1, c->fb.depth, c->fb.normal, c->fb.color, c->fb.hit_id, 0, -1, c->st_depth, c->st_normal, c->st_color, c->st_id, st);
+  }
+  CU(cudaGetLastError());
+  if (depth) CU(cudaMemcpyAsync(depth, c->st_depth, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  if (normal) CU(cudaMemcpyAsync(normal, c->st_normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+  if (color) CU(cudaMemcpyAsync(color, c->st_color, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+  if (hit_id) CU(cudaMemcpyAsync(hit_id, c->st_id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (max_depth) *max_depth = c->stats.max_depth;
+  return CUTRACE_OK;
+}
+
+int cutrace_device_buffers(cutrace_ctx *c, float **depth, float **normal, float **color, uint32_t **hit_id, uint64_t *n_local_px_padded) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  if (depth) *depth = c->fb.depth;
+  if (normal) *normal = c->fb.normal;
+  if (color) *color = c->fb.color;
+  if (hit_id) *hit_id = c->fb.hit_id;
+  if (n_local_px_padded) *n_local_px_padded = c->n_local_px;
+  return CUTRACE_OK;
+}
+
+int cutrace_untile_device(cutrace_ctx *c, uint32_t world, const float *g_depth, const float *g_normal, const float *g_color,
+                          const uint32_t *g_id, uint64_t stride_px, float *depth, float *normal, float *color, uint32_t *hit_id) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  if (world == 0) world = 1;
+  if ((depth && !g_depth) || (normal && !g_normal) || (color && !g_color) || (hit_id && !g_id))
+    return fail(CUTRACE_ERR_INVALID_ARG, "output requested without its gathered input");
+  DeviceGuard g(c->device);
+  cudaEvent_t e0 = c->events[70], e1 = c->events[71];
+  CU(cudaEventRecord(e0, c->stream));
+  launch_untile(c->tm, world, g_depth, g_normal, g_color, g_id, stride_px, -1, depth, normal, color, hit_id, c->stream);
+  CU(cudaEventRecord(e1, c->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventElapsedTime(&c->stats.gather_ms, e0, e1));
+  return CUTRACE_OK;
+}
+
+int cutrace_encode_bytes_device(cutrace_ctx *c, const float *depth, const float *normal, const float *color, float max_depth,
+                                uint64_t n_px, uint8_t *depth_rgb, uint8_t *normal_rgb, uint8_t *color_rgb) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  DeviceGuard g(c->device);
+  launch_encode_bytes(depth, normal, color, max_depth, n_px, depth_rgb, normal_rgb, color_rgb, c->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return CUTRACE_OK;
+}
+
+void *cutrace_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+  return p;
+}
+
+void cutrace_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int cutrace_validate_bvh(cutrace_ctx *c) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  DeviceGuard g(c->device);
+  std::string err;
+  int rc = validate_bvh(c->bvh, c->stream, err);
+  return rc ? fail(rc, err) : CUTRACE_OK;
+}
+
+}  // extern "C"

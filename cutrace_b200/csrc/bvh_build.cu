@@ -1,0 +1,639 @@
+// bvh_build.cu — LBVH construction on the device.
+//
+//   1. prim_bounds_kernel   per-primitive AABB + centroid, scene bounds by ordered-int atomics
+//   2. morton_kernel        63-bit Morton code of the centroid (21 bits / axis)
+//   3. radix_sort_pairs     hand-written stable LSD radix sort, 8 bits / pass (CUB is used only by
+//                           tests as a cross-check, never here)
+//   4. gather_kernel        PrimRec + leaf boxes in sorted order
+//   5. karras_kernel        Karras 2012 "Maximizing parallelism in the construction of BVHs":
+//                           one thread per internal node finds its key range and split
+//   6. refit_kernel         bottom-up boxes, second arrival at a node proceeds (atomic flags)
+//   7. scan + emit_kernel   subtrees of <= leaf_size primitives collapse into leaves (their range is
+//                           contiguous in sorted order); live nodes are compacted and written as
+//                           64-byte two-child-box nodes
+//   8. depth_kernel         deepest leaf, checked against the traversal stack
+//
+// What it replaces: the reference has no hierarchy — every ray tests every object and, after one
+// AABB test per mesh, every triangle of the mesh (inc/ray_cast.hpp:37-52, inc/default_schema.hpp:125-144).
+#include <cstdio>
+#include <vector>
+#include "bvh.cuh"
+
+namespace ctb {
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+      rc = (e_ == cudaErrorMemoryAllocation) ? CUTRACE_ERR_OUT_OF_MEMORY : CUTRACE_ERR_CUDA; \
+      goto done;                                                                         \
+    }                                                                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float ord2f_host(unsigned int u) {
+  unsigned int v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
+
+struct Bounds6 { unsigned int lo[3], hi[3], clo[3], chi[3]; };  // full boxes and centroid boxes (ordered ints)
+
+__global__ void init_bounds_kernel(Bounds6 *b) {
+  if (threadIdx.x < 3) {
+    b->lo[threadIdx.x] = 0xffffffffu; b->hi[threadIdx.x] = 0u;
+    b->clo[threadIdx.x] = 0xffffffffu; b->chi[threadIdx.x] = 0u;
+  }
+}
+
+__global__ void prim_bounds_kernel(const float *__restrict__ p1, const float *__restrict__ p2,
+                                   const float *__restrict__ p3, uint32_t n_tri,
+                                   const float *__restrict__ sc, const float *__restrict__ sr, uint32_t n_sph,
+                                   float4 *__restrict__ lo, float4 *__restrict__ hi, Bounds6 *bounds) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t n = n_tri + n_sph;
+  float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool valid = i < n;
+  if (valid) {
+    if (i < n_tri) {
+      for (int c = 0; c < 3; c++) {
+        float a = p1[3 * (size_t)i + c], b = p2[3 * (size_t)i + c], d = p3[3 * (size_t)i + c];
+        l[c] = fminf(fminf(a, b), d);
+        h[c] = fmaxf(fmaxf(a, b), d);
+      }
+    } else {
+      uint32_t s = i - n_tri;
+      float r = fabsf(sr[s]);
+      r = r + r * 1e-6f;  // sphere roots are computed along the normalised direction; keep a margin
+      for (int c = 0; c < 3; c++) { l[c] = sc[3 * (size_t)s + c] - r; h[c] = sc[3 * (size_t)s + c] + r; }
+    }
+    lo[i] = make_float4(l[0], l[1], l[2], 0.f);
+    hi[i] = make_float4(h[0], h[1], h[2], 0.f);
+  }
+  // warp reduce, one set of atomics per warp
+  for (int c = 0; c < 3; c++) {
+    float cl = valid ? 0.5f * (l[c] + h[c]) : INFINITY, ch = valid ? 0.5f * (l[c] + h[c]) : -INFINITY;
+    float fl = l[c], fh = h[c];
+    for (int o = 16; o > 0; o >>= 1) {
+      fl = fminf(fl, __shfl_xor_sync(0xffffffffu, fl, o));
+      fh = fmaxf(fh, __shfl_xor_sync(0xffffffffu, fh, o));
+      cl = fminf(cl, __shfl_xor_sync(0xffffffffu, cl, o));
+      ch = fmaxf(ch, __shfl_xor_sync(0xffffffffu, ch, o));
+    }
+    if ((threadIdx.x & 31) == 0 && fl <= fh) {
+      atomicMin(&bounds->lo[c], f2ord(fl)); atomicMax(&bounds->hi[c], f2ord(fh));
+      atomicMin(&bounds->clo[c], f2ord(cl)); atomicMax(&bounds->chi[c], f2ord(ch));
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v) {
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void morton_kernel(const float4 *__restrict__ lo, const float4 *__restrict__ hi, uint32_t n,
+                              float3 clo, float3 cinv, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 l = lo[i], h = hi[i];
+  float cx = (0.5f * (l.x + h.x) - clo.x) * cinv.x;
+  float cy = (0.5f * (l.y + h.y) - clo.y) * cinv.y;
+  float cz = (0.5f * (l.z + h.z) - clo.z) * cinv.z;
+  const float S = 2097152.0f;  // 2^21
+  unsigned long long x = (unsigned long long)fminf(fmaxf(cx * S, 0.f), S - 1.f);
+  unsigned long long y = (unsigned long long)fminf(fmaxf(cy * S, 0.f), S - 1.f);
+  unsigned long long z = (unsigned long long)fminf(fmaxf(cz * S, 0.f), S - 1.f);
+  keys[i] = (expand21(x) << 2) | (expand21(y) << 1) | expand21(z);
+  vals[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of uint32 (used by the radix sort and by node compaction)
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total, uint32_t *smem /*>=32*/) {
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  if (lane == 31) smem[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (blockDim.x >> 5) ? smem[lane] : 0;
+    uint32_t wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= (uint32_t)o) wi += t;
+    }
+    smem[lane] = wi - w;  // exclusive warp offsets
+    if (lane == 31) smem[32] = wi;
+  }
+  __syncthreads();
+  uint32_t res = incl - v + smem[warp];
+  if (total) *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void scan_tiles_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n,
+                                  uint32_t *__restrict__ tile_sums) {
+  __shared__ uint32_t sm[33];
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], sum = 0;
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(sum, &total, sm);
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = off; off += v[k]; }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void scan_sums_kernel(uint32_t *__restrict__ sums, uint32_t n_tiles, uint32_t *__restrict__ grand_total) {
+  __shared__ uint32_t sm[33];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n_tiles; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < n_tiles ? sums[i] : 0, total;
+    uint32_t off = block_exclusive_scan(v, &total, sm);
+    if (i < n_tiles) sums[i] = off + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && grand_total) *grand_total = carry;
+}
+
+__global__ void scan_add_kernel(uint32_t *__restrict__ out, uint32_t n, const uint32_t *__restrict__ sums) {
+  uint32_t i = blockIdx.x * SCAN_TILE + threadIdx.x;
+  uint32_t add = sums[blockIdx.x];
+  for (int k = 0; k < SCAN_ITEMS; k++, i += SCAN_THREADS)
+    if (i < n) out[i] += add;
+}
+
+// out may alias in. tile_sums must hold ceil(n/SCAN_TILE) entries; d_total (optional) gets the sum.
+static void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tile_sums, uint32_t *d_total,
+                               cudaStream_t st) {
+  if (n == 0) { if (d_total) cudaMemsetAsync(d_total, 0, 4, st); return; }
+  uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  scan_tiles_kernel<<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, tile_sums);
+  scan_sums_kernel<<<1, 1024, 0, st>>>(tile_sums, tiles, d_total);
+  scan_add_kernel<<<tiles, SCAN_THREADS, 0, st>>>(out, n, tile_sums);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable LSD radix sort of (uint64 key, uint32 value), 8 bits per pass
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 8;                       // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;    // 2048 keys per block
+constexpr int RS_WARP_KEYS = 32 * RS_ROUNDS;       // 256 consecutive keys per warp
+
+// block_hist[d * n_blocks + b] = number of keys with digit d in tile b
+__global__ void rs_hist_kernel(const uint64_t *__restrict__ keys, uint32_t n, int shift, uint32_t *__restrict__ block_hist,
+                               uint32_t n_blocks) {
+  __shared__ uint32_t hist[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t base = blockIdx.x * RS_TILE;
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    uint32_t i = base + r * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&hist[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  block_hist[threadIdx.x * n_blocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+// block_hist now holds exclusive global offsets (digit-major). Order inside a tile: warp w owns keys
+// [base + w*256, base + (w+1)*256) and walks them in rounds of 32 -> (warp, round, lane) = index order.
+__global__ void rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                  uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
+                                  int shift, const uint32_t *__restrict__ block_hist, uint32_t n_blocks) {
+  __shared__ uint32_t cnt[RS_WARPS][256];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&cnt[0][0])[k] = 0;
+  __syncthreads();
+  uint32_t base = blockIdx.x * RS_TILE + warp * RS_WARP_KEYS;
+  uint64_t key[RS_ROUNDS];
+  uint32_t dig[RS_ROUNDS];
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    uint32_t i = base + r * 32 + lane;
+    bool ok = i < n;
+    key[r] = ok ? keys_in[i] : 0ull;
+    dig[r] = ok ? ((uint32_t)(key[r] >> shift) & 255u) : (256u + lane);
+    unsigned m = __match_any_sync(0xffffffffu, dig[r]);
+    if (ok && (m & lt) == 0) cnt[warp][dig[r]] += __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // per digit: global tile offset, then exclusive over warps
+    uint32_t d = threadIdx.x;
+    uint32_t run = block_hist[d * n_blocks + blockIdx.x];
+    for (int w = 0; w < RS_WARPS; w++) { uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
+  }
+  __syncthreads();
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    uint32_t i = base + r * 32 + lane;
+    bool ok = i < n;
+    unsigned m = __match_any_sync(0xffffffffu, dig[r]);
+    uint32_t pos = 0;
+    if (ok) pos = cnt[warp][dig[r]] + __popc(m & lt);
+    __syncwarp();
+    if (ok && (m & lt) == 0) cnt[warp][dig[r]] += __popc(m);
+    __syncwarp();
+    if (ok) { keys_out[pos] = key[r]; vals_out[pos] = vals_in[i]; }
+  }
+}
+
+int radix_sort_pairs(uint64_t *d_keys, uint32_t *d_vals, uint32_t n, cudaStream_t st, std::string &err) {
+  int rc = CUTRACE_OK;
+  if (n < 2) return rc;
+  uint64_t *k2 = nullptr;
+  uint32_t *v2 = nullptr, *hist = nullptr, *tile_sums = nullptr;
+  uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+  uint32_t table = 256u * n_blocks;
+  uint64_t *kin = d_keys, *kout = nullptr;
+  uint32_t *vin = d_vals, *vout = nullptr;
+  CK(cudaMalloc(&k2, sizeof(uint64_t) * n));
+  CK(cudaMalloc(&v2, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&hist, sizeof(uint32_t) * table));
+  CK(cudaMalloc(&tile_sums, sizeof(uint32_t) * ((table + SCAN_TILE - 1) / SCAN_TILE + 1)));
+  kout = k2; vout = v2;
+  for (int pass = 0; pass < 8; pass++) {
+    int shift = pass * 8;
+    rs_hist_kernel<<<n_blocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, n_blocks);
+    exclusive_scan_u32(hist, hist, table, tile_sums, nullptr, st);
+    rs_scatter_kernel<<<n_blocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist, n_blocks);
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  CK(cudaGetLastError());
+  // 8 passes = even number of swaps: the result is back in d_keys / d_vals
+  CK(cudaStreamSynchronize(st));
+done:
+  cudaFree(k2); cudaFree(v2); cudaFree(hist); cudaFree(tile_sums);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather sorted primitive records
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_kernel(const uint32_t *__restrict__ vals, uint32_t n, const float *__restrict__ p1,
+                              const float *__restrict__ p2, const float *__restrict__ p3,
+                              const uint32_t *__restrict__ tri_obj, uint32_t n_tri, const float *__restrict__ sc,
+                              const float *__restrict__ sr, const uint32_t *__restrict__ sph_obj,
+                              const float4 *__restrict__ lo, const float4 *__restrict__ hi, PrimRec *__restrict__ prims,
+                              float4 *__restrict__ leaf_lo, float4 *__restrict__ leaf_hi) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  uint32_t src = vals[k];
+  PrimRec r;
+  if (src < n_tri) {
+    size_t o = 3 * (size_t)src;
+    r.p1x = p1[o]; r.p1y = p1[o + 1]; r.p1z = p1[o + 2];
+    r.p2x = p2[o]; r.p2y = p2[o + 1]; r.p2z = p2[o + 2];
+    r.p3x = p3[o]; r.p3y = p3[o + 1]; r.p3z = p3[o + 2];
+    r.obj = tri_obj[src]; r.idx = src; r.kind = CTB_PRIM_TRI;
+  } else {
+    uint32_t s = src - n_tri;
+    size_t o = 3 * (size_t)s;
+    r.p1x = sc[o]; r.p1y = sc[o + 1]; r.p1z = sc[o + 2];
+    r.p2x = sr[s]; r.p2y = 0.f; r.p2z = 0.f;
+    r.p3x = r.p3y = r.p3z = 0.f;
+    r.obj = sph_obj[s]; r.idx = s; r.kind = CTB_PRIM_SPHERE;
+  }
+  prims[k] = r;
+  leaf_lo[k] = lo[src];
+  leaf_hi[k] = hi[src];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Karras hierarchy
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint64_t *__restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz((unsigned)i ^ (unsigned)j);
+  return __clzll((long long)(a ^ b));
+}
+
+// children: >= 0 internal node index, < 0 leaf ~k
+__global__ void karras_kernel(const uint64_t *__restrict__ keys, int n, int2 *__restrict__ children,
+                              int2 *__restrict__ range, int *__restrict__ parent_node, int *__restrict__ parent_leaf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = delta(keys, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+    if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t == 1) break;
+  }
+  int gamma = i + s * d + min(d, 0);
+  int lo = min(i, j), hi = max(i, j);
+  int left = (lo == gamma) ? ~gamma : gamma;
+  int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+  children[i] = make_int2(left, right);
+  range[i] = make_int2(lo, hi);
+  if (left >= 0) parent_node[left] = i; else parent_leaf[~left] = i;
+  if (right >= 0) parent_node[right] = i; else parent_leaf[~right] = i;
+  if (i == 0) parent_node[0] = -1;
+}
+
+__global__ void refit_kernel(int n, const int2 *__restrict__ children, const int *__restrict__ parent_node,
+                             const int *__restrict__ parent_leaf, const float4 *leaf_lo, const float4 *leaf_hi,
+                             float4 *node_lo, float4 *node_hi, unsigned int *flags) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int node = parent_leaf[k];
+  while (node >= 0) {
+    __threadfence();
+    if (atomicAdd(&flags[node], 1u) == 0u) return;  // first arrival: the sibling subtree is not done yet
+    __threadfence();
+    int2 c = children[node];
+    float4 l0 = c.x >= 0 ? __ldcg(&node_lo[c.x]) : __ldcg(&leaf_lo[~c.x]);
+    float4 h0 = c.x >= 0 ? __ldcg(&node_hi[c.x]) : __ldcg(&leaf_hi[~c.x]);
+    float4 l1 = c.y >= 0 ? __ldcg(&node_lo[c.y]) : __ldcg(&leaf_lo[~c.y]);
+    float4 h1 = c.y >= 0 ? __ldcg(&node_hi[c.y]) : __ldcg(&leaf_hi[~c.y]);
+    __stcg(&node_lo[node], make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f));
+    __stcg(&node_hi[node], make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f));
+    node = parent_node[node];
+  }
+}
+
+__global__ void live_kernel(int n_internal, const int2 *__restrict__ range, uint32_t leaf_size, uint32_t *__restrict__ live) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal) return;
+  int2 r = range[i];
+  live[i] = (uint32_t)(r.y - r.x + 1) > leaf_size ? 1u : 0u;
+}
+
+__global__ void emit_kernel(int n_internal, const int2 *__restrict__ children, const int2 *__restrict__ range,
+                            const uint32_t *__restrict__ compact, uint32_t leaf_size, const float4 *__restrict__ leaf_lo,
+                            const float4 *__restrict__ leaf_hi, const float4 *__restrict__ node_lo,
+                            const float4 *__restrict__ node_hi, float eps, Node *__restrict__ nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal) return;
+  int2 r = range[i];
+  if ((uint32_t)(r.y - r.x + 1) <= leaf_size) return;  // collapsed into a leaf of an ancestor
+  int2 c = children[i];
+  int ref[2];
+  float4 lo[2], hi[2];
+  int cc[2] = {c.x, c.y};
+  for (int s = 0; s < 2; s++) {
+    int ch = cc[s];
+    if (ch < 0) {
+      ref[s] = leaf_encode((uint32_t)~ch, 1u);
+      lo[s] = leaf_lo[~ch]; hi[s] = leaf_hi[~ch];
+    } else {
+      int2 cr = range[ch];
+      uint32_t cnt = (uint32_t)(cr.y - cr.x + 1);
+      ref[s] = cnt <= leaf_size ? leaf_encode((uint32_t)cr.x, cnt) : (int)compact[ch];
+      lo[s] = node_lo[ch]; hi[s] = node_hi[ch];
+    }
+  }
+  Node nd;
+  nd.n0xy = make_float4(lo[0].x - eps, hi[0].x + eps, lo[0].y - eps, hi[0].y + eps);
+  nd.n1xy = make_float4(lo[1].x - eps, hi[1].x + eps, lo[1].y - eps, hi[1].y + eps);
+  nd.nz = make_float4(lo[0].z - eps, hi[0].z + eps, lo[1].z - eps, hi[1].z + eps);
+  nd.meta = make_int4(ref[0], ref[1], r.x, r.y);  // z,w = primitive range (debug / validation)
+  nodes[compact[i]] = nd;
+}
+
+__global__ void depth_kernel(int n_internal, const int2 *__restrict__ range, const int *__restrict__ parent_node,
+                             uint32_t leaf_size, unsigned int *max_depth) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal) return;
+  int2 r = range[i];
+  if ((uint32_t)(r.y - r.x + 1) <= leaf_size) return;
+  unsigned int d = 1;
+  for (int p = parent_node[i]; p >= 0; p = parent_node[p]) d++;
+  atomicMax(max_depth, d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// validation: every primitive covered exactly once, child boxes contain their primitives / grandchildren
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prim_box(const PrimRec &p, float lo[3], float hi[3]) {
+  if (p.kind == CTB_PRIM_TRI) {
+    lo[0] = fminf(fminf(p.p1x, p.p2x), p.p3x); hi[0] = fmaxf(fmaxf(p.p1x, p.p2x), p.p3x);
+    lo[1] = fminf(fminf(p.p1y, p.p2y), p.p3y); hi[1] = fmaxf(fmaxf(p.p1y, p.p2y), p.p3y);
+    lo[2] = fminf(fminf(p.p1z, p.p2z), p.p3z); hi[2] = fmaxf(fmaxf(p.p1z, p.p2z), p.p3z);
+  } else {
+    float r = fabsf(p.p2x);
+    lo[0] = p.p1x - r; hi[0] = p.p1x + r; lo[1] = p.p1y - r; hi[1] = p.p1y + r; lo[2] = p.p1z - r; hi[2] = p.p1z + r;
+  }
+}
+
+__global__ void validate_kernel(const Node *__restrict__ nodes, uint32_t n_nodes, const PrimRec *__restrict__ prims,
+                                uint32_t n_prims, unsigned int *cover, unsigned int *node_refs, unsigned int *errors) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  Node nd = nodes[i];
+  int ch[2] = {nd.meta.x, nd.meta.y};
+  float blo[2][3] = {{nd.n0xy.x, nd.n0xy.z, nd.nz.x}, {nd.n1xy.x, nd.n1xy.z, nd.nz.z}};
+  float bhi[2][3] = {{nd.n0xy.y, nd.n0xy.w, nd.nz.y}, {nd.n1xy.y, nd.n1xy.w, nd.nz.w}};
+  for (int s = 0; s < 2; s++) {
+    if (ch[s] < 0) {
+      uint32_t f = leaf_first(ch[s]), c = leaf_count(ch[s]);
+      for (uint32_t k = f; k < f + c; k++) {
+        if (k >= n_prims) { atomicAdd(errors, 1u); continue; }
+        atomicAdd(&cover[k], 1u);
+        float lo[3], hi[3];
+        prim_box(prims[k], lo, hi);
+        for (int a = 0; a < 3; a++)
+          if (!(lo[a] >= blo[s][a] && hi[a] <= bhi[s][a])) atomicAdd(errors, 1u);
+      }
+    } else {
+      if ((uint32_t)ch[s] >= n_nodes || ch[s] == 0) { atomicAdd(errors, 1u); continue; }
+      atomicAdd(&node_refs[ch[s]], 1u);
+      Node cn = nodes[ch[s]];
+      float clo[3] = {fminf(cn.n0xy.x, cn.n1xy.x), fminf(cn.n0xy.z, cn.n1xy.z), fminf(cn.nz.x, cn.nz.z)};
+      float chi[3] = {fmaxf(cn.n0xy.y, cn.n1xy.y), fmaxf(cn.n0xy.w, cn.n1xy.w), fmaxf(cn.nz.y, cn.nz.w)};
+      for (int a = 0; a < 3; a++)
+        if (!(clo[a] >= blo[s][a] - 1e-30f && chi[a] <= bhi[s][a] + 1e-30f)) atomicAdd(errors, 1u);
+    }
+  }
+}
+
+__global__ void validate_cover_kernel(const unsigned int *cover, uint32_t n_prims, const unsigned int *node_refs,
+                                      uint32_t n_nodes, unsigned int *errors) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_prims && cover[i] != 1u) atomicAdd(errors + 1, 1u);
+  if (i > 0 && i < n_nodes && node_refs[i] != 1u) atomicAdd(errors + 2, 1u);
+}
+
+int validate_bvh(const BvhResult &bvh, cudaStream_t st, std::string &err) {
+  int rc = CUTRACE_OK;
+  unsigned int *cover = nullptr, *refs = nullptr, *errors = nullptr;
+  unsigned int h_err[3] = {0, 0, 0};
+  if (bvh.n_prims == 0) return rc;
+  CK(cudaMalloc(&cover, sizeof(unsigned int) * bvh.n_prims));
+  CK(cudaMalloc(&refs, sizeof(unsigned int) * (bvh.n_nodes + 1)));
+  CK(cudaMalloc(&errors, sizeof(unsigned int) * 3));
+  CK(cudaMemsetAsync(cover, 0, sizeof(unsigned int) * bvh.n_prims, st));
+  CK(cudaMemsetAsync(refs, 0, sizeof(unsigned int) * (bvh.n_nodes + 1), st));
+  CK(cudaMemsetAsync(errors, 0, sizeof(unsigned int) * 3, st));
+  if (bvh.root >= 0 && bvh.root != CTB_SENTINEL) {
+    validate_kernel<<<(bvh.n_nodes + 255) / 256, 256, 0, st>>>(bvh.nodes, bvh.n_nodes, bvh.prims, bvh.n_prims, cover, refs, errors);
+    uint32_t m = bvh.n_prims > bvh.n_nodes ? bvh.n_prims : bvh.n_nodes;
+    validate_cover_kernel<<<(m + 255) / 256, 256, 0, st>>>(cover, bvh.n_prims, refs, bvh.n_nodes, errors);
+  } else if (bvh.root < 0) {
+    if (leaf_first(bvh.root) != 0 || leaf_count(bvh.root) != bvh.n_prims) h_err[1] = 1;
+  }
+  CK(cudaGetLastError());
+  if (bvh.root >= 0 && bvh.root != CTB_SENTINEL) CK(cudaMemcpyAsync(h_err, errors, sizeof h_err, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (h_err[0] || h_err[1] || h_err[2]) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "BVH validation failed: %u box/containment errors, %u primitives not covered exactly once, %u nodes not referenced exactly once",
+             h_err[0], h_err[1], h_err[2]);
+    err = buf;
+    rc = CUTRACE_ERR_INTERNAL;
+  }
+done:
+  cudaFree(cover); cudaFree(refs); cudaFree(errors);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// driver
+// ---------------------------------------------------------------------------------------------
+int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
+  int rc = CUTRACE_OK;
+  cudaStream_t st = in.stream;
+  const uint32_t n = in.n_tri + in.n_sph;
+  uint32_t leaf_size = in.leaf_size ? in.leaf_size : 4;
+  if (leaf_size > CTB_MAX_LEAF) leaf_size = CTB_MAX_LEAF;
+  out = BvhResult();
+  out.n_prims = n;
+  if (n == 0) return rc;
+  if (n >= (1u << 28)) { err = "too many primitives for the leaf encoding (max 2^28-1)"; return CUTRACE_ERR_INVALID_ARG; }
+
+  float4 *lo = nullptr, *hi = nullptr, *leaf_lo = nullptr, *leaf_hi = nullptr, *node_lo = nullptr, *node_hi = nullptr;
+  Bounds6 *d_bounds = nullptr;
+  uint64_t *keys = nullptr;
+  uint32_t *vals = nullptr, *live = nullptr, *tile_sums = nullptr, *d_total = nullptr;
+  int2 *children = nullptr, *range = nullptr;
+  int *parent_node = nullptr, *parent_leaf = nullptr;
+  unsigned int *flags = nullptr, *d_depth = nullptr;
+  Bounds6 hb;
+  const int T = 256;
+  const uint32_t nb = (n + T - 1) / T;
+  const int ni = (int)n - 1;
+
+  CK(cudaMalloc(&lo, sizeof(float4) * n));
+  CK(cudaMalloc(&hi, sizeof(float4) * n));
+  CK(cudaMalloc(&d_bounds, sizeof(Bounds6)));
+  CK(cudaMalloc(&keys, sizeof(uint64_t) * n));
+  CK(cudaMalloc(&vals, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&out.prims, sizeof(PrimRec) * n));
+  CK(cudaMalloc(&leaf_lo, sizeof(float4) * n));
+  CK(cudaMalloc(&leaf_hi, sizeof(float4) * n));
+
+  init_bounds_kernel<<<1, 32, 0, st>>>(d_bounds);
+  prim_bounds_kernel<<<nb, T, 0, st>>>(in.d_p1, in.d_p2, in.d_p3, in.n_tri, in.d_sph_center, in.d_sph_radius, in.n_sph, lo, hi, d_bounds);
+  CK(cudaMemcpyAsync(&hb, d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  {
+    float3 clo, cinv;
+    float cl[3], ch[3], mag = 0.f;
+    for (int c = 0; c < 3; c++) {
+      out.lo[c] = ord2f_host(hb.lo[c]); out.hi[c] = ord2f_host(hb.hi[c]);
+      cl[c] = ord2f_host(hb.clo[c]); ch[c] = ord2f_host(hb.chi[c]);
+      mag = fmaxf(mag, fmaxf(fabsf(out.lo[c]), fabsf(out.hi[c])));
+    }
+    clo = make_float3(cl[0], cl[1], cl[2]);
+    cinv = make_float3(ch[0] > cl[0] ? 1.f / (ch[0] - cl[0]) : 0.f, ch[1] > cl[1] ? 1.f / (ch[1] - cl[1]) : 0.f,
+                       ch[2] > cl[2] ? 1.f / (ch[2] - cl[2]) : 0.f);
+    morton_kernel<<<nb, T, 0, st>>>(lo, hi, n, clo, cinv, keys, vals);
+    rc = radix_sort_pairs(keys, vals, n, st, err);
+    if (rc) goto done;
+    gather_kernel<<<nb, T, 0, st>>>(vals, n, in.d_p1, in.d_p2, in.d_p3, in.d_tri_obj, in.n_tri, in.d_sph_center,
+                                    in.d_sph_radius, in.d_sph_obj, lo, hi, out.prims, leaf_lo, leaf_hi);
+    CK(cudaGetLastError());
+
+    if (n <= leaf_size) {  // the whole scene is one leaf
+      out.root = leaf_encode(0u, n);
+      out.n_nodes = 0;
+      out.depth = 0;
+      CK(cudaStreamSynchronize(st));
+      goto done;
+    }
+
+    // box inflation: the reference's Cramer test accepts rays a few ulp outside the exact triangle,
+    // so boxes get a margin proportional to the scene's coordinate magnitude (DESIGN.md "conservative culling")
+    float eps = fmaxf(mag, 1e-30f) * 2e-6f;
+
+    CK(cudaMalloc(&children, sizeof(int2) * ni));
+    CK(cudaMalloc(&range, sizeof(int2) * ni));
+    CK(cudaMalloc(&parent_node, sizeof(int) * ni));
+    CK(cudaMalloc(&parent_leaf, sizeof(int) * n));
+    CK(cudaMalloc(&node_lo, sizeof(float4) * ni));
+    CK(cudaMalloc(&node_hi, sizeof(float4) * ni));
+    CK(cudaMalloc(&flags, sizeof(unsigned int) * ni));
+    CK(cudaMalloc(&live, sizeof(uint32_t) * ni));
+    CK(cudaMalloc(&tile_sums, sizeof(uint32_t) * ((ni + SCAN_TILE - 1) / SCAN_TILE + 1)));
+    CK(cudaMalloc(&d_total, sizeof(uint32_t)));
+    CK(cudaMalloc(&d_depth, sizeof(unsigned int)));
+    CK(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * ni, st));
+    CK(cudaMemsetAsync(d_depth, 0, sizeof(unsigned int), st));
+    const uint32_t nbi = (ni + T - 1) / T;
+    karras_kernel<<<nbi, T, 0, st>>>(keys, (int)n, children, range, parent_node, parent_leaf);
+    refit_kernel<<<nb, T, 0, st>>>((int)n, children, parent_node, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags);
+    live_kernel<<<nbi, T, 0, st>>>(ni, range, leaf_size, live);
+    exclusive_scan_u32(live, live, (uint32_t)ni, tile_sums, d_total, st);
+    uint32_t n_live = 0;
+    CK(cudaMemcpyAsync(&n_live, d_total, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_live == 0) { err = "internal: LBVH has no live node"; rc = CUTRACE_ERR_INTERNAL; goto done; }
+    out.n_nodes = n_live;
+    CK(cudaMalloc(&out.nodes, sizeof(Node) * n_live));
+    emit_kernel<<<nbi, T, 0, st>>>(ni, children, range, live, leaf_size, leaf_lo, leaf_hi, node_lo, node_hi, eps, out.nodes);
+    depth_kernel<<<nbi, T, 0, st>>>(ni, range, parent_node, leaf_size, d_depth);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&out.depth, d_depth, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out.root = 0;
+    if (out.depth > CTB_STACK - 2) {
+      char buf[128];
+      snprintf(buf, sizeof buf, "LBVH depth %u exceeds the traversal stack (%d)", out.depth, CTB_STACK - 2);
+      err = buf; rc = CUTRACE_ERR_INTERNAL; goto done;
+    }
+  }
+done:
+  cudaFree(lo); cudaFree(hi); cudaFree(d_bounds); cudaFree(keys); cudaFree(vals); cudaFree(leaf_lo); cudaFree(leaf_hi);
+  cudaFree(node_lo); cudaFree(node_hi); cudaFree(children); cudaFree(range); cudaFree(parent_node); cudaFree(parent_leaf);
+  cudaFree(flags); cudaFree(live); cudaFree(tile_sums); cudaFree(d_total); cudaFree(d_depth);
+  if (rc != CUTRACE_OK) {
+    cudaFree(out.prims); cudaFree(out.nodes);
+    out.prims = nullptr; out.nodes = nullptr;
+  }
+  return rc;
+}
+
+}  // namespace ctb

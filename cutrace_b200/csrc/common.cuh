@@ -1,0 +1,147 @@
+// common.cuh — shared device types of the B200 render path (flat SoA scene store, LBVH, queues).
+//
+// Replaces the reference's array-of-tagged-unions scene (inc/gpu_variant.hpp, inc/gpu_array.hpp,
+// inc/gpu_types.hpp:263-287) with 16-byte aligned records that are read with 128-bit loads.
+#ifndef CUTRACE_B200_COMMON_CUH
+#define CUTRACE_B200_COMMON_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/cutrace.h"
+
+namespace ctb {
+
+// ---- float3 math in the reference's expression order (inc/vector.hpp) --------------------------
+// nvcc contracts a*b+c into FMA exactly as it does for the reference (-fmad=true is the default
+// and the reference's CMakeLists.txt sets no fast-math), so these are written as the same
+// expression trees as inc/vector.hpp rather than with explicit fmaf().
+struct vec3 { float x, y, z; };
+
+__host__ __device__ __forceinline__ vec3 mk3(float x, float y, float z) { vec3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ __forceinline__ vec3 vadd(vec3 a, vec3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }   // :100
+__host__ __device__ __forceinline__ vec3 vsub(vec3 a, vec3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }   // :109
+__host__ __device__ __forceinline__ vec3 vscale(vec3 a, float f) { return mk3(f * a.x, f * a.y, f * a.z); }      // :118
+__host__ __device__ __forceinline__ vec3 vmul(vec3 a, vec3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }   // :136
+__host__ __device__ __forceinline__ float vdot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }     // :127
+__host__ __device__ __forceinline__ vec3 vcross(vec3 a, vec3 o) {                                               // :65-71
+  return mk3(a.y * o.z - a.z * o.y, a.z * o.x - a.x * o.z, a.x * o.y - a.y * o.x);
+}
+__host__ __device__ __forceinline__ float vnorm(vec3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }    // :85-92
+__host__ __device__ __forceinline__ vec3 vnormalized(vec3 a) { return vscale(a, 1.0f / vnorm(a)); }             // :77-79
+__host__ __device__ __forceinline__ vec3 vreflect(vec3 incoming, vec3 normal) {                                 // :204-206
+  return vsub(incoming, vscale(normal, 2.0f * vdot(normal, incoming)));
+}
+// matrix::determinant (Sarrus), inc/vector.hpp:218-224, columns c0 c1 c2
+__host__ __device__ __forceinline__ float det3(vec3 c0, vec3 c1, vec3 c2) {
+  float a = c0.x, b = c1.x, c = c2.x, d = c0.y, e = c1.y, f = c2.y, g = c0.z, h = c1.z, i = c2.z;
+  return a * e * i + b * f * g + c * d * h - c * e * g - a * f * h - b * d * i;
+}
+
+// ---- scene records ------------------------------------------------------------------------------
+// One 48-byte record per BVH primitive, stored in BVH-leaf (Morton) order: 3 x LDG.128 / LDS.128.
+// Triangle: p1,p2,p3 = vertices exactly as uploaded (the reference's gpu::schema::triangle is also
+// 48 B, inc/default_schema.hpp:26-30).  Sphere: p1 = centre, p2.x = radius.
+// (obj, idx) implements the reference's tie-break: lowest object index wins an equal-t tie
+// (inc/ray_cast.hpp:43), then lowest triangle index in file order (inc/default_schema.hpp:134).
+struct __align__(16) PrimRec {
+  float p1x, p1y, p1z; uint32_t obj;
+  float p2x, p2y, p2z; uint32_t idx;
+  float p3x, p3y, p3z; uint32_t kind;   // 0 triangle, 1 sphere
+};
+static_assert(sizeof(PrimRec) == 48, "PrimRec must be 48 bytes");
+#define CTB_PRIM_TRI 0u
+#define CTB_PRIM_SPHERE 1u
+
+// 64-byte binary BVH node holding BOTH children's boxes (4 x 128-bit loads per visit).
+//   n0xy = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1xy likewise for child 1
+//   nz   = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//   meta = (c0, c1, -, -)   child >= 0: node index; child < 0: leaf, ~child = (first << 3) | (count-1)
+struct __align__(16) Node {
+  float4 n0xy, n1xy, nz;
+  int4 meta;
+};
+static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
+#define CTB_SENTINEL 0x7fffffff
+#define CTB_STACK 64
+#define CTB_MAX_LEAF 8
+
+__host__ __device__ __forceinline__ int leaf_encode(uint32_t first, uint32_t count) { return ~(int)((first << 3) | (count - 1u)); }
+__host__ __device__ __forceinline__ uint32_t leaf_first(int c) { return ((uint32_t)~c) >> 3; }
+__host__ __device__ __forceinline__ uint32_t leaf_count(int c) { return (((uint32_t)~c) & 7u) + 1u; }
+
+struct __align__(16) PlaneRec {   // plane::intersect, inc/default_schema.hpp:159-207
+  float px, py, pz; uint32_t obj;
+  float nx, ny, nz; uint32_t pad;
+};
+struct __align__(16) MaterialRec {  // phong_material, inc/default_schema.hpp:319-343
+  float r, g, b, specular;
+  float reflect, phong, transparency; uint32_t pad;
+};
+struct __align__(16) LightRec {     // sun / point_light, inc/default_schema.hpp:267-311
+  float vx, vy, vz; uint32_t kind;
+  float r, g, b; uint32_t pad;
+};
+
+struct Camera {   // cam, inc/default_schema.hpp:350-396 (post look_at)
+  vec3 pos, up, forward, right;
+  float ambient;
+  uint32_t w, h;
+};
+
+// ---- wavefront queue records ---------------------------------------------------------------------
+struct __align__(16) RayRec {       // 32 B: secondary ray (reflection / transmission)
+  float ox, oy, oz; uint32_t pix;
+  float dx, dy, dz; float weight;
+};
+struct __align__(16) ShadeRec {     // 48 B: one shaded hit = n_lights shadow rays + Phong
+  float hx, hy, hz; uint32_t pix;   // hit point as the primitive reports it (shadow-ray origin)
+  float nx, ny, nz; uint32_t mat;   // raw normal (normalised inside phong, inc/shading.hpp:83)
+  float ix, iy, iz; float weight;   // incoming ray direction; path weight of this hit's Phong term
+};
+static_assert(sizeof(RayRec) == 32 && sizeof(ShadeRec) == 48, "queue record sizes");
+
+// device-side counters of one frame
+struct FrameCounters {
+  unsigned int n_rays[18];      // rays queued for level L (level 0 = primary, filled by host)
+  unsigned int n_shade[18];     // shade records produced by level L
+  unsigned int work_trace[18];  // work-stealing cursors
+  unsigned int work_shade[18];
+  unsigned long long rays_reflect, rays_transmit, shadow_casts;
+  unsigned int max_depth_bits;  // float bits of the largest finite primary depth
+  unsigned int overflow;        // set if a queue would overflow (cannot happen with worst-case sizing)
+};
+
+// everything a render kernel needs, passed by value (lives in the constant bank)
+struct SceneView {
+  const Node *nodes;
+  const PrimRec *prims;
+  const PlaneRec *planes;
+  const MaterialRec *materials;
+  const LightRec *lights;
+  const uint32_t *obj_material;
+  uint32_t n_prims, n_nodes, n_planes, n_lights, n_materials, n_objects;
+  int root;                 // node index, leaf code, or CTB_SENTINEL (empty BVH)
+  uint32_t smem_nodes;      // nodes [0, smem_nodes) are staged in shared memory
+  uint32_t smem_prims;      // prims [0, smem_prims) are staged in shared memory
+  uint32_t all_opaque;      // no material has transparency >= 1e-6 (shadow rays can be any-hit)
+  uint32_t brute_force;
+  float fudge;
+  Camera cam;
+};
+
+// screen-space tiling of the local framebuffer (tile-major, row-major inside a tile)
+struct TileMap {
+  uint32_t width, height;
+  uint32_t tiles_x, tiles_y;
+  uint32_t rank, world;       // this ctx owns global tiles t with t % world == rank
+  uint32_t n_local_tiles;
+};
+
+__host__ __device__ __forceinline__ uint32_t tile_global_index(const TileMap &tm, uint32_t local_tile) {
+  return local_tile * tm.world + tm.rank;
+}
+
+}  // namespace ctb
+#endif

@@ -1,0 +1,345 @@
+// render.cu — the wavefront pipeline that replaces the reference's recursive one-thread-per-pixel
+// kernel (inc/kernel.hpp:35-60 -> inc/shading.hpp:116-154 -> inc/ray_cast.hpp:29-55).
+//
+// Per bounce level L (0 = primary rays) two persistent, work-stealing kernels run:
+//
+//   trace_kernel  closest hit for every ray of level L (L = 0: rays are generated from the pixel
+//                 index, cam::get_ray inc/default_schema.hpp:376-386).  Level 0 also writes the
+//                 G-buffer (depth / raw normal / object id, inc/kernel.hpp:52-56) and reduces the
+//                 largest finite depth (inc/kernel.hpp:120-125).  Every hit emits one ShadeRec;
+//                 mirror / transparent materials push child rays into the level L+1 queue
+//                 (inc/shading.hpp:130-149), compacted with warp ballot + popc and ONE atomicAdd
+//                 per warp.
+//   shade_kernel  per ShadeRec: all shadow rays (shadow_intensity, inc/shading.hpp:22-45) and the
+//                 Phong sum (inc/shading.hpp:64-99), accumulated into the colour buffer with the
+//                 path weight of the hit.
+//
+// The recursion  rgb = (1-t)*(phong + r*R) + t*T  (inc/shading.hpp:138,148) is unrolled into path
+// weights: own Phong term w*(1-t), reflected child w*(1-t)*r, transmitted child w*t; at the last
+// level (bounces exhausted) the blend is skipped exactly like `if constexpr(bounces != 0)`.
+//
+// Kernels are persistent: grid = SM count x resident CTAs; each warp claims WORK_CHUNK rays at a time
+// from a global cursor (work stealing), so cheap and expensive rays balance without a tail.
+#include "render.cuh"
+#include "trace.cuh"
+
+namespace ctb {
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// stage the BVH nodes and the primitive store in shared memory (MODE 1) — LDS.128 instead of
+// divergent LDG.128 for the small reference scenes whose whole BVH fits next to the SM
+template <int MODE>
+__device__ __forceinline__ void stage_scene(const SceneView &sv, float4 *smem, const float4 *&nodes, const float4 *&prims) {
+  if (MODE == 1) {
+    const float4 *gn = reinterpret_cast<const float4 *>(sv.nodes);
+    const float4 *gp = reinterpret_cast<const float4 *>(sv.prims);
+    uint32_t nn = sv.n_nodes * 4u, np = sv.n_prims * 3u;
+    for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) smem[i] = __ldg(gn + i);
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) smem[nn + i] = __ldg(gp + i);
+    __syncthreads();
+    nodes = smem;
+    prims = smem + nn;
+  } else {
+    nodes = reinterpret_cast<const float4 *>(sv.nodes);
+    prims = reinterpret_cast<const float4 *>(sv.prims);
+  }
+}
+
+// local work index -> pixel.  Inside a 32x32 tile, 32 consecutive indices form an 8x4 pixel block
+// (coherent primary rays per warp); the framebuffer itself is row-major inside the tile.
+__device__ __forceinline__ bool work_to_pixel(const TileMap &tm, uint32_t i, uint32_t &x, uint32_t &y, uint32_t &pix) {
+  uint32_t lt = i >> 10, w = i & 1023u;
+  uint32_t b = w >> 5, l = w & 31u;
+  uint32_t px = ((b & 3u) << 3) + (l & 7u), py = ((b >> 2) << 2) + (l >> 3);
+  uint32_t gt = lt * tm.world + tm.rank;
+  uint32_t tx = gt % tm.tiles_x, ty = gt / tm.tiles_x;
+  x = tx * CUTRACE_TILE + px;
+  y = ty * CUTRACE_TILE + py;
+  pix = (lt << 10) + (py << 5) + px;
+  return x < tm.width && y < tm.height && ty < tm.tiles_y;
+}
+
+// cam::get_ray, inc/default_schema.hpp:376-386
+__device__ __forceinline__ void camera_ray(const Camera &c, uint32_t x, uint32_t y, vec3 &o, vec3 &d) {
+  float aspect = (float)c.w / (float)c.h;
+  vec3 x_v = vscale(c.right, (((float)x / (float)c.w) - 0.5f) * aspect);
+  vec3 y_v = vscale(c.up, 0.5f - ((float)y / (float)c.h));
+  vec3 z_v = c.forward;
+  o = c.pos;
+  d = vnormalized(vadd(vadd(x_v, y_v), z_v));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
+trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t bounces, uint32_t px_base, uint32_t n_px,
+             const RayRec *__restrict__ rays_in, RayRec *__restrict__ rays_out, ShadeRec *__restrict__ shade_out,
+             FrameCounters *ctr, FrameTargets fb) {
+  extern __shared__ float4 smem[];
+  const float4 *nodes, *prims;
+  stage_scene<MODE>(sv, smem, nodes, prims);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = lanemask_lt();
+  const uint32_t n_work = level == 0 ? n_px : ctr->n_rays[level];
+  unsigned long long n_refl = 0, n_trans = 0;
+  float max_depth = 0.f;
+
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&ctr->work_trace[level], (unsigned)WORK_CHUNK);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n_work) break;
+    for (unsigned off = 0; off < (unsigned)WORK_CHUNK && base + off < n_work; off += 32) {
+      const uint32_t i = base + off + lane;
+      bool active = i < n_work;
+      vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
+      float w = 1.0f;
+      uint32_t pix = 0;
+      if (level == 0) {
+        uint32_t x = 0, y = 0;
+        active = active && work_to_pixel(tm, px_base + i, x, y, pix);
+        if (active) camera_ray(sv.cam, x, y, o, d);
+      } else if (active) {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays_in + i);
+        float4 a = __ldcs(rp), b = __ldcs(rp + 1);
+        o = mk3(a.x, a.y, a.z); pix = __float_as_uint(a.w);
+        d = mk3(b.x, b.y, b.z); w = b.w;
+      }
+      Hit h;
+      hit_reset(h);
+      if (active) closest_hit<MODE>(sv, nodes, prims, o, d, sv.fudge, h);
+      const bool hit = active && h.kind >= 0;
+      vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
+      uint32_t mat = 0;
+      float reflect = 0.f, transp = 0.f;
+      if (hit) {
+        hit_surface(sv, prims, MODE == 1, h, o, d, point, nrm);
+        mat = __ldg(sv.obj_material + h.obj);
+        const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
+        float4 m1 = __ldg(mp + 1);
+        reflect = m1.x; transp = m1.z;
+      }
+      if (level == 0 && active) {   // G-buffer, inc/kernel.hpp:52-56
+        fb.depth[pix] = h.t;
+        fb.normal[3 * (size_t)pix] = nrm.x; fb.normal[3 * (size_t)pix + 1] = nrm.y; fb.normal[3 * (size_t)pix + 2] = nrm.z;
+        fb.hit_id[pix] = hit ? h.obj : CUTRACE_NO_HIT;
+        if (hit && isfinite(h.t)) max_depth = fmaxf(max_depth, h.t);
+      }
+      // inc/shading.hpp:126-149
+      bool do_refl = false, do_trans = false;
+      float w_own = w;
+      if (hit && level < bounces) {
+        do_refl = (double)reflect >= 1e-6;
+        do_trans = (double)transp >= 1e-6;
+        if (do_trans) w_own = w * (1.0f - transp);
+      }
+      // ---- shade record: one per hit, warp-aggregated slot allocation ----
+      const unsigned m_hit = __ballot_sync(0xffffffffu, hit);
+      if (m_hit) {
+        unsigned sbase = 0;
+        if (lane == 0) sbase = atomicAdd(&ctr->n_shade[level], (unsigned)__popc(m_hit));
+        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        if (hit) {
+          float4 *sp = reinterpret_cast<float4 *>(shade_out + sbase + __popc(m_hit & lt_mask));
+          __stcs(sp, make_float4(point.x, point.y, point.z, __uint_as_float(pix)));
+          __stcs(sp + 1, make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(mat)));
+          __stcs(sp + 2, make_float4(d.x, d.y, d.z, w_own));
+        }
+      }
+      // ---- child rays ----
+      const unsigned m_r = __ballot_sync(0xffffffffu, do_refl), m_t = __ballot_sync(0xffffffffu, do_trans);
+      if (m_r | m_t) {
+        unsigned rbase = 0;
+        const unsigned nr = __popc(m_r), nt = __popc(m_t);
+        if (lane == 0) rbase = atomicAdd(&ctr->n_rays[level + 1], nr + nt);
+        rbase = __shfl_sync(0xffffffffu, rbase, 0);
+        const vec3 origin = vadd(o, vscale(d, h.t));   // incoming->start + distance * incoming->dir
+        if (do_refl) {
+          vec3 nd = vnormalized(d), nn = vnormalized(nrm);
+          vec3 rd = vreflect(nd, nn);
+          float4 *rp = reinterpret_cast<float4 *>(rays_out + rbase + __popc(m_r & lt_mask));
+          __stcs(rp, make_float4(origin.x, origin.y, origin.z, __uint_as_float(pix)));
+          __stcs(rp + 1, make_float4(rd.x, rd.y, rd.z, w_own * reflect));
+          n_refl++;
+        }
+        if (do_trans) {
+          float4 *rp = reinterpret_cast<float4 *>(rays_out + rbase + nr + __popc(m_t & lt_mask));
+          __stcs(rp, make_float4(origin.x, origin.y, origin.z, __uint_as_float(pix)));
+          __stcs(rp + 1, make_float4(d.x, d.y, d.z, w * transp));
+          n_trans++;
+        }
+      }
+    }
+  }
+  // per-warp totals
+  for (int s = 16; s > 0; s >>= 1) {
+    n_refl += __shfl_xor_sync(0xffffffffu, n_refl, s);
+    n_trans += __shfl_xor_sync(0xffffffffu, n_trans, s);
+    max_depth = fmaxf(max_depth, __shfl_xor_sync(0xffffffffu, max_depth, s));
+  }
+  if (lane == 0) {
+    if (n_refl) atomicAdd(&ctr->rays_reflect, n_refl);
+    if (n_trans) atomicAdd(&ctr->rays_transmit, n_trans);
+    if (level == 0 && max_depth > 0.f) atomicMax(&ctr->max_depth_bits, __float_as_uint(max_depth));
+  }
+}
+
+// shadow_intensity, inc/shading.hpp:22-45
+template <int MODE>
+__device__ __forceinline__ float shadow_intensity(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 o, vec3 d,
+                                                  float max_dist, unsigned long long &casts) {
+  if (sv.all_opaque) {
+    // every crossing adds 1 - 0 = 1 -> the first march step saturates: any surface in (1e-3, max_dist) shadows fully
+    casts++;
+    return any_hit<MODE>(sv, nodes, prims, o, d, (float)(0.0 + 1e-3), max_dist) ? 1.0f : 0.0f;
+  }
+  float intensity = 0.0f, last_hit = 0.0f;
+  for (;;) {
+    Hit h;
+    casts++;
+    closest_hit<MODE>(sv, nodes, prims, o, d, (float)((double)last_hit + 1e-3), h);
+    if (!(h.kind >= 0 && h.t < max_dist)) break;
+    const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + __ldg(sv.obj_material + h.obj));
+    float trans = __ldg(mp + 1).z;
+    intensity += (1.0f - trans);
+    if (intensity >= 1.0f) return 1.0f;
+    last_hit = h.t;
+  }
+  return intensity;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
+shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ shade, FrameCounters *ctr, FrameTargets fb,
+             int atomic_accumulate) {
+  extern __shared__ float4 smem[];
+  const float4 *nodes, *prims;
+  stage_scene<MODE>(sv, smem, nodes, prims);
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t n_work = ctr->n_shade[level];
+  unsigned long long casts = 0;
+
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&ctr->work_shade[level], (unsigned)WORK_CHUNK);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n_work) break;
+    for (unsigned off = 0; off < (unsigned)WORK_CHUNK && base + off < n_work; off += 32) {
+      const uint32_t i = base + off + lane;
+      if (i < n_work) {
+        const float4 *sp = reinterpret_cast<const float4 *>(shade + i);
+        const float4 s0 = __ldcs(sp), s1 = __ldcs(sp + 1), s2 = __ldcs(sp + 2);
+        const vec3 hit = mk3(s0.x, s0.y, s0.z), normal = mk3(s1.x, s1.y, s1.z), in_dir = mk3(s2.x, s2.y, s2.z);
+        const uint32_t pix = __float_as_uint(s0.w), mat = __float_as_uint(s1.w);
+        const float weight = s2.w;
+        // phong, inc/shading.hpp:64-99
+        const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
+        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+        const vec3 diffuse = mk3(m0.x, m0.y, m0.z);
+        const vec3 specular = vscale(diffuse, m0.w);        // *spec = specular * color
+        const float phong_exp = m1.y;
+        vec3 final = vscale(diffuse, sv.cam.ambient);
+        for (uint32_t l = 0; l < sv.n_lights; l++) {
+          const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l);
+          const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
+          vec3 direction;
+          float distance;
+          if (__float_as_uint(l0.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
+            direction = vscale(mk3(l0.x, l0.y, l0.z), -1.0f);
+            distance = INFINITY;
+          } else {                                              // inc/default_schema.hpp:305-308
+            vec3 P = mk3(l0.x, l0.y, l0.z);
+            direction = vnormalized(vsub(P, hit));
+            distance = vnorm(vsub(P, hit));
+          }
+          const vec3 sdir = vnormalized(direction);
+          const float light_dist = distance * vnorm(direction);
+          const vec3 color = mk3(l1.x, l1.y, l1.z);
+          const vec3 nn = vnormalized(normal), nd = sdir;
+          const float shadow_fac = shadow_intensity<MODE>(sv, nodes, prims, hit, sdir, light_dist, casts);
+          if (shadow_fac < 1.0f) {
+            float fd = fmaxf(0.0f, vdot(nn, nd));
+            vec3 ld = vmul(diffuse, color);
+            vec3 hv = vnormalized(vadd(vscale(vnormalized(in_dir), -1.0f), nd));
+            float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+            vec3 ls = vmul(specular, color);
+            vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - shadow_fac);
+            final.x += term.x; final.y += term.y; final.z += term.z;
+          }
+        }
+        float *cp = fb.color + 3 * (size_t)pix;
+        if (atomic_accumulate) {
+          atomicAdd(cp, weight * final.x); atomicAdd(cp + 1, weight * final.y); atomicAdd(cp + 2, weight * final.z);
+        } else {
+          cp[0] += weight * final.x; cp[1] += weight * final.y; cp[2] += weight * final.z;
+        }
+      }
+    }
+  }
+  for (int s = 16; s > 0; s >>= 1) casts += __shfl_xor_sync(0xffffffffu, casts, s);
+  if (lane == 0 && casts) atomicAdd(&ctr->shadow_casts, casts);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
+  int dev = 0, sms = 0, smem_optin = 0;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+  size_t need = (size_t)sv.n_nodes * sizeof(Node) + (size_t)sv.n_prims * sizeof(PrimRec);
+  cfg->mode = 0;
+  cfg->smem_bytes = 0;
+  if (allow_smem && !sv.brute_force && sv.n_prims > 0 && need + 1024 <= (size_t)smem_optin) {
+    cfg->mode = 1;
+    cfg->smem_bytes = need;
+  }
+  int occ_t = 1, occ_s = 1;
+  if (cfg->mode == 1) {
+    if ((e = cudaFuncSetAttribute(trace_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(shade_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, trace_kernel<1>, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, shade_kernel<1>, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
+  } else {
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, trace_kernel<0>, TRACE_THREADS, 0)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, shade_kernel<0>, TRACE_THREADS, 0)) != cudaSuccess) return e;
+  }
+  if (occ_t < 1) occ_t = 1;
+  if (occ_s < 1) occ_s = 1;
+  cfg->grid_trace = sms * occ_t;
+  cfg->grid_shade = sms * occ_s;
+  return cudaSuccess;
+}
+
+static inline int clamp_grid(int persistent, uint32_t work_bound) {
+  uint64_t need = ((uint64_t)work_bound + WORK_CHUNK * (TRACE_THREADS / 32) - 1) / (WORK_CHUNK * (TRACE_THREADS / 32));
+  if (need < 1) need = 1;
+  return (int)(need < (uint64_t)persistent ? need : (uint64_t)persistent);
+}
+
+void launch_trace(const LaunchCfg &cfg, const SceneView &sv, const TileMap &tm, uint32_t level, uint32_t bounces,
+                  uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, ShadeRec *shade_out,
+                  FrameCounters *ctr, const FrameTargets &fb, uint32_t work_bound, cudaStream_t st) {
+  int grid = clamp_grid(cfg.grid_trace, work_bound);
+  if (cfg.mode == 1)
+    trace_kernel<1><<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(sv, tm, level, bounces, px_base, n_px, rays_in, rays_out, shade_out, ctr, fb);
+  else
+    trace_kernel<0><<<grid, TRACE_THREADS, 0, st>>>(sv, tm, level, bounces, px_base, n_px, rays_in, rays_out, shade_out, ctr, fb);
+}
+
+void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, FrameCounters *ctr,
+                  const FrameTargets &fb, bool atomic_accumulate, uint32_t work_bound, cudaStream_t st) {
+  int grid = clamp_grid(cfg.grid_shade, work_bound);
+  if (cfg.mode == 1)
+    shade_kernel<1><<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(sv, level, shade, ctr, fb, atomic_accumulate ? 1 : 0);
+  else
+    shade_kernel<0><<<grid, TRACE_THREADS, 0, st>>>(sv, level, shade, ctr, fb, atomic_accumulate ? 1 : 0);
+}
+
+}  // namespace ctb

@@ -1,0 +1,48 @@
+// render.cuh — launch interface of the wavefront render kernels (render.cu) and output kernels (output.cu).
+#ifndef CUTRACE_B200_RENDER_CUH
+#define CUTRACE_B200_RENDER_CUH
+#include "common.cuh"
+
+namespace ctb {
+
+constexpr int TRACE_THREADS = 512;
+constexpr int WORK_CHUNK = 128;   // rays a warp claims per work-stealing atomic
+#ifndef CTB_MIN_BLOCKS
+#define CTB_MIN_BLOCKS 1   // resident CTAs per SM the register allocator must allow (tuned on B200)
+#endif
+
+struct FrameTargets {   // local tile-major buffers
+  float *depth;         // n_local_px
+  float *normal;        // n_local_px * 3
+  float *color;         // n_local_px * 3
+  uint32_t *hit_id;     // n_local_px
+};
+
+struct LaunchCfg {
+  int mode;             // 0 global, 1 BVH staged in shared memory
+  size_t smem_bytes;
+  int grid_trace, grid_shade;   // persistent grid sizes (multiples of the SM count)
+};
+
+// fills cfg for a scene on the current device; smem budget from the device attributes
+cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg);
+
+// One bounce level of the wavefront. Level 0 generates primary rays for local pixel indices
+// [px_base, px_base + n_px) itself; deeper levels read rays_in (count in ctr->n_rays[level]).
+void launch_trace(const LaunchCfg &cfg, const SceneView &sv, const TileMap &tm, uint32_t level, uint32_t bounces,
+                  uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, ShadeRec *shade_out,
+                  FrameCounters *ctr, const FrameTargets &fb, uint32_t work_bound, cudaStream_t st);
+// shadow rays + Phong for the shade records of one level; accumulates into fb.color
+void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, FrameCounters *ctr,
+                  const FrameTargets &fb, bool atomic_accumulate, uint32_t work_bound, cudaStream_t st);
+
+// output.cu
+void launch_untile(const TileMap &tm, uint32_t world, const float *g_depth, const float *g_normal, const float *g_color,
+                   const uint32_t *g_id, uint64_t stride_px, int only_rank, float *depth, float *normal, float *color,
+                   uint32_t *hit_id, cudaStream_t st);
+void launch_encode_bytes(const float *depth, const float *normal, const float *color, float max_depth, uint64_t n_px,
+                         uint8_t *depth_rgb, uint8_t *normal_rgb, uint8_t *color_rgb, cudaStream_t st);
+void launch_fill_sentinels(float *depth, float *normal, float *color, uint32_t *hit_id, uint64_t n_px, cudaStream_t st);
+
+}  // namespace ctb
+#endif
