@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the cutrace render path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own kernel (sm_100a rebuild)
+
+Metric (BASELINE.json): Mrays/s (primary + secondary) on scene/bunny.json at 3840x2160; ms/frame is
+`ms_per_step`.  Unique rays = primaries + reflection + transmission + shadow rays (one per light per
+shaded hit); the same numerator is used for every implementation.
+
+A step = one frame.  `value` times cutrace_render (+ the NCCL tile gather when N > 1) with the scene
+already resident in HBM; `e2e` times upload (H2D + LBVH build) + render + download into pinned host
+buffers through the C-ABI, every step.  One process per GPU; under torchrun each rank renders its
+interleaved 32x32 tiles, rank 0 gathers.  Timing: CUDA events / device time, max over ranks.
+
+The reference arm runs the UNMODIFIED reference kernel `render_kernel<default_gpu_scene,5>` rebuilt
+for sm_100a from the reference headers in place (oracle/_ref/libcutrace_ref_gpu.so, built by
+oracle/Makefile in the container) — the comparator BASELINE.json's north_star names.  The reference has
+no CPU renderer; its device functions compiled for the host through a qualifier-erasing shim
+(oracle/_ref/libcutrace_ref_host.so) are timed on a bounded pixel sample as `cpu_baseline`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "bunny4k": dict(scene="bunny", width=3840, height=2160, label="scene/bunny.json@3840x2160"),
+    "mirror1080": dict(scene="mirror", width=1920, height=1080, label="scene/mirror.json@1920x1080"),
+    "spheres1080": dict(scene="sphere_plane", width=1920, height=1080, label="scene/sphere_plane.json@1920x1080"),
+    "synthetic10m": dict(scene="grid106", width=7680, height=4320, label="synthetic grid 106x106 (10,112,400 triangles)@7680x4320"),
+}
+
+
+def load_workload(name):
+    from cutrace_b200 import synth
+    from cutrace_b200.scene import FlatScene
+
+    w = WORKLOADS[name]
+    gold = os.path.join(ROOT, "tests", "golden", "scenes")
+    if w["scene"].startswith("grid"):
+        meshes = synth.meshes_from_scenes(FlatScene.load(os.path.join(gold, "bunny.npz")), FlatScene.load(os.path.join(gold, "mirror.npz")))[:2]
+        return synth.grid_scene(meshes, grid=int(w["scene"][4:]), width=w["width"], height=w["height"]), w
+    return FlatScene.load(os.path.join(gold, w["scene"] + ".npz")).with_resolution(w["width"], w["height"]), w
+
+
+def n_primitives(scene):
+    return scene.n_triangles + scene.n_spheres + scene.n_planes
+
+
+def algorithmic_bytes_per_ray(n_prims):
+    """64 B queue traffic + one 64-byte two-child node per level of a balanced tree + one 48-byte triangle."""
+    import math
+
+    return 64 + 64 * math.ceil(math.log2(max(n_prims, 2))) + 48
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(scene, label, seconds_target=12.0):
+    """The reference's device functions compiled for the host (oracle/_ref) on a strided pixel sample."""
+    from oracle import pyoracle as po
+
+    kind = "reference" if po.have_ref_host() else "port"
+    if kind == "port" and not po.have_oracle():
+        po.build()
+    cores = os.cpu_count() or 1
+    w, h = scene.width, scene.height
+    render = (lambda px: po.ref_host_render(scene, px=px, threads=cores)) if kind == "reference" else \
+        (lambda px: po.oracle_render(scene, px=px, threads=cores))
+    # calibrate on a 64x36 strided grid, then size the sample for ~seconds_target
+    def grid(nx, ny):
+        xs = (np.arange(nx) * w) // nx
+        ys = (np.arange(ny) * h) // ny
+        return (ys[:, None] * w + xs[None, :]).reshape(-1).astype(np.uint64)
+
+    px = grid(64, 36)
+    t = time.perf_counter(); render(px); dt = time.perf_counter() - t
+    per_px = dt / len(px)
+    n = int(min(w * h, max(len(px), seconds_target / max(per_px, 1e-9))))
+    ny = max(1, int((n * h / w) ** 0.5)); nx = max(1, n // ny)
+    px = grid(min(nx, w), min(ny, h))
+    cnt = po.oracle_render(scene, px=px[:2048], threads=cores)["counters"]   # unique rays per pixel of the sample
+    rays_per_px = (cnt["rays_primary"] + cnt["rays_reflect"] + cnt["rays_transmit"] + cnt["rays_shadow"]) / min(len(px), 2048)
+    t = time.perf_counter(); render(px); dt = time.perf_counter() - t
+    return {"value": rays_per_px * len(px) / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+            "sample": f"{len(px)} px strided {min(nx, w)}x{min(ny, h)} grid of {label} ({dt:.1f} s, {rays_per_px:.2f} rays/px)"}
+
+
+def run_reference(args, scene, wl):
+    """--impl reference: the reference's own CUDA kernel rebuilt for sm_100a, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    import cutrace_b200 as ct
+
+    base = {"impl": "reference", "metric": "Mrays/s (primary+secondary)", "unit": "Mrays/s", "higher_is_better": True}
+    if not po.have_ref_gpu():
+        # the reference could not be compiled in the container: fall back to its host build / the port
+        cb = cpu_baseline(scene, wl["label"], seconds_target=20.0)
+        line = dict(base, value=cb["value"], n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=None,
+                    scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", config={"workload": wl["label"]},
+                    cpu_baseline=cb, e2e={"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    reference_arm="host build of the reference's device functions (no sm_100a rebuild available)")
+        print(json.dumps(line))
+        return
+    # unique-ray numerator: counted by our renderer on the same frame (identical for every implementation)
+    with ct.Renderer(scene, device=0) as r:
+        rays = r.render()["rays_total"]
+    import ctypes as C
+
+    lib = po._load(po.REF_GPU_SO)
+    with ClockSampler(0) as clk:
+        ref = po.ref_gpu_render(scene, iters=args.steps, warmup=args.warmup)
+        # e2e: the reference's whole operator gpu::render<S,5,256> (managed allocs, launch+sync, 3*h row copies, max scan)
+        fn = lib.cutrace_ref_gpu_render_e2e
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        n = scene.width * scene.height
+        d, nm, c = np.empty(n, np.float32), np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        tot = C.c_float(); rms = C.c_float(); mx = C.c_float()
+        desc = scene.as_desc()
+        e2e_ms = []
+        for i in range(1 + max(1, min(args.steps, 3))):
+            rc = fn(C.byref(desc), 1e-3, d.ctypes.data, nm.ctypes.data, c.ctypes.data, C.byref(rms), C.byref(tot), C.byref(mx))
+            if rc:
+                raise RuntimeError(f"reference e2e failed: {rc}")
+            if i:
+                e2e_ms.append(tot.value)
+    ms = ref["render_ms"]
+    e2e = float(np.mean(e2e_ms))
+    cb = cpu_baseline(scene, wl["label"], seconds_target=10.0)
+    scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in __import__("cutrace_b200.scene", fromlist=["_ARRAY_FIELDS"])._ARRAY_FIELDS)
+    line = dict(base, value=rays / ms / 1e3, n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms, scaling="strong",
+                vs_baseline=None, dtype="f32", data="synthetic (reference scene geometry, fixture tests/golden/scenes)",
+                config={"workload": wl["label"], "rays_per_frame": int(rays), "launch": "<<<w*h/256+1,256>>> render_kernel<S,5>, sm_100a rebuild"},
+                clocks=clk.summary(), gpu_launches=args.steps,
+                e2e={"value": rays / e2e / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e, "h2d_bytes_per_step": int(scene_bytes),
+                     "d2h_bytes_per_step": int(28 * n), "what": "cutrace::gpu::render<S,5,256> total bracket (inc/kernel.hpp:88-126)"},
+                cpu_baseline=cb,
+                reference_arm="reference CUDA kernel rebuilt for sm_100a (the comparator north_star names); cpu_baseline is the reference's device code compiled for the host")
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cutrace_b200", choices=["cutrace_b200", "reference"])
+    ap.add_argument("--workload", default="bunny4k", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    scene, wl = load_workload(args.workload)
+    if args.impl == "reference":
+        run_reference(args, scene, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import cutrace_b200 as ct
+    from cutrace_b200.distributed import TileShardedRenderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: cutrace_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_px = scene.width * scene.height
+    stream = torch.cuda.Stream(device=local_rank)   # the ctx launches on this stream, so torch events see its kernels
+    torch.cuda.set_stream(stream)
+    tsr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream)
+
+    def step():
+        st = tsr.render()
+        if world > 1:
+            tsr.gather()
+        return st
+
+    for _ in range(args.warmup):
+        st = step()
+    barrier()
+    dev_ms, trace_ms, shade_ms = [], [], []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            st = step()
+            dev_ms.append(st["render_ms"]); trace_ms.append(st["trace_ms"]); shade_ms.append(st["shade_ms"])
+        ev1.record(stream)
+        barrier()
+    # exactly K steps between two CUDA events on the launching stream, barrier + synchronize on both sides
+    ms_local = ev0.elapsed_time(ev1) / args.steps
+    rays_local = st["rays_total"]
+    t = torch.tensor([ms_local, float(rays_local), float(np.mean(shade_ms)), float(np.mean(trace_ms)), float(st["rays_shadow"]),
+                      float(np.mean(dev_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_step, rays = float(tmax[0]), float(tsum[1])
+        shade, trace, rays_shadow, render_dev_ms = float(tmax[2]), float(tmax[3]), float(tsum[4]), float(tmax[5])
+    else:
+        ms_step, rays, shade, trace, rays_shadow, render_dev_ms = (float(x) for x in t)
+    launches_per_step = int(st["kernel_launches"]) + (1 if world > 1 and rank == 0 else 0)
+
+    # ---- e2e: upload (H2D + LBVH build) + render + download to pinned host, through the C-ABI ----
+    tsr.close()
+    barrier()
+    import ctypes as C
+
+    lib = ct._lib.load()
+    pinned = {}
+    if rank == 0:
+        for k, (m, dt) in {"depth": (1, np.float32), "normal": (3, np.float32), "color": (3, np.float32)}.items():
+            p = lib.cutrace_host_alloc(n_px * m * 4)
+            pinned[k] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n_px * m,))
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms = []
+    for i in range(2 + e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            r = ct.Renderer(scene, device=local_rank, flags=args.flags, stream=stream.cuda_stream)
+            r.render()
+            md = C.c_float()
+            ct._lib.check(lib.cutrace_download(r._ctx, pinned["depth"].ctypes.data, pinned["normal"].ctypes.data,
+                                               pinned["color"].ctypes.data, None, C.byref(md)))
+            r.close()
+        else:
+            tr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream)
+            stl = tr.render()
+            tr.gather()
+            tr.max_depth(stl["max_depth"])
+            if rank == 0:
+                for k, src in (("depth", tr.out_depth), ("normal", tr.out_normal), ("color", tr.out_color)):
+                    torch.from_numpy(pinned[k]).copy_(src, non_blocking=True)
+            tr.close()
+        barrier()
+        if i >= 2:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e = float(e2e_t[0])
+    from cutrace_b200.scene import _ARRAY_FIELDS
+
+    scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in _ARRAY_FIELDS if k != "obj_kind") + 64
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bpr = algorithmic_bytes_per_ray(n_primitives(scene))
+        dominant = "shade_kernel (shadow rays + Phong)" if shade >= trace else "trace_kernel (closest hit)"
+        dom_ms = max(shade, trace)
+        dom_rays = rays_shadow if shade >= trace else (rays - rays_shadow)
+        achieved = dom_rays * bpr / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        line = {
+            "metric": "Mrays/s (primary+secondary)", "value": rays / ms_step / 1e3, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (reference scene geometry from the committed fixture tests/golden/scenes; no image inputs)",
+            "config": {"workload": wl["label"], "rays_per_frame": int(rays), "primitives": n_primitives(scene), "bounces": 5,
+                       "parallelism": f"tiles{world}" if world > 1 else "single", "l2": "queues+framebuffer per frame > L2 (126 MB)"
+                       if n_px * 28 > 126e6 else "working set < L2; frames are re-rendered back to back",
+                       "timed": "K frames between two CUDA events on the launching stream" + ("" if world == 1 else ", incl. NCCL gather + un-tile"),
+                       "render_device_ms": render_dev_ms},
+            "clocks": clk.summary(),
+            "e2e": {"value": rays / e2e / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e, "h2d_bytes_per_step": int(scene_bytes),
+                    "d2h_bytes_per_step": int(28 * n_px),
+                    "what": "cutrace_upload_scene (H2D + LBVH build) + cutrace_render + cutrace_download into pinned host buffers"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": dominant, "bytes_per_ray": bpr,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "note": "algorithmic bytes/ray (SURVEY §8d) x rays of the dominant kernel / its CUDA-event time; the scene is cache-resident, "
+                                 "so issue-slot utilisation and divergence (profiles/) explain the kernel, not DRAM"},
+            "kernel_ms": {"trace": trace, "shade": shade},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline(scene, wl["label"])
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "absent", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

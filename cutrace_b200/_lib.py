@@ -16,7 +16,7 @@ SYMBOLS = (
     "cutrace_default_opts", "cutrace_upload_scene", "cutrace_render", "cutrace_download", "cutrace_free",
     "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_device_buffers",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free",
-    "cutrace_validate_bvh", "cutrace_abi_version",
+    "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version",
 )
 
 FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE = 1, 2, 4
@@ -84,6 +84,7 @@ def load():
     lib.cutrace_host_free.argtypes = [P]
     lib.cutrace_host_free.restype = None
     lib.cutrace_validate_bvh.argtypes = [P]
+    lib.cutrace_debug_radix_sort.argtypes = [P, P, C.c_uint32, C.c_int]
     lib.cutrace_abi_version.restype = C.c_uint32
     _lib = lib
     return lib

@@ -529,6 +529,29 @@ void cutrace_host_free(void *p) {
   if (p) cudaFreeHost(p);
 }
 
+int cutrace_debug_radix_sort(uint64_t *keys, uint32_t *values, uint32_t n, int device) {
+  if (n && (!keys || !values)) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(CUTRACE_ERR_NO_DEVICE, "no CUDA device");
+  if (device < 0) CU(cudaGetDevice(&device));
+  DeviceGuard g(device);
+  if (n == 0) return CUTRACE_OK;
+  uint64_t *dk = nullptr;
+  uint32_t *dv = nullptr;
+  CU(cudaMalloc(&dk, sizeof(uint64_t) * n));
+  cudaError_t e = cudaMalloc(&dv, sizeof(uint32_t) * n);
+  if (e != cudaSuccess) { cudaFree(dk); return fail(CUTRACE_ERR_OUT_OF_MEMORY, "cudaMalloc failed"); }
+  std::string err;
+  int rc = CUTRACE_OK;
+  if (cudaMemcpy(dk, keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(dv, values, sizeof(uint32_t) * n, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(CUTRACE_ERR_CUDA, "H2D copy failed");
+  if (!rc) { rc = radix_sort_pairs(dk, dv, n, nullptr, err); if (rc) fail(rc, err); }
+  if (!rc && (cudaMemcpy(keys, dk, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess ||
+              cudaMemcpy(values, dv, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess)) rc = fail(CUTRACE_ERR_CUDA, "D2H copy failed");
+  cudaFree(dk); cudaFree(dv);
+  return rc;
+}
+
 int cutrace_validate_bvh(cutrace_ctx *c) {
   if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
   DeviceGuard g(c->device);

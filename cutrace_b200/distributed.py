@@ -1,0 +1,115 @@
+"""Screen-space tile sharding across GPUs: one process per GPU, scene replicated, tiles interleaved.
+
+This is the only place the render path shards: pixels are independent
+(/root/reference/inc/kernel.hpp:37-59 has no inter-thread communication), so rank r renders the
+32x32 tiles t with t % world == r into a tile-major local buffer; ONE exchange step follows — an NCCL
+gather of the float framebuffers to rank 0 over NVLink — and rank 0 un-tiles the gathered buffers into
+row-major images on the device (cutrace_untile_device).  torch.distributed is plumbing only.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import Renderer
+from .scene import TILE
+
+
+def local_tile_count(width, height, world):
+    tiles = ((width + TILE - 1) // TILE) * ((height + TILE - 1) // TILE)
+    return (tiles + world - 1) // world
+
+
+def tiles_of_rank(width, height, rank, world):
+    """Global tile indices owned by ``rank`` (row-major tile order, interleaved)."""
+    tiles = ((width + TILE - 1) // TILE) * ((height + TILE - 1) // TILE)
+    return list(range(rank, tiles, world))
+
+
+def untile_host(parts, width, height, channels):
+    """CPU reference of the un-tile step (used by the gloo tests): ``parts[r]`` is rank r's tile-major
+    buffer of shape (n_local_tiles*1024, channels)."""
+    world = len(parts)
+    tx = (width + TILE - 1) // TILE
+    out = np.zeros((height, width, channels), parts[0].dtype)
+    for y in range(height):
+        for x0 in range(0, width, TILE):
+            gt = (y // TILE) * tx + x0 // TILE
+            r, lt = gt % world, gt // world
+            n = min(TILE, width - x0)
+            src = lt * 1024 + (y % TILE) * TILE
+            out[y, x0:x0 + n] = parts[r].reshape(-1, channels)[src:src + n]
+    return out
+
+
+class _DevArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it (no copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class TileShardedRenderer:
+    """Rank-local renderer + NCCL gather. Requires an initialised torch.distributed process group."""
+
+    def __init__(self, scene, rank, world, device, **kw):
+        import torch
+
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.scene = scene
+        self.device = torch.device("cuda", device)
+        self.r = Renderer(scene, device=device, tile_rank=rank, tile_world=world, **kw)
+        (pd, pn, pc, pi), npx = self.r.device_buffers()
+        self.npx = npx
+        as_t = lambda p, n, ts: torch.as_tensor(_DevArray(p, n, ts), device=self.device)  # noqa: E731
+        self.depth = as_t(pd, npx, "<f4")
+        self.normal = as_t(pn, 3 * npx, "<f4")
+        self.color = as_t(pc, 3 * npx, "<f4")
+        self.hit_id = as_t(pi, npx, "<i4")
+        n = scene.width * scene.height
+        if rank == 0:
+            f32, i32 = torch.float32, torch.int32
+            self.g_depth = torch.empty(world * npx, dtype=f32, device=self.device)
+            self.g_normal = torch.empty(world * 3 * npx, dtype=f32, device=self.device)
+            self.g_color = torch.empty(world * 3 * npx, dtype=f32, device=self.device)
+            self.g_id = torch.empty(world * npx, dtype=i32, device=self.device)
+            self.out_depth = torch.empty(n, dtype=f32, device=self.device)
+            self.out_normal = torch.empty(3 * n, dtype=f32, device=self.device)
+            self.out_color = torch.empty(3 * n, dtype=f32, device=self.device)
+            self.out_id = torch.empty(n, dtype=i32, device=self.device)
+
+    def render(self):
+        return self.r.render()
+
+    def gather(self):
+        """NCCL gather of the four framebuffers to rank 0, then device un-tile on rank 0."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        if self.world == 1:
+            g = (self.depth, self.normal, self.color, self.hit_id)
+        else:
+            pairs = [(self.depth, getattr(self, "g_depth", None), 1), (self.normal, getattr(self, "g_normal", None), 3),
+                     (self.color, getattr(self, "g_color", None), 3), (self.hit_id, getattr(self, "g_id", None), 1)]
+            for src, dst, k in pairs:
+                lst = list(dst.split(k * self.npx)) if self.rank == 0 else None
+                dist.gather(src, lst, dst=0)
+            g = (getattr(self, "g_depth", None), getattr(self, "g_normal", None), getattr(self, "g_color", None),
+                 getattr(self, "g_id", None))
+        if self.rank == 0:
+            torch.cuda.current_stream(self.device).synchronize()
+            self.r.untile_device(self.world, g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), self.npx,
+                                 self.out_depth.data_ptr(), self.out_normal.data_ptr(), self.out_color.data_ptr(),
+                                 self.out_id.data_ptr())
+
+    def max_depth(self, local_max):
+        """max over ranks of the largest finite depth (kernel.hpp:120-125) — a 1-float reduce."""
+        import torch.distributed as dist
+
+        t = self.torch.tensor([local_max], dtype=self.torch.float32, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        self.r.close()

@@ -223,6 +223,10 @@ void cutrace_host_free(void *p);
  * once); returns CUTRACE_OK or CUTRACE_ERR_INTERNAL with a message. */
 int cutrace_validate_bvh(cutrace_ctx *ctx);
 
+/* test hook: the LBVH builder's own stable LSD radix sort on host arrays of n (key, value) pairs,
+ * sorted in place by key (device round trip inside). */
+int cutrace_debug_radix_sort(uint64_t *keys, uint32_t *values, uint32_t n, int device);
+
 uint32_t cutrace_abi_version(void);
 
 #ifdef __cplusplus

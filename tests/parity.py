@@ -1,18 +1,44 @@
-"""Parity metrics between two renders of the same scene (SURVEY.md §8d "Parity tolerances")."""
+"""Parity metrics between two renders of the same scene (SURVEY.md §8d "Parity tolerances").
+
+Two yardsticks:
+  * against the REFERENCE'S OWN CUDA KERNEL rebuilt for sm_100a (oracle/_ref/libcutrace_ref_gpu.so):
+    the tight one — same FMA contraction, same CUDA libm.
+  * against the host oracle (oracle/cutrace_oracle.c == the reference's headers compiled with g++,
+    bit-identical to each other): no FMA contraction and glibc powf/sqrtf, so the reference's own
+    device build already differs from it by up to ~1.4e-4 in sphere normals and ~1.4e-5 in relative
+    depth (measured, profiles/r01_parity.md).  The host tolerances are set just above those measured
+    reference-vs-reference differences.
+Hit ids must agree bit-exactly on >= 99.9 % of the pixels; mismatches are classified as "edge" when
+the reference id image has more than one id in the pixel's 3x3 neighbourhood (silhouette / tie).
+For tiny frames (triangle.json is 400 px, one pixel = 0.25 %) up to 2 edge pixels are allowed.
+"""
 import numpy as np
 
-ID_AGREE_MIN = 0.999        # hit ids bit-exact on >= 99.9 % of the pixels
-DEPTH_TOL = 1e-4            # |dd| <= 1e-4 * max(1, t) on id-agreeing pixels
-NORMAL_TOL = 1e-5           # max-abs on id-agreeing pixels
-PSNR_MIN = 50.0             # colour, float frame clamped to [0,1]
+ID_AGREE_MIN = 0.999
+TOL_REF_GPU = dict(depth=1e-6, normal=1e-5, psnr=50.0)     # vs the reference's sm_100a kernel
+TOL_HOST = dict(depth=1e-4, normal=5e-4, psnr=50.0)        # vs the host oracle / goldens
 
 
-def compare(a, b):
-    """a, b: dicts with depth (n,), normal (n,3), color (n,3), hit_id (n,). Returns a metrics dict."""
+def _edge_mask(ids, width, height):
+    img = ids.reshape(height, width)
+    edge = np.zeros_like(img, dtype=bool)
+    pad = np.pad(img, 1, mode="edge")
+    for dy in (0, 1, 2):
+        for dx in (0, 1, 2):
+            edge |= pad[dy:dy + height, dx:dx + width] != img
+    return edge.reshape(-1)
+
+
+def compare(a, b, width=None, height=None):
+    """a = candidate, b = reference: dicts with depth (n,), normal (n,3), color (n,3), hit_id (n,)."""
     n = a["hit_id"].size
     ida, idb = a["hit_id"].reshape(-1), b["hit_id"].reshape(-1)
     agree = ida == idb
     m = {"pixels": int(n), "id_agree": float(agree.mean()), "id_mismatch": int((~agree).sum())}
+    if width and height and width * height == n:
+        edge = _edge_mask(idb, width, height)
+        m["id_mismatch_edge"] = int((~agree & edge).sum())
+        m["id_mismatch_other"] = int((~agree & ~edge).sum())
     da, db = a["depth"].reshape(-1)[agree], b["depth"].reshape(-1)[agree]
     fin = np.isfinite(da) & np.isfinite(db)
     m["sentinel_mismatch"] = int((np.isfinite(da) != np.isfinite(db)).sum())
@@ -32,9 +58,13 @@ def compare(a, b):
     return m
 
 
-def assert_parity(m, what=""):
-    assert m["id_agree"] >= ID_AGREE_MIN, f"{what}: hit ids agree on {m['id_agree']:.5f} < {ID_AGREE_MIN} ({m})"
+def assert_parity(m, what="", oracle_is_host=False):
+    tol = TOL_HOST if oracle_is_host else TOL_REF_GPU
+    allowed = max(2, int((1.0 - ID_AGREE_MIN) * m["pixels"]))
+    assert m["id_mismatch"] <= allowed, f"{what}: {m['id_mismatch']} hit-id mismatches > {allowed} ({m})"
+    if "id_mismatch_other" in m:
+        assert m["id_mismatch_other"] <= allowed // 10, f"{what}: non-edge hit-id mismatches ({m})"
     assert m["sentinel_mismatch"] == 0, f"{what}: miss sentinels differ ({m})"
-    assert m["depth_max_rel"] <= DEPTH_TOL, f"{what}: depth error {m['depth_max_rel']:.3g} > {DEPTH_TOL} ({m})"
-    assert m["normal_max_abs"] <= NORMAL_TOL, f"{what}: normal error {m['normal_max_abs']:.3g} > {NORMAL_TOL} ({m})"
-    assert m["color_psnr"] >= PSNR_MIN, f"{what}: colour PSNR {m['color_psnr']:.2f} dB < {PSNR_MIN} ({m})"
+    assert m["depth_max_rel"] <= tol["depth"], f"{what}: depth error {m['depth_max_rel']:.3g} > {tol['depth']} ({m})"
+    assert m["normal_max_abs"] <= tol["normal"], f"{what}: normal error {m['normal_max_abs']:.3g} > {tol['normal']} ({m})"
+    assert m["color_psnr"] >= tol["psnr"], f"{what}: colour PSNR {m['color_psnr']:.2f} dB < {tol['psnr']} ({m})"

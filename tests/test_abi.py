@@ -1,0 +1,105 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/cutrace.h declares, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden_scene
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    from cutrace_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        ge.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from cutrace_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "cutrace.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cutrace_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed from include/cutrace.h"
+    assert declared == set(_lib.SYMBOLS), f"binding list and header differ: {declared ^ set(_lib.SYMBOLS)}"
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} is declared in include/cutrace.h but not exported"
+    assert lib.cutrace_abi_version() == 1
+
+
+def test_struct_layouts_match_header(lib):
+    """ctypes mirrors vs the C structs: sizes are computed by compiling a tiny C file."""
+    import subprocess
+    import tempfile
+
+    from cutrace_b200 import _lib
+    from cutrace_b200.scene import cutrace_scene_desc
+
+    src = '#include <stdio.h>\n#include "cutrace.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(cutrace_scene_desc), sizeof(cutrace_opts), sizeof(cutrace_stats));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "t.c"), "w") as f:
+            f.write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == [C.sizeof(cutrace_scene_desc), C.sizeof(_lib.cutrace_opts), C.sizeof(_lib.cutrace_stats)]
+
+
+def test_default_opts_are_the_reference_call(lib):
+    from cutrace_b200 import _lib
+
+    o = _lib.cutrace_opts()
+    lib.cutrace_default_opts(C.byref(o))
+    assert o.bounces == 5 and abs(o.fudge - 1e-3) < 1e-9 and o.device == -1  # main.cu:30
+
+
+def test_invalid_arguments_are_rejected_without_a_device(lib):
+    import cutrace_b200 as ct
+
+    s = load_golden_scene("triangle")
+    d = s.as_desc()
+    d.abi_version = 99
+    ctx = C.c_void_p()
+    assert lib.cutrace_upload_scene(C.byref(d), None, C.byref(ctx)) == -1
+    assert b"abi_version" in lib.cutrace_last_error()
+    bad = load_golden_scene("triangle")
+    bad.obj_material = np.array([7], np.uint32)
+    d = bad.as_desc()
+    assert lib.cutrace_upload_scene(C.byref(d), None, C.byref(ctx)) == -1
+    assert lib.cutrace_render(None, None) == -1
+    assert lib.cutrace_download(None, None, None, None, None, None) == -1
+    nan = load_golden_scene("triangle")
+    nan.tri_p1 = nan.tri_p1.copy()
+    nan.tri_p1[0, 0] = np.nan
+    with pytest.raises(ct.CutraceError):
+        ct.Renderer(nan)
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU the product must fail loudly, never render on the CPU."""
+    import torch
+
+    import cutrace_b200 as ct
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(ct.CutraceError) as e:
+        ct.render(load_golden_scene("triangle"))
+    assert e.value.code == -3
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under cutrace_b200/ may reference it."""
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "cutrace_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(base, fn), errors="replace").read()
+                if re.search(r"(from|import)\s+oracle|pyoracle|cutrace_oracle|libcutrace_ref", txt):
+                    bad.append(fn)
+    assert not bad, bad

@@ -72,5 +72,19 @@ def main():
                 print(f"bunny 4K (global mode) run {i}: render_ms={st['render_ms']:.3f} trace={st['trace_ms']:.3f} shade={st['shade_ms']:.3f}")
 
 
+def ref4k():
+    s = FlatScene.load(os.path.join(GOLD, "scenes", "bunny.npz")).with_resolution(3840, 2160)
+    ref = po.ref_gpu_render(s, iters=2, warmup=1)
+    with ct.Renderer(s) as r:
+        st = r.render()
+        out = r.download()
+    m = compare(out, ref)
+    print(f"bunny 4K vs reference sm_100a kernel: {json.dumps(m)}")
+    print(f"bunny 4K: ref render_ms={ref['render_ms']:.2f}  new render_ms={st['render_ms']:.3f}  rays={st['rays_total']}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--ref4k" in sys.argv:
+        ref4k()
+    else:
+        main()
