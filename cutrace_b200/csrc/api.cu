@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <type_traits>
+#include "alloc.cuh"
 #include "bvh.cuh"
 #include "render.cuh"
 
@@ -85,9 +87,10 @@ struct DeviceGuard {
 };
 
 void free_frame(cutrace_ctx *c) {
-  cudaFree(c->fb.depth); cudaFree(c->fb.normal); cudaFree(c->fb.color); cudaFree(c->fb.hit_id);
-  cudaFree(c->rays[0]); cudaFree(c->rays[1]); cudaFree(c->shade);
-  cudaFree(c->st_depth); cudaFree(c->st_normal); cudaFree(c->st_color); cudaFree(c->st_id);
+  cudaStream_t st = c->stream;
+  dfree(c->fb.depth, st); dfree(c->fb.normal, st); dfree(c->fb.color, st); dfree(c->fb.hit_id, st);
+  dfree(c->rays[0], st); dfree(c->rays[1], st); dfree(c->shade, st);
+  dfree(c->st_depth, st); dfree(c->st_normal, st); dfree(c->st_color, st); dfree(c->st_id, st);
   c->fb = FrameTargets{};
   c->rays[0] = c->rays[1] = nullptr; c->shade = nullptr;
   c->st_depth = c->st_normal = c->st_color = nullptr; c->st_id = nullptr;
@@ -128,15 +131,16 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   c->batch_px = batch;
   c->cap = batch * c->factor;
 
-  CU(cudaMalloc(&c->fb.depth, sizeof(float) * c->n_local_px));
-  CU(cudaMalloc(&c->fb.normal, sizeof(float) * 3 * c->n_local_px));
-  CU(cudaMalloc(&c->fb.color, sizeof(float) * 3 * c->n_local_px));
-  CU(cudaMalloc(&c->fb.hit_id, sizeof(uint32_t) * c->n_local_px));
+  cudaStream_t st = c->stream;
+  CU(dmalloc(&c->fb.depth, sizeof(float) * c->n_local_px, st));
+  CU(dmalloc(&c->fb.normal, sizeof(float) * 3 * c->n_local_px, st));
+  CU(dmalloc(&c->fb.color, sizeof(float) * 3 * c->n_local_px, st));
+  CU(dmalloc(&c->fb.hit_id, sizeof(uint32_t) * c->n_local_px, st));
   if (c->max_children > 0 && b > 0) {
-    CU(cudaMalloc(&c->rays[0], sizeof(RayRec) * c->cap));
-    CU(cudaMalloc(&c->rays[1], sizeof(RayRec) * c->cap));
+    CU(dmalloc(&c->rays[0], sizeof(RayRec) * c->cap, st));
+    CU(dmalloc(&c->rays[1], sizeof(RayRec) * c->cap, st));
   }
-  CU(cudaMalloc(&c->shade, sizeof(ShadeRec) * c->cap));
+  CU(dmalloc(&c->shade, sizeof(ShadeRec) * c->cap, st));
   return CUTRACE_OK;
 }
 
@@ -144,8 +148,9 @@ template <typename T>
 int upload(T **dst, const std::vector<T> &src, cudaStream_t st) {
   *dst = nullptr;
   if (src.empty()) return CUTRACE_OK;
-  CU(cudaMalloc(dst, sizeof(T) * src.size()));
+  CU(dmalloc(dst, sizeof(T) * src.size(), st));
   CU(cudaMemcpyAsync(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));   // src is a temporary host vector
   return CUTRACE_OK;
 }
 
@@ -216,9 +221,10 @@ void cutrace_free(cutrace_ctx *c) {
   DeviceGuard g(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_frame(c);
-  cudaFree(c->bvh.nodes); cudaFree(c->bvh.prims);
-  cudaFree(c->planes); cudaFree(c->materials); cudaFree(c->lights); cudaFree(c->obj_material);
-  cudaFree(c->d_ctr);
+  dfree(c->bvh.nodes, c->stream); dfree(c->bvh.prims, c->stream);
+  dfree(c->planes, c->stream); dfree(c->materials, c->stream); dfree(c->lights, c->stream); dfree(c->obj_material, c->stream);
+  dfree(c->d_ctr, c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -251,6 +257,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   c->opts = o;
   DeviceGuard guard(dev);
   if (!guard.ok) { delete c; return fail(CUTRACE_ERR_CUDA, "cudaSetDevice failed"); }
+  pool_keep_memory(dev);
 
 #define UP(call) do { int rc_ = (call); if (rc_) { cutrace_free(c); return rc_; } } while (0)
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); cutrace_free(c); \
@@ -295,20 +302,20 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   // ---- primitives + LBVH ----
   float *d_p1 = nullptr, *d_p2 = nullptr, *d_p3 = nullptr, *d_sc = nullptr, *d_sr = nullptr;
   uint32_t *d_to = nullptr, *d_so = nullptr;
-  auto free_tmp = [&]() { cudaFree(d_p1); cudaFree(d_p2); cudaFree(d_p3); cudaFree(d_sc); cudaFree(d_sr); cudaFree(d_to); cudaFree(d_so); };
+  auto free_tmp = [&]() { dfree(d_p1, c->stream); dfree(d_p2, c->stream); dfree(d_p3, c->stream); dfree(d_sc, c->stream); dfree(d_sr, c->stream); dfree(d_to, c->stream); dfree(d_so, c->stream); };
 #define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); free_tmp(); cutrace_free(c); \
     return fail(e_ == cudaErrorMemoryAllocation ? CUTRACE_ERR_OUT_OF_MEMORY : CUTRACE_ERR_CUDA, m_); } } while (0)
   const uint64_t nt = s->n_triangles, ns = s->n_spheres;
   if (nt) {
-    CUT(cudaMalloc(&d_p1, sizeof(float) * 3 * nt)); CUT(cudaMalloc(&d_p2, sizeof(float) * 3 * nt));
-    CUT(cudaMalloc(&d_p3, sizeof(float) * 3 * nt)); CUT(cudaMalloc(&d_to, sizeof(uint32_t) * nt));
+    CUT(dmalloc(&d_p1, sizeof(float) * 3 * nt, c->stream)); CUT(dmalloc(&d_p2, sizeof(float) * 3 * nt, c->stream));
+    CUT(dmalloc(&d_p3, sizeof(float) * 3 * nt, c->stream)); CUT(dmalloc(&d_to, sizeof(uint32_t) * nt, c->stream));
     CUT(cudaMemcpyAsync(d_p1, s->tri_p1, sizeof(float) * 3 * nt, cudaMemcpyHostToDevice, c->stream));
     CUT(cudaMemcpyAsync(d_p2, s->tri_p2, sizeof(float) * 3 * nt, cudaMemcpyHostToDevice, c->stream));
     CUT(cudaMemcpyAsync(d_p3, s->tri_p3, sizeof(float) * 3 * nt, cudaMemcpyHostToDevice, c->stream));
     CUT(cudaMemcpyAsync(d_to, s->tri_object, sizeof(uint32_t) * nt, cudaMemcpyHostToDevice, c->stream));
   }
   if (ns) {
-    CUT(cudaMalloc(&d_sc, sizeof(float) * 3 * ns)); CUT(cudaMalloc(&d_sr, sizeof(float) * ns)); CUT(cudaMalloc(&d_so, sizeof(uint32_t) * ns));
+    CUT(dmalloc(&d_sc, sizeof(float) * 3 * ns, c->stream)); CUT(dmalloc(&d_sr, sizeof(float) * ns, c->stream)); CUT(dmalloc(&d_so, sizeof(uint32_t) * ns, c->stream));
     CUT(cudaMemcpyAsync(d_sc, s->sph_center, sizeof(float) * 3 * ns, cudaMemcpyHostToDevice, c->stream));
     CUT(cudaMemcpyAsync(d_sr, s->sph_radius, sizeof(float) * ns, cudaMemcpyHostToDevice, c->stream));
     CUT(cudaMemcpyAsync(d_so, s->sph_object, sizeof(uint32_t) * ns, cudaMemcpyHostToDevice, c->stream));
@@ -341,7 +348,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   sv.fudge = o.fudge;
   set_cam(c, s->cam_pos, s->cam_up, s->cam_forward, s->cam_right, s->ambient);
 
-  CUF(cudaMalloc(&c->d_ctr, sizeof(FrameCounters)));
+  CUF(dmalloc(&c->d_ctr, sizeof(FrameCounters), c->stream));
   CUF(cudaHostAlloc(&c->h_ctr, sizeof(FrameCounters), cudaHostAllocDefault));
   CUF(plan_launch(sv, !(o.flags & CUTRACE_FLAG_NO_SMEM_TOP), &c->cfg));
   sv.smem_nodes = c->cfg.mode == 1 ? sv.n_nodes : 0;
@@ -456,12 +463,12 @@ int cutrace_download(cutrace_ctx *c, float *depth, float *normal, float *color, 
   cudaStream_t st = c->stream;
   const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
   if (c->st_px != n) {
-    cudaFree(c->st_depth); cudaFree(c->st_normal); cudaFree(c->st_color); cudaFree(c->st_id);
+    dfree(c->st_depth, st); dfree(c->st_normal, st); dfree(c->st_color, st); dfree(c->st_id, st);
     c->st_depth = c->st_normal = c->st_color = nullptr; c->st_id = nullptr; c->st_px = 0;
-    CU(cudaMalloc(&c->st_depth, sizeof(float) * n));
-    CU(cudaMalloc(&c->st_normal, sizeof(float) * 3 * n));
-    CU(cudaMalloc(&c->st_color, sizeof(float) * 3 * n));
-    CU(cudaMalloc(&c->st_id, sizeof(uint32_t) * n));
+    CU(dmalloc(&c->st_depth, sizeof(float) * n, st));
+    CU(dmalloc(&c->st_normal, sizeof(float) * 3 * n, st));
+    CU(dmalloc(&c->st_color, sizeof(float) * 3 * n, st));
+    CU(dmalloc(&c->st_id, sizeof(uint32_t) * n, st));
     c->st_px = n;
   }
   if (c->tm.world > 1) {
@@ -539,7 +546,7 @@ int cutrace_debug_radix_sort(uint64_t *keys, uint32_t *values, uint32_t n, int d
   uint64_t *dk = nullptr;
   uint32_t *dv = nullptr;
   CU(cudaMalloc(&dk, sizeof(uint64_t) * n));
-  cudaError_t e = cudaMalloc(&dv, sizeof(uint32_t) * n);
+  cudaError_t e = cudaMalloc(&dv, sizeof(uint32_t) * n);  // plain allocations: test hook, no ctx
   if (e != cudaSuccess) { cudaFree(dk); return fail(CUTRACE_ERR_OUT_OF_MEMORY, "cudaMalloc failed"); }
   std::string err;
   int rc = CUTRACE_OK;

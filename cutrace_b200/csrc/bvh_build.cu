@@ -17,6 +17,8 @@
 // AABB test per mesh, every triangle of the mesh (inc/ray_cast.hpp:37-52, inc/default_schema.hpp:125-144).
 #include <cstdio>
 #include <vector>
+#include <type_traits>
+#include "alloc.cuh"
 #include "bvh.cuh"
 
 namespace ctb {
@@ -271,10 +273,10 @@ int radix_sort_pairs(uint64_t *d_keys, uint32_t *d_vals, uint32_t n, cudaStream_
   uint32_t table = 256u * n_blocks;
   uint64_t *kin = d_keys, *kout = nullptr;
   uint32_t *vin = d_vals, *vout = nullptr;
-  CK(cudaMalloc(&k2, sizeof(uint64_t) * n));
-  CK(cudaMalloc(&v2, sizeof(uint32_t) * n));
-  CK(cudaMalloc(&hist, sizeof(uint32_t) * table));
-  CK(cudaMalloc(&tile_sums, sizeof(uint32_t) * ((table + SCAN_TILE - 1) / SCAN_TILE + 1)));
+  CK(dmalloc(&k2, sizeof(uint64_t) * n, st));
+  CK(dmalloc(&v2, sizeof(uint32_t) * n, st));
+  CK(dmalloc(&hist, sizeof(uint32_t) * table, st));
+  CK(dmalloc(&tile_sums, sizeof(uint32_t) * ((table + SCAN_TILE - 1) / SCAN_TILE + 1), st));
   kout = k2; vout = v2;
   for (int pass = 0; pass < 8; pass++) {
     int shift = pass * 8;
@@ -288,7 +290,7 @@ int radix_sort_pairs(uint64_t *d_keys, uint32_t *d_vals, uint32_t n, cudaStream_
   // 8 passes = even number of swaps: the result is back in d_keys / d_vals
   CK(cudaStreamSynchronize(st));
 done:
-  cudaFree(k2); cudaFree(v2); cudaFree(hist); cudaFree(tile_sums);
+  dfree(k2, st); dfree(v2, st); dfree(hist, st); dfree(tile_sums, st);
   return rc;
 }
 
@@ -492,9 +494,9 @@ int validate_bvh(const BvhResult &bvh, cudaStream_t st, std::string &err) {
   unsigned int *cover = nullptr, *refs = nullptr, *errors = nullptr;
   unsigned int h_err[3] = {0, 0, 0};
   if (bvh.n_prims == 0) return rc;
-  CK(cudaMalloc(&cover, sizeof(unsigned int) * bvh.n_prims));
-  CK(cudaMalloc(&refs, sizeof(unsigned int) * (bvh.n_nodes + 1)));
-  CK(cudaMalloc(&errors, sizeof(unsigned int) * 3));
+  CK(dmalloc(&cover, sizeof(unsigned int) * bvh.n_prims, st));
+  CK(dmalloc(&refs, sizeof(unsigned int) * (bvh.n_nodes + 1), st));
+  CK(dmalloc(&errors, sizeof(unsigned int) * 3, st));
   CK(cudaMemsetAsync(cover, 0, sizeof(unsigned int) * bvh.n_prims, st));
   CK(cudaMemsetAsync(refs, 0, sizeof(unsigned int) * (bvh.n_nodes + 1), st));
   CK(cudaMemsetAsync(errors, 0, sizeof(unsigned int) * 3, st));
@@ -516,7 +518,7 @@ int validate_bvh(const BvhResult &bvh, cudaStream_t st, std::string &err) {
     rc = CUTRACE_ERR_INTERNAL;
   }
 done:
-  cudaFree(cover); cudaFree(refs); cudaFree(errors);
+  dfree(cover, st); dfree(refs, st); dfree(errors, st);
   return rc;
 }
 
@@ -546,14 +548,14 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
   const uint32_t nb = (n + T - 1) / T;
   const int ni = (int)n - 1;
 
-  CK(cudaMalloc(&lo, sizeof(float4) * n));
-  CK(cudaMalloc(&hi, sizeof(float4) * n));
-  CK(cudaMalloc(&d_bounds, sizeof(Bounds6)));
-  CK(cudaMalloc(&keys, sizeof(uint64_t) * n));
-  CK(cudaMalloc(&vals, sizeof(uint32_t) * n));
-  CK(cudaMalloc(&out.prims, sizeof(PrimRec) * n));
-  CK(cudaMalloc(&leaf_lo, sizeof(float4) * n));
-  CK(cudaMalloc(&leaf_hi, sizeof(float4) * n));
+  CK(dmalloc(&lo, sizeof(float4) * n, st));
+  CK(dmalloc(&hi, sizeof(float4) * n, st));
+  CK(dmalloc(&d_bounds, sizeof(Bounds6), st));
+  CK(dmalloc(&keys, sizeof(uint64_t) * n, st));
+  CK(dmalloc(&vals, sizeof(uint32_t) * n, st));
+  CK(dmalloc(&out.prims, sizeof(PrimRec) * n, st));
+  CK(dmalloc(&leaf_lo, sizeof(float4) * n, st));
+  CK(dmalloc(&leaf_hi, sizeof(float4) * n, st));
 
   init_bounds_kernel<<<1, 32, 0, st>>>(d_bounds);
   prim_bounds_kernel<<<nb, T, 0, st>>>(in.d_p1, in.d_p2, in.d_p3, in.n_tri, in.d_sph_center, in.d_sph_radius, in.n_sph, lo, hi, d_bounds);
@@ -589,17 +591,17 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
     // so boxes get a margin proportional to the scene's coordinate magnitude (DESIGN.md "conservative culling")
     float eps = fmaxf(mag, 1e-30f) * 2e-6f;
 
-    CK(cudaMalloc(&children, sizeof(int2) * ni));
-    CK(cudaMalloc(&range, sizeof(int2) * ni));
-    CK(cudaMalloc(&parent_node, sizeof(int) * ni));
-    CK(cudaMalloc(&parent_leaf, sizeof(int) * n));
-    CK(cudaMalloc(&node_lo, sizeof(float4) * ni));
-    CK(cudaMalloc(&node_hi, sizeof(float4) * ni));
-    CK(cudaMalloc(&flags, sizeof(unsigned int) * ni));
-    CK(cudaMalloc(&live, sizeof(uint32_t) * ni));
-    CK(cudaMalloc(&tile_sums, sizeof(uint32_t) * ((ni + SCAN_TILE - 1) / SCAN_TILE + 1)));
-    CK(cudaMalloc(&d_total, sizeof(uint32_t)));
-    CK(cudaMalloc(&d_depth, sizeof(unsigned int)));
+    CK(dmalloc(&children, sizeof(int2) * ni, st));
+    CK(dmalloc(&range, sizeof(int2) * ni, st));
+    CK(dmalloc(&parent_node, sizeof(int) * ni, st));
+    CK(dmalloc(&parent_leaf, sizeof(int) * n, st));
+    CK(dmalloc(&node_lo, sizeof(float4) * ni, st));
+    CK(dmalloc(&node_hi, sizeof(float4) * ni, st));
+    CK(dmalloc(&flags, sizeof(unsigned int) * ni, st));
+    CK(dmalloc(&live, sizeof(uint32_t) * ni, st));
+    CK(dmalloc(&tile_sums, sizeof(uint32_t) * ((ni + SCAN_TILE - 1) / SCAN_TILE + 1), st));
+    CK(dmalloc(&d_total, sizeof(uint32_t), st));
+    CK(dmalloc(&d_depth, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * ni, st));
     CK(cudaMemsetAsync(d_depth, 0, sizeof(unsigned int), st));
     const uint32_t nbi = (ni + T - 1) / T;
@@ -612,7 +614,7 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
     CK(cudaStreamSynchronize(st));
     if (n_live == 0) { err = "internal: LBVH has no live node"; rc = CUTRACE_ERR_INTERNAL; goto done; }
     out.n_nodes = n_live;
-    CK(cudaMalloc(&out.nodes, sizeof(Node) * n_live));
+    CK(dmalloc(&out.nodes, sizeof(Node) * n_live, st));
     emit_kernel<<<nbi, T, 0, st>>>(ni, children, range, live, leaf_size, leaf_lo, leaf_hi, node_lo, node_hi, eps, out.nodes);
     depth_kernel<<<nbi, T, 0, st>>>(ni, range, parent_node, leaf_size, d_depth);
     CK(cudaGetLastError());
@@ -626,11 +628,11 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
     }
   }
 done:
-  cudaFree(lo); cudaFree(hi); cudaFree(d_bounds); cudaFree(keys); cudaFree(vals); cudaFree(leaf_lo); cudaFree(leaf_hi);
-  cudaFree(node_lo); cudaFree(node_hi); cudaFree(children); cudaFree(range); cudaFree(parent_node); cudaFree(parent_leaf);
-  cudaFree(flags); cudaFree(live); cudaFree(tile_sums); cudaFree(d_total); cudaFree(d_depth);
+  dfree(lo, st); dfree(hi, st); dfree(d_bounds, st); dfree(keys, st); dfree(vals, st); dfree(leaf_lo, st); dfree(leaf_hi, st);
+  dfree(node_lo, st); dfree(node_hi, st); dfree(children, st); dfree(range, st); dfree(parent_node, st); dfree(parent_leaf, st);
+  dfree(flags, st); dfree(live, st); dfree(tile_sums, st); dfree(d_total, st); dfree(d_depth, st);
   if (rc != CUTRACE_OK) {
-    cudaFree(out.prims); cudaFree(out.nodes);
+    dfree(out.prims, st); dfree(out.nodes, st);
     out.prims = nullptr; out.nodes = nullptr;
   }
   return rc;

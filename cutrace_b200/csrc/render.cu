@@ -74,7 +74,7 @@ __device__ __forceinline__ void camera_ray(const Camera &c, uint32_t x, uint32_t
   d = vnormalized(vadd(vadd(x_v, y_v), z_v));
 }
 
-template <int MODE>
+template <int MODE, bool BRUTE>
 __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
 trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t bounces, uint32_t px_base, uint32_t n_px,
              const RayRec *__restrict__ rays_in, RayRec *__restrict__ rays_out, ShadeRec *__restrict__ shade_out,
@@ -93,6 +93,7 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
     if (lane == 0) base = atomicAdd(&ctr->work_trace[level], (unsigned)WORK_CHUNK);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= n_work) break;
+#pragma unroll 1
     for (unsigned off = 0; off < (unsigned)WORK_CHUNK && base + off < n_work; off += 32) {
       const uint32_t i = base + off + lane;
       bool active = i < n_work;
@@ -111,13 +112,13 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
       }
       Hit h;
       hit_reset(h);
-      if (active) closest_hit<MODE>(sv, nodes, prims, o, d, sv.fudge, h);
+      if (active) closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
       const bool hit = active && h.kind >= 0;
       vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
       uint32_t mat = 0;
       float reflect = 0.f, transp = 0.f;
       if (hit) {
-        hit_surface(sv, prims, MODE == 1, h, o, d, point, nrm);
+        hit_surface<MODE>(sv, prims, h, o, d, point, nrm);
         mat = __ldg(sv.obj_material + h.obj);
         const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
         float4 m1 = __ldg(mp + 1);
@@ -189,19 +190,19 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
 }
 
 // shadow_intensity, inc/shading.hpp:22-45
-template <int MODE>
+template <int MODE, bool BRUTE, bool OPAQUE>
 __device__ __forceinline__ float shadow_intensity(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 o, vec3 d,
                                                   float max_dist, unsigned long long &casts) {
-  if (sv.all_opaque) {
+  if (OPAQUE) {
     // every crossing adds 1 - 0 = 1 -> the first march step saturates: any surface in (1e-3, max_dist) shadows fully
     casts++;
-    return any_hit<MODE>(sv, nodes, prims, o, d, (float)(0.0 + 1e-3), max_dist) ? 1.0f : 0.0f;
+    return any_hit<MODE, BRUTE>(sv, nodes, prims, o, d, (float)(0.0 + 1e-3), max_dist) ? 1.0f : 0.0f;
   }
   float intensity = 0.0f, last_hit = 0.0f;
   for (;;) {
     Hit h;
     casts++;
-    closest_hit<MODE>(sv, nodes, prims, o, d, (float)((double)last_hit + 1e-3), h);
+    closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, (float)((double)last_hit + 1e-3), h);
     if (!(h.kind >= 0 && h.t < max_dist)) break;
     const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + __ldg(sv.obj_material + h.obj));
     float trans = __ldg(mp + 1).z;
@@ -212,7 +213,7 @@ __device__ __forceinline__ float shadow_intensity(const SceneView &sv, const flo
   return intensity;
 }
 
-template <int MODE>
+template <int MODE, bool BRUTE, bool OPAQUE>
 __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
 shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ shade, FrameCounters *ctr, FrameTargets fb,
              int atomic_accumulate) {
@@ -228,6 +229,7 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
     if (lane == 0) base = atomicAdd(&ctr->work_shade[level], (unsigned)WORK_CHUNK);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= n_work) break;
+#pragma unroll 1
     for (unsigned off = 0; off < (unsigned)WORK_CHUNK && base + off < n_work; off += 32) {
       const uint32_t i = base + off + lane;
       if (i < n_work) {
@@ -260,7 +262,7 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
           const float light_dist = distance * vnorm(direction);
           const vec3 color = mk3(l1.x, l1.y, l1.z);
           const vec3 nn = vnormalized(normal), nd = sdir;
-          const float shadow_fac = shadow_intensity<MODE>(sv, nodes, prims, hit, sdir, light_dist, casts);
+          const float shadow_fac = shadow_intensity<MODE, BRUTE, OPAQUE>(sv, nodes, prims, hit, sdir, light_dist, casts);
           if (shadow_fac < 1.0f) {
             float fd = fmaxf(0.0f, vdot(nn, nd));
             vec3 ld = vmul(diffuse, color);
@@ -287,6 +289,20 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
+typedef void (*trace_fn)(const SceneView, const TileMap, uint32_t, uint32_t, uint32_t, uint32_t, const RayRec *, RayRec *, ShadeRec *,
+                         FrameCounters *, FrameTargets);
+typedef void (*shade_fn)(const SceneView, uint32_t, const ShadeRec *, FrameCounters *, FrameTargets, int);
+
+static trace_fn pick_trace(int mode, bool brute) {
+  if (brute) return trace_kernel<0, true>;
+  return mode == 1 ? trace_kernel<1, false> : trace_kernel<0, false>;
+}
+static shade_fn pick_shade(int mode, bool brute, bool opaque) {
+  if (brute) return opaque ? shade_kernel<0, true, true> : shade_kernel<0, true, false>;
+  if (mode == 1) return opaque ? shade_kernel<1, false, true> : shade_kernel<1, false, false>;
+  return opaque ? shade_kernel<0, false, true> : shade_kernel<0, false, false>;
+}
+
 cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
   int dev = 0, sms = 0, smem_optin = 0;
   cudaError_t e;
@@ -300,16 +316,15 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
     cfg->mode = 1;
     cfg->smem_bytes = need;
   }
+  trace_fn tf = pick_trace(cfg->mode, sv.brute_force != 0);
+  shade_fn sf = pick_shade(cfg->mode, sv.brute_force != 0, sv.all_opaque != 0);
   int occ_t = 1, occ_s = 1;
   if (cfg->mode == 1) {
-    if ((e = cudaFuncSetAttribute(trace_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(shade_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, trace_kernel<1>, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, shade_kernel<1>, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
-  } else {
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, trace_kernel<0>, TRACE_THREADS, 0)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, shade_kernel<0>, TRACE_THREADS, 0)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
   }
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, tf, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, sf, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
   if (occ_t < 1) occ_t = 1;
   if (occ_s < 1) occ_s = 1;
   cfg->grid_trace = sms * occ_t;
@@ -327,19 +342,15 @@ void launch_trace(const LaunchCfg &cfg, const SceneView &sv, const TileMap &tm, 
                   uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, ShadeRec *shade_out,
                   FrameCounters *ctr, const FrameTargets &fb, uint32_t work_bound, cudaStream_t st) {
   int grid = clamp_grid(cfg.grid_trace, work_bound);
-  if (cfg.mode == 1)
-    trace_kernel<1><<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(sv, tm, level, bounces, px_base, n_px, rays_in, rays_out, shade_out, ctr, fb);
-  else
-    trace_kernel<0><<<grid, TRACE_THREADS, 0, st>>>(sv, tm, level, bounces, px_base, n_px, rays_in, rays_out, shade_out, ctr, fb);
+  pick_trace(cfg.mode, sv.brute_force != 0)<<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(sv, tm, level, bounces, px_base, n_px, rays_in,
+                                                                                         rays_out, shade_out, ctr, fb);
 }
 
 void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, FrameCounters *ctr,
                   const FrameTargets &fb, bool atomic_accumulate, uint32_t work_bound, cudaStream_t st) {
   int grid = clamp_grid(cfg.grid_shade, work_bound);
-  if (cfg.mode == 1)
-    shade_kernel<1><<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(sv, level, shade, ctr, fb, atomic_accumulate ? 1 : 0);
-  else
-    shade_kernel<0><<<grid, TRACE_THREADS, 0, st>>>(sv, level, shade, ctr, fb, atomic_accumulate ? 1 : 0);
+  pick_shade(cfg.mode, sv.brute_force != 0, sv.all_opaque != 0)<<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(
+      sv, level, shade, ctr, fb, atomic_accumulate ? 1 : 0);
 }
 
 }  // namespace ctb

@@ -5,10 +5,13 @@
 
 namespace ctb {
 
-constexpr int TRACE_THREADS = 512;
+#ifndef CTB_THREADS
+#define CTB_THREADS 512
+#endif
+constexpr int TRACE_THREADS = CTB_THREADS;
 constexpr int WORK_CHUNK = 128;   // rays a warp claims per work-stealing atomic
 #ifndef CTB_MIN_BLOCKS
-#define CTB_MIN_BLOCKS 1   // resident CTAs per SM the register allocator must allow (tuned on B200)
+#define CTB_MIN_BLOCKS 2   // resident CTAs per SM the register allocator must allow (tuned on B200)
 #endif
 
 struct FrameTargets {   // local tile-major buffers

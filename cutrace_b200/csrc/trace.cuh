@@ -11,6 +11,11 @@
 // The acceptance rule of ray_cast is kept: t > min_dist, strictly closer wins, equal-t ties go to the
 // lowest object index and then the lowest triangle index in file order (inc/ray_cast.hpp:43,
 // inc/default_schema.hpp:134).
+//
+// Code size is a first-class constraint here: the first version of these kernels was 150 KB of SASS
+// and spent 14 of 15 stall cycles per issue in "no instruction" (profiles/r01_*).  Rare paths
+// (spheres, IEEE-division slow paths, brute force, the translucent shadow march) are therefore
+// kept out of line or in separate template instantiations, and leaf loops are not unrolled.
 #ifndef CUTRACE_B200_TRACE_CUH
 #define CUTRACE_B200_TRACE_CUH
 #include "common.cuh"
@@ -38,26 +43,40 @@ __device__ __forceinline__ bool hit_better(const Hit &h, float t, uint32_t obj, 
 }
 
 // triangle::intersect, inc/default_schema.hpp:57-69.  Returns the parametric distance via t.
+// The three quotients are IEEE divisions of the reference's four Sarrus determinants, in its order.
+// Before dividing, triangles whose barycentric numerators already have the wrong sign are rejected:
+// fl(x/alpha) >= 0 can only hold for a negative real quotient if it underflows to -0, which the
+// magnitude guard keeps on the exact path — so the accepted set and every accepted t are unchanged.
 __device__ __forceinline__ bool tri_test(vec3 p1, vec3 p2, vec3 p3, vec3 o, vec3 dir, float min_t, float &t) {
   vec3 a = vsub(p2, p1), b = vsub(p2, p3), c = dir, d = vsub(p2, o);
   float alpha = det3(a, b, c);
-  float beta = det3(d, b, c) / alpha;
-  float gamma = det3(a, d, c) / alpha;
+  float nb = det3(d, b, c);
+  float ng = det3(a, d, c);
+  const float tiny = 1e-30f;
+  bool neg_b = (__float_as_uint(nb) ^ __float_as_uint(alpha)) >> 31;   // quotient negative (or -0)
+  bool neg_g = (__float_as_uint(ng) ^ __float_as_uint(alpha)) >> 31;
+  float aa = fabsf(alpha);
+  if ((neg_b && fabsf(nb) > tiny * aa) || (neg_g && fabsf(ng) > tiny * aa)) return false;
+  float beta = nb / alpha;
+  float gamma = ng / alpha;
+  if (!(beta >= 0 && gamma >= 0 && beta + gamma <= 1)) return false;
   float t0 = det3(a, b, d) / alpha;
   t = t0;
   // `min_t <= t0` is the primitive's own test, `t0 > min_t` is ray_cast's `dist > min_dist`
-  return beta >= 0 && gamma >= 0 && beta + gamma <= 1 && isfinite(t0) && min_t <= t0 && t0 > min_t;
+  return isfinite(t0) && min_t <= t0 && t0 > min_t;
 }
 
-// sphere::intersect, inc/default_schema.hpp:226-243
-__device__ __forceinline__ bool sphere_test(vec3 c, float R, vec3 e, vec3 dir, float min_t, float &t) {
+// sphere::intersect, inc/default_schema.hpp:226-243 (out of line: rare next to triangles)
+__device__ __noinline__ bool sphere_test(float cx, float cy, float cz, float R, vec3 e, vec3 dir, float min_t, float *tout) {
+  vec3 c = mk3(cx, cy, cz);
   vec3 d = vnormalized(dir);
   float dec = -vdot(d, vsub(e, c));
   float sub = dec * dec - vdot(d, d) * (vdot(vsub(e, c), vsub(e, c)) - R * R);
   float t0 = (dec - sqrtf(sub)) / vdot(d, d), t1 = (dec + sqrtf(sub)) / vdot(d, d);
   bool t0v = isfinite(t0) && min_t <= t0, t1v = isfinite(t1) && min_t <= t1;
   if (!t0v && !t1v) return false;
-  t = (t0v && t1v) ? fminf(t0, t1) : (t0v ? t0 : t1);
+  float t = (t0v && t1v) ? fminf(t0, t1) : (t0v ? t0 : t1);
+  *tout = t;
   return t > min_t;
 }
 
@@ -66,22 +85,6 @@ __device__ __forceinline__ bool plane_test(vec3 point, vec3 n, vec3 o, vec3 dir,
   float t0 = vdot(vsub(point, o), n) / vdot(dir, n);
   t = t0;
   return isfinite(t0) && min_t <= t0 && t0 > min_t;
-}
-
-// -------------------------------------------------------------------------------------------------
-// memory access policy: MODE 0 = nodes/primitives in global memory (LDG.128, L1/L2 resident),
-// MODE 1 = the whole BVH and primitive store staged in shared memory (LDS.128)
-// -------------------------------------------------------------------------------------------------
-template <int MODE>
-struct Store {
-  const float4 *nodes;   // 4 x float4 per node
-  const float4 *prims;   // 3 x float4 per primitive
-};
-
-template <int MODE>
-__device__ __forceinline__ float4 ld4(const float4 *p) {
-  if (MODE == 1) return *p;   // shared (generic address resolved at compile time by the caller's pointer)
-  return __ldg(p);
 }
 
 struct RayCtx {
@@ -93,74 +96,90 @@ __device__ __forceinline__ float safe_rcp(float x) {
   return 1.0f / (fabsf(x) < 1e-30f ? copysignf(1e-30f, x) : x);
 }
 
-__device__ __forceinline__ void test_leaf_prim(const float4 *__restrict__ prims, uint32_t k, bool shared, const RayCtx &r,
-                                               float min_t, Hit &h) {
-  float4 q0, q1, q2;
-  if (shared) { q0 = prims[3 * k]; q1 = prims[3 * k + 1]; q2 = prims[3 * k + 2]; }
-  else { q0 = __ldg(&prims[3 * (size_t)k]); q1 = __ldg(&prims[3 * (size_t)k + 1]); q2 = __ldg(&prims[3 * (size_t)k + 2]); }
-  uint32_t obj = __float_as_uint(q0.w), idx = __float_as_uint(q1.w), kind = __float_as_uint(q2.w);
+__device__ __forceinline__ void make_ray(RayCtx &r, vec3 o, vec3 d) {
+  r.o = o; r.d = d;
+  r.inv = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+}
+
+// MODE 0: nodes / primitives in global memory (LDG.128 through L1), MODE 1: staged in shared memory (LDS.128)
+template <int MODE>
+__device__ __forceinline__ float4 ld16(const float4 *p) {
+  if (MODE == 1) return *p;
+  return __ldg(p);
+}
+
+template <int MODE>
+__device__ __forceinline__ void test_prim(const float4 *__restrict__ prims, uint32_t k, const RayCtx &r, float min_t, Hit &h) {
+  const float4 *pp = prims + 3 * (size_t)k;
+  const float4 q0 = ld16<MODE>(pp), q1 = ld16<MODE>(pp + 1), q2 = ld16<MODE>(pp + 2);
   float t;
   bool ok;
-  if (kind == CTB_PRIM_TRI) ok = tri_test(mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), r.o, r.d, min_t, t);
-  else ok = sphere_test(mk3(q0.x, q0.y, q0.z), q1.x, r.o, r.d, min_t, t);
-  if (ok && hit_better(h, t, obj, idx)) { h.t = t; h.obj = obj; h.idx = idx; h.ref = k; h.kind = (int)kind; }
+  if (__float_as_uint(q2.w) == CTB_PRIM_TRI) ok = tri_test(mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), r.o, r.d, min_t, t);
+  else ok = sphere_test(q0.x, q0.y, q0.z, q1.x, r.o, r.d, min_t, &t);
+  if (ok) {
+    const uint32_t obj = __float_as_uint(q0.w), idx = __float_as_uint(q1.w);
+    if (hit_better(h, t, obj, idx)) { h.t = t; h.obj = obj; h.idx = idx; h.ref = k; h.kind = (int)__float_as_uint(q2.w); }
+  }
 }
 
 // Closest hit over the BVH primitives (planes are handled by the caller).  `h` carries the best hit
 // so far in and out.  ANY: stop at the first accepted hit with t < max_t (shadow rays in scenes
-// without translucent materials).  Returns true if ANY found an occluder.
-template <int MODE, bool ANY>
+// without translucent materials) and return true.  while-while traversal: the inner loop walks
+// internal nodes until it reaches a leaf, so the lanes of a warp spend most iterations in the same
+// code; the stack bottom holds the sentinel, so popping needs no emptiness test.
+template <int MODE, bool ANY, bool BRUTE>
 __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__restrict__ nodes, const float4 *__restrict__ prims,
                                          const RayCtx &r, float min_t, float max_t, Hit &h) {
-  const bool shared = MODE == 1;
-  if (sv.brute_force) {
+  if (BRUTE) {
+#pragma unroll 1
     for (uint32_t k = 0; k < sv.n_prims; k++) {
-      test_leaf_prim(prims, k, shared, r, min_t, h);
+      test_prim<MODE>(prims, k, r, min_t, h);
       if (ANY && h.t < max_t) return true;
     }
     return false;
   }
   int stack[CTB_STACK];
-  int sp = 0;
+  stack[0] = CTB_SENTINEL;
+  int sp = 1;
   int cur = sv.root;
   const float slack = 1.0f + 4.0f * 1.1920929e-7f;
   while (cur != CTB_SENTINEL) {
-    if (cur >= 0) {
-      float4 n0, n1, nz;
-      int4 meta;
+#pragma unroll 1
+    while ((unsigned)cur < (unsigned)CTB_SENTINEL) {   // internal node
       const float4 *np = nodes + 4 * (size_t)cur;
-      if (shared) { n0 = np[0]; n1 = np[1]; nz = np[2]; meta = *reinterpret_cast<const int4 *>(np + 3); }
-      else { n0 = __ldg(np); n1 = __ldg(np + 1); nz = __ldg(np + 2); meta = __ldg(reinterpret_cast<const int4 *>(np + 3)); }
-      float limit = ANY ? fminf(max_t, h.t) : h.t;
+      const float4 n0 = ld16<MODE>(np), n1 = ld16<MODE>(np + 1), nz = ld16<MODE>(np + 2);
+      const float4 mf = ld16<MODE>(np + 3);
+      const int c0 = __float_as_int(mf.x), c1 = __float_as_int(mf.y);
+      const float limit = ANY ? fminf(max_t, h.t) : h.t;
       // slabs: (plane - origin) * inv, subtraction first so the error stays relative
-      float c0lox = (n0.x - r.o.x) * r.inv.x, c0hix = (n0.y - r.o.x) * r.inv.x;
-      float c0loy = (n0.z - r.o.y) * r.inv.y, c0hiy = (n0.w - r.o.y) * r.inv.y;
-      float c0loz = (nz.x - r.o.z) * r.inv.z, c0hiz = (nz.y - r.o.z) * r.inv.z;
-      float c1lox = (n1.x - r.o.x) * r.inv.x, c1hix = (n1.y - r.o.x) * r.inv.x;
-      float c1loy = (n1.z - r.o.y) * r.inv.y, c1hiy = (n1.w - r.o.y) * r.inv.y;
-      float c1loz = (nz.z - r.o.z) * r.inv.z, c1hiz = (nz.w - r.o.z) * r.inv.z;
-      float tn0 = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), min_t));
-      float tf0 = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), limit)) * slack;
-      float tn1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), min_t));
-      float tf1 = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), limit)) * slack;
-      bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
+      const float c0lox = (n0.x - r.o.x) * r.inv.x, c0hix = (n0.y - r.o.x) * r.inv.x;
+      const float c0loy = (n0.z - r.o.y) * r.inv.y, c0hiy = (n0.w - r.o.y) * r.inv.y;
+      const float c0loz = (nz.x - r.o.z) * r.inv.z, c0hiz = (nz.y - r.o.z) * r.inv.z;
+      const float c1lox = (n1.x - r.o.x) * r.inv.x, c1hix = (n1.y - r.o.x) * r.inv.x;
+      const float c1loy = (n1.z - r.o.y) * r.inv.y, c1hiy = (n1.w - r.o.y) * r.inv.y;
+      const float c1loz = (nz.z - r.o.z) * r.inv.z, c1hiz = (nz.w - r.o.z) * r.inv.z;
+      const float tn0 = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), min_t));
+      const float tf0 = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), limit)) * slack;
+      const float tn1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), min_t));
+      const float tf1 = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), limit)) * slack;
+      const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
       if (h0 && h1) {
-        bool swap = tn1 < tn0;
-        int near = swap ? meta.y : meta.x, far = swap ? meta.x : meta.y;
-        stack[sp++] = far;
-        cur = near;
-      } else if (h0) {
-        cur = meta.x;
-      } else if (h1) {
-        cur = meta.y;
+        const bool swap = tn1 < tn0;
+        stack[sp++] = swap ? c0 : c1;
+        cur = swap ? c1 : c0;
+      } else if (h0 || h1) {
+        cur = h0 ? c0 : c1;
       } else {
-        cur = sp > 0 ? stack[--sp] : CTB_SENTINEL;
+        cur = stack[--sp];
       }
-    } else {
-      uint32_t first = leaf_first(cur), count = leaf_count(cur);
-      for (uint32_t k = first; k < first + count; k++) test_leaf_prim(prims, k, shared, r, min_t, h);
+    }
+    if (cur == CTB_SENTINEL) break;
+    {   // leaf
+      const uint32_t first = leaf_first(cur), count = leaf_count(cur);
+#pragma unroll 1
+      for (uint32_t k = first; k < first + count; k++) test_prim<MODE>(prims, k, r, min_t, h);
       if (ANY && h.t < max_t) return true;
-      cur = sp > 0 ? stack[--sp] : CTB_SENTINEL;
+      cur = stack[--sp];
     }
   }
   return false;
@@ -169,58 +188,61 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
 // planes: unbounded, kept out of the BVH and always tested (the reference tests them like any other
 // object in its linear walk).  Uniform addresses -> broadcast loads.
 __device__ __forceinline__ void test_planes(const SceneView &sv, const RayCtx &r, float min_t, Hit &h) {
+#pragma unroll 1
   for (uint32_t p = 0; p < sv.n_planes; p++) {
     const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + p);
-    float4 a = __ldg(pp), b = __ldg(pp + 1);
+    const float4 a = __ldg(pp), b = __ldg(pp + 1);
     float t;
     if (plane_test(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), r.o, r.d, min_t, t)) {
-      uint32_t obj = __float_as_uint(a.w);
+      const uint32_t obj = __float_as_uint(a.w);
       if (hit_better(h, t, obj, 0u)) { h.t = t; h.obj = obj; h.idx = 0u; h.ref = p; h.kind = CTB_KIND_PLANE; }
     }
   }
 }
 
 // ray_cast (inc/ray_cast.hpp:29-55) over the flat store + LBVH
-template <int MODE>
+template <int MODE, bool BRUTE>
 __device__ __forceinline__ void closest_hit(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 o, vec3 d,
                                             float min_t, Hit &h) {
   RayCtx r;
-  r.o = o; r.d = d;
-  r.inv = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+  make_ray(r, o, d);
   hit_reset(h);
   test_planes(sv, r, min_t, h);
-  traverse<MODE, false>(sv, nodes, prims, r, min_t, INFINITY, h);
+  traverse<MODE, false, BRUTE>(sv, nodes, prims, r, min_t, INFINITY, h);
 }
 
 // is there any surface with min_t < t < max_t ?  (shadow_intensity with only opaque materials,
 // inc/shading.hpp:32-39: the first march step already saturates the intensity)
-template <int MODE>
+template <int MODE, bool BRUTE>
 __device__ __forceinline__ bool any_hit(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 o, vec3 d,
                                         float min_t, float max_t) {
   RayCtx r;
-  r.o = o; r.d = d;
-  r.inv = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+  make_ray(r, o, d);
+#pragma unroll 1
+  for (uint32_t p = 0; p < sv.n_planes; p++) {
+    const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + p);
+    const float4 a = __ldg(pp), b = __ldg(pp + 1);
+    float t;
+    if (plane_test(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), r.o, r.d, min_t, t) && t < max_t) return true;
+  }
   Hit h;
   hit_reset(h);
-  test_planes(sv, r, min_t, h);
-  if (h.t < max_t) return true;
-  hit_reset(h);
-  return traverse<MODE, true>(sv, nodes, prims, r, min_t, max_t, h);
+  return traverse<MODE, true, BRUTE>(sv, nodes, prims, r, min_t, max_t, h);
 }
 
 // surface point and raw normal of a hit, as the primitive's intersect() reports them
-__device__ __forceinline__ void hit_surface(const SceneView &sv, const float4 *prims, bool shared, const Hit &h, vec3 o, vec3 d,
+template <int MODE>
+__device__ __forceinline__ void hit_surface(const SceneView &sv, const float4 *prims, const Hit &h, vec3 o, vec3 d,
                                             vec3 &point, vec3 &normal) {
   if (h.kind == CTB_KIND_PLANE) {
     const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + h.ref);
-    float4 b = __ldg(pp + 1);
+    const float4 b = __ldg(pp + 1);
     point = vadd(o, vscale(d, h.t));                    // inc/default_schema.hpp:194
     normal = mk3(b.x, b.y, b.z);                        // :195 stored normal, not normalised
     return;
   }
-  float4 q0, q1, q2;
-  if (shared) { q0 = prims[3 * h.ref]; q1 = prims[3 * h.ref + 1]; q2 = prims[3 * h.ref + 2]; }
-  else { q0 = __ldg(&prims[3 * (size_t)h.ref]); q1 = __ldg(&prims[3 * (size_t)h.ref + 1]); q2 = __ldg(&prims[3 * (size_t)h.ref + 2]); }
+  const float4 *pp = prims + 3 * (size_t)h.ref;
+  const float4 q0 = ld16<MODE>(pp), q1 = ld16<MODE>(pp + 1), q2 = ld16<MODE>(pp + 2);
   if (h.kind == CTB_KIND_TRI) {
     vec3 p1 = mk3(q0.x, q0.y, q0.z), p2 = mk3(q1.x, q1.y, q1.z), p3 = mk3(q2.x, q2.y, q2.z);
     point = vadd(o, vscale(d, h.t));                                              // :71
