@@ -190,6 +190,10 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
 }
 
 // shadow_intensity, inc/shading.hpp:22-45
+#ifndef SHADOW_PACKET
+#define SHADOW_PACKET 1   // shadow rays of one hit that traverse together
+#endif
+
 template <int MODE, bool BRUTE, bool OPAQUE>
 __device__ __forceinline__ float shadow_intensity(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 o, vec3 d,
                                                   float max_dist, unsigned long long &casts) {
@@ -214,7 +218,7 @@ __device__ __forceinline__ float shadow_intensity(const SceneView &sv, const flo
 }
 
 template <int MODE, bool BRUTE, bool OPAQUE>
-__global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
+__global__ void __launch_bounds__(TRACE_THREADS, CTB_SHADE_MIN_BLOCKS)
 shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ shade, FrameCounters *ctr, FrameTargets fb,
              int atomic_accumulate) {
   extern __shared__ float4 smem[];
@@ -245,32 +249,82 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
         const vec3 specular = vscale(diffuse, m0.w);        // *spec = specular * color
         const float phong_exp = m1.y;
         vec3 final = vscale(diffuse, sv.cam.ambient);
-        for (uint32_t l = 0; l < sv.n_lights; l++) {
-          const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l);
-          const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
-          vec3 direction;
-          float distance;
-          if (__float_as_uint(l0.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
-            direction = vscale(mk3(l0.x, l0.y, l0.z), -1.0f);
-            distance = INFINITY;
-          } else {                                              // inc/default_schema.hpp:305-308
-            vec3 P = mk3(l0.x, l0.y, l0.z);
-            direction = vnormalized(vsub(P, hit));
-            distance = vnorm(vsub(P, hit));
+        const vec3 nn = vnormalized(normal);
+        const vec3 in_n = vscale(vnormalized(in_dir), -1.0f);
+        if (OPAQUE) {
+          // every material is opaque: the shadow march saturates on its first step, so the K shadow rays
+          // of this hit are any-hit queries and walk the BVH as one packet
+          for (uint32_t l0 = 0; l0 < sv.n_lights; l0 += SHADOW_PACKET) {
+            vec3 sd[SHADOW_PACKET];
+            float md[SHADOW_PACKET];
+            vec3 lcol[SHADOW_PACKET];
+            unsigned valid = 0;
+#pragma unroll
+            for (int k = 0; k < SHADOW_PACKET; k++) {
+              sd[k] = mk3(0.f, 0.f, 1.f); md[k] = 0.f; lcol[k] = mk3(0.f, 0.f, 0.f);
+              if (l0 + k < sv.n_lights) {
+                const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l0 + k);
+                const float4 l0v = __ldg(lp), l1v = __ldg(lp + 1);
+                vec3 direction;
+                float distance;
+                if (__float_as_uint(l0v.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
+                  direction = vscale(mk3(l0v.x, l0v.y, l0v.z), -1.0f);
+                  distance = INFINITY;
+                } else {                                               // inc/default_schema.hpp:305-308
+                  vec3 P = mk3(l0v.x, l0v.y, l0v.z);
+                  direction = vnormalized(vsub(P, hit));
+                  distance = vnorm(vsub(P, hit));
+                }
+                sd[k] = vnormalized(direction);
+                md[k] = distance * vnorm(direction);
+                lcol[k] = mk3(l1v.x, l1v.y, l1v.z);
+                valid |= 1u << k;
+              }
+            }
+            casts += __popc(valid);
+            const unsigned occ = any_hit_packet<MODE, SHADOW_PACKET, BRUTE>(sv, nodes, prims, hit, sd, md, valid);
+#pragma unroll
+            for (int k = 0; k < SHADOW_PACKET; k++) {
+              if ((valid & ~occ) & (1u << k)) {        // shadow_fac = 0 < 1
+                const vec3 nd = sd[k];
+                float fd = fmaxf(0.0f, vdot(nn, nd));
+                vec3 ld = vmul(diffuse, lcol[k]);
+                vec3 hv = vnormalized(vadd(in_n, nd));
+                float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+                vec3 ls = vmul(specular, lcol[k]);
+                vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - 0.0f);
+                final.x += term.x; final.y += term.y; final.z += term.z;
+              }
+            }
           }
-          const vec3 sdir = vnormalized(direction);
-          const float light_dist = distance * vnorm(direction);
-          const vec3 color = mk3(l1.x, l1.y, l1.z);
-          const vec3 nn = vnormalized(normal), nd = sdir;
-          const float shadow_fac = shadow_intensity<MODE, BRUTE, OPAQUE>(sv, nodes, prims, hit, sdir, light_dist, casts);
-          if (shadow_fac < 1.0f) {
-            float fd = fmaxf(0.0f, vdot(nn, nd));
-            vec3 ld = vmul(diffuse, color);
-            vec3 hv = vnormalized(vadd(vscale(vnormalized(in_dir), -1.0f), nd));
-            float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
-            vec3 ls = vmul(specular, color);
-            vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - shadow_fac);
-            final.x += term.x; final.y += term.y; final.z += term.z;
+        } else {
+          for (uint32_t l = 0; l < sv.n_lights; l++) {
+            const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l);
+            const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
+            vec3 direction;
+            float distance;
+            if (__float_as_uint(l0.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
+              direction = vscale(mk3(l0.x, l0.y, l0.z), -1.0f);
+              distance = INFINITY;
+            } else {                                              // inc/default_schema.hpp:305-308
+              vec3 P = mk3(l0.x, l0.y, l0.z);
+              direction = vnormalized(vsub(P, hit));
+              distance = vnorm(vsub(P, hit));
+            }
+            const vec3 sdir = vnormalized(direction);
+            const float light_dist = distance * vnorm(direction);
+            const vec3 color = mk3(l1.x, l1.y, l1.z);
+            const vec3 nd = sdir;
+            const float shadow_fac = shadow_intensity<MODE, BRUTE, false>(sv, nodes, prims, hit, sdir, light_dist, casts);
+            if (shadow_fac < 1.0f) {
+              float fd = fmaxf(0.0f, vdot(nn, nd));
+              vec3 ld = vmul(diffuse, color);
+              vec3 hv = vnormalized(vadd(in_n, nd));
+              float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+              vec3 ls = vmul(specular, color);
+              vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - shadow_fac);
+              final.x += term.x; final.y += term.y; final.z += term.z;
+            }
           }
         }
         float *cp = fb.color + 3 * (size_t)pix;

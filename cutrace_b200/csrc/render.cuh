@@ -10,6 +10,9 @@ namespace ctb {
 #endif
 constexpr int TRACE_THREADS = CTB_THREADS;
 constexpr int WORK_CHUNK = 128;   // rays a warp claims per work-stealing atomic
+#ifndef CTB_SHADE_MIN_BLOCKS
+#define CTB_SHADE_MIN_BLOCKS 2   // measured on B200: 2 CTAs/SM (64 regs) beat 1 CTA/SM for K = 1 (profiles/r01_tuning.md)
+#endif
 #ifndef CTB_MIN_BLOCKS
 #define CTB_MIN_BLOCKS 2   // resident CTAs per SM the register allocator must allow (tuned on B200)
 #endif

@@ -230,6 +230,143 @@ __device__ __forceinline__ bool any_hit(const SceneView &sv, const float4 *nodes
   return traverse<MODE, true, BRUTE>(sv, nodes, prims, r, min_t, max_t, h);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Shadow-ray packets.  All shadow rays of one shaded hit start at the same point (inc/shading.hpp:80),
+// so up to K of them (one per light) walk the BVH together: one stack, one node fetch, the
+// (plane - origin) subtractions and the ray-independent parts of Cramer's rule (a, b, d = p2 - o)
+// shared.  A node is entered if ANY still-unoccluded ray of the packet hits its box; a ray leaves the
+// packet as soon as it finds an occluder in (1e-3, light_dist).  Same accept/reject decisions per ray as
+// any_hit(); returns the bit mask of occluded rays.  `act` = rays that take part.
+// -------------------------------------------------------------------------------------------------
+template <int MODE, int K, bool BRUTE>
+__device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const float4 *__restrict__ nodes,
+                                                   const float4 *__restrict__ prims, vec3 o, const vec3 (&d)[K],
+                                                   const float (&max_t)[K], unsigned act) {
+  const float min_t = (float)(0.0 + 1e-3);   // shadow_intensity: last_hit + 1e-3 with last_hit = 0
+  unsigned occ = 0;
+  // planes: (point - o).n is shared by the packet
+#pragma unroll 1
+  for (uint32_t p = 0; p < sv.n_planes; p++) {
+    const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + p);
+    const float4 a = __ldg(pp), b = __ldg(pp + 1);
+    const vec3 n = mk3(b.x, b.y, b.z);
+    const float num = vdot(vsub(mk3(a.x, a.y, a.z), o), n);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const float den = vdot(d[k], n);
+      // t0 > 1e-3 needs num and den of equal sign; then the exact IEEE quotient decides (plane::intersect)
+      if (!((__float_as_uint(num) ^ __float_as_uint(den)) >> 31) && fabsf(num) < max_t[k] * fabsf(den) * 1.0001f) {
+        const float t0 = num / den;
+        if (isfinite(t0) && min_t <= t0 && t0 > min_t && t0 < max_t[k]) occ |= (act & (1u << k));
+      }
+    }
+  }
+  act &= ~occ;
+  if (!act) return occ;
+
+  if (BRUTE) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < sv.n_prims && act; i++) {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        if (act & (1u << k)) {
+          RayCtx r; r.o = o; r.d = d[k]; r.inv = d[k];
+          Hit h; hit_reset(h);
+          test_prim<MODE>(prims, i, r, min_t, h);
+          if (h.t < max_t[k]) { occ |= 1u << k; act &= ~(1u << k); }
+        }
+      }
+    }
+    return occ;
+  }
+
+  vec3 inv[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) inv[k] = mk3(safe_rcp(d[k].x), safe_rcp(d[k].y), safe_rcp(d[k].z));
+  int stack[CTB_STACK];
+  stack[0] = CTB_SENTINEL;
+  int sp = 1;
+  int cur = sv.root;
+  const float slack = 1.0f + 4.0f * 1.1920929e-7f;
+  while (cur != CTB_SENTINEL) {
+#pragma unroll 1
+    while ((unsigned)cur < (unsigned)CTB_SENTINEL) {
+      const float4 *np = nodes + 4 * (size_t)cur;
+      const float4 n0 = ld16<MODE>(np), n1 = ld16<MODE>(np + 1), nz = ld16<MODE>(np + 2);
+      const float4 mf = ld16<MODE>(np + 3);
+      const int c0 = __float_as_int(mf.x), c1 = __float_as_int(mf.y);
+      const float a0x = n0.x - o.x, b0x = n0.y - o.x, a0y = n0.z - o.y, b0y = n0.w - o.y, a0z = nz.x - o.z, b0z = nz.y - o.z;
+      const float a1x = n1.x - o.x, b1x = n1.y - o.x, a1y = n1.z - o.y, b1y = n1.w - o.y, a1z = nz.z - o.z, b1z = nz.w - o.z;
+      bool h0 = false, h1 = false;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const float lox = a0x * inv[k].x, hix = b0x * inv[k].x, loy = a0y * inv[k].y, hiy = b0y * inv[k].y;
+        const float loz = a0z * inv[k].z, hiz = b0z * inv[k].z;
+        const float tn = fmaxf(fmaxf(fminf(lox, hix), fminf(loy, hiy)), fmaxf(fminf(loz, hiz), min_t));
+        const float tf = fminf(fminf(fmaxf(lox, hix), fmaxf(loy, hiy)), fminf(fmaxf(loz, hiz), max_t[k])) * slack;
+        const float lox1 = a1x * inv[k].x, hix1 = b1x * inv[k].x, loy1 = a1y * inv[k].y, hiy1 = b1y * inv[k].y;
+        const float loz1 = a1z * inv[k].z, hiz1 = b1z * inv[k].z;
+        const float tn1 = fmaxf(fmaxf(fminf(lox1, hix1), fminf(loy1, hiy1)), fmaxf(fminf(loz1, hiz1), min_t));
+        const float tf1 = fminf(fminf(fmaxf(lox1, hix1), fmaxf(loy1, hiy1)), fminf(fmaxf(loz1, hiz1), max_t[k])) * slack;
+        const bool on = (act >> k) & 1u;
+        h0 = h0 || (on && tn <= tf);
+        h1 = h1 || (on && tn1 <= tf1);
+      }
+      if (h0 && h1) { stack[sp++] = c1; cur = c0; }
+      else if (h0 || h1) cur = h0 ? c0 : c1;
+      else cur = stack[--sp];
+    }
+    if (cur == CTB_SENTINEL) break;
+    {
+      const uint32_t first = leaf_first(cur), count = leaf_count(cur);
+#pragma unroll 1
+      for (uint32_t i = first; i < first + count; i++) {
+        const float4 *pp = prims + 3 * (size_t)i;
+        const float4 q0 = ld16<MODE>(pp), q1 = ld16<MODE>(pp + 1), q2 = ld16<MODE>(pp + 2);
+        if (__float_as_uint(q2.w) == CTB_PRIM_TRI) {
+          const vec3 p1 = mk3(q0.x, q0.y, q0.z), p2 = mk3(q1.x, q1.y, q1.z), p3 = mk3(q2.x, q2.y, q2.z);
+          const vec3 a = vsub(p2, p1), b = vsub(p2, p3), dd = vsub(p2, o);
+          unsigned cand = 0;
+          float alpha[K], nb[K], ng[K];
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            alpha[k] = det3(a, b, d[k]);
+            nb[k] = det3(dd, b, d[k]);
+            ng[k] = det3(a, dd, d[k]);
+            const float aa = fabsf(alpha[k]) * 1e-30f;
+            const bool neg_b = (__float_as_uint(nb[k]) ^ __float_as_uint(alpha[k])) >> 31;
+            const bool neg_g = (__float_as_uint(ng[k]) ^ __float_as_uint(alpha[k])) >> 31;
+            if (!((neg_b && fabsf(nb[k]) > aa) || (neg_g && fabsf(ng[k]) > aa))) cand |= 1u << k;
+          }
+          cand &= act;
+          if (cand) {   // exact path of triangle::intersect for the few rays that pass the sign test
+            const float nt = det3(a, b, dd);
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+              if (cand & (1u << k)) {
+                const float beta = nb[k] / alpha[k], gamma = ng[k] / alpha[k];
+                if (beta >= 0 && gamma >= 0 && beta + gamma <= 1) {
+                  const float t0 = nt / alpha[k];
+                  if (isfinite(t0) && min_t <= t0 && t0 > min_t && t0 < max_t[k]) { occ |= 1u << k; act &= ~(1u << k); }
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            float t;
+            if ((act & (1u << k)) && sphere_test(q0.x, q0.y, q0.z, q1.x, o, d[k], min_t, &t) && t < max_t[k]) { occ |= 1u << k; act &= ~(1u << k); }
+          }
+        }
+        if (!act) return occ;
+      }
+      cur = stack[--sp];
+    }
+  }
+  return occ;
+}
+
 // surface point and raw normal of a hit, as the primitive's intersect() reports them
 template <int MODE>
 __device__ __forceinline__ void hit_surface(const SceneView &sv, const float4 *prims, const Hit &h, vec3 o, vec3 d,
