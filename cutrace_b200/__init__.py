@@ -90,6 +90,14 @@ class Renderer:
         out["max_depth"] = md.value
         return out
 
+    def download_bytes(self):
+        """The three 8-bit RGB images of the output stage (inc/images.hpp:26-88), encoded on the device."""
+        n = self.width * self.height
+        d8, n8, c8 = (np.empty((n, 3), np.uint8) for _ in range(3))
+        md = C.c_float()
+        _lib.check(self._lib.cutrace_download_bytes(self._ctx, d8.ctypes.data, n8.ctypes.data, c8.ctypes.data, C.byref(md)))
+        return dict(depth_rgb=d8, normal_rgb=n8, color_rgb=c8, max_depth=md.value)
+
     # -- helpers --------------------------------------------------------------------------------------
     def set_camera(self, pos, up, forward, right, ambient, width, height):
         arr = [(C.c_float * 3)(*[float(x) for x in v]) for v in (pos, up, forward, right)]

@@ -70,6 +70,8 @@ struct cutrace_ctx {
   float *st_depth = nullptr, *st_normal = nullptr, *st_color = nullptr;
   uint32_t *st_id = nullptr;
   uint64_t st_px = 0;
+  uint8_t *st_bytes = nullptr;   // 3 images x n x 3 bytes
+  uint64_t st_bytes_px = 0;
   cutrace_stats stats{};
   bool rendered = false;
   std::vector<cudaEvent_t> events;
@@ -91,6 +93,7 @@ void free_frame(cutrace_ctx *c) {
   dfree(c->fb.depth, st); dfree(c->fb.normal, st); dfree(c->fb.color, st); dfree(c->fb.hit_id, st);
   dfree(c->rays[0], st); dfree(c->rays[1], st); dfree(c->shade, st);
   dfree(c->st_depth, st); dfree(c->st_normal, st); dfree(c->st_color, st); dfree(c->st_id, st);
+  dfree(c->st_bytes, st); c->st_bytes = nullptr; c->st_bytes_px = 0;
   c->fb = FrameTargets{};
   c->rays[0] = c->rays[1] = nullptr; c->shade = nullptr;
   c->st_depth = c->st_normal = c->st_color = nullptr; c->st_id = nullptr;
@@ -456,10 +459,8 @@ int cutrace_get_stats(cutrace_ctx *c, cutrace_stats *stats) {
   return CUTRACE_OK;
 }
 
-int cutrace_download(cutrace_ctx *c, float *depth, float *normal, float *color, uint32_t *hit_id, float *max_depth) {
-  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
-  if (!c->rendered) return fail(CUTRACE_ERR_STATE, "cutrace_download called before cutrace_render");
-  DeviceGuard g(c->device);
+// un-tiles the local buffers into the row-major full-frame staging images (device)
+static int stage_full_frame(cutrace_ctx *c) {
   cudaStream_t st = c->stream;
   const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
   if (c->st_px != n) {
@@ -480,10 +481,46 @@ int cutrace_download(cutrace_ctx *c, float *depth, float *normal, float *color, 
     launch_untile(c->tm, 1, c->fb.depth, c->fb.normal, c->fb.color, c->fb.hit_id, 0, -1, c->st_depth, c->st_normal, c->st_color, c->st_id, st);
   }
   CU(cudaGetLastError());
+  return CUTRACE_OK;
+}
+
+int cutrace_download(cutrace_ctx *c, float *depth, float *normal, float *color, uint32_t *hit_id, float *max_depth) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!c->rendered) return fail(CUTRACE_ERR_STATE, "cutrace_download called before cutrace_render");
+  DeviceGuard g(c->device);
+  cudaStream_t st = c->stream;
+  const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
+  int rc = stage_full_frame(c);
+  if (rc) return rc;
   if (depth) CU(cudaMemcpyAsync(depth, c->st_depth, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
   if (normal) CU(cudaMemcpyAsync(normal, c->st_normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
   if (color) CU(cudaMemcpyAsync(color, c->st_color, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
   if (hit_id) CU(cudaMemcpyAsync(hit_id, c->st_id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (max_depth) *max_depth = c->stats.max_depth;
+  return CUTRACE_OK;
+}
+
+int cutrace_download_bytes(cutrace_ctx *c, uint8_t *depth_rgb, uint8_t *normal_rgb, uint8_t *color_rgb, float *max_depth) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!c->rendered) return fail(CUTRACE_ERR_STATE, "cutrace_download_bytes called before cutrace_render");
+  DeviceGuard g(c->device);
+  cudaStream_t st = c->stream;
+  const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
+  int rc = stage_full_frame(c);
+  if (rc) return rc;
+  if (c->st_bytes_px != n) {
+    dfree(c->st_bytes, st); c->st_bytes = nullptr; c->st_bytes_px = 0;
+    CU(dmalloc(&c->st_bytes, 9 * n, st));
+    c->st_bytes_px = n;
+  }
+  uint8_t *d8 = c->st_bytes, *n8 = c->st_bytes + 3 * n, *c8 = c->st_bytes + 6 * n;
+  launch_encode_bytes(depth_rgb ? c->st_depth : nullptr, normal_rgb ? c->st_normal : nullptr, color_rgb ? c->st_color : nullptr,
+                      c->stats.max_depth, n, d8, n8, c8, st);
+  CU(cudaGetLastError());
+  if (depth_rgb) CU(cudaMemcpyAsync(depth_rgb, d8, 3 * n, cudaMemcpyDeviceToHost, st));
+  if (normal_rgb) CU(cudaMemcpyAsync(normal_rgb, n8, 3 * n, cudaMemcpyDeviceToHost, st));
+  if (color_rgb) CU(cudaMemcpyAsync(color_rgb, c8, 3 * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (max_depth) *max_depth = c->stats.max_depth;
   return CUTRACE_OK;

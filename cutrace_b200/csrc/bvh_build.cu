@@ -570,8 +570,15 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
       mag = fmaxf(mag, fmaxf(fabsf(out.lo[c]), fabsf(out.hi[c])));
     }
     clo = make_float3(cl[0], cl[1], cl[2]);
-    cinv = make_float3(ch[0] > cl[0] ? 1.f / (ch[0] - cl[0]) : 0.f, ch[1] > cl[1] ? 1.f / (ch[1] - cl[1]) : 0.f,
-                       ch[2] > cl[2] ? 1.f / (ch[2] - cl[2]) : 0.f);
+    // ONE scale for the three axes (cubic Morton cells).  Normalising each axis by its own extent makes the
+    // cells of a flat scene (the 106x106 instance grid is 106 x 0.85 x 106) extremely anisotropic: the top of
+    // the tree then splits the thin axis over and over and every ray has to descend both halves
+    // (profiles/r01_v2_synthetic10m.md: 9,000 thread-instructions per primary ray before this change).
+    {
+      float ext = fmaxf(fmaxf(ch[0] - cl[0], ch[1] - cl[1]), ch[2] - cl[2]);
+      float inv = ext > 0.f ? 1.f / ext : 0.f;
+      cinv = make_float3(inv, inv, inv);
+    }
     morton_kernel<<<nb, T, 0, st>>>(lo, hi, n, clo, cinv, keys, vals);
     rc = radix_sort_pairs(keys, vals, n, st, err);
     if (rc) goto done;

@@ -1,0 +1,257 @@
+#include "scene_loader.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "json.hpp"
+
+namespace cthost {
+
+const char *const kSchemaHelp =
+    "Scene schema (as accepted by cutrace's default_schema.hpp):\n"
+    "  { \"camera\":    { \"eye\":[x,y,z], \"up\":[x,y,z], \"look\":[x,y,z], \"near_plane\":n, \"far_plane\":n,\n"
+    "                   \"width\":n, \"height\":n, \"ambient\":n },                  (all mandatory)\n"
+    "    \"materials\": [ { \"type\":\"solid\", \"color\":[r,g,b], \"specular\":0.3, \"reflect\":0, \"phong\":32, \"transparency\":0 } ],\n"
+    "    \"lights\":    [ { \"type\":\"sun\", \"direction\":[x,y,z], \"color\":[1,1,1] } | { \"type\":\"point\", \"point\":[x,y,z], \"color\":[1,1,1] } ],\n"
+    "    \"objects\":   [ { \"type\":\"triangle\", \"p1\":[..], \"p2\":[..], \"p3\":[..], \"material\":i }\n"
+    "                 | { \"type\":\"mesh\", \"file\":\"path.stl\", \"material\":i }\n"
+    "                 | { \"type\":\"plane\", \"point\":[..], \"normal\":[..], \"material\":i }\n"
+    "                 | { \"type\":\"sphere\", \"center\":[..], \"radius\":r, \"material\":i } ] }\n";
+
+cutrace_scene_desc FlatScene::desc() const {
+  cutrace_scene_desc d;
+  memset(&d, 0, sizeof d);
+  d.abi_version = CUTRACE_ABI_VERSION;
+  for (int i = 0; i < 3; i++) { d.cam_pos[i] = cam_pos[i]; d.cam_up[i] = cam_up[i]; d.cam_forward[i] = cam_forward[i]; d.cam_right[i] = cam_right[i]; }
+  d.ambient = ambient; d.width = width; d.height = height;
+  auto ptr = [](const auto &v) { return v.empty() ? nullptr : v.data(); };
+  d.n_triangles = tri_object.size(); d.tri_p1 = ptr(tri_p1); d.tri_p2 = ptr(tri_p2); d.tri_p3 = ptr(tri_p3); d.tri_object = ptr(tri_object);
+  d.n_spheres = sph_object.size(); d.sph_center = ptr(sph_center); d.sph_radius = ptr(sph_radius); d.sph_object = ptr(sph_object);
+  d.n_planes = pl_object.size(); d.pl_point = ptr(pl_point); d.pl_normal = ptr(pl_normal); d.pl_object = ptr(pl_object);
+  d.n_objects = (uint32_t)obj_material.size(); d.obj_material = ptr(obj_material); d.obj_kind = ptr(obj_kind);
+  d.n_materials = (uint32_t)mat_specular.size(); d.mat_color = ptr(mat_color); d.mat_specular = ptr(mat_specular);
+  d.mat_reflect = ptr(mat_reflect); d.mat_phong = ptr(mat_phong); d.mat_transparency = ptr(mat_transparency);
+  d.n_lights = (uint32_t)light_kind.size(); d.light_kind = ptr(light_kind); d.light_vec = ptr(light_vec); d.light_color = ptr(light_color);
+  return d;
+}
+
+// ---- float3 helpers mirroring inc/vector.hpp (host build: no FMA contraction wanted) -----------------
+static inline float norm3(const float v[3]) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+static inline void normalized3(const float v[3], float o[3]) {
+  float f = 1.0f / norm3(v);
+  o[0] = f * v[0]; o[1] = f * v[1]; o[2] = f * v[2];
+}
+static inline void cross3(const float a[3], const float b[3], float o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+void look_at(const float pos[3], const float up_in[3], const float look[3], float forward[3], float right[3], float up[3]) {
+  float d[3] = {look[0] - pos[0], look[1] - pos[1], look[2] - pos[2]}, t[3];
+  normalized3(d, forward);
+  cross3(forward, up_in, t); normalized3(t, right);
+  cross3(right, forward, t); normalized3(t, up);
+}
+
+// ---- STL ---------------------------------------------------------------------------------------------
+bool read_stl(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { err = "cannot open mesh file '" + path + "'"; return false; }
+  std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  if (data.size() >= 84) {
+    uint32_t n;
+    memcpy(&n, data.data() + 80, 4);
+    if (84ull + 50ull * n == data.size()) {
+      for (uint32_t i = 0; i < n; i++) {
+        float v[9];
+        memcpy(v, data.data() + 84 + 50ull * i + 12, 36);   // skip the stored normal (the reference recomputes it)
+        p1.insert(p1.end(), v, v + 3); p2.insert(p2.end(), v + 3, v + 6); p3.insert(p3.end(), v + 6, v + 9);
+      }
+      return true;
+    }
+  }
+  std::istringstream in(data);
+  std::string tok;
+  std::vector<float> verts;
+  while (in >> tok) {
+    if (tok == "vertex") {
+      double x, y, z;
+      if (!(in >> x >> y >> z)) { err = "bad vertex in ASCII STL '" + path + "'"; return false; }
+      verts.push_back((float)x); verts.push_back((float)y); verts.push_back((float)z);
+    }
+  }
+  if (verts.empty() || verts.size() % 9) { err = "cannot read STL file '" + path + "'"; return false; }
+  for (size_t i = 0; i < verts.size(); i += 9) {
+    p1.insert(p1.end(), &verts[i], &verts[i] + 3); p2.insert(p2.end(), &verts[i + 3], &verts[i + 3] + 3);
+    p3.insert(p3.end(), &verts[i + 6], &verts[i + 6] + 3);
+  }
+  return true;
+}
+
+// ---- coercion (inc/json_helpers.hpp:88-126) -------------------------------------------------------------
+static bool get_num(const JsonValue &o, const char *key, double &out, std::string &err, const double *def = nullptr) {
+  const JsonValue *v = o.find(key);
+  if (!v) {
+    if (def) { out = *def; return true; }
+    err = std::string("Cannot find key '") + key + "' in object.";
+    return false;
+  }
+  if (!v->is_number()) { err = std::string("Expected a value of type number for '") + key + "'."; return false; }
+  out = v->num;
+  return true;
+}
+static bool get_vec(const JsonValue &o, const char *key, float out[3], std::string &err, const float *def = nullptr) {
+  const JsonValue *v = o.find(key);
+  if (!v) {
+    if (def) { memcpy(out, def, 12); return true; }
+    err = std::string("Cannot find key '") + key + "' in object.";
+    return false;
+  }
+  if (!v->is_array() || v->arr.size() != 3 || !v->arr[0].is_number() || !v->arr[1].is_number() || !v->arr[2].is_number()) {
+    err = std::string("Expected a 3-element array of numbers for '") + key + "'.";
+    return false;
+  }
+  for (int i = 0; i < 3; i++) out[i] = (float)v->arr[i].num;
+  return true;
+}
+static void push3(std::vector<float> &v, const float p[3]) { v.insert(v.end(), p, p + 3); }
+
+bool load_scene_text(const std::string &text, const LoadOptions &opt, FlatScene &s, std::vector<std::string> &errors) {
+  s = FlatScene();
+  JsonValue root;
+  std::string err;
+  JsonParser parser(text);
+  if (!parser.parse(root, err)) { errors.push_back("JSON parse error: " + err); return false; }
+  if (!root.is_object()) { errors.push_back("Value is not a JSON object."); return false; }
+  const size_t before = errors.size();
+
+  // ---- materials first: object material indices are range-checked (the reference would read out of bounds)
+  const JsonValue *mats = root.find("materials");
+  if (!mats || !mats->is_array()) errors.push_back("Could not find 'materials' array.");
+  else {
+    for (size_t i = 0; i < mats->arr.size(); i++) {
+      const JsonValue &m = mats->arr[i];
+      auto bad = [&](const std::string &why) { errors.push_back("Error while loading material #" + std::to_string(i) + ": " + why); };
+      if (!m.is_object()) { bad("Value is not a JSON object."); continue; }
+      const JsonValue *ty = m.find("type");
+      if (!(ty && ty->is_string() && ty->str == "solid") && !(opt.accept_aliases && !ty)) { bad("No matching material type (expected \"solid\")."); continue; }
+      float col[3];
+      double spec, refl, ph, tr;
+      const double d_spec = 0.3, d_zero = 0.0, d_ph = 32.0;   // inc/default_schema.hpp:754-764 (0.3f, 0, 32, 0)
+      if (!get_vec(m, "color", col, err) || !get_num(m, "specular", spec, err, &d_spec) || !get_num(m, "reflect", refl, err, &d_zero) ||
+          !get_num(m, "phong", ph, err, &d_ph) || !get_num(m, "transparency", tr, err, &d_zero)) { bad(err); continue; }
+      push3(s.mat_color, col);
+      s.mat_specular.push_back(m.find("specular") ? (float)spec : 0.3f);
+      s.mat_reflect.push_back((float)refl); s.mat_phong.push_back((float)ph); s.mat_transparency.push_back((float)tr);
+    }
+  }
+  const size_t n_mat = s.mat_specular.size();
+
+  const JsonValue *lights = root.find("lights");
+  if (!lights || !lights->is_array()) errors.push_back("Could not find 'lights' array.");
+  else {
+    const float white[3] = {1, 1, 1};
+    for (size_t i = 0; i < lights->arr.size(); i++) {
+      const JsonValue &l = lights->arr[i];
+      auto bad = [&](const std::string &why) { errors.push_back("Error while loading light #" + std::to_string(i) + ": " + why); };
+      if (!l.is_object()) { bad("Value is not a JSON object."); continue; }
+      const JsonValue *ty = l.find("type");
+      float v[3], c[3];
+      if (ty && ty->is_string() && ty->str == "sun") {
+        if (!get_vec(l, "direction", v, err) || !get_vec(l, "color", c, err, white)) { bad(err); continue; }
+        s.light_kind.push_back(CUTRACE_LIGHT_SUN);
+      } else if (ty && ty->is_string() && ty->str == "point") {
+        const char *key = (opt.accept_aliases && !l.find("point") && l.find("position")) ? "position" : "point";
+        if (!get_vec(l, key, v, err) || !get_vec(l, "color", c, err, white)) { bad(err); continue; }
+        s.light_kind.push_back(CUTRACE_LIGHT_POINT);
+      } else { bad("No matching light type (expected \"sun\" or \"point\")."); continue; }
+      push3(s.light_vec, v); push3(s.light_color, c);
+    }
+  }
+
+  const JsonValue *objs = root.find("objects");
+  if (!objs || !objs->is_array()) errors.push_back("Could not find 'objects' array.");
+  else {
+    for (size_t i = 0; i < objs->arr.size(); i++) {
+      const JsonValue &o = objs->arr[i];
+      auto bad = [&](const std::string &why) { errors.push_back("Error while loading object #" + std::to_string(i) + ": " + why); };
+      if (!o.is_object()) { bad("Value is not a JSON object."); continue; }
+      const JsonValue *ty = o.find("type");
+      std::string type = (ty && ty->is_string()) ? ty->str : "";
+      if (opt.accept_aliases && type == "model") type = "mesh";
+      const uint32_t id = (uint32_t)s.obj_material.size();
+      double mat_d;
+      if (!get_num(o, "material", mat_d, err)) { bad(err); continue; }
+      const size_t mat = (size_t)mat_d;   // (size_t) cast of the double
+      if (mat_d < 0 || mat >= n_mat) { bad("material index " + std::to_string((long long)mat_d) + " out of range"); continue; }
+      if (type == "triangle") {
+        float a[3], b[3], c[3];
+        const JsonValue *pts = o.find("points");
+        if (opt.accept_aliases && !o.find("p1") && pts && pts->is_array() && pts->arr.size() == 3) {
+          JsonValue tmp; tmp.kind = JsonValue::Object; tmp.obj["p1"] = pts->arr[0]; tmp.obj["p2"] = pts->arr[1]; tmp.obj["p3"] = pts->arr[2];
+          if (!get_vec(tmp, "p1", a, err) || !get_vec(tmp, "p2", b, err) || !get_vec(tmp, "p3", c, err)) { bad(err); continue; }
+        } else if (!get_vec(o, "p1", a, err) || !get_vec(o, "p2", b, err) || !get_vec(o, "p3", c, err)) { bad(err); continue; }
+        push3(s.tri_p1, a); push3(s.tri_p2, b); push3(s.tri_p3, c); s.tri_object.push_back(id);
+        s.obj_kind.push_back(CUTRACE_OBJ_TRIANGLE);
+      } else if (type == "mesh") {
+        const JsonValue *file = o.find("file");
+        if (!file || !file->is_string()) { bad("Cannot find key 'file' in object."); continue; }
+        std::string path = file->str;
+        if (!opt.base_dir.empty() && !path.empty() && path[0] != '/') path = opt.base_dir + "/" + path;
+        size_t n0 = s.tri_p1.size() / 3;
+        if (!read_stl(path, s.tri_p1, s.tri_p2, s.tri_p3, err)) { bad(err); continue; }
+        s.tri_object.insert(s.tri_object.end(), s.tri_p1.size() / 3 - n0, id);
+        s.obj_kind.push_back(CUTRACE_OBJ_MESH);
+      } else if (type == "plane") {
+        float p[3], n[3];
+        if (!get_vec(o, "point", p, err) || !get_vec(o, "normal", n, err)) { bad(err); continue; }
+        push3(s.pl_point, p); push3(s.pl_normal, n); s.pl_object.push_back(id);
+        s.obj_kind.push_back(CUTRACE_OBJ_PLANE);
+      } else if (type == "sphere") {
+        float c[3];
+        double r;
+        if (!get_vec(o, "center", c, err) || !get_num(o, "radius", r, err)) { bad(err); continue; }
+        push3(s.sph_center, c); s.sph_radius.push_back((float)r); s.sph_object.push_back(id);
+        s.obj_kind.push_back(CUTRACE_OBJ_SPHERE);
+      } else { bad("No matching object type (expected triangle, mesh, plane or sphere)."); continue; }
+      s.obj_material.push_back((uint32_t)mat);
+    }
+  }
+
+  const JsonValue *cam = root.find("camera");
+  if (!cam || !cam->is_object()) errors.push_back("Could not find 'camera' object or it's invalid.");
+  else {
+    // defaults of inc/default_schema.hpp:835-842, only reachable with accept_aliases (the keys are mandatory)
+    const float d_eye[3] = {0, 0, 0}, d_up[3] = {0, 1, 0}, d_look[3] = {0, 0, 1};
+    const double d_near = 0.1f, d_far = 100.0f, d_w = 1920, d_h = 1080, d_amb = 0.1f;
+    const bool al = opt.accept_aliases;
+    float eye[3], up[3], look[3];
+    double nearp, farp, w, h, amb;
+    if (!get_vec(*cam, "eye", eye, err, al ? d_eye : nullptr) || !get_vec(*cam, "up", up, err, al ? d_up : nullptr) ||
+        !get_vec(*cam, "look", look, err, al ? d_look : nullptr) || !get_num(*cam, "near_plane", nearp, err, al ? &d_near : nullptr) ||
+        !get_num(*cam, "far_plane", farp, err, al ? &d_far : nullptr) || !get_num(*cam, "width", w, err, al ? &d_w : nullptr) ||
+        !get_num(*cam, "height", h, err, al ? &d_h : nullptr) || !get_num(*cam, "ambient", amb, err, al ? &d_amb : nullptr)) {
+      errors.push_back("Could not find 'camera' object or it's invalid: " + err);
+    } else if (!(w >= 1 && h >= 1 && w < 65536.0 * 4 && h < 65536.0 * 4)) {
+      errors.push_back("Could not find 'camera' object or it's invalid: width/height out of range");
+    } else {
+      memcpy(s.cam_pos, eye, 12);
+      look_at(eye, up, look, s.cam_forward, s.cam_right, s.cam_up);
+      s.near_plane = (float)nearp; s.far_plane = (float)farp; s.ambient = (float)amb;
+      s.width = (uint32_t)(size_t)w; s.height = (uint32_t)(size_t)h;
+    }
+  }
+  return errors.size() == before;
+}
+
+bool load_scene_file(const std::string &path, const LoadOptions &opt, FlatScene &out, std::vector<std::string> &errors) {
+  std::ifstream f(path);
+  if (!f) { errors.push_back("Error while loading file '" + path + "': cannot open"); return false; }
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return load_scene_text(ss.str(), opt, out, errors);
+}
+
+}  // namespace cthost

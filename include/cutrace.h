@@ -181,6 +181,13 @@ int cutrace_render(cutrace_ctx *ctx, cutrace_stats *stats);
 int cutrace_download(cutrace_ctx *ctx, float *depth, float *normal, float *color, uint32_t *hit_id,
                      float *max_depth);
 
+/* Output stage fused on the device (inc/images.hpp:26-88 + main.cu:34-36): the three 8-bit RGB images
+ * the reference hands to stbi_write_jpg — depth (nearest = brightest, relative to max_depth), normal
+ * (0.5 + 0.5 n), colour (clamped) — 9 bytes per pixel over PCIe instead of 28.  Each buffer is
+ * width*height*3 bytes and may be NULL. */
+int cutrace_download_bytes(cutrace_ctx *ctx, uint8_t *depth_rgb, uint8_t *normal_rgb, uint8_t *color_rgb,
+                           float *max_depth);
+
 void cutrace_free(cutrace_ctx *ctx);
 
 /* thread-local, never NULL */
