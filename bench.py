@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--workload", default="bunny4k", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--verbose", action="store_true", help="per-rank timing lines on stderr")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -253,6 +254,9 @@ def main():
     # exactly K steps between two CUDA events on the launching stream, barrier + synchronize on both sides
     ms_local = ev0.elapsed_time(ev1) / args.steps
     rays_local = st["rays_total"]
+    if args.verbose:
+        print(f"[rank {rank}] step {ms_local:.3f} ms  render {np.mean(dev_ms):.3f} (trace {np.mean(trace_ms):.3f} shade {np.mean(shade_ms):.3f})  "
+              f"rays {rays_local}  px {st['local_pixels']}", file=sys.stderr, flush=True)
     t = torch.tensor([ms_local, float(rays_local), float(np.mean(shade_ms)), float(np.mean(trace_ms)), float(st["rays_shadow"]),
                       float(np.mean(dev_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -264,8 +268,18 @@ def main():
         ms_step, rays, shade, trace, rays_shadow, render_dev_ms = (float(x) for x in t)
     launches_per_step = int(st["kernel_launches"]) + (1 if world > 1 and rank == 0 else 0)
 
-    # ---- e2e: upload (H2D + LBVH build) + render + download to pinned host, through the C-ABI ----
+    # per-kernel times need a serialised frame (by default the shade kernels overlap the trace chain): two extra
+    # frames with CUTRACE_FLAG_SERIALIZE, outside the timed region, CUDA events on the launching stream
     tsr.close()
+    ser = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags | ct.FLAG_SERIALIZE, stream=stream.cuda_stream)
+    ser.render()
+    sst = ser.render()
+    ser.close()
+    ks = torch.tensor([sst["shade_ms"], sst["trace_ms"], sst["render_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ks, op=dist.ReduceOp.MAX)
+    shade, trace, serial_ms = float(ks[0]), float(ks[1]), float(ks[2])
+    # ---- e2e: upload (H2D + LBVH build) + render + download to pinned host, through the C-ABI ----
     barrier()
     import ctypes as C
 
@@ -339,7 +353,8 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "algorithmic bytes/ray (SURVEY §8d) x rays of the dominant kernel / its CUDA-event time; the scene is cache-resident, "
                                  "so issue-slot utilisation and divergence (profiles/) explain the kernel, not DRAM"},
-            "kernel_ms": {"trace": trace, "shade": shade},
+            "kernel_ms": {"trace": trace, "shade": shade, "serialized_frame": serial_ms,
+                          "note": "measured on a frame rendered with CUTRACE_FLAG_SERIALIZE (one stream); the timed frames overlap shade(L) with trace(L+1..)"},
         }
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -19,7 +19,7 @@ SYMBOLS = (
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version",
 )
 
-FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE = 1, 2, 4
+FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE = 1, 2, 4, 8
 
 
 class cutrace_opts(C.Structure):

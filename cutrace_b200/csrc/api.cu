@@ -60,7 +60,11 @@ struct cutrace_ctx {
   uint64_t n_local_px = 0;   // padded: n_local_tiles * 1024
   FrameTargets fb{};
   RayRec *rays[2] = {nullptr, nullptr};
-  ShadeRec *shade = nullptr;
+  ShadeRec *shade[16] = {};          // one shade queue per bounce level (shade(L) overlaps trace(L+1..))
+  uint64_t shade_cap[16] = {};
+  float *level_color = nullptr;      // levels x batch_px x 3: per-level partial images (non-branching scenes)
+  uint32_t *nlev = nullptr;          // n_local_px: number of levels that contributed to a pixel
+  cudaStream_t aux[2] = {nullptr, nullptr};
   uint64_t batch_px = 0, cap = 0;
   uint32_t factor = 1;
   FrameCounters *d_ctr = nullptr;
@@ -91,11 +95,14 @@ struct DeviceGuard {
 void free_frame(cutrace_ctx *c) {
   cudaStream_t st = c->stream;
   dfree(c->fb.depth, st); dfree(c->fb.normal, st); dfree(c->fb.color, st); dfree(c->fb.hit_id, st);
-  dfree(c->rays[0], st); dfree(c->rays[1], st); dfree(c->shade, st);
+  dfree(c->rays[0], st); dfree(c->rays[1], st);
+  for (int i = 0; i < 16; i++) { dfree(c->shade[i], st); c->shade[i] = nullptr; c->shade_cap[i] = 0; }
+  dfree(c->level_color, st); dfree(c->nlev, st);
+  c->level_color = nullptr; c->nlev = nullptr;
   dfree(c->st_depth, st); dfree(c->st_normal, st); dfree(c->st_color, st); dfree(c->st_id, st);
   dfree(c->st_bytes, st); c->st_bytes = nullptr; c->st_bytes_px = 0;
   c->fb = FrameTargets{};
-  c->rays[0] = c->rays[1] = nullptr; c->shade = nullptr;
+  c->rays[0] = c->rays[1] = nullptr;
   c->st_depth = c->st_normal = c->st_color = nullptr; c->st_id = nullptr;
   c->st_px = 0;
   c->rendered = false;
@@ -119,13 +126,21 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   c->sv.cam.w = width; c->sv.cam.h = height;
 
   uint32_t b = c->opts.bounces;
-  c->factor = (c->max_children >= 2 && b > 0) ? (1u << b) : 1u;
+  const bool branching = c->max_children >= 2 && b > 0;
+  const uint32_t levels = c->max_children > 0 ? b + 1 : 1;
+  c->factor = branching ? (1u << b) : 1u;
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
-  uint64_t fb_bytes = c->n_local_px * 32ull;
+  uint64_t fb_bytes = c->n_local_px * 36ull;
   double budget = (double)free_b * 0.6 - (double)fb_bytes;
   if (const char *e = getenv("CUTRACE_QUEUE_BUDGET_MB")) budget = atof(e) * 1048576.0;
-  double per_px = (double)c->factor * (2.0 * sizeof(RayRec) + sizeof(ShadeRec));
+  // bytes of queue memory per batch pixel: two ping-pong ray queues of the worst-case level, one shade queue per
+  // level (level L holds at most 2^L hits per pixel when a material both reflects and transmits, else 1), and the
+  // per-level partial colour images of the non-branching path
+  double shade_per_px = 0;
+  for (uint32_t L = 0; L < levels; L++) shade_per_px += (branching ? (double)(1u << L) : 1.0) * sizeof(ShadeRec);
+  double per_px = (c->max_children > 0 && b > 0 ? (double)c->factor * 2.0 * sizeof(RayRec) : 0.0) + shade_per_px +
+                  (branching ? 0.0 : 12.0 * levels);
   uint64_t batch = budget > per_px * 1024.0 ? (uint64_t)(budget / per_px) : 1024ull;
   batch = (batch / 1024ull) * 1024ull;
   if (batch < 1024) batch = 1024;
@@ -143,7 +158,14 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
     CU(dmalloc(&c->rays[0], sizeof(RayRec) * c->cap, st));
     CU(dmalloc(&c->rays[1], sizeof(RayRec) * c->cap, st));
   }
-  CU(dmalloc(&c->shade, sizeof(ShadeRec) * c->cap, st));
+  for (uint32_t L = 0; L < levels; L++) {
+    c->shade_cap[L] = batch * (branching ? (1ull << L) : 1ull);
+    CU(dmalloc(&c->shade[L], sizeof(ShadeRec) * c->shade_cap[L], st));
+  }
+  if (!branching) {
+    CU(dmalloc(&c->level_color, sizeof(float) * 3 * batch * levels, st));
+    CU(dmalloc(&c->nlev, sizeof(uint32_t) * c->n_local_px, st));
+  }
   return CUTRACE_OK;
 }
 
@@ -230,6 +252,7 @@ void cutrace_free(cutrace_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; i++) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -266,8 +289,14 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); cutrace_free(c); \
     return fail(e_ == cudaErrorMemoryAllocation ? CUTRACE_ERR_OUT_OF_MEMORY : CUTRACE_ERR_CUDA, m_); } } while (0)
 
-  if (o.stream) c->stream = (cudaStream_t)o.stream;
-  else { CUF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  {
+    int pr_least = 0, pr_greatest = 0;
+    CUF(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+    if (o.stream) c->stream = (cudaStream_t)o.stream;
+    else { CUF(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr_greatest)); c->own_stream = true; }
+    // shade kernels run on two lower-priority streams so that the trace chain (the critical path) gets SMs first
+    for (int i = 0; i < 2; i++) CUF(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, pr_least));
+  }
   for (int i = 0; i < 72; i++) { cudaEvent_t ev; CUF(cudaEventCreate(&ev)); c->events.push_back(ev); }
 
   // ---- flat records ----
@@ -408,23 +437,35 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   }
   cudaEvent_t ev_begin = c->events[0], ev_end = c->events[1];
   CU(cudaEventRecord(ev_begin, st));
-  CU(cudaMemsetAsync(c->fb.color, 0, sizeof(float) * 3 * c->n_local_px, st));
+  const bool branching = c->max_children >= 2 && bounces > 0;
+  const bool serialize = (c->opts.flags & CUTRACE_FLAG_SERIALIZE) != 0;
+  if (branching) CU(cudaMemsetAsync(c->fb.color, 0, sizeof(float) * 3 * c->n_local_px, st));
   float max_depth = 0.f;
-  const bool atomic_acc = c->max_children >= 2;
   for (uint64_t base = 0; base < c->n_local_px; base += c->batch_px) {
     const uint32_t n_px = (uint32_t)std::min<uint64_t>(c->batch_px, c->n_local_px - base);
     CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(FrameCounters), st));
-    size_t ev = 2;
+    // Dependencies of one frame: trace(L) -> trace(L+1) (ray queue) and trace(L) -> shade(L) (shade queue L).
+    // The trace chain runs on the ctx stream; shade(L) runs on one of two auxiliary streams behind an event, so
+    // the persistent CTAs of later kernels fill the SMs that the tail of an earlier kernel leaves idle.
     for (uint32_t L = 0; L < levels; L++) {
-      uint64_t bound = (uint64_t)n_px * (c->max_children >= 2 ? (1ull << L) : 1ull);
-      if (bound > c->cap) bound = c->cap;
+      uint64_t bound = (uint64_t)n_px * (branching ? (1ull << L) : 1ull);
+      if (bound > c->shade_cap[L]) bound = c->shade_cap[L];
       RayRec *in = c->rays[L & 1], *outq = c->rays[(L + 1) & 1];
-      CU(cudaEventRecord(c->events[ev++], st));
-      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade, c->d_ctr, c->fb, (uint32_t)bound, st);
-      CU(cudaEventRecord(c->events[ev++], st));
-      launch_shade(c->cfg, c->sv, L, c->shade, c->d_ctr, c->fb, atomic_acc, (uint32_t)bound, st);
-      CU(cudaEventRecord(c->events[ev++], st));
+      cudaEvent_t e0 = c->events[2 + 3 * L], e1 = c->events[3 + 3 * L], e2 = c->events[4 + 3 * L];
+      if (serialize) CU(cudaEventRecord(e0, st));
+      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade[L], c->d_ctr, c->fb, c->nlev, (uint32_t)bound, st);
+      CU(cudaEventRecord(e1, st));
+      cudaStream_t ss = serialize ? st : c->aux[L & 1];
+      if (!serialize) CU(cudaStreamWaitEvent(ss, e1, 0));
+      float *lc = branching ? nullptr : c->level_color + (size_t)L * 3 * c->batch_px;
+      launch_shade(c->cfg, c->sv, L, c->shade[L], c->d_ctr, c->fb, branching, lc, (uint32_t)base, (uint32_t)bound, ss);
+      CU(cudaEventRecord(e2, ss));
       S.kernel_launches += 2;
+    }
+    if (!serialize) for (uint32_t L = 0; L < levels; L++) CU(cudaStreamWaitEvent(st, c->events[4 + 3 * L], 0));
+    if (!branching) {
+      launch_combine(c->nlev, c->level_color, 3ull * c->batch_px, levels, (uint32_t)base, n_px, c->fb.color, st);
+      S.kernel_launches += 1;
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
@@ -439,11 +480,13 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     float md;
     memcpy(&md, &h.max_depth_bits, 4);
     if (md > max_depth) max_depth = md;
-    for (uint32_t L = 0; L < levels; L++) {
-      float a = 0.f, b = 0.f;
-      CU(cudaEventElapsedTime(&a, c->events[2 + 3 * L], c->events[3 + 3 * L]));
-      CU(cudaEventElapsedTime(&b, c->events[3 + 3 * L], c->events[4 + 3 * L]));
-      S.trace_ms += a; S.shade_ms += b;
+    if (serialize) {
+      for (uint32_t L = 0; L < levels; L++) {
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, c->events[2 + 3 * L], c->events[3 + 3 * L]));
+        CU(cudaEventElapsedTime(&b, c->events[3 + 3 * L], c->events[4 + 3 * L]));
+        S.trace_ms += a; S.shade_ms += b;
+      }
     }
   }
   CU(cudaEventElapsedTime(&S.render_ms, ev_begin, ev_end));

@@ -31,6 +31,28 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
+// Work stealing with guided chunk sizes: a warp claims `remaining / (2 * warps in flight)` items, at least one
+// warp-iteration (32) and at most WORK_CHUNK_MAX.  Large claims while there is plenty of work keep the cursor
+// atomics rare; 32-item claims at the end keep the tail short — at deep bounce levels of the 10 M-triangle scene a
+// few grazing rays cost milliseconds each and fixed 128-ray claims left the GPU idle behind them
+// (profiles/r01_tuning.md, "tile scaling").
+__device__ __forceinline__ bool claim_work(unsigned *cursor, unsigned n_work, unsigned lane, unsigned &base, unsigned &end) {
+  unsigned b = 0, chunk = 0;
+  if (lane == 0) {
+    const unsigned cur = *reinterpret_cast<volatile unsigned *>(cursor);
+    const unsigned remaining = cur < n_work ? n_work - cur : 0u;
+    const unsigned warps = gridDim.x * (blockDim.x >> 5);
+    chunk = remaining / (2u * warps);
+    chunk = chunk < 32u ? 32u : (chunk > (unsigned)WORK_CHUNK_MAX ? (unsigned)WORK_CHUNK_MAX : chunk);
+    chunk &= ~31u;
+    b = atomicAdd(cursor, chunk);
+  }
+  base = __shfl_sync(0xffffffffu, b, 0);
+  chunk = __shfl_sync(0xffffffffu, chunk, 0);
+  end = base + chunk < n_work ? base + chunk : n_work;
+  return base < n_work;
+}
+
 // stage the BVH nodes and the primitive store in shared memory (MODE 1) — LDS.128 instead of
 // divergent LDG.128 for the small reference scenes whose whole BVH fits next to the SM
 template <int MODE>
@@ -78,7 +100,7 @@ template <int MODE, bool BRUTE>
 __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
 trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t bounces, uint32_t px_base, uint32_t n_px,
              const RayRec *__restrict__ rays_in, RayRec *__restrict__ rays_out, ShadeRec *__restrict__ shade_out,
-             FrameCounters *ctr, FrameTargets fb) {
+             FrameCounters *ctr, FrameTargets fb, uint32_t *__restrict__ nlev) {
   extern __shared__ float4 smem[];
   const float4 *nodes, *prims;
   stage_scene<MODE>(sv, smem, nodes, prims);
@@ -89,12 +111,10 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
   float max_depth = 0.f;
 
   for (;;) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&ctr->work_trace[level], (unsigned)WORK_CHUNK);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n_work) break;
+    unsigned base, end;
+    if (!claim_work(&ctr->work_trace[level], n_work, lane, base, end)) break;
 #pragma unroll 1
-    for (unsigned off = 0; off < (unsigned)WORK_CHUNK && base + off < n_work; off += 32) {
+    for (unsigned off = 0; base + off < end; off += 32) {
       const uint32_t i = base + off + lane;
       bool active = i < n_work;
       vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
@@ -129,7 +149,10 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
         fb.normal[3 * (size_t)pix] = nrm.x; fb.normal[3 * (size_t)pix + 1] = nrm.y; fb.normal[3 * (size_t)pix + 2] = nrm.z;
         fb.hit_id[pix] = hit ? h.obj : CUTRACE_NO_HIT;
         if (hit && isfinite(h.t)) max_depth = fmaxf(max_depth, h.t);
+        if (nlev && !hit) nlev[pix] = 0u;
       }
+      // number of bounce levels that contributed to this pixel so far (levels run in order on one stream)
+      if (nlev && hit) nlev[pix] = level + 1u;
       // inc/shading.hpp:126-149
       bool do_refl = false, do_trans = false;
       float w_own = w;
@@ -220,7 +243,7 @@ __device__ __forceinline__ float shadow_intensity(const SceneView &sv, const flo
 template <int MODE, bool BRUTE, bool OPAQUE>
 __global__ void __launch_bounds__(TRACE_THREADS, CTB_SHADE_MIN_BLOCKS)
 shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ shade, FrameCounters *ctr, FrameTargets fb,
-             int atomic_accumulate) {
+             int atomic_accumulate, float *__restrict__ level_color, uint32_t px_base) {
   extern __shared__ float4 smem[];
   const float4 *nodes, *prims;
   stage_scene<MODE>(sv, smem, nodes, prims);
@@ -229,12 +252,10 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
   unsigned long long casts = 0;
 
   for (;;) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&ctr->work_shade[level], (unsigned)WORK_CHUNK);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n_work) break;
+    unsigned base, end;
+    if (!claim_work(&ctr->work_shade[level], n_work, lane, base, end)) break;
 #pragma unroll 1
-    for (unsigned off = 0; off < (unsigned)WORK_CHUNK && base + off < n_work; off += 32) {
+    for (unsigned off = 0; base + off < end; off += 32) {
       const uint32_t i = base + off + lane;
       if (i < n_work) {
         const float4 *sp = reinterpret_cast<const float4 *>(shade + i);
@@ -327,6 +348,11 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
             }
           }
         }
+        if (level_color) {   // one hit per pixel and level: plain store into this level's partial image
+          float *lp = level_color + 3 * (size_t)(pix - px_base);
+          lp[0] = weight * final.x; lp[1] = weight * final.y; lp[2] = weight * final.z;
+          continue;
+        }
         float *cp = fb.color + 3 * (size_t)pix;
         if (atomic_accumulate) {
           atomicAdd(cp, weight * final.x); atomicAdd(cp + 1, weight * final.y); atomicAdd(cp + 2, weight * final.z);
@@ -343,9 +369,31 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
+// colour of a pixel = sum of its per-level partial images in level order (same order as a serial accumulation)
+__global__ void combine_levels_kernel(const uint32_t *__restrict__ nlev, const float *__restrict__ level_color, uint64_t level_stride,
+                                      uint32_t levels, uint32_t px_base, uint32_t n_px, float *__restrict__ color) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  uint32_t n = nlev[px_base + i];
+  n = n < levels ? n : levels;
+  float r = 0.f, g = 0.f, b = 0.f;
+  for (uint32_t l = 0; l < n; l++) {
+    const float *p = level_color + l * level_stride + 3 * (size_t)i;
+    r += p[0]; g += p[1]; b += p[2];
+  }
+  float *o = color + 3 * (size_t)(px_base + i);
+  o[0] = r; o[1] = g; o[2] = b;
+}
+
+void launch_combine(const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels, uint32_t px_base,
+                    uint32_t n_px, float *color, cudaStream_t st) {
+  if (!n_px) return;
+  combine_levels_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(nlev, level_color, level_stride, levels, px_base, n_px, color);
+}
+
 typedef void (*trace_fn)(const SceneView, const TileMap, uint32_t, uint32_t, uint32_t, uint32_t, const RayRec *, RayRec *, ShadeRec *,
-                         FrameCounters *, FrameTargets);
-typedef void (*shade_fn)(const SceneView, uint32_t, const ShadeRec *, FrameCounters *, FrameTargets, int);
+                         FrameCounters *, FrameTargets, uint32_t *);
+typedef void (*shade_fn)(const SceneView, uint32_t, const ShadeRec *, FrameCounters *, FrameTargets, int, float *, uint32_t);
 
 static trace_fn pick_trace(int mode, bool brute) {
   if (brute) return trace_kernel<0, true>;
@@ -387,24 +435,25 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
 }
 
 static inline int clamp_grid(int persistent, uint32_t work_bound) {
-  uint64_t need = ((uint64_t)work_bound + WORK_CHUNK * (TRACE_THREADS / 32) - 1) / (WORK_CHUNK * (TRACE_THREADS / 32));
+  uint64_t need = ((uint64_t)work_bound + 32 * (TRACE_THREADS / 32) - 1) / (32 * (TRACE_THREADS / 32));
   if (need < 1) need = 1;
   return (int)(need < (uint64_t)persistent ? need : (uint64_t)persistent);
 }
 
 void launch_trace(const LaunchCfg &cfg, const SceneView &sv, const TileMap &tm, uint32_t level, uint32_t bounces,
                   uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, ShadeRec *shade_out,
-                  FrameCounters *ctr, const FrameTargets &fb, uint32_t work_bound, cudaStream_t st) {
+                  FrameCounters *ctr, const FrameTargets &fb, uint32_t *nlev, uint32_t work_bound, cudaStream_t st) {
   int grid = clamp_grid(cfg.grid_trace, work_bound);
   pick_trace(cfg.mode, sv.brute_force != 0)<<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(sv, tm, level, bounces, px_base, n_px, rays_in,
-                                                                                         rays_out, shade_out, ctr, fb);
+                                                                                         rays_out, shade_out, ctr, fb, nlev);
 }
 
 void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, FrameCounters *ctr,
-                  const FrameTargets &fb, bool atomic_accumulate, uint32_t work_bound, cudaStream_t st) {
+                  const FrameTargets &fb, bool atomic_accumulate, float *level_color, uint32_t px_base, uint32_t work_bound,
+                  cudaStream_t st) {
   int grid = clamp_grid(cfg.grid_shade, work_bound);
   pick_shade(cfg.mode, sv.brute_force != 0, sv.all_opaque != 0)<<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(
-      sv, level, shade, ctr, fb, atomic_accumulate ? 1 : 0);
+      sv, level, shade, ctr, fb, atomic_accumulate ? 1 : 0, level_color, px_base);
 }
 
 }  // namespace ctb

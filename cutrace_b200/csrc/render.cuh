@@ -9,7 +9,7 @@ namespace ctb {
 #define CTB_THREADS 512
 #endif
 constexpr int TRACE_THREADS = CTB_THREADS;
-constexpr int WORK_CHUNK = 128;   // rays a warp claims per work-stealing atomic
+constexpr int WORK_CHUNK_MAX = 512;   // most rays a warp claims per work-stealing atomic (guided: shrinks to 32 at the tail)
 #ifndef CTB_SHADE_MIN_BLOCKS
 #define CTB_SHADE_MIN_BLOCKS 2   // measured on B200: 2 CTAs/SM (64 regs) beat 1 CTA/SM for K = 1 (profiles/r01_tuning.md)
 #endif
@@ -37,10 +37,14 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg);
 // [px_base, px_base + n_px) itself; deeper levels read rays_in (count in ctr->n_rays[level]).
 void launch_trace(const LaunchCfg &cfg, const SceneView &sv, const TileMap &tm, uint32_t level, uint32_t bounces,
                   uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, ShadeRec *shade_out,
-                  FrameCounters *ctr, const FrameTargets &fb, uint32_t work_bound, cudaStream_t st);
+                  FrameCounters *ctr, const FrameTargets &fb, uint32_t *nlev, uint32_t work_bound, cudaStream_t st);
 // shadow rays + Phong for the shade records of one level; accumulates into fb.color
 void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, FrameCounters *ctr,
-                  const FrameTargets &fb, bool atomic_accumulate, uint32_t work_bound, cudaStream_t st);
+                  const FrameTargets &fb, bool atomic_accumulate, float *level_color, uint32_t px_base, uint32_t work_bound,
+                  cudaStream_t st);
+// colour[px] = sum over levels l < nlev[px] of level_color[l][px - px_base], in level order
+void launch_combine(const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels, uint32_t px_base,
+                    uint32_t n_px, float *color, cudaStream_t st);
 
 // output.cu
 void launch_untile(const TileMap &tm, uint32_t world, const float *g_depth, const float *g_normal, const float *g_color,

@@ -44,12 +44,14 @@ def grid_scene(meshes, grid=106, width=7680, height=4320, seed=0, n_lights=3):
             okind.append(OBJ_MESH)
     n_inst = G * G
     half = 0.5 * G + 1.0
-    # floor + two mirror walls behind the grid
-    pl_point = np.array([[0, 0, 0], [0, 0, half], [-half, 0, 0]], np.float32)
-    pl_normal = np.array([[0, 1, 0], [0, 0, -1], [1, 0, 0]], np.float32)
-    pl_object = np.arange(n_inst, n_inst + 3, dtype=np.uint32)
-    omat += [0, 8, 8]
-    okind += [OBJ_PLANE] * 3
+    # a closed hall like the reference's own box scenes (mirror.json / bunny.json): floor, ceiling, two mirror walls
+    # behind the grid and two matte walls behind the camera
+    top = 0.9 * G
+    pl_point = np.array([[0, 0, 0], [0, 0, half], [-half, 0, 0], [half, 0, 0], [0, 0, -half], [0, top, 0]], np.float32)
+    pl_normal = np.array([[0, 1, 0], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, -1, 0]], np.float32)
+    pl_object = np.arange(n_inst, n_inst + 6, dtype=np.uint32)
+    omat += [0, 8, 8, 0, 0, 0]
+    okind += [OBJ_PLANE] * 6
     mat_color = np.array([[0.8, 0.8, 0.8], [0.894, 0.102, 0.110], [0.216, 0.494, 0.722], [0.302, 0.686, 0.290],
                           [1.0, 0.498, 0.0], [0.596, 0.306, 0.639], [0.9, 0.9, 0.3], [0.7, 0.7, 0.75], [0.1, 0.1, 0.1]], np.float32)
     mat_specular = np.array([0.2, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.6, 0.1], np.float32)
@@ -58,7 +60,7 @@ def grid_scene(meshes, grid=106, width=7680, height=4320, seed=0, n_lights=3):
     mat_transparency = np.zeros(9, np.float32)
     lights = np.array([[0.0, 0.6 * G, -0.2 * G], [-0.3 * G, 0.5 * G, 0.3 * G], [0.3 * G, 0.4 * G, -0.4 * G], [0, 0.8 * G, 0]],
                       np.float32)[:n_lights]
-    eye = np.array([0.35 * G, 0.45 * G, -0.75 * G], np.float32)
+    eye = np.array([0.30 * G, 0.34 * G, -0.46 * G], np.float32)   # inside the hall, looking down across the grid
     fwd, right, up = look_at(eye, [0, 1, 0], [0, 0, 0])
     return FlatScene(
         cam_pos=eye, cam_up=up, cam_forward=fwd, cam_right=right, ambient=0.02, width=width, height=height,

@@ -124,6 +124,8 @@ typedef struct cutrace_scene_desc {
 #define CUTRACE_FLAG_NO_SMEM_TOP 1u    /* do not stage the top of the BVH in shared memory */
 #define CUTRACE_FLAG_VALIDATE_BVH 2u   /* run the device-side BVH validator after the build */
 #define CUTRACE_FLAG_BRUTE_FORCE 4u    /* debug: skip the BVH, test every primitive per ray */
+#define CUTRACE_FLAG_SERIALIZE 8u      /* run every kernel of a frame on one stream (per-kernel trace_ms / shade_ms are
+                                          only measured in this mode); default: shade kernels overlap the trace chain */
 
 typedef struct cutrace_opts {
   float fudge;          /* min hit distance; the reference passes 1e-3 (main.cu:30)            */
