@@ -26,6 +26,22 @@ using namespace ctb;
 
 static thread_local std::string g_err = "";
 
+#ifdef CTB_TIMING   // developer instrumentation (tools/build_variant.sh timing -DCTB_TIMING); never on in the product build
+#include <chrono>
+struct PhaseTimer {
+  std::chrono::high_resolution_clock::time_point t = std::chrono::high_resolution_clock::now();
+  void lap(const char *what) {
+    auto n = std::chrono::high_resolution_clock::now();
+    fprintf(stderr, "  [ctb-timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+#define LAP(x) ptimer.lap(x)
+#else
+struct PhaseTimer {};
+#define LAP(x)
+#endif
+
 static int fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
@@ -41,6 +57,26 @@ static int fail(int code, const std::string &msg) {
                   std::string(#call) + ": " + cudaGetErrorString(e_));                                \
     }                                                                                                 \
   } while (0)
+
+// cudaHostAlloc / cudaFreeHost cost 1-3 ms each (measured, tools/e2e_probe.py); the small pinned block every ctx
+// needs for its frame counters is therefore recycled through a process-wide free list.
+#include <mutex>
+static std::mutex g_pinned_mu;
+static std::vector<FrameCounters *> g_pinned_free;
+static FrameCounters *pinned_counters_get() {
+  {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    if (!g_pinned_free.empty()) { FrameCounters *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
+  }
+  FrameCounters *p = nullptr;
+  if (cudaHostAlloc(&p, sizeof(FrameCounters), cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  return p;
+}
+static void pinned_counters_put(FrameCounters *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  g_pinned_free.push_back(p);
+}
 
 struct cutrace_ctx {
   int device = 0;
@@ -250,7 +286,7 @@ void cutrace_free(cutrace_ctx *c) {
   dfree(c->planes, c->stream); dfree(c->materials, c->stream); dfree(c->lights, c->stream); dfree(c->obj_material, c->stream);
   dfree(c->d_ctr, c->stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->h_ctr) cudaFreeHost(c->h_ctr);
+  pinned_counters_put(c->h_ctr);
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   for (int i = 0; i < 2; i++) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -277,6 +313,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   if (dev < 0) CU(cudaGetDevice(&dev));
   if (dev >= n_dev) return fail(CUTRACE_ERR_NO_DEVICE, "requested CUDA device ordinal does not exist");
 
+  PhaseTimer ptimer; (void)ptimer;
   cutrace_ctx *c = new (std::nothrow) cutrace_ctx();
   if (!c) return fail(CUTRACE_ERR_OUT_OF_MEMORY, "host allocation failed");
   c->device = dev;
@@ -297,7 +334,9 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
     // shade kernels run on two lower-priority streams so that the trace chain (the critical path) gets SMs first
     for (int i = 0; i < 2; i++) CUF(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, pr_least));
   }
+  LAP("validate + streams");
   for (int i = 0; i < 72; i++) { cudaEvent_t ev; CUF(cudaEventCreate(&ev)); c->events.push_back(ev); }
+  LAP("72 events");
 
   // ---- flat records ----
   std::vector<PlaneRec> planes(s->n_planes);
@@ -330,6 +369,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   UP(upload(&c->materials, mats, c->stream));
   UP(upload(&c->lights, lights, c->stream));
   UP(upload(&c->obj_material, omat, c->stream));
+  LAP("small record uploads");
 
   // ---- primitives + LBVH ----
   float *d_p1 = nullptr, *d_p2 = nullptr, *d_p3 = nullptr, *d_sc = nullptr, *d_sr = nullptr;
@@ -352,6 +392,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
     CUT(cudaMemcpyAsync(d_sr, s->sph_radius, sizeof(float) * ns, cudaMemcpyHostToDevice, c->stream));
     CUT(cudaMemcpyAsync(d_so, s->sph_object, sizeof(uint32_t) * ns, cudaMemcpyHostToDevice, c->stream));
   }
+  LAP("primitive H2D");
   BvhInput bi;
   bi.d_p1 = d_p1; bi.d_p2 = d_p2; bi.d_p3 = d_p3; bi.d_tri_obj = d_to; bi.n_tri = (uint32_t)nt;
   bi.d_sph_center = d_sc; bi.d_sph_radius = d_sr; bi.d_sph_obj = d_so; bi.n_sph = (uint32_t)ns;
@@ -364,6 +405,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   CUT(cudaStreamSynchronize(c->stream));
   CUT(cudaEventElapsedTime(&c->stats.build_ms, c->events[0], c->events[1]));
   free_tmp();
+  LAP("build_bvh");
   if (o.flags & CUTRACE_FLAG_VALIDATE_BVH) {
     rc = validate_bvh(c->bvh, c->stream, berr);
     if (rc) { cutrace_free(c); return fail(rc, berr); }
@@ -381,11 +423,15 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   set_cam(c, s->cam_pos, s->cam_up, s->cam_forward, s->cam_right, s->ambient);
 
   CUF(dmalloc(&c->d_ctr, sizeof(FrameCounters), c->stream));
-  CUF(cudaHostAlloc(&c->h_ctr, sizeof(FrameCounters), cudaHostAllocDefault));
+  c->h_ctr = pinned_counters_get();
+  if (!c->h_ctr) { cutrace_free(c); return fail(CUTRACE_ERR_OUT_OF_MEMORY, "cudaHostAlloc failed"); }
+  LAP("ctr alloc");
   CUF(plan_launch(sv, !(o.flags & CUTRACE_FLAG_NO_SMEM_TOP), &c->cfg));
+  LAP("plan_launch");
   sv.smem_nodes = c->cfg.mode == 1 ? sv.n_nodes : 0;
   sv.smem_prims = c->cfg.mode == 1 ? sv.n_prims : 0;
   UP(alloc_frame(c, s->width, s->height));
+  LAP("alloc_frame");
   c->stats.bvh_nodes = c->bvh.n_nodes;
   c->stats.bvh_depth = c->bvh.depth;
   c->stats.smem_nodes = sv.smem_nodes;

@@ -84,8 +84,13 @@ def read_stl(path):
     The reference imports meshes with Assimp (inc/default_schema.hpp:516-545) and reads only
     mVertices/mFaces; for STL that is the facet list in file order, stored normals ignored.
     """
-    with open(path, "rb") as f:
-        data = f.read()
+    try:
+        with open(path, "rb") as f:
+            data = f.read()
+    except OSError as e:
+        # the reference silently loads an EMPTY mesh when Assimp cannot read the file
+        # (inc/default_schema.hpp:522 `if(scene == nullptr) return;`); here that is an error
+        raise SceneError(f"cannot open mesh file {path!r}") from e
     if len(data) >= 84:
         (n,) = struct.unpack_from("<I", data, 80)
         if 84 + 50 * n == len(data):

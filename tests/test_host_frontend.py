@@ -1,0 +1,140 @@
+"""The callers either side of the path: the C++ scene front-end (JSON + STL), the JPEG writer and
+the CLI's exit codes.  No GPU needed."""
+import io
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, REF, ROOT, load_golden_scene
+
+
+@pytest.fixture(scope="module")
+def host():
+    from cutrace_b200 import host as h
+
+    if not os.path.exists(h.HOST_LIB_PATH) or not os.path.exists(os.path.join(ROOT, "bin", "cutrace")):
+        subprocess.run(["make", "-C", ROOT, "host", "cli"], check=True, stdout=subprocess.DEVNULL)
+    h.load()
+    return h
+
+
+def _same(a, b):
+    da, db = a.to_npz_dict(), b.to_npz_dict()
+    return [k for k in da if not np.array_equal(np.asarray(da[k]), np.asarray(db[k]))]
+
+
+def test_cpp_loader_equals_python_mirror_on_own_scene(host):
+    from cutrace_b200.scene import load_scene_json
+
+    path = os.path.join(ROOT, "scenes", "solids.json")
+    a = host.load_scene(path, base_dir=ROOT)
+    b = load_scene_json(path, base_dir=ROOT)
+    assert _same(a, b) == []
+    assert a.n_triangles == 4 + 8 + 1 and a.n_spheres == 1 and a.n_planes == 1 and a.n_objects == 5   # ASCII + binary STL + loose triangle
+    assert a.obj_kind.tolist() == [1, 1, 2, 3, 0]
+    assert a.mat_specular.tolist() == pytest.approx([0.5, 0.3, 0.2, 0.7])      # default 0.3 (default_schema.hpp:754-764)
+    assert a.mat_phong.tolist() == [64, 32, 300, 500] and a.mat_transparency.tolist() == [0, 0, 0, 0.5]
+    assert a.light_color[1].tolist() == [1, 1, 1]                                # default white
+    # look_at: unit, orthogonal basis
+    f, r, u = a.cam_forward, a.cam_right, a.cam_up
+    assert abs(np.dot(f, r)) < 1e-6 and abs(np.dot(f, u)) < 1e-6 and abs(np.linalg.norm(u) - 1) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "scene")), reason="reference tree not present")
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_cpp_loader_reads_the_reference_scenes(host, name):
+    a = host.load_scene(os.path.join(REF, "scene", f"{name}.json"), base_dir=REF)
+    assert _same(a, load_golden_scene(name)) == []
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "scene")), reason="reference tree not present")
+def test_stale_schema_is_rejected_like_the_reference(host):
+    """scene/bunny_small.json uses schema.md's stale spelling; default_schema.hpp rejects it."""
+    from cutrace_b200.scene import SceneError
+
+    p = os.path.join(REF, "scene", "bunny_small.json")
+    with pytest.raises(SceneError) as e:
+        host.load_scene(p, base_dir=REF)
+    assert "material #0" in str(e.value) and "light #0" in str(e.value)
+    s = host.load_scene(p, base_dir=REF, accept_aliases=True)      # documented superset
+    assert s.n_triangles == 1000
+
+
+BAD = {
+    "not json": "{ this is not json",
+    "missing camera": {"objects": [], "lights": [], "materials": []},
+    "camera key missing": {"objects": [], "lights": [], "materials": [], "camera": {"eye": [0, 0, 0]}},
+    "bad material index": {"objects": [{"type": "sphere", "center": [0, 0, 0], "radius": 1, "material": 3}], "lights": [],
+                           "materials": [{"type": "solid", "color": [1, 1, 1]}],
+                           "camera": {"eye": [0, 0, -5], "up": [0, 1, 0], "look": [0, 0, 0], "near_plane": 0.1, "far_plane": 10, "width": 8, "height": 8, "ambient": 0.1}},
+    "unknown object type": {"objects": [{"type": "torus", "material": 0}], "lights": [], "materials": [{"type": "solid", "color": [1, 1, 1]}],
+                            "camera": {"eye": [0, 0, -5], "up": [0, 1, 0], "look": [0, 0, 0], "near_plane": 0.1, "far_plane": 10, "width": 8, "height": 8, "ambient": 0.1}},
+    "vector of two": {"objects": [{"type": "plane", "point": [0, 0], "normal": [0, 1, 0], "material": 0}], "lights": [],
+                      "materials": [{"type": "solid", "color": [1, 1, 1]}],
+                      "camera": {"eye": [0, 0, -5], "up": [0, 1, 0], "look": [0, 0, 0], "near_plane": 0.1, "far_plane": 10, "width": 8, "height": 8, "ambient": 0.1}},
+    "missing mesh file": {"objects": [{"type": "mesh", "file": "does/not/exist.stl", "material": 0}], "lights": [],
+                          "materials": [{"type": "solid", "color": [1, 1, 1]}],
+                          "camera": {"eye": [0, 0, -5], "up": [0, 1, 0], "look": [0, 0, 0], "near_plane": 0.1, "far_plane": 10, "width": 8, "height": 8, "ambient": 0.1}},
+}
+
+
+@pytest.mark.parametrize("what", list(BAD))
+def test_rejected_scenes_and_cli_exit_codes(host, tmp_path, what):
+    from cutrace_b200.scene import SceneError, load_scene_json
+
+    doc = BAD[what]
+    p = tmp_path / "scene.json"
+    p.write_text(doc if isinstance(doc, str) else json.dumps(doc))
+    with pytest.raises(SceneError):
+        host.load_scene(str(p))
+    with pytest.raises(SceneError):
+        load_scene_json(str(p))
+    r = subprocess.run([os.path.join(ROOT, "bin", "cutrace"), str(p)], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 254            # exit -2 like main.cu:16-19
+    assert r.stderr.strip() and "Scene schema" in r.stdout
+
+
+def test_cli_usage(host):
+    r = subprocess.run([os.path.join(ROOT, "bin", "cutrace")], capture_output=True, text=True)
+    assert r.returncode == 255 and "Usage:" in r.stderr and "<scene file>" in r.stderr     # main.cu:9-12
+
+
+def test_jpeg_writer_decodes_like_a_q90_420_jpeg(host, tmp_path, oracle):
+    from PIL import Image
+
+    s = host.load_scene(os.path.join(ROOT, "scenes", "solids.json"), base_dir=ROOT).with_resolution(203, 117)   # not a multiple of 16
+    o = oracle.oracle_render(s)
+    d8, n8, c8 = oracle.encode_bytes(o["depth"], o["normal"], o["color"], oracle.max_depth(o["depth"]))
+    for name, img in (("frame", c8), ("normal_map", n8), ("depth_map", d8)):
+        rgb = img.reshape(s.height, s.width, 3)
+        path = str(tmp_path / f"{name}.jpg")
+        host.write_jpeg(path, rgb, 90)
+        im = Image.open(path)
+        assert im.size == (s.width, s.height) and im.mode == "RGB"
+        got = np.asarray(im.convert("RGB")).astype(np.float64)
+        buf = io.BytesIO()
+        Image.fromarray(rgb).save(buf, "JPEG", quality=90, subsampling=2)
+        pil = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")).astype(np.float64)
+        psnr = lambda a: 10 * np.log10(255.0 ** 2 / max(((a - rgb) ** 2).mean(), 1e-12))   # noqa: E731
+        assert psnr(got) > psnr(pil) - 1.5, (name, psnr(got), psnr(pil))        # as good as libjpeg at the same settings
+        assert 0.6 < os.path.getsize(path) / len(buf.getvalue()) < 1.6
+
+
+def test_look_at_matches_python(host):
+    import ctypes as C
+
+    from cutrace_b200.scene import look_at
+
+    lib = host.load()
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        pos, up, look = (rng.normal(size=3).astype(np.float32) for _ in range(3))
+        out = [(C.c_float * 3)() for _ in range(3)]
+        arr = [(C.c_float * 3)(*v) for v in (pos, up, look)]
+        lib.cutrace_host_look_at(arr[0], arr[1], arr[2], out[0], out[1], out[2])
+        f, r, u = look_at(pos, up, look)
+        assert np.array_equal(np.array(out[0][:], np.float32), f) and np.array_equal(np.array(out[1][:], np.float32), r)
+        assert np.array_equal(np.array(out[2][:], np.float32), u)
