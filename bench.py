@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--verbose", action="store_true", help="per-rank timing lines on stderr")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "gather"],
+                    help="N > 1: peer = kernels store into rank 0's frame over NVLink (CUDA IPC), gather = NCCL gather + un-tile")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -231,7 +233,9 @@ def main():
     n_px = scene.width * scene.height
     stream = torch.cuda.Stream(device=local_rank)   # the ctx launches on this stream, so torch events see its kernels
     torch.cuda.set_stream(stream)
-    tsr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream)
+    tsr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream,
+                              exchange=args.exchange)
+    exchange = tsr.exchange
 
     def step():
         st = tsr.render()
@@ -266,12 +270,13 @@ def main():
         shade, trace, rays_shadow, render_dev_ms = float(tmax[2]), float(tmax[3]), float(tsum[4]), float(tmax[5])
     else:
         ms_step, rays, shade, trace, rays_shadow, render_dev_ms = (float(x) for x in t)
-    launches_per_step = int(st["kernel_launches"]) + (1 if world > 1 and rank == 0 else 0)
+    launches_per_step = int(st["kernel_launches"]) + (1 if world > 1 and rank == 0 and exchange == "gather" else 0)
 
     # per-kernel times need a serialised frame (by default the shade kernels overlap the trace chain): two extra
     # frames with CUTRACE_FLAG_SERIALIZE, outside the timed region, CUDA events on the launching stream
     tsr.close()
-    ser = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags | ct.FLAG_SERIALIZE, stream=stream.cuda_stream)
+    ser = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags | ct.FLAG_SERIALIZE, stream=stream.cuda_stream,
+                              exchange="gather")
     ser.render()
     sst = ser.render()
     ser.close()
@@ -302,13 +307,15 @@ def main():
                                                pinned["color"].ctypes.data, None, C.byref(md)))
             r.close()
         else:
-            tr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream)
+            tr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream,
+                                     exchange=args.exchange)
             stl = tr.render()
             tr.gather()
             tr.max_depth(stl["max_depth"])
             if rank == 0:
                 for k, src in (("depth", tr.out_depth), ("normal", tr.out_normal), ("color", tr.out_color)):
                     torch.from_numpy(pinned[k]).copy_(src, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
             tr.close()
         barrier()
         if i >= 2:
@@ -339,9 +346,9 @@ def main():
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (reference scene geometry from the committed fixture tests/golden/scenes; no image inputs)",
             "config": {"workload": wl["label"], "rays_per_frame": int(rays), "primitives": n_primitives(scene), "bounces": 5,
-                       "parallelism": f"tiles{world}" if world > 1 else "single", "l2": "queues+framebuffer per frame > L2 (126 MB)"
+                       "parallelism": f"tiles{world}/{exchange}" if world > 1 else "single", "l2": "queues+framebuffer per frame > L2 (126 MB)"
                        if n_px * 28 > 126e6 else "working set < L2; frames are re-rendered back to back",
-                       "timed": "K frames between two CUDA events on the launching stream" + ("" if world == 1 else ", incl. NCCL gather + un-tile"),
+                       "timed": "K frames between two CUDA events on the launching stream" + ("" if world == 1 else (", incl. the rank barrier (tiles are stored into rank 0's frame over NVLink by the kernels)" if exchange == "peer" else ", incl. NCCL gather + un-tile")),
                        "render_device_ms": render_dev_ms},
             "clocks": clk.summary(),
             "e2e": {"value": rays / e2e / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e, "h2d_bytes_per_step": int(scene_bytes),

@@ -118,6 +118,23 @@ class Renderer:
         _lib.check(self._lib.cutrace_device_buffers(self._ctx, *[C.byref(x) for x in p], C.byref(n)))
         return [x.value for x in p], n.value
 
+    def frame_device(self):
+        """(depth, normal, color, hit_id) device pointers of this ctx's own row-major frame."""
+        p = [C.c_void_p() for _ in range(4)]
+        _lib.check(self._lib.cutrace_frame_device(self._ctx, *[C.byref(x) for x in p]))
+        return [x.value for x in p]
+
+    def frame_ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _lib.check(self._lib.cutrace_frame_ipc_export(self._ctx, buf))
+        return buf.raw
+
+    def frame_ipc_import(self, handle: bytes):
+        _lib.check(self._lib.cutrace_frame_ipc_import(self._ctx, C.create_string_buffer(handle, 64)))
+
+    def frame_attach(self, block_ptr):
+        _lib.check(self._lib.cutrace_frame_attach(self._ctx, block_ptr))
+
     def untile_device(self, world, g_depth, g_normal, g_color, g_id, stride_px, depth, normal, color, hit_id):
         _lib.check(self._lib.cutrace_untile_device(self._ctx, world, g_depth, g_normal, g_color, g_id, stride_px,
                                                    depth, normal, color, hit_id))

@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("CUTRACE_B200_LIB") or os.path.join(HERE, "lib", "libc
 # every symbol include/cutrace.h declares
 SYMBOLS = (
     "cutrace_default_opts", "cutrace_upload_scene", "cutrace_render", "cutrace_download", "cutrace_download_bytes", "cutrace_free",
-    "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_device_buffers",
+    "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_device_buffers", "cutrace_frame_device",
+    "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free",
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version",
 )
@@ -78,6 +79,10 @@ def load():
                                        C.POINTER(C.c_float), C.c_float, C.c_uint32, C.c_uint32]
     lib.cutrace_get_stats.argtypes = [P, C.POINTER(cutrace_stats)]
     lib.cutrace_device_buffers.argtypes = [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(C.c_uint64)]
+    lib.cutrace_frame_device.argtypes = [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P)]
+    lib.cutrace_frame_ipc_export.argtypes = [P, P]
+    lib.cutrace_frame_ipc_import.argtypes = [P, P]
+    lib.cutrace_frame_attach.argtypes = [P, P]
     lib.cutrace_untile_device.argtypes = [P, C.c_uint32, P, P, P, P, C.c_uint64, P, P, P, P]
     lib.cutrace_encode_bytes_device.argtypes = [P, P, P, P, C.c_float, C.c_uint64, P, P, P]
     lib.cutrace_host_alloc.argtypes = [C.c_size_t]

@@ -94,7 +94,12 @@ struct cutrace_ctx {
   // frame
   TileMap tm{};
   uint64_t n_local_px = 0;   // padded: n_local_tiles * 1024
-  FrameTargets fb{};
+  FrameTargets fb{};                 // tile-major local buffers (sharded ctx without a peer frame: NCCL-gather path)
+  float *frame = nullptr;            // own row-major full frame: depth n | normal 3n | colour 3n | id n (one block)
+  bool frame_is_ipc = false;         // allocated with cudaMalloc and exported through CUDA IPC
+  void *peer_frame = nullptr;        // another ctx's frame (CUDA IPC import or same-process attach): stored into over NVLink
+  bool peer_is_ipc = false;
+  float *local_color = nullptr;      // tile-major colour accumulator (branching scenes: float atomics)
   RayRec *rays[2] = {nullptr, nullptr};
   ShadeRec *shade[16] = {};          // one shade queue per bounce level (shade(L) overlaps trace(L+1..))
   uint64_t shade_cap[16] = {};
@@ -107,8 +112,7 @@ struct cutrace_ctx {
   FrameCounters *h_ctr = nullptr;   // pinned
   LaunchCfg cfg{};
   // download staging (row-major full frame), lazily allocated
-  float *st_depth = nullptr, *st_normal = nullptr, *st_color = nullptr;
-  uint32_t *st_id = nullptr;
+  float *st_depth = nullptr;         // staging frame block (same layout as `frame`)
   uint64_t st_px = 0;
   uint8_t *st_bytes = nullptr;   // 3 images x n x 3 bytes
   uint64_t st_bytes_px = 0;
@@ -131,15 +135,19 @@ struct DeviceGuard {
 void free_frame(cutrace_ctx *c) {
   cudaStream_t st = c->stream;
   dfree(c->fb.depth, st); dfree(c->fb.normal, st); dfree(c->fb.color, st); dfree(c->fb.hit_id, st);
+  if (c->frame_is_ipc) { if (st) cudaStreamSynchronize(st); cudaFree(c->frame); } else dfree(c->frame, st);
+  if (c->peer_frame && c->peer_is_ipc) { if (st) cudaStreamSynchronize(st); cudaIpcCloseMemHandle(c->peer_frame); }
+  dfree(c->local_color, st);
+  c->frame = nullptr; c->frame_is_ipc = false; c->peer_frame = nullptr; c->local_color = nullptr;
   dfree(c->rays[0], st); dfree(c->rays[1], st);
   for (int i = 0; i < 16; i++) { dfree(c->shade[i], st); c->shade[i] = nullptr; c->shade_cap[i] = 0; }
   dfree(c->level_color, st); dfree(c->nlev, st);
   c->level_color = nullptr; c->nlev = nullptr;
-  dfree(c->st_depth, st); dfree(c->st_normal, st); dfree(c->st_color, st); dfree(c->st_id, st);
+  dfree(c->st_depth, st);
   dfree(c->st_bytes, st); c->st_bytes = nullptr; c->st_bytes_px = 0;
   c->fb = FrameTargets{};
   c->rays[0] = c->rays[1] = nullptr;
-  c->st_depth = c->st_normal = c->st_color = nullptr; c->st_id = nullptr;
+  c->st_depth = nullptr;
   c->st_px = 0;
   c->rendered = false;
 }
@@ -186,10 +194,15 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   c->cap = batch * c->factor;
 
   cudaStream_t st = c->stream;
-  CU(dmalloc(&c->fb.depth, sizeof(float) * c->n_local_px, st));
-  CU(dmalloc(&c->fb.normal, sizeof(float) * 3 * c->n_local_px, st));
-  CU(dmalloc(&c->fb.color, sizeof(float) * 3 * c->n_local_px, st));
-  CU(dmalloc(&c->fb.hit_id, sizeof(uint32_t) * c->n_local_px, st));
+  if (c->tm.world > 1) {   // sharded: tile-major local buffers for the gather path (unused once a peer frame is imported)
+    CU(dmalloc(&c->fb.depth, sizeof(float) * c->n_local_px, st));
+    CU(dmalloc(&c->fb.normal, sizeof(float) * 3 * c->n_local_px, st));
+    CU(dmalloc(&c->fb.color, sizeof(float) * 3 * c->n_local_px, st));
+    CU(dmalloc(&c->fb.hit_id, sizeof(uint32_t) * c->n_local_px, st));
+  } else {                 // one GPU: results are written row-major, no un-tile pass
+    CU(dmalloc(&c->frame, 32ull * width * height, st));
+  }
+  if (branching) CU(dmalloc(&c->local_color, sizeof(float) * 3 * c->n_local_px, st));
   if (c->max_children > 0 && b > 0) {
     CU(dmalloc(&c->rays[0], sizeof(RayRec) * c->cap, st));
     CU(dmalloc(&c->rays[1], sizeof(RayRec) * c->cap, st));
@@ -248,6 +261,24 @@ int validate_desc(const cutrace_scene_desc *s) {
       !all_finite(s->sph_radius, s->n_spheres))
     return fail(CUTRACE_ERR_INVALID_ARG, "non-finite vertex / sphere data");
   return CUTRACE_OK;
+}
+
+// row-major frame block -> the four images
+FrameTargets frame_views(float *block, uint64_t n) {
+  FrameTargets t{};
+  t.depth = block; t.normal = block + n; t.color = block + 4 * n; t.hit_id = reinterpret_cast<uint32_t *>(block + 7 * n);
+  t.row_major = 1;
+  return t;
+}
+
+// where this ctx's kernels store their results (see FrameTargets)
+FrameTargets frame_targets(const cutrace_ctx *c) {
+  const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
+  if (c->peer_frame) return frame_views(static_cast<float *>(c->peer_frame), n);
+  if (c->frame) return frame_views(c->frame, n);
+  FrameTargets t = c->fb;
+  t.row_major = 0;
+  return t;
 }
 
 void set_cam(cutrace_ctx *c, const float pos[3], const float up[3], const float fwd[3], const float right[3], float ambient) {
@@ -485,7 +516,10 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   CU(cudaEventRecord(ev_begin, st));
   const bool branching = c->max_children >= 2 && bounces > 0;
   const bool serialize = (c->opts.flags & CUTRACE_FLAG_SERIALIZE) != 0;
-  if (branching) CU(cudaMemsetAsync(c->fb.color, 0, sizeof(float) * 3 * c->n_local_px, st));
+  if (branching) CU(cudaMemsetAsync(c->local_color, 0, sizeof(float) * 3 * c->n_local_px, st));
+  const FrameTargets out = frame_targets(c);
+  FrameTargets acc{};   // shade kernels of a branching scene accumulate here
+  acc.color = c->local_color;
   float max_depth = 0.f;
   for (uint64_t base = 0; base < c->n_local_px; base += c->batch_px) {
     const uint32_t n_px = (uint32_t)std::min<uint64_t>(c->batch_px, c->n_local_px - base);
@@ -499,20 +533,18 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       RayRec *in = c->rays[L & 1], *outq = c->rays[(L + 1) & 1];
       cudaEvent_t e0 = c->events[2 + 3 * L], e1 = c->events[3 + 3 * L], e2 = c->events[4 + 3 * L];
       if (serialize) CU(cudaEventRecord(e0, st));
-      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade[L], c->d_ctr, c->fb, c->nlev, (uint32_t)bound, st);
+      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade[L], c->d_ctr, out, c->nlev, (uint32_t)bound, st);
       CU(cudaEventRecord(e1, st));
       cudaStream_t ss = serialize ? st : c->aux[L & 1];
       if (!serialize) CU(cudaStreamWaitEvent(ss, e1, 0));
       float *lc = branching ? nullptr : c->level_color + (size_t)L * 3 * c->batch_px;
-      launch_shade(c->cfg, c->sv, L, c->shade[L], c->d_ctr, c->fb, branching, lc, (uint32_t)base, (uint32_t)bound, ss);
+      launch_shade(c->cfg, c->sv, L, c->shade[L], c->d_ctr, acc, branching, lc, (uint32_t)base, (uint32_t)bound, ss);
       CU(cudaEventRecord(e2, ss));
       S.kernel_launches += 2;
     }
     if (!serialize) for (uint32_t L = 0; L < levels; L++) CU(cudaStreamWaitEvent(st, c->events[4 + 3 * L], 0));
-    if (!branching) {
-      launch_combine(c->nlev, c->level_color, 3ull * c->batch_px, levels, (uint32_t)base, n_px, c->fb.color, st);
-      S.kernel_launches += 1;
-    }
+    launch_combine(c->tm, c->nlev, c->level_color, 3ull * c->batch_px, branching ? 0u : levels, c->local_color, (uint32_t)base, n_px, out, st);
+    S.kernel_launches += 1;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     if (base + c->batch_px >= c->n_local_px) CU(cudaEventRecord(ev_end, st));
@@ -548,27 +580,23 @@ int cutrace_get_stats(cutrace_ctx *c, cutrace_stats *stats) {
   return CUTRACE_OK;
 }
 
-// un-tiles the local buffers into the row-major full-frame staging images (device)
-static int stage_full_frame(cutrace_ctx *c) {
+// Row-major device images of the last frame: the ctx's own frame, or (sharded ctx on the gather path) its tiles
+// un-tiled into a staging frame whose foreign tiles read as misses.
+static int full_frame_views(cutrace_ctx *c, FrameTargets *v) {
   cudaStream_t st = c->stream;
   const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
+  if (c->peer_frame) return fail(CUTRACE_ERR_STATE, "this ctx renders into another ctx's frame (cutrace_frame_ipc_import); download from the exporting ctx");
+  if (c->frame) { *v = frame_views(c->frame, n); return CUTRACE_OK; }
   if (c->st_px != n) {
-    dfree(c->st_depth, st); dfree(c->st_normal, st); dfree(c->st_color, st); dfree(c->st_id, st);
-    c->st_depth = c->st_normal = c->st_color = nullptr; c->st_id = nullptr; c->st_px = 0;
-    CU(dmalloc(&c->st_depth, sizeof(float) * n, st));
-    CU(dmalloc(&c->st_normal, sizeof(float) * 3 * n, st));
-    CU(dmalloc(&c->st_color, sizeof(float) * 3 * n, st));
-    CU(dmalloc(&c->st_id, sizeof(uint32_t) * n, st));
+    dfree(c->st_depth, st);
+    c->st_depth = nullptr; c->st_px = 0;
+    CU(dmalloc(&c->st_depth, 32ull * n, st));
     c->st_px = n;
   }
-  if (c->tm.world > 1) {
-    // sharded ctx: foreign tiles read as misses; the real multi-GPU path gathers device buffers instead
-    launch_fill_sentinels(c->st_depth, c->st_normal, c->st_color, c->st_id, n, st);
-    launch_untile(c->tm, c->tm.world, c->fb.depth, c->fb.normal, c->fb.color, c->fb.hit_id, 0, (int)c->tm.rank, c->st_depth,
-                  c->st_normal, c->st_color, c->st_id, st);
-  } else {
-    launch_untile(c->tm, 1, c->fb.depth, c->fb.normal, c->fb.color, c->fb.hit_id, 0, -1, c->st_depth, c->st_normal, c->st_color, c->st_id, st);
-  }
+  *v = frame_views(c->st_depth, n);
+  launch_fill_sentinels(v->depth, v->normal, v->color, v->hit_id, n, st);
+  launch_untile(c->tm, c->tm.world, c->fb.depth, c->fb.normal, c->fb.color, c->fb.hit_id, 0, (int)c->tm.rank, v->depth, v->normal, v->color,
+                v->hit_id, st);
   CU(cudaGetLastError());
   return CUTRACE_OK;
 }
@@ -579,12 +607,13 @@ int cutrace_download(cutrace_ctx *c, float *depth, float *normal, float *color, 
   DeviceGuard g(c->device);
   cudaStream_t st = c->stream;
   const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
-  int rc = stage_full_frame(c);
+  FrameTargets v;
+  int rc = full_frame_views(c, &v);
   if (rc) return rc;
-  if (depth) CU(cudaMemcpyAsync(depth, c->st_depth, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-  if (normal) CU(cudaMemcpyAsync(normal, c->st_normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
-  if (color) CU(cudaMemcpyAsync(color, c->st_color, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
-  if (hit_id) CU(cudaMemcpyAsync(hit_id, c->st_id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+  if (depth) CU(cudaMemcpyAsync(depth, v.depth, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  if (normal) CU(cudaMemcpyAsync(normal, v.normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+  if (color) CU(cudaMemcpyAsync(color, v.color, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+  if (hit_id) CU(cudaMemcpyAsync(hit_id, v.hit_id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (max_depth) *max_depth = c->stats.max_depth;
   return CUTRACE_OK;
@@ -596,7 +625,8 @@ int cutrace_download_bytes(cutrace_ctx *c, uint8_t *depth_rgb, uint8_t *normal_r
   DeviceGuard g(c->device);
   cudaStream_t st = c->stream;
   const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
-  int rc = stage_full_frame(c);
+  FrameTargets v;
+  int rc = full_frame_views(c, &v);
   if (rc) return rc;
   if (c->st_bytes_px != n) {
     dfree(c->st_bytes, st); c->st_bytes = nullptr; c->st_bytes_px = 0;
@@ -604,7 +634,7 @@ int cutrace_download_bytes(cutrace_ctx *c, uint8_t *depth_rgb, uint8_t *normal_r
     c->st_bytes_px = n;
   }
   uint8_t *d8 = c->st_bytes, *n8 = c->st_bytes + 3 * n, *c8 = c->st_bytes + 6 * n;
-  launch_encode_bytes(depth_rgb ? c->st_depth : nullptr, normal_rgb ? c->st_normal : nullptr, color_rgb ? c->st_color : nullptr,
+  launch_encode_bytes(depth_rgb ? v.depth : nullptr, normal_rgb ? v.normal : nullptr, color_rgb ? v.color : nullptr,
                       c->stats.max_depth, n, d8, n8, c8, st);
   CU(cudaGetLastError());
   if (depth_rgb) CU(cudaMemcpyAsync(depth_rgb, d8, 3 * n, cudaMemcpyDeviceToHost, st));
@@ -612,6 +642,63 @@ int cutrace_download_bytes(cutrace_ctx *c, uint8_t *depth_rgb, uint8_t *normal_r
   if (color_rgb) CU(cudaMemcpyAsync(color_rgb, c8, 3 * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (max_depth) *max_depth = c->stats.max_depth;
+  return CUTRACE_OK;
+}
+
+int cutrace_frame_device(cutrace_ctx *c, float **depth, float **normal, float **color, uint32_t **hit_id) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  if (!c->frame) return fail(CUTRACE_ERR_STATE, "this ctx has no row-major frame of its own (sharded ctx without cutrace_frame_ipc_export)");
+  FrameTargets v = frame_views(c->frame, (uint64_t)c->tm.width * c->tm.height);
+  if (depth) *depth = v.depth;
+  if (normal) *normal = v.normal;
+  if (color) *color = v.color;
+  if (hit_id) *hit_id = v.hit_id;
+  return CUTRACE_OK;
+}
+
+int cutrace_frame_ipc_export(cutrace_ctx *c, void *handle) {
+  if (!c || !handle) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == CUTRACE_IPC_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard g(c->device);
+  CU(cudaStreamSynchronize(c->stream));
+  if (!c->frame_is_ipc) {   // pool memory cannot be exported: give the frame its own cudaMalloc block
+    float *blk = nullptr;
+    CU(cudaMalloc(&blk, 32ull * c->tm.width * c->tm.height));
+    dfree(c->frame, c->stream);
+    c->frame = blk;
+    c->frame_is_ipc = true;
+    c->rendered = false;
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->frame));
+  memcpy(handle, &h, sizeof h);
+  return CUTRACE_OK;
+}
+
+int cutrace_frame_ipc_import(cutrace_ctx *c, const void *handle) {
+  if (!c || !handle) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(c->device);
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->peer_frame && c->peer_is_ipc) cudaIpcCloseMemHandle(c->peer_frame);
+  c->peer_frame = nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void *p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->peer_frame = p;
+  c->peer_is_ipc = true;
+  c->rendered = false;
+  return CUTRACE_OK;
+}
+
+int cutrace_frame_attach(cutrace_ctx *c, void *frame_block) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  DeviceGuard g(c->device);
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->peer_frame && c->peer_is_ipc) cudaIpcCloseMemHandle(c->peer_frame);
+  c->peer_frame = frame_block;   // NULL detaches
+  c->peer_is_ipc = false;
+  c->rendered = false;
   return CUTRACE_OK;
 }
 

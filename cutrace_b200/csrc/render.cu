@@ -119,11 +119,10 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
       bool active = i < n_work;
       vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
       float w = 1.0f;
-      uint32_t pix = 0;
+      uint32_t pix = 0, gx = 0, gy = 0;
       if (level == 0) {
-        uint32_t x = 0, y = 0;
-        active = active && work_to_pixel(tm, px_base + i, x, y, pix);
-        if (active) camera_ray(sv.cam, x, y, o, d);
+        active = active && work_to_pixel(tm, px_base + i, gx, gy, pix);
+        if (active) camera_ray(sv.cam, gx, gy, o, d);
       } else if (active) {
         const float4 *rp = reinterpret_cast<const float4 *>(rays_in + i);
         float4 a = __ldcs(rp), b = __ldcs(rp + 1);
@@ -145,9 +144,10 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
         reflect = m1.x; transp = m1.z;
       }
       if (level == 0 && active) {   // G-buffer, inc/kernel.hpp:52-56
-        fb.depth[pix] = h.t;
-        fb.normal[3 * (size_t)pix] = nrm.x; fb.normal[3 * (size_t)pix + 1] = nrm.y; fb.normal[3 * (size_t)pix + 2] = nrm.z;
-        fb.hit_id[pix] = hit ? h.obj : CUTRACE_NO_HIT;
+        const size_t gi = fb.row_major ? (size_t)gy * tm.width + gx : (size_t)pix;   // possibly peer memory (NVLink store)
+        fb.depth[gi] = h.t;
+        fb.normal[3 * gi] = nrm.x; fb.normal[3 * gi + 1] = nrm.y; fb.normal[3 * gi + 2] = nrm.z;
+        fb.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
         if (hit && isfinite(h.t)) max_depth = fmaxf(max_depth, h.t);
         if (nlev && !hit) nlev[pix] = 0u;
       }
@@ -369,26 +369,39 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
-// colour of a pixel = sum of its per-level partial images in level order (same order as a serial accumulation)
-__global__ void combine_levels_kernel(const uint32_t *__restrict__ nlev, const float *__restrict__ level_color, uint64_t level_stride,
-                                      uint32_t levels, uint32_t px_base, uint32_t n_px, float *__restrict__ color) {
+// colour of a pixel = sum of its per-level partial images in level order (same order as a serial accumulation),
+// stored where the frame lives: tile-major local buffer, own row-major frame, or a peer GPU's frame over NVLink
+__global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restrict__ nlev, const float *__restrict__ level_color,
+                                      uint64_t level_stride, uint32_t levels, const float *__restrict__ local_color,
+                                      uint32_t px_base, uint32_t n_px, FrameTargets out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_px) return;
-  uint32_t n = nlev[px_base + i];
-  n = n < levels ? n : levels;
+  const uint32_t pix = px_base + i;
+  // local tile-major index -> pixel (row-major inside the 32x32 tile)
+  const uint32_t lt = pix >> 10, w = pix & 1023u;
+  const uint32_t gt = lt * tm.world + tm.rank;
+  const uint32_t x = (gt % tm.tiles_x) * CUTRACE_TILE + (w & 31u), y = (gt / tm.tiles_x) * CUTRACE_TILE + (w >> 5);
+  if (x >= tm.width || y >= tm.height) return;
   float r = 0.f, g = 0.f, b = 0.f;
-  for (uint32_t l = 0; l < n; l++) {
-    const float *p = level_color + l * level_stride + 3 * (size_t)i;
-    r += p[0]; g += p[1]; b += p[2];
+  if (levels == 0) {
+    const float *p = local_color + 3 * (size_t)pix;
+    r = p[0]; g = p[1]; b = p[2];
+  } else {
+    uint32_t n = nlev[pix];
+    n = n < levels ? n : levels;
+    for (uint32_t l = 0; l < n; l++) {
+      const float *p = level_color + l * level_stride + 3 * (size_t)i;
+      r += p[0]; g += p[1]; b += p[2];
+    }
   }
-  float *o = color + 3 * (size_t)(px_base + i);
+  float *o = out.color + 3 * (out.row_major ? (size_t)y * tm.width + x : (size_t)pix);
   o[0] = r; o[1] = g; o[2] = b;
 }
 
-void launch_combine(const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels, uint32_t px_base,
-                    uint32_t n_px, float *color, cudaStream_t st) {
+void launch_combine(const TileMap &tm, const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels,
+                    const float *local_color, uint32_t px_base, uint32_t n_px, const FrameTargets &out, cudaStream_t st) {
   if (!n_px) return;
-  combine_levels_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(nlev, level_color, level_stride, levels, px_base, n_px, color);
+  combine_levels_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(tm, nlev, level_color, level_stride, levels, local_color, px_base, n_px, out);
 }
 
 typedef void (*trace_fn)(const SceneView, const TileMap, uint32_t, uint32_t, uint32_t, uint32_t, const RayRec *, RayRec *, ShadeRec *,

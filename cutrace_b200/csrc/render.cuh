@@ -17,11 +17,16 @@ constexpr int WORK_CHUNK_MAX = 512;   // most rays a warp claims per work-steali
 #define CTB_MIN_BLOCKS 2   // resident CTAs per SM the register allocator must allow (tuned on B200)
 #endif
 
-struct FrameTargets {   // local tile-major buffers
-  float *depth;         // n_local_px
-  float *normal;        // n_local_px * 3
-  float *color;         // n_local_px * 3
-  uint32_t *hit_id;     // n_local_px
+// Where a frame's results go.  row_major = 0: this ctx's tile-major local buffers (index = local pixel index; the
+// NCCL-gather path un-tiles them later).  row_major = 1: a row-major full frame (index = y*width + x) — the ctx's own
+// frame on one GPU, or rank 0's frame mapped through CUDA IPC on the other ranks, in which case the G-buffer and the
+// final colour are stored straight into the peer GPU's HBM over NVLink by the kernels that produce them.
+struct FrameTargets {
+  float *depth;         // n px
+  float *normal;        // n px * 3
+  float *color;         // n px * 3
+  uint32_t *hit_id;     // n px
+  uint32_t row_major;
 };
 
 struct LaunchCfg {
@@ -42,9 +47,10 @@ void launch_trace(const LaunchCfg &cfg, const SceneView &sv, const TileMap &tm, 
 void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, FrameCounters *ctr,
                   const FrameTargets &fb, bool atomic_accumulate, float *level_color, uint32_t px_base, uint32_t work_bound,
                   cudaStream_t st);
-// colour[px] = sum over levels l < nlev[px] of level_color[l][px - px_base], in level order
-void launch_combine(const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels, uint32_t px_base,
-                    uint32_t n_px, float *color, cudaStream_t st);
+// colour[px] = sum over levels l < nlev[px] of level_color[l][px - px_base], in level order; levels == 0: copy the
+// locally accumulated colour (branching scenes) instead.  Writes into `out` in its layout.
+void launch_combine(const TileMap &tm, const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels,
+                    const float *local_color, uint32_t px_base, uint32_t n_px, const FrameTargets &out, cudaStream_t st);
 
 // output.cu
 void launch_untile(const TileMap &tm, uint32_t world, const float *g_depth, const float *g_normal, const float *g_color,

@@ -49,9 +49,17 @@ class _DevArray:
 
 
 class TileShardedRenderer:
-    """Rank-local renderer + NCCL gather. Requires an initialised torch.distributed process group."""
+    """Rank-local renderer of a tile-sharded frame.  Requires an initialised torch.distributed process group when
+    world > 1.
 
-    def __init__(self, scene, rank, world, device, **kw):
+    Default exchange ("peer"): rank 0 exports its row-major frame through CUDA IPC, the other ranks import it and
+    their kernels store the G-buffer / final colour of their tiles straight into rank 0's HBM over NVLink — the
+    transfer is fused into the producing kernels, and the only collective left is the 1-float max-depth all-reduce,
+    which doubles as the barrier.  Fallback ("gather", also selectable): NCCL gather of the tile-major rank buffers
+    to rank 0 followed by the device un-tile kernel.
+    """
+
+    def __init__(self, scene, rank, world, device, exchange="peer", **kw):
         import torch
 
         self.torch = torch
@@ -59,51 +67,84 @@ class TileShardedRenderer:
         self.scene = scene
         self.device = torch.device("cuda", device)
         self.r = Renderer(scene, device=device, tile_rank=rank, tile_world=world, **kw)
-        (pd, pn, pc, pi), npx = self.r.device_buffers()
-        self.npx = npx
-        as_t = lambda p, n, ts: torch.as_tensor(_DevArray(p, n, ts), device=self.device)  # noqa: E731
-        self.depth = as_t(pd, npx, "<f4")
-        self.normal = as_t(pn, 3 * npx, "<f4")
-        self.color = as_t(pc, 3 * npx, "<f4")
-        self.hit_id = as_t(pi, npx, "<i4")
+        self.exchange = "none" if world == 1 else exchange
         n = scene.width * scene.height
-        if rank == 0:
-            f32, i32 = torch.float32, torch.int32
-            self.g_depth = torch.empty(world * npx, dtype=f32, device=self.device)
-            self.g_normal = torch.empty(world * 3 * npx, dtype=f32, device=self.device)
-            self.g_color = torch.empty(world * 3 * npx, dtype=f32, device=self.device)
-            self.g_id = torch.empty(world * npx, dtype=i32, device=self.device)
-            self.out_depth = torch.empty(n, dtype=f32, device=self.device)
-            self.out_normal = torch.empty(3 * n, dtype=f32, device=self.device)
-            self.out_color = torch.empty(3 * n, dtype=f32, device=self.device)
-            self.out_id = torch.empty(n, dtype=i32, device=self.device)
+        as_t = lambda p, cnt, ts: torch.as_tensor(_DevArray(p, cnt, ts), device=self.device)  # noqa: E731
+        if self.exchange == "peer":
+            self.exchange = "peer" if self._setup_peer() else "gather"
+        if self.exchange == "gather":
+            (pd, pn, pc, pi), npx = self.r.device_buffers()
+            self.npx = npx
+            self.depth = as_t(pd, npx, "<f4")
+            self.normal = as_t(pn, 3 * npx, "<f4")
+            self.color = as_t(pc, 3 * npx, "<f4")
+            self.hit_id = as_t(pi, npx, "<i4")
+            if rank == 0:
+                f32, i32 = torch.float32, torch.int32
+                self.g_depth = torch.empty(world * npx, dtype=f32, device=self.device)
+                self.g_normal = torch.empty(world * 3 * npx, dtype=f32, device=self.device)
+                self.g_color = torch.empty(world * 3 * npx, dtype=f32, device=self.device)
+                self.g_id = torch.empty(world * npx, dtype=i32, device=self.device)
+                self.out_depth = torch.empty(n, dtype=f32, device=self.device)
+                self.out_normal = torch.empty(3 * n, dtype=f32, device=self.device)
+                self.out_color = torch.empty(3 * n, dtype=f32, device=self.device)
+                self.out_id = torch.empty(n, dtype=i32, device=self.device)
+        elif rank == 0:
+            pd, pn, pc, pi = self.r.frame_device()
+            self.out_depth, self.out_normal = as_t(pd, n, "<f4"), as_t(pn, 3 * n, "<f4")
+            self.out_color, self.out_id = as_t(pc, 3 * n, "<f4"), as_t(pi, n, "<i4")
+
+    def _setup_peer(self):
+        """rank 0 exports, everybody else imports; all ranks agree on success (else every rank falls back)."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        h = torch.zeros(64, dtype=torch.uint8, device=self.device)
+        ok = 1
+        try:
+            if self.rank == 0:
+                h.copy_(torch.frombuffer(bytearray(self.r.frame_ipc_export()), dtype=torch.uint8))
+        except Exception:  # noqa: BLE001
+            ok = 0
+        dist.broadcast(h, src=0)
+        if self.rank != 0 and ok:
+            try:
+                self.r.frame_ipc_import(bytes(h.cpu().numpy().tobytes()))
+            except Exception:  # noqa: BLE001
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and self.rank != 0:
+            self.r.frame_attach(None)
+        return int(flag.item()) == 1
 
     def render(self):
         return self.r.render()
 
     def gather(self):
-        """NCCL gather of the four framebuffers to rank 0, then device un-tile on rank 0."""
+        """Completes the frame on rank 0.  peer: the stores already happened, only the ranks are synchronised (by the
+        max-depth all-reduce the caller issues, or this barrier).  gather: NCCL gather + device un-tile on rank 0."""
         import torch.distributed as dist
 
         torch = self.torch
         if self.world == 1:
-            g = (self.depth, self.normal, self.color, self.hit_id)
-        else:
-            pairs = [(self.depth, getattr(self, "g_depth", None), 1), (self.normal, getattr(self, "g_normal", None), 3),
-                     (self.color, getattr(self, "g_color", None), 3), (self.hit_id, getattr(self, "g_id", None), 1)]
-            for src, dst, k in pairs:
-                lst = list(dst.split(k * self.npx)) if self.rank == 0 else None
-                dist.gather(src, lst, dst=0)
-            g = (getattr(self, "g_depth", None), getattr(self, "g_normal", None), getattr(self, "g_color", None),
-                 getattr(self, "g_id", None))
+            return
+        if self.exchange == "peer":
+            dist.barrier()
+            return
+        pairs = [(self.depth, getattr(self, "g_depth", None), 1), (self.normal, getattr(self, "g_normal", None), 3),
+                 (self.color, getattr(self, "g_color", None), 3), (self.hit_id, getattr(self, "g_id", None), 1)]
+        for src, dst, k in pairs:
+            lst = list(dst.split(k * self.npx)) if self.rank == 0 else None
+            dist.gather(src, lst, dst=0)
         if self.rank == 0:
             torch.cuda.current_stream(self.device).synchronize()
-            self.r.untile_device(self.world, g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), self.npx,
-                                 self.out_depth.data_ptr(), self.out_normal.data_ptr(), self.out_color.data_ptr(),
-                                 self.out_id.data_ptr())
+            self.r.untile_device(self.world, self.g_depth.data_ptr(), self.g_normal.data_ptr(), self.g_color.data_ptr(),
+                                 self.g_id.data_ptr(), self.npx, self.out_depth.data_ptr(), self.out_normal.data_ptr(),
+                                 self.out_color.data_ptr(), self.out_id.data_ptr())
 
     def max_depth(self, local_max):
-        """max over ranks of the largest finite depth (kernel.hpp:120-125) — a 1-float reduce."""
+        """max over ranks of the largest finite depth (kernel.hpp:120-125) — a 1-float all-reduce."""
         import torch.distributed as dist
 
         t = self.torch.tensor([local_max], dtype=self.torch.float32, device=self.device)

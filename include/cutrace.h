@@ -210,6 +210,24 @@ int cutrace_get_stats(cutrace_ctx *ctx, cutrace_stats *stats);
 int cutrace_device_buffers(cutrace_ctx *ctx, float **depth, float **normal, float **color,
                            uint32_t **hit_id, uint64_t *n_local_px_padded);
 
+/* Row-major device images of this ctx's own frame (one-GPU ctx, or the exporting ctx of a sharded render): what
+ * cutrace_download copies.  Valid until the next set_camera/free. */
+int cutrace_frame_device(cutrace_ctx *ctx, float **depth, float **normal, float **color, uint32_t **hit_id);
+
+/* Multi-GPU without a gather: the ctx that owns the final frame (normally tile_rank 0) exports it through CUDA IPC;
+ * the other ranks' ctxs import the handle and from then on their kernels store the G-buffer and the final colour of
+ * their tiles straight into that frame over NVLink (peer stores fused into the producing kernels).  The caller only
+ * has to synchronise the ranks (a barrier / the max-depth all-reduce) before downloading from the exporting ctx.
+ * `handle` is CUTRACE_IPC_HANDLE_BYTES bytes, to be shipped to the other processes by the caller.  Re-export after
+ * cutrace_set_camera changes the resolution. */
+#define CUTRACE_IPC_HANDLE_BYTES 64
+int cutrace_frame_ipc_export(cutrace_ctx *ctx, void *handle);
+int cutrace_frame_ipc_import(cutrace_ctx *ctx, const void *handle);
+/* Same idea inside one process (several ctxs / GPUs driven by one host thread, peer access enabled by the caller):
+ * `frame_block` is the depth pointer cutrace_frame_device returned for the owning ctx (the frame is one block of
+ * 32*width*height bytes).  NULL detaches. */
+int cutrace_frame_attach(cutrace_ctx *ctx, void *frame_block);
+
 /* Un-tiles `world` gathered rank buffers (each laid out as cutrace_device_buffers describes, rank r
  * at gathered + r*stride elements of the respective type) into row-major full-frame DEVICE images
  * on the ctx's device.  Any of the pointers may be NULL. */

@@ -209,6 +209,33 @@ def test_tile_sharding_equals_single_ctx(ct):
     assert rays == st["rays_total"]
 
 
+def test_peer_frame_stores_equal_single_ctx(ct):
+    """The gather-free multi-GPU path on one GPU: three sharded ctxs store their tiles straight into rank 0's row-major
+    frame (cutrace_frame_attach = the in-process form of cutrace_frame_ipc_import); the assembled frame is bit-identical
+    to the unsharded render."""
+    for name, res in (("mirror", (333, 205)), ("sphere_plane", (200, 120))):
+        s = load_golden_scene(name).with_resolution(*res)
+        full, st = gpu_render(ct, s)
+        rs = [ct.Renderer(s, tile_rank=r, tile_world=3) for r in range(3)]
+        rs[0].frame_ipc_export()                 # gives rank 0 an exportable row-major frame of its own
+        block = rs[0].frame_device()[0]
+        for r in rs[1:]:
+            r.frame_attach(block)
+        rays = sum(r.render()["rays_total"] for r in rs)
+        out = rs[0].download()
+        with pytest.raises(ct.CutraceError):     # a ctx that renders into somebody else's frame has nothing to download
+            rs[1].download()
+        for k in ("depth", "normal", "hit_id"):
+            assert np.array_equal(out[k].view(np.uint32), full[k].view(np.uint32)), (name, k)
+        if name == "mirror":
+            assert np.array_equal(out["color"].view(np.uint32), full["color"].view(np.uint32))
+        else:
+            assert np.abs(out["color"] - full["color"]).max() < 1e-5     # branching scene: float atomics
+        assert rays == st["rays_total"]
+        for r in rs:
+            r.close()
+
+
 def test_untile_of_gathered_rank_buffers(ct):
     """cutrace_untile_device on a rank-major concatenation of tile-major buffers (what the NCCL gather
     produces) against the host re-implementation in cutrace_b200.distributed.untile_host."""
@@ -218,7 +245,7 @@ def test_untile_of_gathered_rank_buffers(ct):
 
     s = load_golden_scene("sphere_plane").with_resolution(200, 120)
     world = 2
-    rs = [TileShardedRenderer(s, rank=r, world=world, device=0) for r in range(world)]
+    rs = [TileShardedRenderer(s, rank=r, world=world, device=0, exchange="gather") for r in range(world)]
     for r in rs:
         r.render()
     npx = rs[0].npx
