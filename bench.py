@@ -64,41 +64,47 @@ def algorithmic_bytes_per_ray(n_prims):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks + throttle reasons during the timed region: ONE `nvidia-smi -lms 100` child (B200_PROFILING.md)."""
 
-    def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.1)
+    def __init__(self, index, enabled=True):
+        self.index, self.enabled, self.proc, self.lines = index, enabled, None, []
 
     def __enter__(self):
-        self._t.start()
+        if self.enabled:
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                time.sleep(0.25)   # let the first sample land before the timed region starts
+            except Exception:  # noqa: BLE001
+                self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+                self.lines = [ln for ln in out.splitlines() if ln.strip()]
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
 
     def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        mhz, mx, reasons = [], None, set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            try:
+                mhz.append(float(p[0])); mx = float(p[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(self.NAMES, p[2:]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(mhz)}
 
 
 def cpu_baseline(scene, label, seconds_target=12.0):
@@ -231,7 +237,7 @@ def main():
         torch.cuda.synchronize()
 
     n_px = scene.width * scene.height
-    stream = torch.cuda.Stream(device=local_rank)   # the ctx launches on this stream, so torch events see its kernels
+    stream = torch.cuda.Stream(device=local_rank, priority=-1)   # the ctx launches its trace chain on this (high-priority) stream; torch events see its kernels
     torch.cuda.set_stream(stream)
     tsr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream,
                               exchange=args.exchange)
@@ -248,7 +254,7 @@ def main():
     barrier()
     dev_ms, trace_ms, shade_ms = [], [], []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
         ev0.record(stream)
         for _ in range(args.steps):
             st = step()

@@ -116,6 +116,9 @@ struct cutrace_ctx {
   uint64_t st_px = 0;
   uint8_t *st_bytes = nullptr;   // 3 images x n x 3 bytes
   uint64_t st_bytes_px = 0;
+  uint32_t graph_launches = 0;
+  cudaGraphExec_t graph = nullptr;   // the whole frame (all streams) captured once, replayed per cutrace_render
+  bool graph_failed = false;
   cutrace_stats stats{};
   bool rendered = false;
   std::vector<cudaEvent_t> events;
@@ -132,7 +135,14 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// the captured frame bakes in camera, resolution, queue and frame pointers: drop it whenever one of them changes
+void drop_graph(cutrace_ctx *c) {
+  if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+  c->graph_failed = false;
+}
+
 void free_frame(cutrace_ctx *c) {
+  drop_graph(c);
   cudaStream_t st = c->stream;
   dfree(c->fb.depth, st); dfree(c->fb.normal, st); dfree(c->fb.color, st); dfree(c->fb.hit_id, st);
   if (c->frame_is_ipc) { if (st) cudaStreamSynchronize(st); cudaFree(c->frame); } else dfree(c->frame, st);
@@ -478,6 +488,7 @@ int cutrace_set_camera(cutrace_ctx *c, const float pos[3], const float up[3], co
   if (!c || !pos || !up || !forward || !right) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
   DeviceGuard g(c->device);
   CU(cudaStreamSynchronize(c->stream));
+  drop_graph(c);
   set_cam(c, pos, up, forward, right, ambient);
   if (width != c->tm.width || height != c->tm.height) {
     int rc = alloc_frame(c, width, height);
@@ -513,39 +524,85 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     S.rays_primary = px;
   }
   cudaEvent_t ev_begin = c->events[0], ev_end = c->events[1];
-  CU(cudaEventRecord(ev_begin, st));
   const bool branching = c->max_children >= 2 && bounces > 0;
   const bool serialize = (c->opts.flags & CUTRACE_FLAG_SERIALIZE) != 0;
-  if (branching) CU(cudaMemsetAsync(c->local_color, 0, sizeof(float) * 3 * c->n_local_px, st));
   const FrameTargets out = frame_targets(c);
+  // a peer frame gets its G-buffer from a coalescing export kernel; trace(0) then writes the local tile-major buffers
+  FrameTargets gbuf = out, gsrc{};
+  if (c->peer_frame && c->fb.depth) { gbuf = c->fb; gbuf.row_major = 0; gsrc = gbuf; }
   FrameTargets acc{};   // shade kernels of a branching scene accumulate here
   acc.color = c->local_color;
-  float max_depth = 0.f;
-  for (uint64_t base = 0; base < c->n_local_px; base += c->batch_px) {
-    const uint32_t n_px = (uint32_t)std::min<uint64_t>(c->batch_px, c->n_local_px - base);
-    CU(cudaMemsetAsync(c->d_ctr, 0, sizeof(FrameCounters), st));
-    // Dependencies of one frame: trace(L) -> trace(L+1) (ray queue) and trace(L) -> shade(L) (shade queue L).
-    // The trace chain runs on the ctx stream; shade(L) runs on one of two auxiliary streams behind an event, so
-    // the persistent CTAs of later kernels fill the SMs that the tail of an earlier kernel leaves idle.
+  uint32_t launches = 0;
+
+  // Everything one batch of pixels needs, in dependency order.
+  //   trace(L) -> trace(L+1) (ray queue)   and   trace(L) -> shade(L) (shade queue L)
+  // The trace chain runs on the ctx stream; shade(L) runs on one of two auxiliary streams behind an event, so the
+  // persistent CTAs of later kernels fill the SMs that the tail of an earlier kernel leaves idle.
+  auto enqueue = [&](uint64_t base, uint32_t n_px) -> cudaError_t {
+    cudaError_t e;
+#define EQ(call) do { e = (call); if (e != cudaSuccess) return e; } while (0)
+    if (branching && base == 0) EQ(cudaMemsetAsync(c->local_color, 0, sizeof(float) * 3 * c->n_local_px, st));
+    EQ(cudaMemsetAsync(c->d_ctr, 0, sizeof(FrameCounters), st));
     for (uint32_t L = 0; L < levels; L++) {
       uint64_t bound = (uint64_t)n_px * (branching ? (1ull << L) : 1ull);
       if (bound > c->shade_cap[L]) bound = c->shade_cap[L];
       RayRec *in = c->rays[L & 1], *outq = c->rays[(L + 1) & 1];
       cudaEvent_t e0 = c->events[2 + 3 * L], e1 = c->events[3 + 3 * L], e2 = c->events[4 + 3 * L];
-      if (serialize) CU(cudaEventRecord(e0, st));
-      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade[L], c->d_ctr, out, c->nlev, (uint32_t)bound, st);
-      CU(cudaEventRecord(e1, st));
+      if (serialize) EQ(cudaEventRecord(e0, st));
+      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade[L], c->d_ctr, gbuf, c->nlev, (uint32_t)bound, st);
+      EQ(cudaEventRecord(e1, st));
+      if (L == 0 && gsrc.depth) {   // peer frame: ship the G-buffer now, under the remaining levels
+        cudaStream_t xs = serialize ? st : c->aux[1];
+        if (!serialize) EQ(cudaStreamWaitEvent(xs, e1, 0));
+        launch_export_gbuffer(c->tm, (uint32_t)base, n_px, gsrc, out, xs);
+        EQ(cudaEventRecord(c->events[60], xs));
+        launches += 1;
+      }
       cudaStream_t ss = serialize ? st : c->aux[L & 1];
-      if (!serialize) CU(cudaStreamWaitEvent(ss, e1, 0));
+      if (!serialize) EQ(cudaStreamWaitEvent(ss, e1, 0));
       float *lc = branching ? nullptr : c->level_color + (size_t)L * 3 * c->batch_px;
       launch_shade(c->cfg, c->sv, L, c->shade[L], c->d_ctr, acc, branching, lc, (uint32_t)base, (uint32_t)bound, ss);
-      CU(cudaEventRecord(e2, ss));
-      S.kernel_launches += 2;
+      EQ(cudaEventRecord(e2, ss));
+      launches += 2;
     }
-    if (!serialize) for (uint32_t L = 0; L < levels; L++) CU(cudaStreamWaitEvent(st, c->events[4 + 3 * L], 0));
-    launch_combine(c->tm, c->nlev, c->level_color, 3ull * c->batch_px, branching ? 0u : levels, c->local_color, (uint32_t)base, n_px, out, st);
-    S.kernel_launches += 1;
-    CU(cudaGetLastError());
+    if (!serialize) for (uint32_t L = 0; L < levels; L++) EQ(cudaStreamWaitEvent(st, c->events[4 + 3 * L], 0));
+    if (!serialize && gsrc.depth) EQ(cudaStreamWaitEvent(st, c->events[60], 0));
+    launch_combine(c->tm, c->nlev, c->level_color, 3ull * c->batch_px, branching ? 0u : levels, c->local_color, (uint32_t)base, n_px, out,
+                   FrameTargets{}, st);
+    launches += 1;
+    return cudaGetLastError();
+#undef EQ
+  };
+
+  // One batch (the normal case): the frame is a CUDA graph, captured from the code above on the first call and
+  // replayed afterwards — one launch instead of ~40 API calls, which is what a 0.05 .. 2 ms frame is bound by.
+  const bool single_batch = c->batch_px >= c->n_local_px;
+  const bool use_graph = single_batch && !serialize && !c->graph_failed && !getenv("CUTRACE_NO_GRAPH");
+  if (use_graph && !c->graph) {
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      e = enqueue(0, (uint32_t)c->n_local_px);
+      cudaError_t e2 = cudaStreamEndCapture(st, &g);
+      if (e == cudaSuccess) e = e2;
+      if (e == cudaSuccess) e = cudaGraphInstantiate(&c->graph, g, 0);
+      if (g) cudaGraphDestroy(g);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); c->graph = nullptr; c->graph_failed = true; }
+    c->graph_launches = launches;   // kernels per frame, remembered for the replays
+  }
+  float max_depth = 0.f;
+  CU(cudaEventRecord(ev_begin, st));
+  for (uint64_t base = 0; base < c->n_local_px; base += c->batch_px) {
+    const uint32_t n_px = (uint32_t)std::min<uint64_t>(c->batch_px, c->n_local_px - base);
+    if (c->graph && use_graph) {
+      CU(cudaGraphLaunch(c->graph, st));
+      S.kernel_launches = c->graph_launches;
+    } else {
+      launches = 0;
+      CU(enqueue(base, n_px));
+      S.kernel_launches += launches;
+    }
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     if (base + c->batch_px >= c->n_local_px) CU(cudaEventRecord(ev_end, st));
     CU(cudaStreamSynchronize(st));
@@ -668,6 +725,7 @@ int cutrace_frame_ipc_export(cutrace_ctx *c, void *handle) {
     c->frame = blk;
     c->frame_is_ipc = true;
     c->rendered = false;
+    drop_graph(c);
   }
   cudaIpcMemHandle_t h;
   CU(cudaIpcGetMemHandle(&h, c->frame));
@@ -688,6 +746,7 @@ int cutrace_frame_ipc_import(cutrace_ctx *c, const void *handle) {
   c->peer_frame = p;
   c->peer_is_ipc = true;
   c->rendered = false;
+  drop_graph(c);
   return CUTRACE_OK;
 }
 
@@ -699,6 +758,7 @@ int cutrace_frame_attach(cutrace_ctx *c, void *frame_block) {
   c->peer_frame = frame_block;   // NULL detaches
   c->peer_is_ipc = false;
   c->rendered = false;
+  drop_graph(c);
   return CUTRACE_OK;
 }
 

@@ -373,7 +373,7 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
 // stored where the frame lives: tile-major local buffer, own row-major frame, or a peer GPU's frame over NVLink
 __global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restrict__ nlev, const float *__restrict__ level_color,
                                       uint64_t level_stride, uint32_t levels, const float *__restrict__ local_color,
-                                      uint32_t px_base, uint32_t n_px, FrameTargets out) {
+                                      uint32_t px_base, uint32_t n_px, FrameTargets out, FrameTargets gsrc) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_px) return;
   const uint32_t pix = px_base + i;
@@ -394,14 +394,48 @@ __global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restri
       r += p[0]; g += p[1]; b += p[2];
     }
   }
-  float *o = out.color + 3 * (out.row_major ? (size_t)y * tm.width + x : (size_t)pix);
+  const size_t gi = out.row_major ? (size_t)y * tm.width + x : (size_t)pix;
+  float *o = out.color + 3 * gi;
   o[0] = r; o[1] = g; o[2] = b;
+  if (gsrc.depth) {
+    // peer frame: the level-0 G-buffer was written to the local tile-major buffers (small 8x4-block stores are slow
+    // over NVLink); it travels here together with the colour, one 32-pixel tile row (128..384 contiguous bytes) per warp
+    out.depth[gi] = gsrc.depth[pix];
+    out.hit_id[gi] = gsrc.hit_id[pix];
+    out.normal[3 * gi] = gsrc.normal[3 * (size_t)pix]; out.normal[3 * gi + 1] = gsrc.normal[3 * (size_t)pix + 1];
+    out.normal[3 * gi + 2] = gsrc.normal[3 * (size_t)pix + 2];
+  }
+}
+
+// forwards the level-0 G-buffer of this rank's tiles (tile-major, local) to a row-major frame in peer memory: one
+// 32-pixel tile row per warp -> 128 / 384-byte contiguous NVLink stores.  Runs on an auxiliary stream right after
+// trace(0), i.e. the transfer overlaps the remaining bounce levels.
+__global__ void export_gbuffer_kernel(const TileMap tm, uint32_t px_base, uint32_t n_px, FrameTargets src, FrameTargets out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const uint32_t pix = px_base + i;
+  const uint32_t lt = pix >> 10, w = pix & 1023u;
+  const uint32_t gt = lt * tm.world + tm.rank;
+  const uint32_t x = (gt % tm.tiles_x) * CUTRACE_TILE + (w & 31u), y = (gt / tm.tiles_x) * CUTRACE_TILE + (w >> 5);
+  if (x >= tm.width || y >= tm.height) return;
+  const size_t gi = (size_t)y * tm.width + x;
+  out.depth[gi] = src.depth[pix];
+  out.hit_id[gi] = src.hit_id[pix];
+  out.normal[3 * gi] = src.normal[3 * (size_t)pix]; out.normal[3 * gi + 1] = src.normal[3 * (size_t)pix + 1];
+  out.normal[3 * gi + 2] = src.normal[3 * (size_t)pix + 2];
+}
+
+void launch_export_gbuffer(const TileMap &tm, uint32_t px_base, uint32_t n_px, const FrameTargets &src, const FrameTargets &out,
+                           cudaStream_t st) {
+  if (!n_px) return;
+  export_gbuffer_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(tm, px_base, n_px, src, out);
 }
 
 void launch_combine(const TileMap &tm, const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels,
-                    const float *local_color, uint32_t px_base, uint32_t n_px, const FrameTargets &out, cudaStream_t st) {
+                    const float *local_color, uint32_t px_base, uint32_t n_px, const FrameTargets &out, const FrameTargets &gsrc,
+                    cudaStream_t st) {
   if (!n_px) return;
-  combine_levels_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(tm, nlev, level_color, level_stride, levels, local_color, px_base, n_px, out);
+  combine_levels_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(tm, nlev, level_color, level_stride, levels, local_color, px_base, n_px, out, gsrc);
 }
 
 typedef void (*trace_fn)(const SceneView, const TileMap, uint32_t, uint32_t, uint32_t, uint32_t, const RayRec *, RayRec *, ShadeRec *,

@@ -48,9 +48,14 @@ void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, con
                   const FrameTargets &fb, bool atomic_accumulate, float *level_color, uint32_t px_base, uint32_t work_bound,
                   cudaStream_t st);
 // colour[px] = sum over levels l < nlev[px] of level_color[l][px - px_base], in level order; levels == 0: copy the
-// locally accumulated colour (branching scenes) instead.  Writes into `out` in its layout.
+// locally accumulated colour (branching scenes) instead.  Writes into `out` in its layout; gsrc.depth != NULL: also
+// forwards the tile-major G-buffer gsrc to `out` (peer frame).
 void launch_combine(const TileMap &tm, const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels,
-                    const float *local_color, uint32_t px_base, uint32_t n_px, const FrameTargets &out, cudaStream_t st);
+                    const float *local_color, uint32_t px_base, uint32_t n_px, const FrameTargets &out, const FrameTargets &gsrc,
+                    cudaStream_t st);
+
+void launch_export_gbuffer(const TileMap &tm, uint32_t px_base, uint32_t n_px, const FrameTargets &src, const FrameTargets &out,
+                           cudaStream_t st);
 
 // output.cu
 void launch_untile(const TileMap &tm, uint32_t world, const float *g_depth, const float *g_normal, const float *g_color,
