@@ -255,6 +255,7 @@ def main():
     dev_ms, trace_ms, shade_ms = [], [], []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
+        barrier()   # rank 0 spent 0.25 s starting the sampler: line the ranks up again before the timed region
         ev0.record(stream)
         for _ in range(args.steps):
             st = step()
