@@ -461,6 +461,8 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   sv.all_opaque = all_opaque ? 1u : 0u;
   sv.brute_force = (o.flags & CUTRACE_FLAG_BRUTE_FORCE) ? 1u : 0u;
   sv.fudge = o.fudge;
+  sv.scene_mag = 0.f;
+  for (int a = 0; a < 3; a++) sv.scene_mag = fmaxf(sv.scene_mag, fmaxf(fabsf(c->bvh.lo[a]), fabsf(c->bvh.hi[a])));
   set_cam(c, s->cam_pos, s->cam_up, s->cam_forward, s->cam_right, s->ambient);
 
   CUF(dmalloc(&c->d_ctr, sizeof(FrameCounters), c->stream));

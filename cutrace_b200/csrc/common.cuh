@@ -128,6 +128,7 @@ struct SceneView {
   uint32_t all_opaque;      // no material has transparency >= 1e-6 (shadow rays can be any-hit)
   uint32_t brute_force;
   float fudge;
+  float scene_mag;          // largest |coordinate| of the BVH primitives (box inflation is 2e-6 * scene_mag)
   Camera cam;
 };
 

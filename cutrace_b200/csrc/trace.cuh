@@ -87,18 +87,36 @@ __device__ __forceinline__ bool plane_test(vec3 point, vec3 n, vec3 o, vec3 dir,
   return isfinite(t0) && min_t <= t0 && t0 > min_t;
 }
 
+// Slab test data of a ray.  Box distances are evaluated as fma(plane, inv, -o*inv): one FFMA per plane.  Its absolute
+// error is <= 2^-24 (|o*inv| + |t|).  The |t| part is covered by the 4-ulp relative slack on t_far.  The |o*inv| part
+// equals moving the box plane by |o| * 2^-24 in SPACE, whatever inv is — and the boxes are inflated by 2e-6 * (largest
+// scene coordinate) at build time, which covers it for every ray that starts within 8x the scene's coordinate range
+// (all secondary and shadow rays, any sane camera).  Only rays from further away get the explicit t-space bound
+// `eabs` (which would otherwise let rays with a tiny direction component through every box).  Culling thus stays
+// conservative: a box is never skipped when the reference's Cramer test could accept one of its triangles.  `inv`
+// may be 1 ulp off (MUFU.RCP): that only perturbs the direction used for CULLING; primitive tests use exact o and d.
 struct RayCtx {
   vec3 o, d;
-  vec3 inv;   // 1 / d with zeros replaced
+  vec3 inv;   // ~1 / d, zeros replaced by +-1e-30
+  vec3 oi;    // o * inv
+  float eabs;
 };
 
 __device__ __forceinline__ float safe_rcp(float x) {
-  return 1.0f / (fabsf(x) < 1e-30f ? copysignf(1e-30f, x) : x);
+  return __fdividef(1.0f, fabsf(x) < 1e-30f ? copysignf(1e-30f, x) : x);
 }
 
-__device__ __forceinline__ void make_ray(RayCtx &r, vec3 o, vec3 d) {
+__device__ __forceinline__ void make_ray(RayCtx &r, vec3 o, vec3 d, float scene_mag) {
   r.o = o; r.d = d;
   r.inv = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+  r.oi = mk3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
+  r.eabs = 0.f;
+  if (fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) > 8.0f * scene_mag) {   // far-away origin (distant camera)
+    // an axis the ray does not move along (|d| < 1e-20) only decides by the SIGN of its huge slab distances
+    const float ex = fabsf(d.x) < 1e-20f ? 0.f : fabsf(r.oi.x), ey = fabsf(d.y) < 1e-20f ? 0.f : fabsf(r.oi.y),
+                ez = fabsf(d.z) < 1e-20f ? 0.f : fabsf(r.oi.z);
+    r.eabs = 2.4e-7f * fmaxf(fmaxf(ex, ey), ez);
+  }
 }
 
 // MODE 0: nodes / primitives in global memory (LDG.128 through L1), MODE 1: staged in shared memory (LDS.128)
@@ -151,17 +169,17 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
       const float4 mf = ld16<MODE>(np + 3);
       const int c0 = __float_as_int(mf.x), c1 = __float_as_int(mf.y);
       const float limit = ANY ? fminf(max_t, h.t) : h.t;
-      // slabs: (plane - origin) * inv, subtraction first so the error stays relative
-      const float c0lox = (n0.x - r.o.x) * r.inv.x, c0hix = (n0.y - r.o.x) * r.inv.x;
-      const float c0loy = (n0.z - r.o.y) * r.inv.y, c0hiy = (n0.w - r.o.y) * r.inv.y;
-      const float c0loz = (nz.x - r.o.z) * r.inv.z, c0hiz = (nz.y - r.o.z) * r.inv.z;
-      const float c1lox = (n1.x - r.o.x) * r.inv.x, c1hix = (n1.y - r.o.x) * r.inv.x;
-      const float c1loy = (n1.z - r.o.y) * r.inv.y, c1hiy = (n1.w - r.o.y) * r.inv.y;
-      const float c1loz = (nz.z - r.o.z) * r.inv.z, c1hiz = (nz.w - r.o.z) * r.inv.z;
+      // slabs: one FFMA per box plane (error budget: see RayCtx)
+      const float c0lox = fmaf(n0.x, r.inv.x, -r.oi.x), c0hix = fmaf(n0.y, r.inv.x, -r.oi.x);
+      const float c0loy = fmaf(n0.z, r.inv.y, -r.oi.y), c0hiy = fmaf(n0.w, r.inv.y, -r.oi.y);
+      const float c0loz = fmaf(nz.x, r.inv.z, -r.oi.z), c0hiz = fmaf(nz.y, r.inv.z, -r.oi.z);
+      const float c1lox = fmaf(n1.x, r.inv.x, -r.oi.x), c1hix = fmaf(n1.y, r.inv.x, -r.oi.x);
+      const float c1loy = fmaf(n1.z, r.inv.y, -r.oi.y), c1hiy = fmaf(n1.w, r.inv.y, -r.oi.y);
+      const float c1loz = fmaf(nz.z, r.inv.z, -r.oi.z), c1hiz = fmaf(nz.w, r.inv.z, -r.oi.z);
       const float tn0 = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), min_t));
-      const float tf0 = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), limit)) * slack;
+      const float tf0 = fmaf(fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), limit)), slack, r.eabs);
       const float tn1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), min_t));
-      const float tf1 = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), limit)) * slack;
+      const float tf1 = fmaf(fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), limit)), slack, r.eabs);
       const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
       if (h0 && h1) {
         const bool swap = tn1 < tn0;
@@ -205,7 +223,7 @@ template <int MODE, bool BRUTE>
 __device__ __forceinline__ void closest_hit(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 o, vec3 d,
                                             float min_t, Hit &h) {
   RayCtx r;
-  make_ray(r, o, d);
+  make_ray(r, o, d, sv.scene_mag);
   hit_reset(h);
   test_planes(sv, r, min_t, h);
   traverse<MODE, false, BRUTE>(sv, nodes, prims, r, min_t, INFINITY, h);
@@ -217,7 +235,7 @@ template <int MODE, bool BRUTE>
 __device__ __forceinline__ bool any_hit(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 o, vec3 d,
                                         float min_t, float max_t) {
   RayCtx r;
-  make_ray(r, o, d);
+  make_ray(r, o, d, sv.scene_mag);
 #pragma unroll 1
   for (uint32_t p = 0; p < sv.n_planes; p++) {
     const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + p);
@@ -270,7 +288,7 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
 #pragma unroll
       for (int k = 0; k < K; k++) {
         if (act & (1u << k)) {
-          RayCtx r; r.o = o; r.d = d[k]; r.inv = d[k];
+          RayCtx r; make_ray(r, o, d[k], sv.scene_mag);
           Hit h; hit_reset(h);
           test_prim<MODE>(prims, i, r, min_t, h);
           if (h.t < max_t[k]) { occ |= 1u << k; act &= ~(1u << k); }
@@ -280,9 +298,9 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
     return occ;
   }
 
-  vec3 inv[K];
+  RayCtx rc[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) inv[k] = mk3(safe_rcp(d[k].x), safe_rcp(d[k].y), safe_rcp(d[k].z));
+  for (int k = 0; k < K; k++) make_ray(rc[k], o, d[k], sv.scene_mag);
   int stack[CTB_STACK];
   stack[0] = CTB_SENTINEL;
   int sp = 1;
@@ -295,19 +313,20 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
       const float4 n0 = ld16<MODE>(np), n1 = ld16<MODE>(np + 1), nz = ld16<MODE>(np + 2);
       const float4 mf = ld16<MODE>(np + 3);
       const int c0 = __float_as_int(mf.x), c1 = __float_as_int(mf.y);
-      const float a0x = n0.x - o.x, b0x = n0.y - o.x, a0y = n0.z - o.y, b0y = n0.w - o.y, a0z = nz.x - o.z, b0z = nz.y - o.z;
-      const float a1x = n1.x - o.x, b1x = n1.y - o.x, a1y = n1.z - o.y, b1y = n1.w - o.y, a1z = nz.z - o.z, b1z = nz.w - o.z;
       bool h0 = false, h1 = false;
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        const float lox = a0x * inv[k].x, hix = b0x * inv[k].x, loy = a0y * inv[k].y, hiy = b0y * inv[k].y;
-        const float loz = a0z * inv[k].z, hiz = b0z * inv[k].z;
+        const RayCtx &r = rc[k];
+        const float lox = fmaf(n0.x, r.inv.x, -r.oi.x), hix = fmaf(n0.y, r.inv.x, -r.oi.x);
+        const float loy = fmaf(n0.z, r.inv.y, -r.oi.y), hiy = fmaf(n0.w, r.inv.y, -r.oi.y);
+        const float loz = fmaf(nz.x, r.inv.z, -r.oi.z), hiz = fmaf(nz.y, r.inv.z, -r.oi.z);
         const float tn = fmaxf(fmaxf(fminf(lox, hix), fminf(loy, hiy)), fmaxf(fminf(loz, hiz), min_t));
-        const float tf = fminf(fminf(fmaxf(lox, hix), fmaxf(loy, hiy)), fminf(fmaxf(loz, hiz), max_t[k])) * slack;
-        const float lox1 = a1x * inv[k].x, hix1 = b1x * inv[k].x, loy1 = a1y * inv[k].y, hiy1 = b1y * inv[k].y;
-        const float loz1 = a1z * inv[k].z, hiz1 = b1z * inv[k].z;
+        const float tf = fmaf(fminf(fminf(fmaxf(lox, hix), fmaxf(loy, hiy)), fminf(fmaxf(loz, hiz), max_t[k])), slack, r.eabs);
+        const float lox1 = fmaf(n1.x, r.inv.x, -r.oi.x), hix1 = fmaf(n1.y, r.inv.x, -r.oi.x);
+        const float loy1 = fmaf(n1.z, r.inv.y, -r.oi.y), hiy1 = fmaf(n1.w, r.inv.y, -r.oi.y);
+        const float loz1 = fmaf(nz.z, r.inv.z, -r.oi.z), hiz1 = fmaf(nz.w, r.inv.z, -r.oi.z);
         const float tn1 = fmaxf(fmaxf(fminf(lox1, hix1), fminf(loy1, hiy1)), fmaxf(fminf(loz1, hiz1), min_t));
-        const float tf1 = fminf(fminf(fmaxf(lox1, hix1), fmaxf(loy1, hiy1)), fminf(fmaxf(loz1, hiz1), max_t[k])) * slack;
+        const float tf1 = fmaf(fminf(fminf(fmaxf(lox1, hix1), fmaxf(loy1, hiy1)), fminf(fmaxf(loz1, hiz1), max_t[k])), slack, r.eabs);
         const bool on = (act >> k) & 1u;
         h0 = h0 || (on && tn <= tf);
         h1 = h1 || (on && tn1 <= tf1);
