@@ -301,17 +301,16 @@ def main():
         for k, (m, dt) in {"depth": (1, np.float32), "normal": (3, np.float32), "color": (3, np.float32)}.items():
             p = lib.cutrace_host_alloc(n_px * m * 4)
             pinned[k] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n_px * m,))
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(5, min(args.steps, 20))
     e2e_ms = []
     for i in range(2 + e2e_steps):
         barrier()
         t0 = time.perf_counter()
         if world == 1:
             r = ct.Renderer(scene, device=local_rank, flags=args.flags, stream=stream.cuda_stream)
-            r.render()
             md = C.c_float()
-            ct._lib.check(lib.cutrace_download(r._ctx, pinned["depth"].ctypes.data, pinned["normal"].ctypes.data,
-                                               pinned["color"].ctypes.data, None, C.byref(md)))
+            ct._lib.check(lib.cutrace_render_download(r._ctx, pinned["depth"].ctypes.data, pinned["normal"].ctypes.data,
+                                                      pinned["color"].ctypes.data, None, C.byref(md), None))
             r.close()
         else:
             tr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream,
@@ -327,10 +326,14 @@ def main():
         barrier()
         if i >= 2:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
-    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
+    if args.verbose:
+        print(f"[rank {rank}] e2e frames (ms): " + " ".join(f"{x:.2f}" for x in e2e_ms), file=sys.stderr, flush=True)
+    # per-frame wall time of the whole call sequence; the MEDIAN is reported (one frame in ~10 shows a 30-100 ms host
+    # hiccup in cudaFree/stream teardown on these boxes), mean and max are kept next to it
+    e2e_t = torch.tensor([float(np.median(e2e_ms)), float(np.mean(e2e_ms)), float(np.max(e2e_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e = float(e2e_t[0])
+    e2e, e2e_mean, e2e_max = (float(x) for x in e2e_t)
     from cutrace_b200.scene import _ARRAY_FIELDS
 
     scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in _ARRAY_FIELDS if k != "obj_kind") + 64
@@ -358,9 +361,10 @@ def main():
                        "timed": "K frames between two CUDA events on the launching stream" + ("" if world == 1 else (", incl. the rank barrier (tiles are stored into rank 0's frame over NVLink by the kernels)" if exchange == "peer" else ", incl. NCCL gather + un-tile")),
                        "render_device_ms": render_dev_ms},
             "clocks": clk.summary(),
-            "e2e": {"value": rays / e2e / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e, "h2d_bytes_per_step": int(scene_bytes),
+            "e2e": {"value": rays / e2e / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e, "ms_per_frame_mean": e2e_mean, "ms_per_frame_max": e2e_max,
+                    "frames": len(e2e_ms), "statistic": "median", "h2d_bytes_per_step": int(scene_bytes),
                     "d2h_bytes_per_step": int(28 * n_px),
-                    "what": "cutrace_upload_scene (H2D + LBVH build) + cutrace_render + cutrace_download into pinned host buffers"},
+                    "what": "cutrace_upload_scene (H2D + LBVH build) + cutrace_render_download (render; depth/normal D2H under the bounce levels, colour D2H at the end) into pinned host buffers + cutrace_free, every frame"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": dominant, "bytes_per_ray": bpr,

@@ -90,6 +90,20 @@ class Renderer:
         out["max_depth"] = md.value
         return out
 
+    def render_download(self, into=None):
+        """cutrace_render_download: render and fill host images in one call (G-buffer copies overlap the bounce levels)."""
+        n = self.width * self.height
+        out = into or {}
+        shapes = {"depth": ((n,), np.float32), "normal": ((n, 3), np.float32), "color": ((n, 3), np.float32), "hit_id": ((n,), np.uint32)}
+        for k, (shape, dt) in shapes.items():
+            if k not in out:
+                out[k] = np.empty(shape, dt)
+        md, st = C.c_float(), cutrace_stats()
+        _lib.check(self._lib.cutrace_render_download(self._ctx, out["depth"].ctypes.data, out["normal"].ctypes.data, out["color"].ctypes.data,
+                                                     out["hit_id"].ctypes.data, C.byref(md), C.byref(st)))
+        out["max_depth"] = md.value
+        return out, st.as_dict()
+
     def download_bytes(self):
         """The three 8-bit RGB images of the output stage (inc/images.hpp:26-88), encoded on the device."""
         n = self.width * self.height

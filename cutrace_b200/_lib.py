@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("CUTRACE_B200_LIB") or os.path.join(HERE, "lib", "libc
 
 # every symbol include/cutrace.h declares
 SYMBOLS = (
-    "cutrace_default_opts", "cutrace_upload_scene", "cutrace_render", "cutrace_download", "cutrace_download_bytes", "cutrace_free",
+    "cutrace_default_opts", "cutrace_upload_scene", "cutrace_render", "cutrace_download", "cutrace_render_download", "cutrace_download_bytes", "cutrace_free",
     "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_device_buffers", "cutrace_frame_device",
     "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free",
@@ -71,6 +71,7 @@ def load():
     lib.cutrace_upload_scene.argtypes = [P, C.POINTER(cutrace_opts), C.POINTER(P)]
     lib.cutrace_render.argtypes = [P, C.POINTER(cutrace_stats)]
     lib.cutrace_download.argtypes = [P, P, P, P, P, C.POINTER(C.c_float)]
+    lib.cutrace_render_download.argtypes = [P, P, P, P, P, C.POINTER(C.c_float), C.POINTER(cutrace_stats)]
     lib.cutrace_download_bytes.argtypes = [P, P, P, P, C.POINTER(C.c_float)]
     lib.cutrace_free.argtypes = [P]
     lib.cutrace_free.restype = None

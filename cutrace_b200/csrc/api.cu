@@ -106,6 +106,9 @@ struct cutrace_ctx {
   float *level_color = nullptr;      // levels x batch_px x 3: per-level partial images (non-branching scenes)
   uint32_t *nlev = nullptr;          // n_local_px: number of levels that contributed to a pixel
   cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;   // D2H of the G-buffer underneath the bounce levels (cutrace_render_download)
+  cudaEvent_t ev_gbuf = nullptr;        // "primary rays done": recorded inside the frame (external event when captured)
+  bool want_gbuf_event = false;
   uint64_t batch_px = 0, cap = 0;
   uint32_t factor = 1;
   FrameCounters *d_ctr = nullptr;
@@ -121,6 +124,9 @@ struct cutrace_ctx {
   bool graph_failed = false;
   cutrace_stats stats{};
   bool rendered = false;
+  // host destinations of an in-flight cutrace_render_download (NULL otherwise)
+  float *dl_depth = nullptr, *dl_normal = nullptr;
+  uint32_t *dl_id = nullptr;
   std::vector<cudaEvent_t> events;
 };
 
@@ -330,6 +336,8 @@ void cutrace_free(cutrace_ctx *c) {
   pinned_counters_put(c->h_ctr);
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   for (int i = 0; i < 2; i++) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_gbuf) cudaEventDestroy(c->ev_gbuf);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -374,6 +382,8 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
     else { CUF(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr_greatest)); c->own_stream = true; }
     // shade kernels run on two lower-priority streams so that the trace chain (the critical path) gets SMs first
     for (int i = 0; i < 2; i++) CUF(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, pr_least));
+    CUF(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUF(cudaEventCreateWithFlags(&c->ev_gbuf, cudaEventDisableTiming));
   }
   LAP("validate + streams");
   for (int i = 0; i < 72; i++) { cudaEvent_t ev; CUF(cudaEventCreate(&ev)); c->events.push_back(ev); }
@@ -540,6 +550,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   //   trace(L) -> trace(L+1) (ray queue)   and   trace(L) -> shade(L) (shade queue L)
   // The trace chain runs on the ctx stream; shade(L) runs on one of two auxiliary streams behind an event, so the
   // persistent CTAs of later kernels fill the SMs that the tail of an earlier kernel leaves idle.
+  bool capturing = false;
   auto enqueue = [&](uint64_t base, uint32_t n_px) -> cudaError_t {
     cudaError_t e;
 #define EQ(call) do { e = (call); if (e != cudaSuccess) return e; } while (0)
@@ -553,6 +564,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       if (serialize) EQ(cudaEventRecord(e0, st));
       launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade[L], c->d_ctr, gbuf, c->nlev, (uint32_t)bound, st);
       EQ(cudaEventRecord(e1, st));
+      if (L == 0) EQ(cudaEventRecordWithFlags(c->ev_gbuf, st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
       if (L == 0 && gsrc.depth) {   // peer frame: ship the G-buffer now, under the remaining levels
         cudaStream_t xs = serialize ? st : c->aux[1];
         if (!serialize) EQ(cudaStreamWaitEvent(xs, e1, 0));
@@ -584,7 +596,9 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
+      capturing = true;
       e = enqueue(0, (uint32_t)c->n_local_px);
+      capturing = false;
       cudaError_t e2 = cudaStreamEndCapture(st, &g);
       if (e == cudaSuccess) e = e2;
       if (e == cudaSuccess) e = cudaGraphInstantiate(&c->graph, g, 0);
@@ -604,6 +618,16 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       launches = 0;
       CU(enqueue(base, n_px));
       S.kernel_launches += launches;
+    }
+    if (single_batch && c->frame && !c->peer_frame && (c->dl_depth || c->dl_normal || c->dl_id)) {
+      // G-buffer -> host underneath the remaining bounce levels (copy engine; the frame is already row-major)
+      const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
+      const FrameTargets v = frame_views(c->frame, n);
+      CU(cudaStreamWaitEvent(c->copy_stream, c->ev_gbuf, 0));
+      if (c->dl_depth) CU(cudaMemcpyAsync(c->dl_depth, v.depth, sizeof(float) * n, cudaMemcpyDeviceToHost, c->copy_stream));
+      if (c->dl_id) CU(cudaMemcpyAsync(c->dl_id, v.hit_id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->copy_stream));
+      if (c->dl_normal) CU(cudaMemcpyAsync(c->dl_normal, v.normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->copy_stream));
+      c->dl_depth = c->dl_normal = nullptr; c->dl_id = nullptr;   // consumed
     }
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     if (base + c->batch_px >= c->n_local_px) CU(cudaEventRecord(ev_end, st));
@@ -630,6 +654,25 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   S.max_depth = max_depth;
   c->rendered = true;
   if (stats) *stats = S;
+  return CUTRACE_OK;
+}
+
+int cutrace_render_download(cutrace_ctx *c, float *depth, float *normal, float *color, uint32_t *hit_id, float *max_depth,
+                            cutrace_stats *stats) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  const bool fused = c->frame && !c->peer_frame && c->batch_px >= c->n_local_px;
+  if (fused) { c->dl_depth = depth; c->dl_normal = normal; c->dl_id = hit_id; }
+  int rc = cutrace_render(c, stats);
+  const bool early = fused && !c->dl_depth && !c->dl_normal && !c->dl_id;   // render consumed the request
+  c->dl_depth = c->dl_normal = nullptr; c->dl_id = nullptr;
+  if (rc) return rc;
+  if (!early) return cutrace_download(c, depth, normal, color, hit_id, max_depth);
+  DeviceGuard g(c->device);
+  const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
+  if (color) CU(cudaMemcpyAsync(color, frame_views(c->frame, n).color, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->copy_stream));
+  if (max_depth) *max_depth = c->stats.max_depth;
   return CUTRACE_OK;
 }
 

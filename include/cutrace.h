@@ -183,6 +183,14 @@ int cutrace_render(cutrace_ctx *ctx, cutrace_stats *stats);
 int cutrace_download(cutrace_ctx *ctx, float *depth, float *normal, float *color, uint32_t *hit_id,
                      float *max_depth);
 
+/* cutrace_render + cutrace_download in one call — the shape of the reference operator, which renders AND fills the
+ * host images (inc/kernel.hpp:86-126).  The depth / normal / id images are final after the primary rays, so their
+ * device->host copies run on a copy stream underneath the remaining bounce levels; only the colour copy is left for
+ * the end.  Same arguments as cutrace_download (+ stats); host buffers should be pinned (cutrace_host_alloc) for the
+ * copies to overlap.  Falls back to render-then-download for sharded ctxs. */
+int cutrace_render_download(cutrace_ctx *ctx, float *depth, float *normal, float *color, uint32_t *hit_id,
+                            float *max_depth, cutrace_stats *stats);
+
 /* Output stage fused on the device (inc/images.hpp:26-88 + main.cu:34-36): the three 8-bit RGB images
  * the reference hands to stbi_write_jpg — depth (nearest = brightest, relative to max_depth), normal
  * (0.5 + 0.5 n), colour (clamped) — 9 bytes per pixel over PCIe instead of 28.  Each buffer is

@@ -398,3 +398,29 @@ def test_overlapped_and_serialized_frames_are_bit_identical(ct):
         else:                    # material 1 reflects AND transmits: float atomics, order-dependent last bits
             assert np.abs(a["color"] - b["color"]).max() < 1e-5
         assert sa["rays_total"] == sb["rays_total"] and sb["trace_ms"] > 0 and sb["shade_ms"] > 0
+
+
+def test_render_download_fused_equals_render_then_download(ct):
+    """cutrace_render_download (G-buffer copies under the bounce levels, colour at the end) must return exactly what
+    cutrace_render + cutrace_download return — also right after a camera change, when the frame still holds the
+    previous view until the primary rays have been traced (a copy that started too early would return the old view)."""
+    s = load_golden_scene("bunny").with_resolution(1280, 720)
+    eye2 = np.array([0.2, 0.5, 2.2], np.float32)
+    f2, r2, u2 = ct.look_at(eye2, [0, 1, 0], [0, 0, 0])
+    with ct.Renderer(s) as r:
+        a, sta = r.render_download()
+        r.render()
+        b = r.download()
+        for k in ("depth", "normal", "color", "hit_id"):
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+        assert a["max_depth"] == b["max_depth"] and sta["rays_total"] > 0
+        for _ in range(3):    # replayed graph
+            c, _ = r.render_download()
+            assert np.array_equal(c["color"].view(np.uint32), b["color"].view(np.uint32))
+        r.set_camera(eye2, u2, f2, r2, s.ambient, s.width, s.height)
+        d, _ = r.render_download()
+        r.render()
+        e = r.download()
+        for k in ("depth", "normal", "color", "hit_id"):
+            assert np.array_equal(d[k].view(np.uint32), e[k].view(np.uint32)), k
+        assert not np.array_equal(d["depth"], b["depth"])
