@@ -350,6 +350,13 @@ def main():
         dom_ms = max(shade, trace)
         dom_rays = rays_shadow if shade >= trace else (rays - rays_shadow)
         achieved = dom_rays * bpr / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(wl["label"], {})
+            key = "shade_kernel" if shade >= trace else "trace_kernel"
+            traffic = tr[key]["mean_traffic_bytes"] if world == 1 and key in tr else None
+        except Exception:  # noqa: BLE001
+            pass
         line = {
             "metric": "Mrays/s (primary+secondary)", "value": rays / ms_step / 1e3, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -367,7 +374,9 @@ def main():
                     "what": "cutrace_upload_scene (H2D + LBVH build) + cutrace_render_download (render; depth/normal D2H under the bounce levels, colour D2H at the end) into pinned host buffers + cutrace_free, every frame"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": dominant, "bytes_per_ray": bpr,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "algorithmic_bytes_per_launch": dom_rays * bpr / max(1, int(st["kernel_launches"]) // 2),
+                         "kernel": dominant, "bytes_per_ray": bpr,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "algorithmic bytes/ray (SURVEY §8d) x rays of the dominant kernel / its CUDA-event time; the scene is cache-resident, "
                                  "so issue-slot utilisation and divergence (profiles/) explain the kernel, not DRAM"},
