@@ -105,7 +105,7 @@ struct cutrace_ctx {
   uint64_t shade_cap[16] = {};
   float *level_color = nullptr;      // levels x batch_px x 3: per-level partial images (non-branching scenes)
   uint32_t *nlev = nullptr;          // n_local_px: number of levels that contributed to a pixel
-  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // [0],[1]: shade kernels; [2]: G-buffer export to a peer frame
   cudaStream_t copy_stream = nullptr;   // D2H of the G-buffer underneath the bounce levels (cutrace_render_download)
   cudaEvent_t ev_gbuf = nullptr;        // "primary rays done": recorded inside the frame (external event when captured)
   bool want_gbuf_event = false;
@@ -147,6 +147,21 @@ void drop_graph(cutrace_ctx *c) {
   c->graph_failed = false;
 }
 
+// multiplier of the tile permutation (see TileMap): ~0.618 n, odd, coprime to n; and its inverse mod n
+void tile_permutation(uint32_t n, uint32_t world, uint32_t *a_out, uint32_t *ainv_out) {
+  *a_out = 1; *ainv_out = 1;
+  if (world <= 1 || n < 3) return;
+  auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
+  uint64_t a = ((uint64_t)n * 618ull / 1000ull) | 1ull;
+  while (a < n && gcd(a, n) != 1) a += 2;
+  if (a >= n) return;
+  // inverse by extended Euclid
+  long long t = 0, nt = 1, r = n, nr = (long long)a;
+  while (nr) { long long q = r / nr, tmp = t - q * nt; t = nt; nt = tmp; tmp = r - q * nr; r = nr; nr = tmp; }
+  if (t < 0) t += n;
+  *a_out = (uint32_t)a; *ainv_out = (uint32_t)t;
+}
+
 void free_frame(cutrace_ctx *c) {
   drop_graph(c);
   cudaStream_t st = c->stream;
@@ -181,6 +196,8 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   uint32_t total_tiles = tm.tiles_x * tm.tiles_y;
   // every rank gets the same padded tile count so that gathered rank buffers have one stride
   tm.n_local_tiles = (total_tiles + tm.world - 1) / tm.world;
+  tm.n_tiles = total_tiles;
+  tile_permutation(total_tiles, tm.world, &tm.perm_a, &tm.perm_ainv);
   c->tm = tm;
   c->n_local_px = (uint64_t)tm.n_local_tiles * 1024ull;
   c->sv.cam.w = width; c->sv.cam.h = height;
@@ -335,7 +352,7 @@ void cutrace_free(cutrace_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   pinned_counters_put(c->h_ctr);
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
-  for (int i = 0; i < 2; i++) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
+  for (int i = 0; i < 3; i++) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_gbuf) cudaEventDestroy(c->ev_gbuf);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -381,7 +398,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
     if (o.stream) c->stream = (cudaStream_t)o.stream;
     else { CUF(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr_greatest)); c->own_stream = true; }
     // shade kernels run on two lower-priority streams so that the trace chain (the critical path) gets SMs first
-    for (int i = 0; i < 2; i++) CUF(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, pr_least));
+    for (int i = 0; i < 3; i++) CUF(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, pr_least));
     CUF(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUF(cudaEventCreateWithFlags(&c->ev_gbuf, cudaEventDisableTiming));
   }
@@ -526,9 +543,8 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     const TileMap &tm = c->tm;
     uint64_t px = 0;
     for (uint32_t lt = 0; lt < tm.n_local_tiles; lt++) {
-      uint32_t gt = lt * tm.world + tm.rank;
-      if (gt >= tm.tiles_x * tm.tiles_y) continue;
-      uint32_t tx = gt % tm.tiles_x, ty = gt / tm.tiles_x;
+      uint32_t tx, ty;
+      if (!tile_of_slot(tm, lt * tm.world + tm.rank, tx, ty)) continue;
       uint32_t w = std::min(CUTRACE_TILE, tm.width - tx * CUTRACE_TILE), h = std::min(CUTRACE_TILE, tm.height - ty * CUTRACE_TILE);
       px += (uint64_t)w * h;
     }
@@ -566,7 +582,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       EQ(cudaEventRecord(e1, st));
       if (L == 0) EQ(cudaEventRecordWithFlags(c->ev_gbuf, st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
       if (L == 0 && gsrc.depth) {   // peer frame: ship the G-buffer now, under the remaining levels
-        cudaStream_t xs = serialize ? st : c->aux[1];
+        cudaStream_t xs = serialize ? st : c->aux[2];
         if (!serialize) EQ(cudaStreamWaitEvent(xs, e1, 0));
         launch_export_gbuffer(c->tm, (uint32_t)base, n_px, gsrc, out, xs);
         EQ(cudaEventRecord(c->events[60], xs));

@@ -132,16 +132,38 @@ struct SceneView {
   Camera cam;
 };
 
-// screen-space tiling of the local framebuffer (tile-major, row-major inside a tile)
+// Screen-space tiling.  The frame is cut into 32x32 tiles; tile "slots" 0..n_tiles-1 are dealt round-robin to the
+// ranks (slot s belongs to rank s % world, local tile s / world) and slot s shows screen tile (s * perm_a) % n_tiles.
+// The multiplicative permutation (perm_a coprime to n_tiles, ~0.618 n) scatters every rank's tiles over the whole
+// image: with plain interleaving a rank owned vertical stripes and the 8-way shards of bunny.json differed by 20 % in
+// cost (profiles/r01_tuning.md).  One rank: perm_a = 1 (natural order).
 struct TileMap {
   uint32_t width, height;
   uint32_t tiles_x, tiles_y;
-  uint32_t rank, world;       // this ctx owns global tiles t with t % world == rank
-  uint32_t n_local_tiles;
+  uint32_t rank, world;       // this ctx owns slots s with s % world == rank
+  uint32_t n_local_tiles;     // ceil(n_tiles / world): the same padded count on every rank
+  uint32_t n_tiles, perm_a, perm_ainv;
 };
 
-__host__ __device__ __forceinline__ uint32_t tile_global_index(const TileMap &tm, uint32_t local_tile) {
-  return local_tile * tm.world + tm.rank;
+// slot -> screen tile coordinates; false for the padding slots of the last local tile
+__host__ __device__ __forceinline__ bool tile_of_slot(const TileMap &tm, uint32_t slot, uint32_t &tx, uint32_t &ty) {
+  if (slot >= tm.n_tiles) return false;
+  const uint32_t t = (uint32_t)(((unsigned long long)slot * tm.perm_a) % tm.n_tiles);
+  tx = t % tm.tiles_x;
+  ty = t / tm.tiles_x;
+  return true;
+}
+// screen tile index (ty * tiles_x + tx) -> slot
+__host__ __device__ __forceinline__ uint32_t slot_of_tile(const TileMap &tm, uint32_t t) {
+  return (uint32_t)(((unsigned long long)t * tm.perm_ainv) % tm.n_tiles);
+}
+// local pixel index (tile-major, row-major inside the tile) -> pixel; false outside the image
+__host__ __device__ __forceinline__ bool pixel_of_local(const TileMap &tm, uint32_t pix, uint32_t &x, uint32_t &y) {
+  uint32_t tx, ty;
+  if (!tile_of_slot(tm, (pix >> 10) * tm.world + tm.rank, tx, ty)) return false;
+  x = tx * CUTRACE_TILE + (pix & 31u);
+  y = ty * CUTRACE_TILE + ((pix & 1023u) >> 5);
+  return x < tm.width && y < tm.height;
 }
 
 }  // namespace ctb

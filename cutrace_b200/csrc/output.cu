@@ -11,8 +11,8 @@ __global__ void untile_kernel(TileMap tm, uint32_t world, const float *__restric
                               uint32_t *__restrict__ hit_id) {
   uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= tm.width || y >= tm.height) return;
-  uint32_t gt = (y / CUTRACE_TILE) * tm.tiles_x + x / CUTRACE_TILE;
-  uint32_t rank = gt % world, lt = gt / world;
+  const uint32_t slot = slot_of_tile(tm, (y / CUTRACE_TILE) * tm.tiles_x + x / CUTRACE_TILE);
+  uint32_t rank = slot % world, lt = slot / world;
   if (only_rank >= 0) {   // a single rank's buffer: foreign tiles keep whatever the destination holds
     if ((int)rank != only_rank) return;
     rank = 0;

@@ -78,12 +78,12 @@ __device__ __forceinline__ bool work_to_pixel(const TileMap &tm, uint32_t i, uin
   uint32_t lt = i >> 10, w = i & 1023u;
   uint32_t b = w >> 5, l = w & 31u;
   uint32_t px = ((b & 3u) << 3) + (l & 7u), py = ((b >> 2) << 2) + (l >> 3);
-  uint32_t gt = lt * tm.world + tm.rank;
-  uint32_t tx = gt % tm.tiles_x, ty = gt / tm.tiles_x;
+  uint32_t tx, ty;
+  if (!tile_of_slot(tm, lt * tm.world + tm.rank, tx, ty)) return false;
   x = tx * CUTRACE_TILE + px;
   y = ty * CUTRACE_TILE + py;
   pix = (lt << 10) + (py << 5) + px;
-  return x < tm.width && y < tm.height && ty < tm.tiles_y;
+  return x < tm.width && y < tm.height;
 }
 
 // cam::get_ray, inc/default_schema.hpp:376-386
@@ -377,11 +377,8 @@ __global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restri
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_px) return;
   const uint32_t pix = px_base + i;
-  // local tile-major index -> pixel (row-major inside the 32x32 tile)
-  const uint32_t lt = pix >> 10, w = pix & 1023u;
-  const uint32_t gt = lt * tm.world + tm.rank;
-  const uint32_t x = (gt % tm.tiles_x) * CUTRACE_TILE + (w & 31u), y = (gt / tm.tiles_x) * CUTRACE_TILE + (w >> 5);
-  if (x >= tm.width || y >= tm.height) return;
+  uint32_t x, y;
+  if (!pixel_of_local(tm, pix, x, y)) return;
   float r = 0.f, g = 0.f, b = 0.f;
   if (levels == 0) {
     const float *p = local_color + 3 * (size_t)pix;
@@ -414,10 +411,8 @@ __global__ void export_gbuffer_kernel(const TileMap tm, uint32_t px_base, uint32
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_px) return;
   const uint32_t pix = px_base + i;
-  const uint32_t lt = pix >> 10, w = pix & 1023u;
-  const uint32_t gt = lt * tm.world + tm.rank;
-  const uint32_t x = (gt % tm.tiles_x) * CUTRACE_TILE + (w & 31u), y = (gt / tm.tiles_x) * CUTRACE_TILE + (w >> 5);
-  if (x >= tm.width || y >= tm.height) return;
+  uint32_t x, y;
+  if (!pixel_of_local(tm, pix, x, y)) return;
   const size_t gi = (size_t)y * tm.width + x;
   out.depth[gi] = src.depth[pix];
   out.hit_id[gi] = src.hit_id[pix];

@@ -14,15 +14,34 @@ from . import Renderer
 from .scene import TILE
 
 
+def n_tiles(width, height):
+    return ((width + TILE - 1) // TILE) * ((height + TILE - 1) // TILE)
+
+
 def local_tile_count(width, height, world):
-    tiles = ((width + TILE - 1) // TILE) * ((height + TILE - 1) // TILE)
-    return (tiles + world - 1) // world
+    return (n_tiles(width, height) + world - 1) // world
+
+
+def tile_permutation(n, world):
+    """(a, a^-1 mod n) of the multiplicative tile permutation (TileMap in csrc/common.cuh): slot s shows screen tile
+    (s * a) % n; slots are dealt round-robin to the ranks.  One rank: identity."""
+    import math
+
+    if world <= 1 or n < 3:
+        return 1, 1
+    a = (n * 618 // 1000) | 1
+    while a < n and math.gcd(a, n) != 1:
+        a += 2
+    if a >= n:
+        return 1, 1
+    return a, pow(a, -1, n)
 
 
 def tiles_of_rank(width, height, rank, world):
-    """Global tile indices owned by ``rank`` (row-major tile order, interleaved)."""
-    tiles = ((width + TILE - 1) // TILE) * ((height + TILE - 1) // TILE)
-    return list(range(rank, tiles, world))
+    """Screen tile indices (row-major tile order) owned by ``rank``, in local-tile order."""
+    n = n_tiles(width, height)
+    a, _ = tile_permutation(n, world)
+    return [(s * a) % n for s in range(rank, n, world)]
 
 
 def untile_host(parts, width, height, channels):
@@ -30,14 +49,16 @@ def untile_host(parts, width, height, channels):
     buffer of shape (n_local_tiles*1024, channels)."""
     world = len(parts)
     tx = (width + TILE - 1) // TILE
+    n = n_tiles(width, height)
+    _, ainv = tile_permutation(n, world)
     out = np.zeros((height, width, channels), parts[0].dtype)
     for y in range(height):
         for x0 in range(0, width, TILE):
-            gt = (y // TILE) * tx + x0 // TILE
-            r, lt = gt % world, gt // world
-            n = min(TILE, width - x0)
+            slot = (((y // TILE) * tx + x0 // TILE) * ainv) % n
+            r, lt = slot % world, slot // world
+            cnt = min(TILE, width - x0)
             src = lt * 1024 + (y % TILE) * TILE
-            out[y, x0:x0 + n] = parts[r].reshape(-1, channels)[src:src + n]
+            out[y, x0:x0 + cnt] = parts[r].reshape(-1, channels)[src:src + cnt]
     return out
 
 

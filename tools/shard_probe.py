@@ -10,10 +10,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="synthetic10m")
 ap.add_argument("--world", type=int, default=1)
 ap.add_argument("--frames", type=int, default=3)
+ap.add_argument("--rank", type=int, default=0)
+ap.add_argument("--serial-only", action="store_true")
 a = ap.parse_args()
 scene, wl = bench.load_workload(a.workload)
-for label, flags in (("overlap", 0), ("serial", ct.FLAG_SERIALIZE)):
-    with ct.Renderer(scene, tile_rank=0, tile_world=a.world, flags=flags) as r:
+for label, flags in ((("serial", ct.FLAG_SERIALIZE),) if a.serial_only else (("overlap", 0), ("serial", ct.FLAG_SERIALIZE))):
+    with ct.Renderer(scene, tile_rank=a.rank, tile_world=a.world, flags=flags) as r:
         for i in range(a.frames):
             st = r.render()
-        print(f"world={a.world} {label:8s} render={st['render_ms']:.3f} trace={st['trace_ms']:.3f} shade={st['shade_ms']:.3f} rays={st['rays_total']}")
+        print(f"world={a.world} rank={a.rank} {label:8s} render={st['render_ms']:.3f} trace={st['trace_ms']:.3f} shade={st['shade_ms']:.3f} rays={st['rays_total']}")
