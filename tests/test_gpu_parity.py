@@ -424,3 +424,42 @@ def test_render_download_fused_equals_render_then_download(ct):
         for k in ("depth", "normal", "color", "hit_id"):
             assert np.array_equal(d[k].view(np.uint32), e[k].view(np.uint32)), k
         assert not np.array_equal(d["depth"], b["depth"])
+
+
+def test_set_camera_resizes_and_reuses_the_scene(ct):
+    """cutrace_set_camera: new resolution / view on an uploaded scene (no rebuild) == a fresh ctx."""
+    s = load_golden_scene("mirror").with_resolution(320, 180)
+    big = s.with_resolution(500, 281)
+    fresh, _ = gpu_render(ct, big)
+    with ct.Renderer(s) as r:
+        r.render()
+        r.set_resolution(500, 281)
+        r.render()
+        out = r.download()
+        for k in ("depth", "normal", "color", "hit_id"):
+            assert np.array_equal(out[k].view(np.uint32), fresh[k].view(np.uint32)), k
+        r.set_resolution(320, 180)
+        r.render()
+        small = r.download()
+    again, _ = gpu_render(ct, s)
+    for k in ("depth", "normal", "color", "hit_id"):
+        assert np.array_equal(small[k].view(np.uint32), again[k].view(np.uint32)), k
+
+
+def test_pixel_batches_equal_one_batch(ct, monkeypatch):
+    """When the worst-case queues do not fit the memory budget the frame is rendered in pixel batches
+    (CUTRACE_QUEUE_BUDGET_MB forces that here); the result must not change."""
+    for name, res in (("bunny", (640, 360)), ("sphere_plane", (320, 180))):
+        s = load_golden_scene(name).with_resolution(*res)
+        one, st1 = gpu_render(ct, s)
+        monkeypatch.setenv("CUTRACE_QUEUE_BUDGET_MB", "8" if name == "bunny" else "24")
+        many, st2 = gpu_render(ct, s)
+        monkeypatch.delenv("CUTRACE_QUEUE_BUDGET_MB")
+        assert st2["kernel_launches"] > st1["kernel_launches"], "the budget did not force batches"
+        for k in ("depth", "normal", "hit_id"):
+            assert np.array_equal(one[k].view(np.uint32), many[k].view(np.uint32)), (name, k)
+        if name == "bunny":
+            assert np.array_equal(one["color"].view(np.uint32), many["color"].view(np.uint32))
+        else:
+            assert np.abs(one["color"] - many["color"]).max() < 1e-5
+        assert st1["rays_total"] == st2["rays_total"] and st1["max_depth"] == st2["max_depth"]
