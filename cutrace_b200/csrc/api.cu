@@ -496,9 +496,26 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   c->h_ctr = pinned_counters_get();
   if (!c->h_ctr) { cutrace_free(c); return fail(CUTRACE_ERR_OUT_OF_MEMORY, "cudaHostAlloc failed"); }
   LAP("ctr alloc");
+  {
+    // shared-memory plan: everything (nodes + primitives) if it fits next to the SM, else the top of the tree
+    int smem_optin = 0;
+    CUF(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t whole = (size_t)sv.n_nodes * sizeof(Node) + (size_t)sv.n_prims * sizeof(PrimRec);
+    const bool allow = !(o.flags & CUTRACE_FLAG_NO_SMEM_TOP) && !sv.brute_force;
+    sv.smem_nodes = 0;
+    if (allow && whole + 1024 > (size_t)smem_optin && sv.root == 0 && sv.n_nodes > 0) {
+      uint32_t want = CTB_SMEM_TOP_NODES, n_top = 0;
+      if (const char *e = getenv("CUTRACE_SMEM_TOP_NODES")) want = (uint32_t)atoi(e);
+      std::string terr;
+      rc = reorder_top(c->bvh, want, c->stream, &n_top, terr);
+      if (rc) { cutrace_free(c); return fail(rc, terr); }
+      sv.nodes = c->bvh.nodes;
+      sv.smem_nodes = n_top;
+    }
+  }
   CUF(plan_launch(sv, !(o.flags & CUTRACE_FLAG_NO_SMEM_TOP), &c->cfg));
   LAP("plan_launch");
-  sv.smem_nodes = c->cfg.mode == 1 ? sv.n_nodes : 0;
+  if (c->cfg.mode == 1) sv.smem_nodes = sv.n_nodes;
   sv.smem_prims = c->cfg.mode == 1 ? sv.n_prims : 0;
   UP(alloc_frame(c, s->width, s->height));
   LAP("alloc_frame");

@@ -30,6 +30,8 @@ struct BvhResult {
 
 // returns cutrace_status; on failure `err` has the message and nothing is left allocated
 int build_bvh(const BvhInput &in, BvhResult &out, std::string &err);
+// moves the first S nodes in breadth-first order to the front of bvh.nodes (the part kernels stage in shared memory)
+int reorder_top(BvhResult &bvh, uint32_t S, cudaStream_t stream, uint32_t *n_top_out, std::string &err);
 // device-side self check, see cutrace_validate_bvh()
 int validate_bvh(const BvhResult &bvh, cudaStream_t stream, std::string &err);
 // radix sort entry point (exposed for the sort unit test): sorts n (key,value) pairs ascending, stable.

@@ -438,6 +438,102 @@ __global__ void depth_kernel(int n_internal, const int2 *__restrict__ range, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// BFS relabelling of the top of the tree: the first `S` nodes in breadth-first order move to the front of the node
+// array (indices 0..S-1, root stays 0) so that a kernel can stage "the top of the BVH" in shared memory with one
+// contiguous copy; every other node keeps its relative (Morton) order behind them.
+// ---------------------------------------------------------------------------------------------
+__global__ void bfs_top_kernel(const Node *__restrict__ nodes, uint32_t n_nodes, uint32_t S, uint32_t *__restrict__ order,
+                               uint32_t *__restrict__ n_top_out) {
+  __shared__ uint32_t sm[33];
+  __shared__ uint32_t head, tail;
+  if (threadIdx.x == 0) { order[0] = 0; head = 0; tail = 1; }
+  __syncthreads();
+  while (head < tail && tail < S) {
+    const uint32_t h0 = head, t0 = tail;
+    uint32_t produced = 0;
+    for (uint32_t base = h0; base < t0; base += blockDim.x) {   // deterministic order: parent order, child 0 before child 1
+      const uint32_t i = base + threadIdx.x;
+      int c0 = -1, c1 = -1;
+      if (i < t0) { const int4 m = nodes[order[i]].meta; c0 = m.x; c1 = m.y; }
+      const uint32_t cnt = (c0 >= 0 ? 1u : 0u) + (c1 >= 0 ? 1u : 0u);
+      uint32_t total;
+      uint32_t off = block_exclusive_scan(cnt, &total, sm) + t0 + produced;
+      if (c0 >= 0) { if (off < S) order[off] = (uint32_t)c0; off++; }
+      if (c1 >= 0) { if (off < S) order[off] = (uint32_t)c1; }
+      produced += total;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { head = t0; tail = t0 + produced < S ? t0 + produced : S; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_top_out = tail;
+}
+
+__global__ void top_flags_kernel(const uint32_t *__restrict__ order, uint32_t n_top, uint32_t *__restrict__ newidx,
+                                 uint32_t *__restrict__ rest_flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_top) { newidx[order[i]] = i; rest_flag[order[i]] = 0u; }
+}
+
+__global__ void rest_index_kernel(const uint32_t *__restrict__ rest_flag, const uint32_t *__restrict__ rest_scan, uint32_t n_nodes,
+                                  uint32_t n_top, uint32_t *__restrict__ newidx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_nodes && rest_flag[i]) newidx[i] = n_top + rest_scan[i];
+}
+
+__global__ void permute_nodes_kernel(const Node *__restrict__ in, uint32_t n_nodes, const uint32_t *__restrict__ newidx,
+                                     Node *__restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  Node nd = in[i];
+  if (nd.meta.x >= 0) nd.meta.x = (int)newidx[nd.meta.x];
+  if (nd.meta.y >= 0) nd.meta.y = (int)newidx[nd.meta.y];
+  out[newidx[i]] = nd;
+}
+
+__global__ void fill_u32_kernel(uint32_t *p, uint32_t n, uint32_t v) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int reorder_top(BvhResult &bvh, uint32_t S, cudaStream_t st, uint32_t *n_top_out, std::string &err) {
+  int rc = CUTRACE_OK;
+  *n_top_out = 0;
+  if (bvh.root != 0 || bvh.n_nodes == 0 || S == 0) return rc;
+  const uint32_t n = bvh.n_nodes;
+  if (S > n) S = n;
+  uint32_t *order = nullptr, *newidx = nullptr, *flag = nullptr, *scan = nullptr, *tile_sums = nullptr, *d_ntop = nullptr;
+  Node *out = nullptr;
+  uint32_t n_top = 0;
+  const int T = 256;
+  const uint32_t nb = (n + T - 1) / T;
+  CK(dmalloc(&order, sizeof(uint32_t) * S, st));
+  CK(dmalloc(&newidx, sizeof(uint32_t) * n, st));
+  CK(dmalloc(&flag, sizeof(uint32_t) * n, st));
+  CK(dmalloc(&scan, sizeof(uint32_t) * n, st));
+  CK(dmalloc(&tile_sums, sizeof(uint32_t) * ((n + SCAN_TILE - 1) / SCAN_TILE + 1), st));
+  CK(dmalloc(&d_ntop, sizeof(uint32_t), st));
+  CK(dmalloc(&out, sizeof(Node) * n, st));
+  bfs_top_kernel<<<1, 1024, 0, st>>>(bvh.nodes, n, S, order, d_ntop);
+  CK(cudaMemcpyAsync(&n_top, d_ntop, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  fill_u32_kernel<<<nb, T, 0, st>>>(flag, n, 1u);
+  top_flags_kernel<<<(n_top + T - 1) / T, T, 0, st>>>(order, n_top, newidx, flag);
+  exclusive_scan_u32(flag, scan, n, tile_sums, nullptr, st);
+  rest_index_kernel<<<nb, T, 0, st>>>(flag, scan, n, n_top, newidx);
+  permute_nodes_kernel<<<nb, T, 0, st>>>(bvh.nodes, n, newidx, out);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  dfree(bvh.nodes, st);
+  bvh.nodes = out;
+  out = nullptr;
+  *n_top_out = n_top;
+done:
+  dfree(order, st); dfree(newidx, st); dfree(flag, st); dfree(scan, st); dfree(tile_sums, st); dfree(d_ntop, st); dfree(out, st);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // validation: every primitive covered exactly once, child boxes contain their primitives / grandchildren
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prim_box(const PrimRec &p, float lo[3], float hi[3]) {

@@ -66,6 +66,10 @@ static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
 #define CTB_SENTINEL 0x7fffffff
 #define CTB_STACK 64
 #define CTB_MAX_LEAF 8
+#ifndef CTB_SMEM_TOP_NODES
+#define CTB_SMEM_TOP_NODES 0      // nodes of the BVH top (breadth-first) staged in shared memory for scenes that do not fit;
+                                  // measured slower than L1 on B200 (profiles/r01_tuning.md), so off unless CUTRACE_SMEM_TOP_NODES is set
+#endif
 
 __host__ __device__ __forceinline__ int leaf_encode(uint32_t first, uint32_t count) { return ~(int)((first << 3) | (count - 1u)); }
 __host__ __device__ __forceinline__ uint32_t leaf_first(int c) { return ((uint32_t)~c) >> 3; }

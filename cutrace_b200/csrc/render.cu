@@ -67,6 +67,12 @@ __device__ __forceinline__ void stage_scene(const SceneView &sv, float4 *smem, c
     nodes = smem;
     prims = smem + nn;
   } else {
+    if (MODE == 2) {   // top of the BVH (first smem_nodes nodes, breadth-first) -> shared memory
+      const float4 *gn = reinterpret_cast<const float4 *>(sv.nodes);
+      const uint32_t nn = sv.smem_nodes * 4u;
+      for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) smem[i] = __ldg(gn + i);
+      __syncthreads();
+    }
     nodes = reinterpret_cast<const float4 *>(sv.nodes);
     prims = reinterpret_cast<const float4 *>(sv.prims);
   }
@@ -439,11 +445,13 @@ typedef void (*shade_fn)(const SceneView, uint32_t, const ShadeRec *, FrameCount
 
 static trace_fn pick_trace(int mode, bool brute) {
   if (brute) return trace_kernel<0, true>;
+  if (mode == 2) return trace_kernel<2, false>;
   return mode == 1 ? trace_kernel<1, false> : trace_kernel<0, false>;
 }
 static shade_fn pick_shade(int mode, bool brute, bool opaque) {
   if (brute) return opaque ? shade_kernel<0, true, true> : shade_kernel<0, true, false>;
   if (mode == 1) return opaque ? shade_kernel<1, false, true> : shade_kernel<1, false, false>;
+  if (mode == 2) return opaque ? shade_kernel<2, false, true> : shade_kernel<2, false, false>;
   return opaque ? shade_kernel<0, false, true> : shade_kernel<0, false, false>;
 }
 
@@ -459,11 +467,14 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
   if (allow_smem && !sv.brute_force && sv.n_prims > 0 && need + 1024 <= (size_t)smem_optin) {
     cfg->mode = 1;
     cfg->smem_bytes = need;
+  } else if (allow_smem && !sv.brute_force && sv.smem_nodes > 0) {
+    cfg->mode = 2;   // api.cu moved the top sv.smem_nodes nodes (breadth-first) to the front of the node array
+    cfg->smem_bytes = (size_t)sv.smem_nodes * sizeof(Node);
   }
   trace_fn tf = pick_trace(cfg->mode, sv.brute_force != 0);
   shade_fn sf = pick_shade(cfg->mode, sv.brute_force != 0, sv.all_opaque != 0);
   int occ_t = 1, occ_s = 1;
-  if (cfg->mode == 1) {
+  if (cfg->mode != 0) {
     if ((e = cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
   }

@@ -119,11 +119,31 @@ __device__ __forceinline__ void make_ray(RayCtx &r, vec3 o, vec3 d, float scene_
   }
 }
 
-// MODE 0: nodes / primitives in global memory (LDG.128 through L1), MODE 1: staged in shared memory (LDS.128)
+// MODE 0: nodes / primitives in global memory (LDG.128 through L1)
+// MODE 1: the whole BVH and primitive store staged in shared memory (LDS.128) — the reference scenes
+// MODE 2: the top `sv.smem_nodes` nodes (breadth-first) staged in shared memory, everything else global — big scenes
 template <int MODE>
 __device__ __forceinline__ float4 ld16(const float4 *p) {
   if (MODE == 1) return *p;
   return __ldg(p);
+}
+
+struct NodeData { float4 n0, n1, nz, mf; };
+
+template <int MODE>
+__device__ __forceinline__ NodeData load_node(const SceneView &sv, const float4 *__restrict__ nodes, int cur) {
+  NodeData n;
+  if (MODE == 2) {
+    extern __shared__ float4 ctb_dyn_smem[];
+    if ((uint32_t)cur < sv.smem_nodes) {
+      const float4 *np = ctb_dyn_smem + 4 * cur;
+      n.n0 = np[0]; n.n1 = np[1]; n.nz = np[2]; n.mf = np[3];
+      return n;
+    }
+  }
+  const float4 *np = nodes + 4 * (size_t)cur;
+  n.n0 = ld16<MODE>(np); n.n1 = ld16<MODE>(np + 1); n.nz = ld16<MODE>(np + 2); n.mf = ld16<MODE>(np + 3);
+  return n;
 }
 
 template <int MODE>
@@ -164,10 +184,9 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
   while (cur != CTB_SENTINEL) {
 #pragma unroll 1
     while ((unsigned)cur < (unsigned)CTB_SENTINEL) {   // internal node
-      const float4 *np = nodes + 4 * (size_t)cur;
-      const float4 n0 = ld16<MODE>(np), n1 = ld16<MODE>(np + 1), nz = ld16<MODE>(np + 2);
-      const float4 mf = ld16<MODE>(np + 3);
-      const int c0 = __float_as_int(mf.x), c1 = __float_as_int(mf.y);
+      const NodeData nd = load_node<MODE>(sv, nodes, cur);
+      const float4 n0 = nd.n0, n1 = nd.n1, nz = nd.nz;
+      const int c0 = __float_as_int(nd.mf.x), c1 = __float_as_int(nd.mf.y);
       const float limit = ANY ? fminf(max_t, h.t) : h.t;
       // slabs: one FFMA per box plane (error budget: see RayCtx)
       const float c0lox = fmaf(n0.x, r.inv.x, -r.oi.x), c0hix = fmaf(n0.y, r.inv.x, -r.oi.x);
@@ -309,10 +328,9 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
   while (cur != CTB_SENTINEL) {
 #pragma unroll 1
     while ((unsigned)cur < (unsigned)CTB_SENTINEL) {
-      const float4 *np = nodes + 4 * (size_t)cur;
-      const float4 n0 = ld16<MODE>(np), n1 = ld16<MODE>(np + 1), nz = ld16<MODE>(np + 2);
-      const float4 mf = ld16<MODE>(np + 3);
-      const int c0 = __float_as_int(mf.x), c1 = __float_as_int(mf.y);
+      const NodeData nd = load_node<MODE>(sv, nodes, cur);
+      const float4 n0 = nd.n0, n1 = nd.n1, nz = nd.nz;
+      const int c0 = __float_as_int(nd.mf.x), c1 = __float_as_int(nd.mf.y);
       bool h0 = false, h1 = false;
 #pragma unroll
       for (int k = 0; k < K; k++) {

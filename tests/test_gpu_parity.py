@@ -463,3 +463,26 @@ def test_pixel_batches_equal_one_batch(ct, monkeypatch):
         else:
             assert np.abs(one["color"] - many["color"]).max() < 1e-5
         assert st1["rays_total"] == st2["rays_total"] and st1["max_depth"] == st2["max_depth"]
+
+
+def test_top_of_bvh_in_shared_memory_mode(ct, oracle, monkeypatch):
+    """MODE 2 (breadth-first top of the tree staged in shared memory, rest global; off by default because it measured
+    slower) stays correct: the BVH validates after the relabelling and a pixel subset matches the oracle."""
+    from cutrace_b200 import synth
+
+    meshes = synth.meshes_from_scenes(load_golden_scene("bunny"), load_golden_scene("mirror"))[:2]
+    s = synth.grid_scene(meshes, grid=12, width=480, height=270)   # 129,600 triangles: does not fit in shared memory
+    base, st0 = gpu_render(ct, s)
+    monkeypatch.setenv("CUTRACE_SMEM_TOP_NODES", "700")
+    with ct.Renderer(s, flags=ct.FLAG_VALIDATE_BVH) as r:
+        r.validate_bvh()
+        st = r.render()
+        out = r.download()
+    monkeypatch.delenv("CUTRACE_SMEM_TOP_NODES")
+    assert st["smem_nodes"] == 700 and st0["smem_nodes"] == 0
+    m = compare(out, base, s.width, s.height)
+    assert m["id_mismatch"] <= 2 and m["depth_max_rel"] <= 1e-6, m
+    px = np.random.default_rng(2).choice(s.width * s.height, 1000, replace=False).astype(np.uint64)
+    ref = oracle.oracle_render(s, px=px)
+    sub = {k: out[k][px.astype(np.int64)] for k in ("depth", "normal", "color", "hit_id")}
+    assert_parity(compare(sub, ref), "MODE 2 subset vs oracle", oracle_is_host=True)
