@@ -17,7 +17,7 @@ SYMBOLS = (
     "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_device_buffers", "cutrace_frame_device",
     "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free",
-    "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version",
+    "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version", "cutrace_tile_size",
 )
 
 FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE = 1, 2, 4, 8
@@ -93,6 +93,7 @@ def load():
     lib.cutrace_validate_bvh.argtypes = [P]
     lib.cutrace_debug_radix_sort.argtypes = [P, P, C.c_uint32, C.c_int]
     lib.cutrace_abi_version.restype = C.c_uint32
+    lib.cutrace_tile_size.restype = C.c_uint32
     _lib = lib
     return lib
 

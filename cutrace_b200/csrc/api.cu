@@ -93,7 +93,7 @@ struct cutrace_ctx {
   int max_children = 0;
   // frame
   TileMap tm{};
-  uint64_t n_local_px = 0;   // padded: n_local_tiles * 1024
+  uint64_t n_local_px = 0;   // padded: n_local_tiles * CUTRACE_TILE_PIXELS
   FrameTargets fb{};                 // tile-major local buffers (sharded ctx without a peer frame: NCCL-gather path)
   float *frame = nullptr;            // own row-major full frame: depth n | normal 3n | colour 3n | id n (one block)
   bool frame_is_ipc = false;         // allocated with cudaMalloc and exported through CUDA IPC
@@ -199,7 +199,7 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   tm.n_tiles = total_tiles;
   tile_permutation(total_tiles, tm.world, &tm.perm_a, &tm.perm_ainv);
   c->tm = tm;
-  c->n_local_px = (uint64_t)tm.n_local_tiles * 1024ull;
+  c->n_local_px = (uint64_t)tm.n_local_tiles * CUTRACE_TILE_PIXELS;
   c->sv.cam.w = width; c->sv.cam.h = height;
 
   uint32_t b = c->opts.bounces;
@@ -328,6 +328,8 @@ void set_cam(cutrace_ctx *c, const float pos[3], const float up[3], const float 
 extern "C" {
 
 uint32_t cutrace_abi_version(void) { return CUTRACE_ABI_VERSION; }
+
+uint32_t cutrace_tile_size(void) { return CUTRACE_TILE; }
 
 const char *cutrace_last_error(void) { return g_err.c_str(); }
 
@@ -598,24 +600,29 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade[L], c->d_ctr, gbuf, c->nlev, (uint32_t)bound, st);
       EQ(cudaEventRecord(e1, st));
       if (L == 0) EQ(cudaEventRecordWithFlags(c->ev_gbuf, st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-      if (L == 0 && gsrc.depth) {   // peer frame: ship the G-buffer now, under the remaining levels
-        cudaStream_t xs = serialize ? st : c->aux[2];
-        if (!serialize) EQ(cudaStreamWaitEvent(xs, e1, 0));
-        launch_export_gbuffer(c->tm, (uint32_t)base, n_px, gsrc, out, xs);
-        EQ(cudaEventRecord(c->events[60], xs));
-        launches += 1;
-      }
       cudaStream_t ss = serialize ? st : c->aux[L & 1];
       if (!serialize) EQ(cudaStreamWaitEvent(ss, e1, 0));
       float *lc = branching ? nullptr : c->level_color + (size_t)L * 3 * c->batch_px;
       launch_shade(c->cfg, c->sv, L, c->shade[L], c->d_ctr, acc, branching, lc, (uint32_t)base, (uint32_t)bound, ss);
       EQ(cudaEventRecord(e2, ss));
       launches += 2;
+      if (L == 0 && gsrc.depth && !getenv("CUTRACE_DEBUG_SKIP_EXPORT")) {   // peer frame: ship the G-buffer now, under the remaining levels
+        cudaStream_t xs = serialize ? st : c->aux[2];
+        if (!serialize) EQ(cudaStreamWaitEvent(xs, e1, 0));
+        launch_export_gbuffer(c->tm, (uint32_t)base, n_px, gsrc, out, xs);
+        EQ(cudaEventRecord(c->events[60], xs));
+        launches += 1;
+      }
+
     }
     if (!serialize) for (uint32_t L = 0; L < levels; L++) EQ(cudaStreamWaitEvent(st, c->events[4 + 3 * L], 0));
-    if (!serialize && gsrc.depth) EQ(cudaStreamWaitEvent(st, c->events[60], 0));
-    launch_combine(c->tm, c->nlev, c->level_color, 3ull * c->batch_px, branching ? 0u : levels, c->local_color, (uint32_t)base, n_px, out,
-                   FrameTargets{}, st);
+    if (!serialize && gsrc.depth && !getenv("CUTRACE_DEBUG_SKIP_EXPORT")) EQ(cudaStreamWaitEvent(st, c->events[60], 0));
+    {
+      FrameTargets cout = out;
+      if (c->peer_frame && c->fb.color && getenv("CUTRACE_DEBUG_LOCAL_COLOR")) { cout = c->fb; cout.row_major = 0; }   // timing experiment only
+      launch_combine(c->tm, c->nlev, c->level_color, 3ull * c->batch_px, branching ? 0u : levels, c->local_color, (uint32_t)base, n_px, cout,
+                     FrameTargets{}, st);
+    }
     launches += 1;
     return cudaGetLastError();
 #undef EQ

@@ -136,7 +136,7 @@ struct SceneView {
   Camera cam;
 };
 
-// Screen-space tiling.  The frame is cut into 32x32 tiles; tile "slots" 0..n_tiles-1 are dealt round-robin to the
+// Screen-space tiling.  The frame is cut into CUTRACE_TILE x CUTRACE_TILE tiles; tile "slots" 0..n_tiles-1 are dealt round-robin to the
 // ranks (slot s belongs to rank s % world, local tile s / world) and slot s shows screen tile (s * perm_a) % n_tiles.
 // The multiplicative permutation (perm_a coprime to n_tiles, ~0.618 n) scatters every rank's tiles over the whole
 // image: with plain interleaving a rank owned vertical stripes and the 8-way shards of bunny.json differed by 20 % in
@@ -164,9 +164,9 @@ __host__ __device__ __forceinline__ uint32_t slot_of_tile(const TileMap &tm, uin
 // local pixel index (tile-major, row-major inside the tile) -> pixel; false outside the image
 __host__ __device__ __forceinline__ bool pixel_of_local(const TileMap &tm, uint32_t pix, uint32_t &x, uint32_t &y) {
   uint32_t tx, ty;
-  if (!tile_of_slot(tm, (pix >> 10) * tm.world + tm.rank, tx, ty)) return false;
-  x = tx * CUTRACE_TILE + (pix & 31u);
-  y = ty * CUTRACE_TILE + ((pix & 1023u) >> 5);
+  if (!tile_of_slot(tm, (pix >> (2 * CUTRACE_TILE_SHIFT)) * tm.world + tm.rank, tx, ty)) return false;
+  x = tx * CUTRACE_TILE + (pix & (CUTRACE_TILE - 1u));
+  y = ty * CUTRACE_TILE + ((pix & (CUTRACE_TILE_PIXELS - 1u)) >> CUTRACE_TILE_SHIFT);
   return x < tm.width && y < tm.height;
 }
 

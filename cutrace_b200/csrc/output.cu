@@ -17,7 +17,7 @@ __global__ void untile_kernel(TileMap tm, uint32_t world, const float *__restric
     if ((int)rank != only_rank) return;
     rank = 0;
   }
-  uint64_t src = (uint64_t)rank * stride_px + ((uint64_t)lt << 10) + ((y % CUTRACE_TILE) << 5) + (x % CUTRACE_TILE);
+  uint64_t src = (uint64_t)rank * stride_px + ((uint64_t)lt << (2 * CUTRACE_TILE_SHIFT)) + ((y % CUTRACE_TILE) << CUTRACE_TILE_SHIFT) + (x % CUTRACE_TILE);
   uint64_t dst = (uint64_t)y * tm.width + x;
   if (depth) depth[dst] = g_depth[src];
   if (hit_id) hit_id[dst] = g_id[src];

@@ -78,17 +78,19 @@ __device__ __forceinline__ void stage_scene(const SceneView &sv, float4 *smem, c
   }
 }
 
-// local work index -> pixel.  Inside a 32x32 tile, 32 consecutive indices form an 8x4 pixel block
+// local work index -> pixel.  Inside a tile, 32 consecutive indices form an 8x4 pixel block
 // (coherent primary rays per warp); the framebuffer itself is row-major inside the tile.
 __device__ __forceinline__ bool work_to_pixel(const TileMap &tm, uint32_t i, uint32_t &x, uint32_t &y, uint32_t &pix) {
-  uint32_t lt = i >> 10, w = i & 1023u;
+  static_assert(CUTRACE_TILE_SHIFT >= 3, "a tile holds whole 8x4 warp blocks");
+  constexpr uint32_t BX_SHIFT = CUTRACE_TILE_SHIFT - 3;   // log2(8x4 blocks per tile row)
+  uint32_t lt = i >> (2 * CUTRACE_TILE_SHIFT), w = i & (CUTRACE_TILE_PIXELS - 1u);
   uint32_t b = w >> 5, l = w & 31u;
-  uint32_t px = ((b & 3u) << 3) + (l & 7u), py = ((b >> 2) << 2) + (l >> 3);
+  uint32_t px = ((b & ((1u << BX_SHIFT) - 1u)) << 3) + (l & 7u), py = ((b >> BX_SHIFT) << 2) + (l >> 3);
   uint32_t tx, ty;
   if (!tile_of_slot(tm, lt * tm.world + tm.rank, tx, ty)) return false;
   x = tx * CUTRACE_TILE + px;
   y = ty * CUTRACE_TILE + py;
-  pix = (lt << 10) + (py << 5) + px;
+  pix = (lt << (2 * CUTRACE_TILE_SHIFT)) + (py << CUTRACE_TILE_SHIFT) + px;
   return x < tm.width && y < tm.height;
 }
 
@@ -414,22 +416,26 @@ __global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restri
 // 32-pixel tile row per warp -> 128 / 384-byte contiguous NVLink stores.  Runs on an auxiliary stream right after
 // trace(0), i.e. the transfer overlaps the remaining bounce levels.
 __global__ void export_gbuffer_kernel(const TileMap tm, uint32_t px_base, uint32_t n_px, FrameTargets src, FrameTargets out) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_px) return;
-  const uint32_t pix = px_base + i;
-  uint32_t x, y;
-  if (!pixel_of_local(tm, pix, x, y)) return;
-  const size_t gi = (size_t)y * tm.width + x;
-  out.depth[gi] = src.depth[pix];
-  out.hit_id[gi] = src.hit_id[pix];
-  out.normal[3 * gi] = src.normal[3 * (size_t)pix]; out.normal[3 * gi + 1] = src.normal[3 * (size_t)pix + 1];
-  out.normal[3 * gi + 2] = src.normal[3 * (size_t)pix + 2];
+  // a SMALL grid-stride grid: the kernel is bound by the NVLink stores (all ranks push into rank 0 at the same moment),
+  // and every resident CTA of it takes SM slots away from the persistent trace/shade CTAs it is supposed to run under
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += gridDim.x * blockDim.x) {
+    const uint32_t pix = px_base + i;
+    uint32_t x, y;
+    if (!pixel_of_local(tm, pix, x, y)) continue;
+    const size_t gi = (size_t)y * tm.width + x;
+    out.depth[gi] = src.depth[pix];
+    out.hit_id[gi] = src.hit_id[pix];
+    out.normal[3 * gi] = src.normal[3 * (size_t)pix]; out.normal[3 * gi + 1] = src.normal[3 * (size_t)pix + 1];
+    out.normal[3 * gi + 2] = src.normal[3 * (size_t)pix + 2];
+  }
 }
 
 void launch_export_gbuffer(const TileMap &tm, uint32_t px_base, uint32_t n_px, const FrameTargets &src, const FrameTargets &out,
                            cudaStream_t st) {
   if (!n_px) return;
-  export_gbuffer_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(tm, px_base, n_px, src, out);
+  uint32_t grid = (n_px + 255) / 256;
+  if (grid > CTB_EXPORT_CTAS) grid = CTB_EXPORT_CTAS;
+  export_gbuffer_kernel<<<grid, 256, 0, st>>>(tm, px_base, n_px, src, out);
 }
 
 void launch_combine(const TileMap &tm, const uint32_t *nlev, const float *level_color, uint64_t level_stride, uint32_t levels,

@@ -10,6 +10,9 @@ namespace ctb {
 #endif
 constexpr int TRACE_THREADS = CTB_THREADS;
 constexpr int WORK_CHUNK_MAX = 512;   // most rays a warp claims per work-stealing atomic (guided: shrinks to 32 at the tail)
+#ifndef CTB_EXPORT_CTAS
+#define CTB_EXPORT_CTAS 74   // CTAs of the G-buffer export kernel (half a CTA per SM: it must not crowd out the render kernels)
+#endif
 #ifndef CTB_SHADE_MIN_BLOCKS
 #define CTB_SHADE_MIN_BLOCKS 2   // measured on B200: 2 CTAs/SM (64 regs) beat 1 CTA/SM for K = 1 (profiles/r01_tuning.md)
 #endif

@@ -46,7 +46,7 @@ def tiles_of_rank(width, height, rank, world):
 
 def untile_host(parts, width, height, channels):
     """CPU reference of the un-tile step (used by the gloo tests): ``parts[r]`` is rank r's tile-major
-    buffer of shape (n_local_tiles*1024, channels)."""
+    buffer of shape (n_local_tiles*TILE*TILE, channels)."""
     world = len(parts)
     tx = (width + TILE - 1) // TILE
     n = n_tiles(width, height)
@@ -57,7 +57,7 @@ def untile_host(parts, width, height, channels):
             slot = (((y // TILE) * tx + x0 // TILE) * ainv) % n
             r, lt = slot % world, slot // world
             cnt = min(TILE, width - x0)
-            src = lt * 1024 + (y % TILE) * TILE
+            src = lt * TILE * TILE + (y % TILE) * TILE
             out[y, x0:x0 + cnt] = parts[r].reshape(-1, channels)[src:src + cnt]
     return out
 

@@ -25,7 +25,7 @@ import numpy as np
 ABI_VERSION = 1
 LIGHT_SUN, LIGHT_POINT = 0, 1
 NO_HIT = 0xFFFFFFFF
-TILE = 32
+TILE = 16   # CUTRACE_TILE of include/cutrace.h (tests check it against cutrace_tile_size())
 
 # object kinds = variant order of default_gpu_object (inc/default_schema.hpp:920)
 OBJ_TRIANGLE, OBJ_MESH, OBJ_PLANE, OBJ_SPHERE = 0, 1, 2, 3

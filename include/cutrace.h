@@ -141,7 +141,9 @@ typedef struct cutrace_opts {
   uint32_t reserved[7];
 } cutrace_opts;
 
-#define CUTRACE_TILE 32u
+#define CUTRACE_TILE_SHIFT 4u                 /* log2 of the tile edge */
+#define CUTRACE_TILE (1u << CUTRACE_TILE_SHIFT) /* 16 x 16 pixels: fine enough to balance 8 ranks (profiles/r01_tuning.md) */
+#define CUTRACE_TILE_PIXELS (CUTRACE_TILE * CUTRACE_TILE)
 
 typedef struct cutrace_stats {
   float build_ms;       /* LBVH build inside cutrace_upload_scene (device time)               */
@@ -213,7 +215,7 @@ int cutrace_set_camera(cutrace_ctx *ctx, const float pos[3], const float up[3], 
 int cutrace_get_stats(cutrace_ctx *ctx, cutrace_stats *stats);
 
 /* Device-resident results of the last render, tile-major local layout: pixel j of local tile i is
- * at (i*CUTRACE_TILE*CUTRACE_TILE + j).  Pointers stay valid until the next set_camera/free.
+ * at (i*CUTRACE_TILE_PIXELS + j).  Pointers stay valid until the next set_camera/free.
  * Used by the multi-GPU gather (NCCL over the caller's communicator, or peer copies). */
 int cutrace_device_buffers(cutrace_ctx *ctx, float **depth, float **normal, float **color,
                            uint32_t **hit_id, uint64_t *n_local_px_padded);
@@ -263,6 +265,8 @@ int cutrace_validate_bvh(cutrace_ctx *ctx);
 int cutrace_debug_radix_sort(uint64_t *keys, uint32_t *values, uint32_t n, int device);
 
 uint32_t cutrace_abi_version(void);
+/* edge of the screen tiles the sharding works in (CUTRACE_TILE of the library that is loaded) */
+uint32_t cutrace_tile_size(void);
 
 #ifdef __cplusplus
 }

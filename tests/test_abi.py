@@ -31,6 +31,9 @@ def test_header_symbols_exported(lib):
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} is declared in include/cutrace.h but not exported"
     assert lib.cutrace_abi_version() == 1
+    from cutrace_b200.scene import TILE
+
+    assert lib.cutrace_tile_size() == TILE
 
 
 def test_struct_layouts_match_header(lib):

@@ -32,8 +32,8 @@ def _worker(rank, world, port, w, h, out_path):
     s = FlatScene.load(os.path.join(ROOT, "tests", "golden", "scenes", "mirror.npz")).with_resolution(w, h)
     tx = (w + TILE - 1) // TILE
     nlt = local_tile_count(w, h, world)
-    depth = torch.full((nlt * 1024,), float("inf"))
-    color = torch.zeros((nlt * 1024, 3))
+    depth = torch.full((nlt * TILE * TILE,), float("inf"))
+    color = torch.zeros((nlt * TILE * TILE, 3))
     px, dst = [], []
     for lt, gt in enumerate(tiles_of_rank(w, h, rank, world)):
         ty, txi = divmod(gt, tx)
@@ -42,7 +42,7 @@ def _worker(rank, world, port, w, h, out_path):
                 x, y = txi * TILE + pxx, ty * TILE + py
                 if x < w and y < h:
                     px.append(y * w + x)
-                    dst.append(lt * 1024 + py * TILE + pxx)
+                    dst.append(lt * TILE * TILE + py * TILE + pxx)
     o = po.oracle_render(s, px=np.asarray(px, np.uint64), threads=2)
     depth[dst] = torch.from_numpy(o["depth"])
     color[dst] = torch.from_numpy(o["color"])
@@ -78,6 +78,7 @@ def test_tile_ownership_is_a_partition():
 
     for (w, h, world) in [(20, 20, 1), (3840, 2160, 8), (100, 70, 3), (7680, 4320, 4)]:
         allt = sorted(t for r in range(world) for t in tiles_of_rank(w, h, r, world))
-        n = ((w + 31) // 32) * ((h + 31) // 32)
+        from cutrace_b200.scene import TILE
+        n = ((w + TILE - 1) // TILE) * ((h + TILE - 1) // TILE)
         assert allt == list(range(n))
         assert all(len(tiles_of_rank(w, h, r, world)) <= local_tile_count(w, h, world) for r in range(world))

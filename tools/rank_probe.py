@@ -35,12 +35,18 @@ with ct.Renderer(scene, device=lr, tile_rank=rank, tile_world=world) as r:
     def step():
         ms = r.render()["render_ms"]; dist.barrier(); return ms
     sync, c_sync = timed(step, 20)
-tsr = TileShardedRenderer(scene, rank=rank, world=world, device=lr, exchange="peer")
-tsr.render()
-def step2():
-    ms = tsr.render()["render_ms"]; tsr.gather(); return ms
-peer, c_peer = timed(step2, 20)
+res = {}
+for label, env in (("peer", {}), ("no-export", {"CUTRACE_DEBUG_SKIP_EXPORT": "1"}), ("no-export,local-colour", {"CUTRACE_DEBUG_SKIP_EXPORT": "1", "CUTRACE_DEBUG_LOCAL_COLOR": "1"}),
+                   ("export,local-colour", {"CUTRACE_DEBUG_LOCAL_COLOR": "1"})):
+    for k in ("CUTRACE_DEBUG_SKIP_EXPORT", "CUTRACE_DEBUG_LOCAL_COLOR"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    tsr = TileShardedRenderer(scene, rank=rank, world=world, device=lr, exchange="peer")
+    tsr.render()
+    def step2():
+        ms = tsr.render()["render_ms"]; tsr.gather(); return ms
+    res[label], _ = timed(step2, 20)
+    tsr.close()
 stop.set()
-print(f"[rank {rank}] full-frame {full:.3f} ms @{c_full} MHz | shard no-sync {alone:.3f} @{c_alone} | shard+barrier {sync:.3f} @{c_sync} | peer({tsr.exchange}) {peer:.3f} @{c_peer}", flush=True)
-tsr.close()
+print(f"[rank {rank}] full-frame {full:.3f} ms @{c_full} MHz | shard no-sync {alone:.3f} | shard+barrier {sync:.3f} | " + " | ".join(f"{k} {v:.3f}" for k, v in res.items()), flush=True)
 dist.destroy_process_group()
