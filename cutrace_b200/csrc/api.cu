@@ -9,6 +9,7 @@
 //                         (inc/kernel.hpp:110-125) with one device un-tile + one copy per image.
 // There is NO CPU fallback anywhere in this library: without a CUDA device every entry point
 // fails with CUTRACE_ERR_NO_DEVICE.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +28,6 @@ using namespace ctb;
 static thread_local std::string g_err = "";
 
 #ifdef CTB_TIMING   // developer instrumentation (tools/build_variant.sh timing -DCTB_TIMING); never on in the product build
-#include <chrono>
 struct PhaseTimer {
   std::chrono::high_resolution_clock::time_point t = std::chrono::high_resolution_clock::now();
   void lap(const char *what) {
@@ -206,11 +206,22 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   const bool branching = c->max_children >= 2 && b > 0;
   const uint32_t levels = c->max_children > 0 ? b + 1 : 1;
   c->factor = branching ? (1u << b) : 1u;
-  size_t free_b = 0, total_b = 0;
-  CU(cudaMemGetInfo(&free_b, &total_b));
   uint64_t fb_bytes = c->n_local_px * 36ull;
-  double budget = (double)free_b * 0.6 - (double)fb_bytes;
+  // queue budget: 60 % of the free HBM.  cudaMemGetInfo costs 30-70 ms once gigabytes sit in the memory pool
+  // (tools/build_probe.py), so it is only asked when the worst-case queues of the whole frame exceed 8 GB.
+  double budget = 8.0 * 1073741824.0;
   if (const char *e = getenv("CUTRACE_QUEUE_BUDGET_MB")) budget = atof(e) * 1048576.0;
+  else {
+    double shade_all = 0;
+    for (uint32_t L = 0; L < levels; L++) shade_all += (branching ? (double)(1u << L) : 1.0) * sizeof(ShadeRec);
+    const double need_all = (double)c->n_local_px * ((c->max_children > 0 && b > 0 ? (double)c->factor * 2.0 * sizeof(RayRec) : 0.0) + shade_all +
+                                                     (branching ? 0.0 : 12.0 * levels));
+    if (need_all > budget) {
+      size_t free_b = 0, total_b = 0;
+      CU(cudaMemGetInfo(&free_b, &total_b));
+      budget = (double)free_b * 0.6 - (double)fb_bytes;
+    }
+  }
   // bytes of queue memory per batch pixel: two ping-pong ray queues of the worst-case level, one shade queue per
   // level (level L holds at most 2^L hits per pixel when a material both reflects and transmits, else 1), and the
   // per-level partial colour images of the non-branching path
@@ -281,18 +292,13 @@ int validate_desc(const cutrace_scene_desc *s) {
   if (s->n_triangles + s->n_spheres >= (1ull << 28)) return fail(CUTRACE_ERR_INVALID_ARG, "too many primitives (max 2^28-1)");
   for (uint32_t i = 0; i < s->n_objects; i++)
     if (s->obj_material[i] >= s->n_materials) return fail(CUTRACE_ERR_INVALID_ARG, "object material index out of range");
-  for (uint64_t i = 0; i < s->n_triangles; i++)
-    if (s->tri_object[i] >= s->n_objects) return fail(CUTRACE_ERR_INVALID_ARG, "tri_object index out of range");
-  for (uint64_t i = 0; i < s->n_spheres; i++)
-    if (s->sph_object[i] >= s->n_objects) return fail(CUTRACE_ERR_INVALID_ARG, "sph_object index out of range");
+  // triangle / sphere coordinates and their object indices are validated on the device (prim_bounds_kernel)
   for (uint64_t i = 0; i < s->n_planes; i++)
     if (s->pl_object[i] >= s->n_objects) return fail(CUTRACE_ERR_INVALID_ARG, "pl_object index out of range");
   for (uint32_t i = 0; i < s->n_lights; i++)
     if (s->light_kind[i] > CUTRACE_LIGHT_POINT) return fail(CUTRACE_ERR_INVALID_ARG, "unknown light kind");
-  if (!all_finite(s->tri_p1, 3 * s->n_triangles) || !all_finite(s->tri_p2, 3 * s->n_triangles) ||
-      !all_finite(s->tri_p3, 3 * s->n_triangles) || !all_finite(s->sph_center, 3 * s->n_spheres) ||
-      !all_finite(s->sph_radius, s->n_spheres))
-    return fail(CUTRACE_ERR_INVALID_ARG, "non-finite vertex / sphere data");
+  if (!all_finite(s->pl_point, 3 * s->n_planes) || !all_finite(s->pl_normal, 3 * s->n_planes))
+    return fail(CUTRACE_ERR_INVALID_ARG, "non-finite plane data");
   return CUTRACE_OK;
 }
 
@@ -466,6 +472,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   BvhInput bi;
   bi.d_p1 = d_p1; bi.d_p2 = d_p2; bi.d_p3 = d_p3; bi.d_tri_obj = d_to; bi.n_tri = (uint32_t)nt;
   bi.d_sph_center = d_sc; bi.d_sph_radius = d_sr; bi.d_sph_obj = d_so; bi.n_sph = (uint32_t)ns;
+  bi.n_objects = s->n_objects;
   bi.leaf_size = o.leaf_size; bi.stream = c->stream;
   CUT(cudaEventRecord(c->events[0], c->stream));
   std::string berr;

@@ -15,6 +15,7 @@ struct BvhInput {
   const float *d_sph_center = nullptr, *d_sph_radius = nullptr;
   const uint32_t *d_sph_obj = nullptr;
   uint32_t n_sph = 0;
+  uint32_t n_objects = 0;     // object indices of the primitives are range-checked on the device
   uint32_t leaf_size = 4;
   cudaStream_t stream = nullptr;
 };

@@ -335,6 +335,19 @@ def test_errors_on_gpu(ct):
         buf = np.empty(400, np.float32)
         assert lib.cutrace_download(r._ctx, buf.ctypes.data, None, None, None, None) == -5   # before any render
         assert b"before" in lib.cutrace_last_error()
+    # primitive data is validated on the device, next to the bounds computation
+    bad = load_golden_scene("bunny")
+    bad.tri_p2 = bad.tri_p2.copy()
+    bad.tri_p2[123, 1] = np.inf
+    with pytest.raises(ct.CutraceError) as e:
+        ct.Renderer(bad)
+    assert e.value.code == -1 and "non-finite" in str(e.value)
+    bad = load_golden_scene("bunny")
+    bad.tri_object = bad.tri_object.copy()
+    bad.tri_object[7] = 99
+    with pytest.raises(ct.CutraceError) as e:
+        ct.Renderer(bad)
+    assert e.value.code == -1 and "out of range" in str(e.value)
     with pytest.raises(ct.CutraceError):
         ct.Renderer(s, device=99)
     with pytest.raises(ct.CutraceError):
