@@ -25,7 +25,7 @@ $(LIB): $(OBJS)
 HOST := cutrace_b200/host
 HOSTLIB := cutrace_b200/lib/libcutrace_host.so
 HOSTCXX := $(if $(wildcard /usr/bin/g++),/usr/bin/g++,g++)
-HOSTFLAGS := -std=c++17 -O2 -ffp-contract=off -fPIC -Wall
+HOSTFLAGS := -std=c++17 -O2 -ffp-contract=off -fPIC -Wall -pthread
 
 host: $(HOSTLIB)
 $(HOSTLIB): $(HOST)/scene_loader.cpp $(HOST)/jpeg.cpp $(HOST)/host_api.cpp $(wildcard $(HOST)/*.hpp) include/cutrace.h include/cutrace_host.h

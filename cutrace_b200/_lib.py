@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("CUTRACE_B200_LIB") or os.path.join(HERE, "lib", "libc
 SYMBOLS = (
     "cutrace_default_opts", "cutrace_upload_scene", "cutrace_render", "cutrace_download", "cutrace_render_download", "cutrace_download_bytes", "cutrace_free",
     "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_device_buffers", "cutrace_frame_device",
-    "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach",
+    "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach", "cutrace_enable_peer_access",
+    "cutrace_set_frame_max_depth",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free",
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version", "cutrace_tile_size",
 )
@@ -84,6 +85,8 @@ def load():
     lib.cutrace_frame_ipc_export.argtypes = [P, P]
     lib.cutrace_frame_ipc_import.argtypes = [P, P]
     lib.cutrace_frame_attach.argtypes = [P, P]
+    lib.cutrace_enable_peer_access.argtypes = [C.c_int, C.c_int]
+    lib.cutrace_set_frame_max_depth.argtypes = [P, C.c_float]
     lib.cutrace_untile_device.argtypes = [P, C.c_uint32, P, P, P, P, C.c_uint64, P, P, P, P]
     lib.cutrace_encode_bytes_device.argtypes = [P, P, P, P, C.c_float, C.c_uint64, P, P, P]
     lib.cutrace_host_alloc.argtypes = [C.c_size_t]

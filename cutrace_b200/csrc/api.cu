@@ -842,6 +842,25 @@ int cutrace_frame_ipc_import(cutrace_ctx *c, const void *handle) {
   return CUTRACE_OK;
 }
 
+int cutrace_enable_peer_access(int device, int peer_device) {
+  if (device == peer_device) return CUTRACE_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(CUTRACE_ERR_NO_DEVICE, "cudaSetDevice failed");
+  int can = 0;
+  CU(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  if (!can) return fail(CUTRACE_ERR_CUDA, "devices cannot access each other's memory");
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return CUTRACE_OK; }
+  CU(e);
+  return CUTRACE_OK;
+}
+
+int cutrace_set_frame_max_depth(cutrace_ctx *c, float max_depth) {
+  if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  c->stats.max_depth = max_depth;
+  return CUTRACE_OK;
+}
+
 int cutrace_frame_attach(cutrace_ctx *c, void *frame_block) {
   if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
   DeviceGuard g(c->device);

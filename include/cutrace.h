@@ -237,6 +237,11 @@ int cutrace_frame_ipc_import(cutrace_ctx *ctx, const void *handle);
  * `frame_block` is the depth pointer cutrace_frame_device returned for the owning ctx (the frame is one block of
  * 32*width*height bytes).  NULL detaches. */
 int cutrace_frame_attach(cutrace_ctx *ctx, void *frame_block);
+/* helpers for a one-process multi-GPU host: peer access from `device` to `peer_device` (idempotent), and the frame-wide
+ * max depth (max over the ranks' cutrace_stats.max_depth, kernel.hpp:120-125) that cutrace_download_bytes of the ctx
+ * owning the frame should use for the depth image. */
+int cutrace_enable_peer_access(int device, int peer_device);
+int cutrace_set_frame_max_depth(cutrace_ctx *ctx, float max_depth);
 
 /* Un-tiles `world` gathered rank buffers (each laid out as cutrace_device_buffers describes, rank r
  * at gathered + r*stride elements of the respective type) into row-major full-frame DEVICE images

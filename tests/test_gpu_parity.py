@@ -499,3 +499,30 @@ def test_top_of_bvh_in_shared_memory_mode(ct, oracle, monkeypatch):
     ref = oracle.oracle_render(s, px=px)
     sub = {k: out[k][px.astype(np.int64)] for k in ("depth", "normal", "color", "hit_id")}
     assert_parity(compare(sub, ref), "MODE 2 subset vs oracle", oracle_is_host=True)
+
+
+def test_cli_multi_gpu_in_one_process(ct, oracle, tmp_path):
+    """`cutrace --gpus 2`: one process, one ctx and one host thread per GPU, GPU 1 stores its tiles into GPU 0's frame
+    over NVLink (cutrace_enable_peer_access + cutrace_frame_attach).  Needs two GPUs."""
+    import subprocess
+
+    import torch
+
+    from conftest import ROOT
+    from cutrace_b200 import host
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "bin", "cutrace")
+    outs = {}
+    for gpus in (1, 2):
+        d = tmp_path / f"g{gpus}"
+        d.mkdir()
+        r = subprocess.run([exe, os.path.join(ROOT, "scenes", "solids.json"), "--out-dir", str(d), "--dump-raw", "--gpus", str(gpus),
+                            "--width", "640", "--height", "400"], capture_output=True, text=True, cwd=ROOT)
+        assert r.returncode == 0, r.stderr
+        outs[gpus] = {k: np.fromfile(d / f"{k}.{e}", t) for k, e, t in (("depth", "f32", np.float32), ("normal", "f32", np.float32),
+                                                                       ("color", "f32", np.float32), ("hit_id", "u32", np.uint32))}
+    for k in ("depth", "normal", "hit_id"):
+        assert np.array_equal(outs[1][k].view(np.uint32), outs[2][k].view(np.uint32)), k
+    assert np.abs(outs[1]["color"] - outs[2]["color"]).max() < 1e-5    # solids.json has a reflecting + transmitting sphere: float atomics
