@@ -20,6 +20,10 @@
 #define CUTRACE_B200_TRACE_CUH
 #include "common.cuh"
 
+#ifndef CTB_SPECULATIVE
+#define CTB_SPECULATIVE 0
+#endif
+
 namespace ctb {
 
 #define CTB_KIND_TRI 0
@@ -180,6 +184,9 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
   stack[0] = CTB_SENTINEL;
   int sp = 1;
   int cur = sv.root;
+#if CTB_SPECULATIVE
+  int pending = 0;   // a postponed leaf (leaf codes are negative, 0 = none)
+#endif
   const float slack = 1.0f + 4.0f * 1.1920929e-7f;
   while (cur != CTB_SENTINEL) {
 #pragma unroll 1
@@ -209,7 +216,21 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
       } else {
         cur = stack[--sp];
       }
+#if CTB_SPECULATIVE
+      // speculative traversal: the first leaf a lane finds is postponed and the lane keeps walking nodes, so the lanes
+      // of a warp leave the node loop together less often (they stay until they hold a second leaf or run dry)
+      if (cur < 0 && pending == 0) { pending = cur; cur = stack[--sp]; }
+#endif
     }
+#if CTB_SPECULATIVE
+    if (pending) {
+      const uint32_t first = leaf_first(pending), count = leaf_count(pending);
+#pragma unroll 1
+      for (uint32_t k = first; k < first + count; k++) test_prim<MODE>(prims, k, r, min_t, h);
+      if (ANY && h.t < max_t) return true;
+      pending = 0;
+    }
+#endif
     if (cur == CTB_SENTINEL) break;
     {   // leaf
       const uint32_t first = leaf_first(cur), count = leaf_count(cur);
