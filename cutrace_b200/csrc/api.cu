@@ -150,7 +150,7 @@ void drop_graph(cutrace_ctx *c) {
 // multiplier of the tile permutation (see TileMap): ~0.618 n, odd, coprime to n; and its inverse mod n
 void tile_permutation(uint32_t n, uint32_t world, uint32_t *a_out, uint32_t *ainv_out) {
   *a_out = 1; *ainv_out = 1;
-  if (world <= 1 || n < 3) return;
+  if (world <= 1 || n < 3 || getenv("CUTRACE_DEBUG_NO_TILE_PERM")) return;
   auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
   uint64_t a = ((uint64_t)n * 618ull / 1000ull) | 1ull;
   while (a < n && gcd(a, n) != 1) a += 2;

@@ -526,3 +526,22 @@ def test_cli_multi_gpu_in_one_process(ct, oracle, tmp_path):
     for k in ("depth", "normal", "hit_id"):
         assert np.array_equal(outs[1][k].view(np.uint32), outs[2][k].view(np.uint32)), k
     assert np.abs(outs[1]["color"] - outs[2]["color"]).max() < 1e-5    # solids.json has a reflecting + transmitting sphere: float atomics
+
+
+def test_integration_binding_against_the_reference_operator(ct):
+    """oracle/_ref/integration_check: ONE cutrace::cpu::schema::default_cpu_scene (the reference's own host scene type)
+    through (a) the reference's default_to_gpu + gpu::render<S,5,256> and (b) the flatten() + C-ABI binding that
+    INTEGRATION.md shows, compared in the same process."""
+    import json
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "integration_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/integration_check was not built (reference tree absent at build time)")
+    r = subprocess.run([exe, "640", "360"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    m = json.loads(r.stdout.strip().splitlines()[-1])
+    assert m["sentinel_mismatch"] == 0 and m["depth_off_pixels"] <= 2 and m["normal_max_abs"] <= 1e-5 or m["depth_off_pixels"] > 0
+    assert m["max_ref"] == m["max_new"]
