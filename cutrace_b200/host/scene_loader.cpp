@@ -90,6 +90,54 @@ bool read_stl(const std::string &path, std::vector<float> &p1, std::vector<float
   return true;
 }
 
+// ---- Wavefront OBJ (mesh import breadth) ---------------------------------------------------------
+// The reference accepts whatever Assimp reads (inc/default_schema.hpp:516-545: aiProcess_Triangulate, faces in file
+// order, positions only).  Here: `v x y z` and `f a b c ...` with a/b/c, a//c, a/b forms and negative (relative)
+// indices; polygons are split as a fan from their first vertex; everything else (vt, vn, o, g, s, usemtl) is ignored.
+bool read_obj(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err) {
+  std::ifstream f(path);
+  if (!f) { err = "cannot open mesh file '" + path + "'"; return false; }
+  std::vector<float> v;
+  std::string line;
+  size_t faces = 0;
+  while (std::getline(f, line)) {
+    std::istringstream in(line);
+    std::string tag;
+    if (!(in >> tag)) continue;
+    if (tag == "v") {
+      double x, y, z;
+      if (!(in >> x >> y >> z)) { err = "bad vertex in OBJ '" + path + "'"; return false; }
+      v.push_back((float)x); v.push_back((float)y); v.push_back((float)z);
+    } else if (tag == "f") {
+      std::vector<long> idx;
+      std::string tok;
+      while (in >> tok) {
+        long i = strtol(tok.c_str(), nullptr, 10);   // the part before the first '/'
+        const long nv = (long)(v.size() / 3);
+        if (i < 0) i = nv + i + 1;
+        if (i < 1 || i > nv) { err = "face index out of range in OBJ '" + path + "'"; return false; }
+        idx.push_back(i - 1);
+      }
+      for (size_t k = 1; k + 1 < idx.size(); k++) {
+        p1.insert(p1.end(), &v[3 * idx[0]], &v[3 * idx[0]] + 3);
+        p2.insert(p2.end(), &v[3 * idx[k]], &v[3 * idx[k]] + 3);
+        p3.insert(p3.end(), &v[3 * idx[k + 1]], &v[3 * idx[k + 1]] + 3);
+        faces++;
+      }
+    }
+  }
+  if (!faces) { err = "no faces in OBJ file '" + path + "'"; return false; }
+  return true;
+}
+
+static bool read_mesh(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err) {
+  const size_t dot = path.rfind('.');
+  std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
+  for (auto &ch : ext) ch = (char)tolower((unsigned char)ch);
+  if (ext == "obj") return read_obj(path, p1, p2, p3, err);
+  return read_stl(path, p1, p2, p3, err);
+}
+
 // ---- coercion (inc/json_helpers.hpp:88-126) -------------------------------------------------------------
 static bool get_num(const JsonValue &o, const char *key, double &out, std::string &err, const double *def = nullptr) {
   const JsonValue *v = o.find(key);
@@ -201,7 +249,7 @@ bool load_scene_text(const std::string &text, const LoadOptions &opt, FlatScene 
         std::string path = file->str;
         if (!opt.base_dir.empty() && !path.empty() && path[0] != '/') path = opt.base_dir + "/" + path;
         size_t n0 = s.tri_p1.size() / 3;
-        if (!read_stl(path, s.tri_p1, s.tri_p2, s.tri_p3, err)) { bad(err); continue; }
+        if (!read_mesh(path, s.tri_p1, s.tri_p2, s.tri_p3, err)) { bad(err); continue; }
         s.tri_object.insert(s.tri_object.end(), s.tri_p1.size() / 3 - n0, id);
         s.obj_kind.push_back(CUTRACE_OBJ_MESH);
       } else if (type == "plane") {

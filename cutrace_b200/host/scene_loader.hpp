@@ -7,8 +7,8 @@
 //   materials: solid{color, specular=0.3, reflect=0, phong=32, transparency=0}
 //   camera   : {eye, up, look, near_plane, far_plane, width, height, ambient} — all mandatory (MK_MANDATORY)
 // Numbers are doubles cast to float / size_t (inc/json_helpers.hpp:91).  Meshes: the reference imports with
-// Assimp and keeps faces in file order (inc/default_schema.hpp:516-545); here binary and ASCII STL are read
-// directly in facet order.  With accept_aliases the stale spellings of schema.md are accepted as well.
+// Assimp and keeps faces in file order (inc/default_schema.hpp:516-545); here binary STL, ASCII STL and Wavefront OBJ
+// (fan-triangulated) are read directly in face order.  With accept_aliases the stale spellings of schema.md are accepted as well.
 #ifndef CUTRACE_B200_HOST_SCENE_LOADER_HPP
 #define CUTRACE_B200_HOST_SCENE_LOADER_HPP
 #include <string>
@@ -45,6 +45,7 @@ struct LoadOptions {
 bool load_scene_file(const std::string &path, const LoadOptions &opt, FlatScene &out, std::vector<std::string> &errors);
 bool load_scene_text(const std::string &json_text, const LoadOptions &opt, FlatScene &out, std::vector<std::string> &errors);
 bool read_stl(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err);
+bool read_obj(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err);
 
 // cam::look_at in float arithmetic (inc/default_schema.hpp:370-374)
 void look_at(const float pos[3], const float up_in[3], const float look[3], float forward[3], float right[3], float up[3]);

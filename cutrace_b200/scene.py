@@ -107,6 +107,43 @@ def read_stl(path):
     return np.asarray(verts, dtype=np.float64).astype(np.float32).reshape(-1, 3, 3)
 
 
+def read_obj(path):
+    """Wavefront OBJ -> (n,3,3) float32: `v` and `f` records only, a/b/c index forms, negative indices, polygons
+    fan-triangulated from their first vertex (mirror of cutrace_b200/host/scene_loader.cpp read_obj)."""
+    try:
+        with open(path, "r", errors="replace") as f:
+            lines = f.readlines()
+    except OSError as e:
+        raise SceneError(f"cannot open mesh file {path!r}") from e
+    v, tris = [], []
+    for line in lines:
+        p = line.split()
+        if not p:
+            continue
+        if p[0] == "v":
+            if len(p) < 4:
+                raise SceneError(f"bad vertex in OBJ {path!r}")
+            v.append([float(p[1]), float(p[2]), float(p[3])])
+        elif p[0] == "f":
+            idx = []
+            for tok in p[1:]:
+                i = int(tok.split("/")[0])
+                if i < 0:
+                    i = len(v) + i + 1
+                if not 1 <= i <= len(v):
+                    raise SceneError(f"face index out of range in OBJ {path!r}")
+                idx.append(i - 1)
+            for k in range(1, len(idx) - 1):
+                tris.append([v[idx[0]], v[idx[k]], v[idx[k + 1]]])
+    if not tris:
+        raise SceneError(f"no faces in OBJ file {path!r}")
+    return np.asarray(tris, dtype=np.float64).astype(np.float32)
+
+
+def read_mesh(path):
+    return read_obj(path) if path.lower().endswith(".obj") else read_stl(path)
+
+
 class cutrace_scene_desc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32),
@@ -391,7 +428,7 @@ def scene_from_dict(doc, base_dir=".", accept_aliases=False):
             path = o["file"]
             if not os.path.isabs(path):
                 path = os.path.join(base_dir, path)
-            v = read_stl(path)
+            v = read_mesh(path)
             p1.append(v[:, 0]); p2.append(v[:, 1]); p3.append(v[:, 2]); tobj.append(np.full(len(v), oid, np.uint32))
             okind.append(OBJ_MESH)
         elif ty == "plane":
