@@ -120,6 +120,7 @@ struct cutrace_ctx {
   uint8_t *st_bytes = nullptr;   // 3 images x n x 3 bytes
   uint64_t st_bytes_px = 0;
   uint32_t graph_launches = 0;
+  bool env_no_graph = false, env_skip_export = false, env_local_color = false;   // developer toggles, read once at upload
   cudaGraphExec_t graph = nullptr;   // the whole frame (all streams) captured once, replayed per cutrace_render
   bool graph_failed = false;
   cutrace_stats stats{};
@@ -395,6 +396,9 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   DeviceGuard guard(dev);
   if (!guard.ok) { delete c; return fail(CUTRACE_ERR_CUDA, "cudaSetDevice failed"); }
   pool_keep_memory(dev);
+  c->env_no_graph = getenv("CUTRACE_NO_GRAPH") != nullptr;
+  c->env_skip_export = getenv("CUTRACE_DEBUG_SKIP_EXPORT") != nullptr;      // timing experiments of profiles/r01_tuning.md only:
+  c->env_local_color = c->env_local_color != nullptr;      // they leave the peer frame incomplete
 
 #define UP(call) do { int rc_ = (call); if (rc_) { cutrace_free(c); return rc_; } } while (0)
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); cutrace_free(c); \
@@ -613,7 +617,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       launch_shade(c->cfg, c->sv, L, c->shade[L], c->d_ctr, acc, branching, lc, (uint32_t)base, (uint32_t)bound, ss);
       EQ(cudaEventRecord(e2, ss));
       launches += 2;
-      if (L == 0 && gsrc.depth && !getenv("CUTRACE_DEBUG_SKIP_EXPORT")) {   // peer frame: ship the G-buffer now, under the remaining levels
+      if (L == 0 && gsrc.depth && !c->env_skip_export) {   // peer frame: ship the G-buffer now, under the remaining levels
         cudaStream_t xs = serialize ? st : c->aux[2];
         if (!serialize) EQ(cudaStreamWaitEvent(xs, e1, 0));
         launch_export_gbuffer(c->tm, (uint32_t)base, n_px, gsrc, out, xs);
@@ -623,10 +627,10 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
 
     }
     if (!serialize) for (uint32_t L = 0; L < levels; L++) EQ(cudaStreamWaitEvent(st, c->events[4 + 3 * L], 0));
-    if (!serialize && gsrc.depth && !getenv("CUTRACE_DEBUG_SKIP_EXPORT")) EQ(cudaStreamWaitEvent(st, c->events[60], 0));
+    if (!serialize && gsrc.depth && !c->env_skip_export) EQ(cudaStreamWaitEvent(st, c->events[60], 0));
     {
       FrameTargets cout = out;
-      if (c->peer_frame && c->fb.color && getenv("CUTRACE_DEBUG_LOCAL_COLOR")) { cout = c->fb; cout.row_major = 0; }   // timing experiment only
+      if (c->peer_frame && c->fb.color && c->env_local_color) { cout = c->fb; cout.row_major = 0; }   // timing experiment only
       launch_combine(c->tm, c->nlev, c->level_color, 3ull * c->batch_px, branching ? 0u : levels, c->local_color, (uint32_t)base, n_px, cout,
                      FrameTargets{}, st);
     }
@@ -638,7 +642,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   // One batch (the normal case): the frame is a CUDA graph, captured from the code above on the first call and
   // replayed afterwards — one launch instead of ~40 API calls, which is what a 0.05 .. 2 ms frame is bound by.
   const bool single_batch = c->batch_px >= c->n_local_px;
-  const bool use_graph = single_batch && !serialize && !c->graph_failed && !getenv("CUTRACE_NO_GRAPH");
+  const bool use_graph = single_batch && !serialize && !c->graph_failed && !c->env_no_graph;
   if (use_graph && !c->graph) {
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
