@@ -398,7 +398,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   pool_keep_memory(dev);
   c->env_no_graph = getenv("CUTRACE_NO_GRAPH") != nullptr;
   c->env_skip_export = getenv("CUTRACE_DEBUG_SKIP_EXPORT") != nullptr;      // timing experiments of profiles/r01_tuning.md only:
-  c->env_local_color = c->env_local_color != nullptr;      // they leave the peer frame incomplete
+  c->env_local_color = getenv("CUTRACE_DEBUG_LOCAL_COLOR") != nullptr;      // they leave the peer frame incomplete
 
 #define UP(call) do { int rc_ = (call); if (rc_) { cutrace_free(c); return rc_; } } while (0)
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); cutrace_free(c); \
