@@ -234,9 +234,11 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   batch = (batch / 1024ull) * 1024ull;
   if (batch < 1024) batch = 1024;
   if (batch > c->n_local_px) batch = c->n_local_px;
-  while (batch * c->factor >= (1ull << 31) && batch > 1024) batch = ((batch / 2) / 1024ull) * 1024ull;
+  while (batch * c->factor >= (1ull << 31) - (1ull << 24) && batch > 1024) batch = ((batch / 2) / 1024ull) * 1024ull;
   c->batch_px = batch;
-  c->cap = batch * c->factor;
+  // every producer warp may leave one partly used slot block per queue behind
+  const uint64_t slack = (uint64_t)c->cfg.grid_trace * (TRACE_THREADS / 32) * SLOT_BLOCK;
+  c->cap = batch * c->factor + slack;
 
   cudaStream_t st = c->stream;
   if (c->tm.world > 1) {   // sharded: tile-major local buffers for the gather path (unused once a peer frame is imported)
@@ -253,7 +255,7 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
     CU(dmalloc(&c->rays[1], sizeof(RayRec) * c->cap, st));
   }
   for (uint32_t L = 0; L < levels; L++) {
-    c->shade_cap[L] = batch * (branching ? (1ull << L) : 1ull);
+    c->shade_cap[L] = batch * (branching ? (1ull << L) : 1ull) + slack;
     CU(dmalloc(&c->shade[L], sizeof(ShadeRec) * c->shade_cap[L], st));
   }
   if (!branching) {
@@ -603,7 +605,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     if (branching && base == 0) EQ(cudaMemsetAsync(c->local_color, 0, sizeof(float) * 3 * c->n_local_px, st));
     EQ(cudaMemsetAsync(c->d_ctr, 0, sizeof(FrameCounters), st));
     for (uint32_t L = 0; L < levels; L++) {
-      uint64_t bound = (uint64_t)n_px * (branching ? (1ull << L) : 1ull);
+      uint64_t bound = (uint64_t)n_px * (branching ? (1ull << L) : 1ull) + (uint64_t)c->cfg.grid_trace * (TRACE_THREADS / 32) * SLOT_BLOCK;
       if (bound > c->shade_cap[L]) bound = c->shade_cap[L];
       RayRec *in = c->rays[L & 1], *outq = c->rays[(L + 1) & 1];
       cudaEvent_t e0 = c->events[2 + 3 * L], e1 = c->events[3 + 3 * L], e2 = c->events[4 + 3 * L];
@@ -688,7 +690,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     S.rays_reflect += h.rays_reflect;
     S.rays_transmit += h.rays_transmit;
     S.shadow_casts += h.shadow_casts;
-    for (uint32_t L = 0; L < levels; L++) S.rays_shadow += (uint64_t)h.n_shade[L] * c->sv.n_lights;
+    S.rays_shadow += (uint64_t)h.shade_records * c->sv.n_lights;
     float md;
     memcpy(&md, &h.max_depth_bits, 4);
     if (md > max_depth) max_depth = md;

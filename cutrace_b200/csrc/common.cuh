@@ -108,11 +108,11 @@ static_assert(sizeof(RayRec) == 32 && sizeof(ShadeRec) == 48, "queue record size
 
 // device-side counters of one frame
 struct FrameCounters {
-  unsigned int n_rays[18];      // rays queued for level L (level 0 = primary, filled by host)
-  unsigned int n_shade[18];     // shade records produced by level L
+  unsigned int n_rays[18];      // ray-queue slots reserved for level L (valid rays + retired holes)
+  unsigned int n_shade[18];     // shade-queue slots reserved by level L (valid records + retired holes)
   unsigned int work_trace[18];  // work-stealing cursors
   unsigned int work_shade[18];
-  unsigned long long rays_reflect, rays_transmit, shadow_casts;
+  unsigned long long rays_reflect, rays_transmit, shadow_casts, shade_records;
   unsigned int max_depth_bits;  // float bits of the largest finite primary depth
   unsigned int overflow;        // set if a queue would overflow (cannot happen with worst-case sizing)
 };

@@ -115,8 +115,13 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = lanemask_lt();
   const uint32_t n_work = level == 0 ? n_px : ctr->n_rays[level];
-  unsigned long long n_refl = 0, n_trans = 0;
+  unsigned long long n_refl = 0, n_trans = 0, n_shaded = 0;
   float max_depth = 0.f;
+  unsigned s_next = 0, s_end = 0, r_next = 0, r_end = 0;   // this warp's reserved slot blocks (warp-uniform)
+  // block size: 1/8 of what a warp is expected to emit over the kernel, 32..SLOT_BLOCK — every warp leaves half a block
+  // of holes behind on average, so small levels (deep bounces, 1/8 shards) fall back to one reservation per iteration
+  unsigned slot_block = (n_work / (gridDim.x * (blockDim.x >> 5) * 8u)) & ~31u;
+  slot_block = slot_block < 32u ? 32u : (slot_block > (unsigned)SLOT_BLOCK ? (unsigned)SLOT_BLOCK : slot_block);
 
   for (;;) {
     unsigned base, end;
@@ -136,6 +141,7 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
         float4 a = __ldcs(rp), b = __ldcs(rp + 1);
         o = mk3(a.x, a.y, a.z); pix = __float_as_uint(a.w);
         d = mk3(b.x, b.y, b.z); w = b.w;
+        active = pix != CTB_HOLE;
       }
       Hit h;
       hit_reset(h);
@@ -169,52 +175,78 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
         do_trans = (double)transp >= 1e-6;
         if (do_trans) w_own = w * (1.0f - transp);
       }
-      // ---- shade record: one per hit, warp-aggregated slot allocation ----
+      // ---- output slots.  A warp reserves SLOT_BLOCK queue slots with ONE atomicAdd and fills them over the next
+      // iterations (ballot + popc compaction inside the warp); the unused tail of a block is retired as holes
+      // (pix = CTB_HOLE).  One same-address atomic WITH return per warp-iteration and queue had made the trace
+      // kernels wait on the L2 atomic unit (ncu: long_scoreboard 11.5 warp-cycles per issue, 45 % issue slots).
       const unsigned m_hit = __ballot_sync(0xffffffffu, hit);
       if (m_hit) {
-        unsigned sbase = 0;
-        if (lane == 0) sbase = atomicAdd(&ctr->n_shade[level], (unsigned)__popc(m_hit));
-        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        const unsigned n_hit = __popc(m_hit);
+        if (s_next + n_hit > s_end) {
+          for (unsigned k = s_next + lane; k < s_end; k += 32)
+            __stcs(reinterpret_cast<float4 *>(shade_out + k), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
+          unsigned b = 0;
+          const unsigned blk = slot_block > n_hit ? slot_block : n_hit;
+          if (lane == 0) b = atomicAdd(&ctr->n_shade[level], blk);
+          s_next = __shfl_sync(0xffffffffu, b, 0);
+          s_end = s_next + blk;
+        }
         if (hit) {
-          float4 *sp = reinterpret_cast<float4 *>(shade_out + sbase + __popc(m_hit & lt_mask));
+          float4 *sp = reinterpret_cast<float4 *>(shade_out + s_next + __popc(m_hit & lt_mask));
           __stcs(sp, make_float4(point.x, point.y, point.z, __uint_as_float(pix)));
           __stcs(sp + 1, make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(mat)));
           __stcs(sp + 2, make_float4(d.x, d.y, d.z, w_own));
+          n_shaded++;
         }
+        s_next += n_hit;
       }
       // ---- child rays ----
       const unsigned m_r = __ballot_sync(0xffffffffu, do_refl), m_t = __ballot_sync(0xffffffffu, do_trans);
       if (m_r | m_t) {
-        unsigned rbase = 0;
         const unsigned nr = __popc(m_r), nt = __popc(m_t);
-        if (lane == 0) rbase = atomicAdd(&ctr->n_rays[level + 1], nr + nt);
-        rbase = __shfl_sync(0xffffffffu, rbase, 0);
+        if (r_next + nr + nt > r_end) {
+          for (unsigned k = r_next + lane; k < r_end; k += 32)
+            __stcs(reinterpret_cast<float4 *>(rays_out + k), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
+          unsigned b = 0;
+          const unsigned blk = slot_block > nr + nt ? slot_block : nr + nt;
+          if (lane == 0) b = atomicAdd(&ctr->n_rays[level + 1], blk);
+          r_next = __shfl_sync(0xffffffffu, b, 0);
+          r_end = r_next + blk;
+        }
         const vec3 origin = vadd(o, vscale(d, h.t));   // incoming->start + distance * incoming->dir
         if (do_refl) {
           vec3 nd = vnormalized(d), nn = vnormalized(nrm);
           vec3 rd = vreflect(nd, nn);
-          float4 *rp = reinterpret_cast<float4 *>(rays_out + rbase + __popc(m_r & lt_mask));
+          float4 *rp = reinterpret_cast<float4 *>(rays_out + r_next + __popc(m_r & lt_mask));
           __stcs(rp, make_float4(origin.x, origin.y, origin.z, __uint_as_float(pix)));
           __stcs(rp + 1, make_float4(rd.x, rd.y, rd.z, w_own * reflect));
           n_refl++;
         }
         if (do_trans) {
-          float4 *rp = reinterpret_cast<float4 *>(rays_out + rbase + nr + __popc(m_t & lt_mask));
+          float4 *rp = reinterpret_cast<float4 *>(rays_out + r_next + nr + __popc(m_t & lt_mask));
           __stcs(rp, make_float4(origin.x, origin.y, origin.z, __uint_as_float(pix)));
           __stcs(rp + 1, make_float4(d.x, d.y, d.z, w * transp));
           n_trans++;
         }
+        r_next += nr + nt;
       }
     }
   }
+  // retire the unused tails of this warp's last blocks
+  for (unsigned k = s_next + lane; k < s_end; k += 32)
+    __stcs(reinterpret_cast<float4 *>(shade_out + k), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
+  for (unsigned k = r_next + lane; k < r_end; k += 32)
+    __stcs(reinterpret_cast<float4 *>(rays_out + k), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
   // per-warp totals
   for (int s = 16; s > 0; s >>= 1) {
     n_refl += __shfl_xor_sync(0xffffffffu, n_refl, s);
     n_trans += __shfl_xor_sync(0xffffffffu, n_trans, s);
+    n_shaded += __shfl_xor_sync(0xffffffffu, n_shaded, s);
     max_depth = fmaxf(max_depth, __shfl_xor_sync(0xffffffffu, max_depth, s));
   }
   if (lane == 0) {
     if (n_refl) atomicAdd(&ctr->rays_reflect, n_refl);
+    if (n_shaded) atomicAdd(&ctr->shade_records, n_shaded);
     if (n_trans) atomicAdd(&ctr->rays_transmit, n_trans);
     if (level == 0 && max_depth > 0.f) atomicMax(&ctr->max_depth_bits, __float_as_uint(max_depth));
   }
@@ -271,6 +303,7 @@ shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ sh
         const vec3 hit = mk3(s0.x, s0.y, s0.z), normal = mk3(s1.x, s1.y, s1.z), in_dir = mk3(s2.x, s2.y, s2.z);
         const uint32_t pix = __float_as_uint(s0.w), mat = __float_as_uint(s1.w);
         const float weight = s2.w;
+        if (pix == CTB_HOLE) continue;   // retired tail of a producer warp's slot block
         // phong, inc/shading.hpp:64-99
         const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
         const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);

@@ -10,6 +10,8 @@ namespace ctb {
 #endif
 constexpr int TRACE_THREADS = CTB_THREADS;
 constexpr int WORK_CHUNK_MAX = 512;   // most rays a warp claims per work-stealing atomic (guided: shrinks to 32 at the tail)
+constexpr int SLOT_BLOCK = 256;   // queue slots a warp reserves per atomicAdd (>= 64: one warp-iteration emits <= 32 + 32 rays)
+#define CTB_HOLE 0xffffffffu       // pix of a retired (unused) queue slot
 #ifndef CTB_EXPORT_CTAS
 #define CTB_EXPORT_CTAS 74   // CTAs of the G-buffer export kernel (half a CTA per SM: it must not crowd out the render kernels)
 #endif
