@@ -120,8 +120,8 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
   unsigned s_next = 0, s_end = 0, r_next = 0, r_end = 0;   // this warp's reserved slot blocks (warp-uniform)
   // block size: 1/8 of what a warp is expected to emit over the kernel, 32..SLOT_BLOCK — every warp leaves half a block
   // of holes behind on average, so small levels (deep bounces, 1/8 shards) fall back to one reservation per iteration
-  unsigned slot_block = (n_work / (gridDim.x * (blockDim.x >> 5) * 8u)) & ~31u;
-  slot_block = slot_block < 32u ? 32u : (slot_block > (unsigned)SLOT_BLOCK ? (unsigned)SLOT_BLOCK : slot_block);
+  unsigned slot_block = (n_work / (gridDim.x * (blockDim.x >> 5) * (unsigned)CTB_SLOT_DIV)) & ~31u;
+  slot_block = slot_block < (unsigned)CTB_SLOT_MIN ? (unsigned)CTB_SLOT_MIN : (slot_block > (unsigned)SLOT_BLOCK ? (unsigned)SLOT_BLOCK : slot_block);
 
   for (;;) {
     unsigned base, end;

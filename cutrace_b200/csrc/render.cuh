@@ -11,6 +11,12 @@ namespace ctb {
 constexpr int TRACE_THREADS = CTB_THREADS;
 constexpr int WORK_CHUNK_MAX = 512;   // most rays a warp claims per work-stealing atomic (guided: shrinks to 32 at the tail)
 constexpr int SLOT_BLOCK = 256;   // queue slots a warp reserves per atomicAdd (>= 64: one warp-iteration emits <= 32 + 32 rays)
+#ifndef CTB_SLOT_DIV
+#define CTB_SLOT_DIV 8
+#endif
+#ifndef CTB_SLOT_MIN
+#define CTB_SLOT_MIN 64
+#endif
 #define CTB_HOLE 0xffffffffu       // pix of a retired (unused) queue slot
 #ifndef CTB_EXPORT_CTAS
 #define CTB_EXPORT_CTAS 74   // CTAs of the G-buffer export kernel (half a CTA per SM: it must not crowd out the render kernels)
