@@ -122,3 +122,74 @@ def random_soup(n_tri=200, n_sph=5, n_planes=2, n_lights=2, width=96, height=64,
         light_vec=np.array([[-1, -1, 1], [-3, 5, -4], [3, 4, -2], [0.5, -1, 0.2]], np.float32)[:n_lights],
         light_color=np.full((n_lights, 3), 0.6, np.float32),
     )
+
+
+def write_scene_files(scene, out_dir, eye, up, look, name="scene", near_plane=0.1, far_plane=1000.0):
+    """Writes ``scene`` as files a stock cutrace reads: ``<name>.json`` in the reference's schema
+    (/root/reference/inc/default_schema.hpp:487-897: objects/lights/materials/camera, every camera key present) and
+    one binary STL per mesh object (80-byte header, uint32 count, 50-byte records; the stored facet normal is zero —
+    the reference recomputes it, default_schema.hpp:72).  float32 values are written with their shortest exact decimal,
+    so loading the files back gives the same arrays bit for bit.  ``eye/up/look`` are the camera's JSON parameters (a
+    FlatScene only keeps the vectors look_at derived from them).  Mesh paths in the JSON are relative to ``out_dir``:
+    the reference resolves them against the CWD (schema.md:73-74).  Returns the JSON path."""
+    import json
+    import os
+    import struct
+
+    from .scene import LIGHT_SUN, OBJ_MESH, OBJ_PLANE, OBJ_SPHERE, OBJ_TRIANGLE
+
+    def f(x):
+        return float(np.float32(x))          # json writes repr(double) — exact, and it rounds back to the same float32
+
+    def v3(a):
+        return [f(a[0]), f(a[1]), f(a[2])]
+
+    os.makedirs(out_dir, exist_ok=True)
+    objects = []
+    order = np.argsort(scene.tri_object, kind="stable")
+    first = np.searchsorted(scene.tri_object[order], np.arange(scene.n_objects + 1))
+    sph = {int(o): i for i, o in enumerate(scene.sph_object)}
+    pl = {int(o): i for i, o in enumerate(scene.pl_object)}
+    for o in range(scene.n_objects):
+        kind, mat = int(scene.obj_kind[o]), int(scene.obj_material[o])
+        tri = order[first[o]:first[o + 1]]
+        if kind == OBJ_TRIANGLE:
+            t = int(tri[0])
+            objects.append({"type": "triangle", "p1": v3(scene.tri_p1[t]), "p2": v3(scene.tri_p2[t]), "p3": v3(scene.tri_p3[t]),
+                            "material": mat})
+        elif kind == OBJ_MESH:
+            rel = f"{name}_mesh{o:04d}.stl"
+            rec = np.zeros((len(tri), 50), np.uint8)
+            verts = np.stack([scene.tri_p1[tri], scene.tri_p2[tri], scene.tri_p3[tri]], axis=1).astype("<f4")
+            rec[:, 12:48] = verts.reshape(len(tri), 9).view(np.uint8).reshape(len(tri), 36)
+            with open(os.path.join(out_dir, rel), "wb") as fh:
+                fh.write(b"cutrace-b200 synthetic instance".ljust(80, b"\0"))
+                fh.write(struct.pack("<I", len(tri)))
+                fh.write(rec.tobytes())
+            objects.append({"type": "mesh", "file": rel, "material": mat})
+        elif kind == OBJ_PLANE:
+            i = pl[o]
+            objects.append({"type": "plane", "point": v3(scene.pl_point[i]), "normal": v3(scene.pl_normal[i]), "material": mat})
+        elif kind == OBJ_SPHERE:
+            i = sph[o]
+            objects.append({"type": "sphere", "center": v3(scene.sph_center[i]), "radius": f(scene.sph_radius[i]), "material": mat})
+        else:
+            raise ValueError(f"object {o} has unknown kind {kind}")
+    lights = [{"type": "sun", "direction": v3(v), "color": v3(c)} if int(k) == LIGHT_SUN else
+              {"type": "point", "point": v3(v), "color": v3(c)}
+              for k, v, c in zip(scene.light_kind, scene.light_vec, scene.light_color)]
+    materials = [{"type": "solid", "color": v3(scene.mat_color[i]), "specular": f(scene.mat_specular[i]),
+                  "reflect": f(scene.mat_reflect[i]), "phong": f(scene.mat_phong[i]),
+                  "transparency": f(scene.mat_transparency[i])} for i in range(len(scene.mat_specular))]
+    camera = {"eye": v3(eye), "up": v3(up), "look": v3(look), "near_plane": near_plane, "far_plane": far_plane,
+              "width": int(scene.width), "height": int(scene.height), "ambient": f(scene.ambient)}
+    path = os.path.join(out_dir, f"{name}.json")
+    with open(path, "w") as fh:
+        json.dump({"objects": objects, "lights": lights, "materials": materials, "camera": camera}, fh, indent=1)
+    return path
+
+
+def grid_camera(grid):
+    """(eye, up, look) that grid_scene() aims its camera with — the JSON camera of write_scene_files()."""
+    G = int(grid)
+    return np.array([0.30 * G, 0.34 * G, -0.46 * G], np.float32), [0, 1, 0], [0, 0, 0]
