@@ -380,7 +380,7 @@ def main():
                          "algorithmic_bytes_per_launch": dom_rays * bpr / max(1, int(st["kernel_launches"]) // 2),
                          "kernel": dominant, "bytes_per_ray": bpr,
                          "ncu": dict(ncu_facts, source="profiles/ncu_traffic.json (committed ncu --set full capture of this kernel)",
-                                     reading="the kernel is issue-bound, not DRAM-bound: issue slots busy ~80 %, ~21 of 32 lanes active per instruction"),
+                                     reading="the kernel is issue-bound, not DRAM-bound: see issue_slots_busy_pct / active_threads_per_warp_instruction (of 32) / dram_throughput_pct"),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "algorithmic bytes/ray (SURVEY §8d) x rays of the dominant kernel / its CUDA-event time; the scene is cache-resident, "
                                  "so issue-slot utilisation and divergence (profiles/) explain the kernel, not DRAM"},
