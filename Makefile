@@ -13,6 +13,7 @@ OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU))
 HDRS := $(wildcard $(SRC)/*.cuh) include/cutrace.h
 
 all: $(LIB) host cli
+lib: $(LIB)
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -43,4 +44,4 @@ oracle:
 
 clean:
 	rm -rf build bin $(LIB) $(HOSTLIB)
-.PHONY: all oracle clean host cli
+.PHONY: all lib oracle clean host cli

@@ -137,6 +137,25 @@ def cpu_baseline(scene, label, seconds_target=12.0):
             "sample": f"{len(px)} px strided {min(nx, w)}x{min(ny, h)} grid of {label} ({dt:.1f} s, {rays_per_px:.2f} rays/px)"}
 
 
+def ensure_library():
+    """The product has no fallback: a snapshot without the built .so compiles it (nvcc is in the image) before anything runs.
+    Under torchrun local rank 0 builds and the other ranks wait for the file."""
+    lib_path = os.path.join(ROOT, "cutrace_b200", "lib", "libcutrace_b200.so")
+    if os.path.exists(lib_path):
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        subprocess.run(["make", "-C", ROOT, "-j4", "lib"], check=True, stdout=sys.stderr)
+    else:
+        t0, last, stable = time.time(), -1, 0
+        while stable < 3:   # present and unchanged for three seconds: the linker has finished writing it
+            if time.time() - t0 > 900:
+                raise RuntimeError(f"{lib_path} was not built")
+            time.sleep(1.0)
+            size = os.path.getsize(lib_path) if os.path.exists(lib_path) else -1
+            stable = stable + 1 if (size > 0 and size == last) else 0
+            last = size
+
+
 def run_reference(args, scene, wl):
     """--impl reference: the reference's own CUDA kernel rebuilt for sm_100a, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -217,6 +236,7 @@ def main():
     import torch
     import torch.distributed as dist
 
+    ensure_library()
     import cutrace_b200 as ct
     from cutrace_b200.distributed import TileShardedRenderer
 

@@ -23,8 +23,13 @@ def ct():
 
     if not torch.cuda.is_available():
         pytest.fail("GPU tests need a CUDA device (the product has no CPU path)")
-    import cutrace_b200
+    import subprocess
 
+    import cutrace_b200
+    from conftest import ROOT
+
+    if not os.path.exists(cutrace_b200._lib.LIB_PATH):   # snapshot without the built .so: compile it, never fall back
+        subprocess.run(["make", "-C", ROOT, "-j4", "lib"], check=True, stdout=subprocess.DEVNULL)
     cutrace_b200._lib.load()
     return cutrace_b200
 
