@@ -393,6 +393,35 @@ def test_cli_end_to_end(ct, oracle, tmp_path):
         assert 10 * np.log10(255.0 ** 2 / max(mse, 1e-9)) > 30.0, fn
 
 
+def test_cli_renders_the_synthetic_grid_from_json_and_stl_files(ct, tmp_path):
+    """the G=3 grid written as reference-schema JSON + one binary STL per instance, rendered by
+    the CLI from the files (cwd = their directory, like the reference resolves mesh paths) == the in-memory scene
+    rendered through the C-ABI, bit for bit (both front-ends give the same arrays, the path is deterministic)."""
+    import subprocess
+
+    from conftest import ROOT
+    from cutrace_b200 import synth
+
+    exe = os.path.join(ROOT, "bin", "cutrace")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", ROOT, "cli"], check=True, stdout=subprocess.DEVNULL)
+    meshes = synth.meshes_from_scenes(load_golden_scene("bunny"), load_golden_scene("mirror"))[:2]
+    s = synth.grid_scene(meshes, grid=3, width=192, height=108)
+    synth.write_scene_files(s, str(tmp_path), *synth.grid_camera(3), name="grid3")
+    r = subprocess.run([exe, "grid3.json", "--dump-raw"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert " -> Have 15   objects:" in r.stdout and " -> Have 3    lights:" in r.stdout
+    out, st = gpu_render(ct, s)
+    n = s.width * s.height
+    assert np.array_equal(np.fromfile(tmp_path / "hit_id.u32", np.uint32), out["hit_id"].reshape(-1))
+    assert np.array_equal(np.fromfile(tmp_path / "depth.f32", np.float32), out["depth"].reshape(-1))
+    assert np.array_equal(np.fromfile(tmp_path / "normal.f32", np.float32), out["normal"].reshape(-1))
+    assert np.array_equal(np.fromfile(tmp_path / "color.f32", np.float32), out["color"].reshape(-1))
+    assert (out["hit_id"].reshape(-1) < 9).any()                      # the instances are on screen
+    for fn in ("depth_map.jpg", "normal_map.jpg", "frame.jpg"):
+        assert os.path.getsize(tmp_path / fn) > 500
+
+
 def test_download_bytes_equals_host_output_stage(ct, oracle):
     s = load_golden_scene("mirror").with_resolution(240, 135)
     with ct.Renderer(s) as r:
