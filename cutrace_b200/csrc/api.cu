@@ -78,10 +78,73 @@ static void pinned_counters_put(FrameCounters *p) {
   g_pinned_free.push_back(p);
 }
 
+// Streams and events of a ctx are recycled the same way: creating five streams and 73 events and destroying them again
+// costs ~0.5 ms per ctx (measured with -DCTB_TIMING: 0.25 ms + 0.28 ms), 4 % of an upload-render-download-free cycle
+// of bunny.json at 4K.  A set goes back to the free list of its device in cutrace_free, after all its streams are idle.
+struct StreamSet {
+  int device = -1;
+  cudaStream_t main = nullptr;         // high priority: the trace chain (unused when the caller brings a stream)
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // low priority: shade kernels, G-buffer export
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_gbuf = nullptr;
+  std::vector<cudaEvent_t> events;
+};
+#define CTB_N_EVENTS 72
+static std::mutex g_streams_mu;
+static std::vector<StreamSet *> g_streams_free;
+static void stream_set_destroy(StreamSet *ss) {
+  if (!ss) return;
+  for (cudaEvent_t e : ss->events) cudaEventDestroy(e);
+  for (int i = 0; i < 3; i++) if (ss->aux[i]) cudaStreamDestroy(ss->aux[i]);
+  if (ss->copy) cudaStreamDestroy(ss->copy);
+  if (ss->ev_gbuf) cudaEventDestroy(ss->ev_gbuf);
+  if (ss->main) cudaStreamDestroy(ss->main);
+  delete ss;
+}
+// the current device must be `device`
+static cudaError_t stream_set_get(int device, StreamSet **out) {
+  {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    for (size_t i = 0; i < g_streams_free.size(); i++)
+      if (g_streams_free[i]->device == device) {
+        *out = g_streams_free[i];
+        g_streams_free.erase(g_streams_free.begin() + (long)i);
+        return cudaSuccess;
+      }
+  }
+  StreamSet *ss = new StreamSet;
+  ss->device = device;
+  cudaError_t e;
+  int pr_least = 0, pr_greatest = 0;
+#define SS(call) do { e = (call); if (e != cudaSuccess) { stream_set_destroy(ss); return e; } } while (0)
+  SS(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+  SS(cudaStreamCreateWithPriority(&ss->main, cudaStreamNonBlocking, pr_greatest));
+  // shade kernels run on two lower-priority streams so that the trace chain (the critical path) gets SMs first
+  for (int i = 0; i < 3; i++) SS(cudaStreamCreateWithPriority(&ss->aux[i], cudaStreamNonBlocking, pr_least));
+  SS(cudaStreamCreateWithFlags(&ss->copy, cudaStreamNonBlocking));
+  SS(cudaEventCreateWithFlags(&ss->ev_gbuf, cudaEventDisableTiming));
+  for (int i = 0; i < CTB_N_EVENTS; i++) { cudaEvent_t ev; SS(cudaEventCreate(&ev)); ss->events.push_back(ev); }
+#undef SS
+  *out = ss;
+  return cudaSuccess;
+}
+static void stream_set_put(StreamSet *ss) {
+  if (!ss) return;
+  cudaStreamSynchronize(ss->main);
+  for (int i = 0; i < 3; i++) cudaStreamSynchronize(ss->aux[i]);
+  cudaStreamSynchronize(ss->copy);
+  {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    if (g_streams_free.size() < 32) { g_streams_free.push_back(ss); return; }
+  }
+  stream_set_destroy(ss);
+}
+
 struct cutrace_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  StreamSet *streams = nullptr;
   cutrace_opts opts{};
   // scene
   BvhResult bvh;
@@ -121,6 +184,8 @@ struct cutrace_ctx {
   uint64_t st_bytes_px = 0;
   uint32_t graph_launches = 0;
   bool env_no_graph = false, env_skip_export = false, env_local_color = false;   // developer toggles, read once at upload
+  bool env_graph_first = false;
+  uint32_t frames_rendered = 0;      // frames since the scene / camera / frame binding last changed
   cudaGraphExec_t graph = nullptr;   // the whole frame (all streams) captured once, replayed per cutrace_render
   bool graph_failed = false;
   cutrace_stats stats{};
@@ -146,6 +211,7 @@ struct DeviceGuard {
 void drop_graph(cutrace_ctx *c) {
   if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
   c->graph_failed = false;
+  c->frames_rendered = 0;
 }
 
 // multiplier of the tile permutation (see TileMap): ~0.618 n, odd, coprime to n; and its inverse mod n
@@ -355,18 +421,19 @@ void cutrace_default_opts(cutrace_opts *o) {
 void cutrace_free(cutrace_ctx *c) {
   if (!c) return;
   DeviceGuard g(c->device);
+  PhaseTimer ptimer; (void)ptimer;
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_frame(c);
+  LAP("free: frame + graph");
   dfree(c->bvh.nodes, c->stream); dfree(c->bvh.prims, c->stream);
   dfree(c->planes, c->stream); dfree(c->materials, c->stream); dfree(c->lights, c->stream); dfree(c->obj_material, c->stream);
   dfree(c->d_ctr, c->stream);
+  LAP("free: scene buffers");
   if (c->stream) cudaStreamSynchronize(c->stream);
   pinned_counters_put(c->h_ctr);
-  for (cudaEvent_t e : c->events) cudaEventDestroy(e);
-  for (int i = 0; i < 3; i++) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
-  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-  if (c->ev_gbuf) cudaEventDestroy(c->ev_gbuf);
-  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  LAP("free: sync");
+  stream_set_put(c->streams);   // waits for every stream of the set, then recycles it
+  LAP("free: events + streams");
   delete c;
 }
 
@@ -399,6 +466,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   if (!guard.ok) { delete c; return fail(CUTRACE_ERR_CUDA, "cudaSetDevice failed"); }
   pool_keep_memory(dev);
   c->env_no_graph = getenv("CUTRACE_NO_GRAPH") != nullptr;
+  c->env_graph_first = getenv("CUTRACE_GRAPH_FIRST") != nullptr;
   c->env_skip_export = getenv("CUTRACE_DEBUG_SKIP_EXPORT") != nullptr;      // timing experiments of profiles/r01_tuning.md only:
   c->env_local_color = getenv("CUTRACE_DEBUG_LOCAL_COLOR") != nullptr;      // they leave the peer frame incomplete
 
@@ -406,19 +474,14 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); cutrace_free(c); \
     return fail(e_ == cudaErrorMemoryAllocation ? CUTRACE_ERR_OUT_OF_MEMORY : CUTRACE_ERR_CUDA, m_); } } while (0)
 
-  {
-    int pr_least = 0, pr_greatest = 0;
-    CUF(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
-    if (o.stream) c->stream = (cudaStream_t)o.stream;
-    else { CUF(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr_greatest)); c->own_stream = true; }
-    // shade kernels run on two lower-priority streams so that the trace chain (the critical path) gets SMs first
-    for (int i = 0; i < 3; i++) CUF(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, pr_least));
-    CUF(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CUF(cudaEventCreateWithFlags(&c->ev_gbuf, cudaEventDisableTiming));
-  }
-  LAP("validate + streams");
-  for (int i = 0; i < 72; i++) { cudaEvent_t ev; CUF(cudaEventCreate(&ev)); c->events.push_back(ev); }
-  LAP("72 events");
+  CUF(stream_set_get(c->device, &c->streams));
+  if (o.stream) c->stream = (cudaStream_t)o.stream;
+  else { c->stream = c->streams->main; c->own_stream = true; }
+  for (int i = 0; i < 3; i++) c->aux[i] = c->streams->aux[i];
+  c->copy_stream = c->streams->copy;
+  c->ev_gbuf = c->streams->ev_gbuf;
+  c->events = c->streams->events;
+  LAP("validate + streams + events");
 
   // ---- flat records ----
   std::vector<PlaneRec> planes(s->n_planes);
@@ -583,6 +646,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     S.local_pixels = px;
     S.rays_primary = px;
   }
+  PhaseTimer ptimer; (void)ptimer;
   cudaEvent_t ev_begin = c->events[0], ev_end = c->events[1];
   const bool branching = c->max_children >= 2 && bounces > 0;
   const bool serialize = (c->opts.flags & CUTRACE_FLAG_SERIALIZE) != 0;
@@ -641,10 +705,13 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
 #undef EQ
   };
 
-  // One batch (the normal case): the frame is a CUDA graph, captured from the code above on the first call and
-  // replayed afterwards — one launch instead of ~40 API calls, which is what a 0.05 .. 2 ms frame is bound by.
+  // One batch (the normal case): the frame is a CUDA graph, captured from the code above and replayed afterwards — one
+  // launch instead of ~40 API calls, which is what a 0.05 .. 2 ms frame is bound by.  The FIRST frame of a ctx is
+  // enqueued directly: capture + instantiate cost more than the ~40 calls they replace, and a caller that renders one
+  // frame per scene (the reference's main.cu does) never gets that back; the graph is built on the second frame.
   const bool single_batch = c->batch_px >= c->n_local_px;
-  const bool use_graph = single_batch && !serialize && !c->graph_failed && !c->env_no_graph;
+  const bool use_graph = single_batch && !serialize && !c->graph_failed && !c->env_no_graph &&
+                         (c->frames_rendered > 0 || c->env_graph_first);
   if (use_graph && !c->graph) {
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
@@ -659,6 +726,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     }
     if (e != cudaSuccess) { cudaGetLastError(); c->graph = nullptr; c->graph_failed = true; }
     c->graph_launches = launches;   // kernels per frame, remembered for the replays
+    LAP("render: graph capture+instantiate");
   }
   float max_depth = 0.f;
   CU(cudaEventRecord(ev_begin, st));
@@ -684,7 +752,9 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     }
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     if (base + c->batch_px >= c->n_local_px) CU(cudaEventRecord(ev_end, st));
+    LAP("render: enqueue");
     CU(cudaStreamSynchronize(st));
+    LAP("render: wait for the frame");
     const FrameCounters &h = *c->h_ctr;
     if (h.overflow) return fail(CUTRACE_ERR_INTERNAL, "internal: ray queue overflow");
     S.rays_reflect += h.rays_reflect;
@@ -706,6 +776,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   CU(cudaEventElapsedTime(&S.render_ms, ev_begin, ev_end));
   S.max_depth = max_depth;
   c->rendered = true;
+  c->frames_rendered++;
   if (stats) *stats = S;
   return CUTRACE_OK;
 }
@@ -722,9 +793,12 @@ int cutrace_render_download(cutrace_ctx *c, float *depth, float *normal, float *
   if (!early) return cutrace_download(c, depth, normal, color, hit_id, max_depth);
   DeviceGuard g(c->device);
   const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
+  PhaseTimer ptimer; (void)ptimer;
   if (color) CU(cudaMemcpyAsync(color, frame_views(c->frame, n).color, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  LAP("render_download: colour D2H");
   CU(cudaStreamSynchronize(c->copy_stream));
+  LAP("render_download: G-buffer D2H tail");
   if (max_depth) *max_depth = c->stats.max_depth;
   return CUTRACE_OK;
 }

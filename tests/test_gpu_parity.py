@@ -447,6 +447,23 @@ def test_overlapped_and_serialized_frames_are_bit_identical(ct):
         assert sa["rays_total"] == sb["rays_total"] and sb["trace_ms"] > 0 and sb["shade_ms"] > 0
 
 
+def test_direct_first_frame_and_graph_replays_are_bit_identical(ct):
+    """The first frame of a ctx is enqueued stream by stream, the second captures the CUDA graph, later ones replay it:
+    same bits and same counters every time (bunny.json: one ray per pixel and level, deterministic sum)."""
+    s = load_golden_scene("bunny").with_resolution(320, 180)
+    with ct.Renderer(s) as r:
+        frames = []
+        for _ in range(4):
+            st = r.render()
+            frames.append((r.download(), st))
+    a, sa = frames[0]
+    for b, sb in frames[1:]:
+        for k in ("depth", "normal", "color", "hit_id"):
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+        assert sa["rays_total"] == sb["rays_total"] and sa["kernel_launches"] == sb["kernel_launches"] == 13
+        assert a["max_depth"] == b["max_depth"]
+
+
 def test_render_download_fused_equals_render_then_download(ct):
     """cutrace_render_download (G-buffer copies under the bounce levels, colour at the end) must return exactly what
     cutrace_render + cutrace_download return — also right after a camera change, when the frame still holds the
