@@ -298,9 +298,49 @@ __global__ void rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const ui
   }
 }
 
+// Up to SMALL_SORT_MAX pairs (the reference's own scenes: 1 .. 1005 primitives) are sorted by ONE block in shared memory
+// instead of 8 passes x 5 launches: a bitonic network over (key, input position), which orders equal keys by position
+// and therefore gives exactly the stable result of the LSD passes.  0.2 ms -> ~0.02 ms of the 0.4 ms LBVH build of bunny.json.
+constexpr uint32_t SMALL_SORT_MAX = 2048;
+__global__ void __launch_bounds__(1024) small_sort_kernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t n) {
+  __shared__ uint64_t sk[SMALL_SORT_MAX];
+  __shared__ uint32_t sp[SMALL_SORT_MAX], sv[SMALL_SORT_MAX];
+  uint32_t P = 2;
+  while (P < n) P <<= 1;
+  for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+    sk[i] = i < n ? keys[i] : ~0ull;     // padding sorts to the end (and behind real ~0 keys: larger position)
+    sp[i] = i;
+    sv[i] = i < n ? vals[i] : 0u;
+  }
+  __syncthreads();
+  for (uint32_t k = 2; k <= P; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        const uint32_t q = i ^ j;
+        if (q > i) {
+          const uint64_t a = sk[i], b = sk[q];
+          const uint32_t pa = sp[i], pb = sp[q];
+          const bool up = (i & k) == 0;                       // ascending run
+          const bool a_gt_b = a > b || (a == b && pa > pb);
+          if (a_gt_b == up) { sk[i] = b; sk[q] = a; sp[i] = pb; sp[q] = pa; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { keys[i] = sk[i]; vals[i] = sv[sp[i]]; }
+}
+
 int radix_sort_pairs(uint64_t *d_keys, uint32_t *d_vals, uint32_t n, cudaStream_t st, std::string &err) {
   int rc = CUTRACE_OK;
   if (n < 2) return rc;
+  if (n <= SMALL_SORT_MAX) {
+    small_sort_kernel<<<1, 1024, 0, st>>>(d_keys, d_vals, n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { err = std::string("small_sort_kernel: ") + cudaGetErrorString(e); return CUTRACE_ERR_CUDA; }
+    return rc;
+  }
   uint64_t *k2 = nullptr;
   uint32_t *v2 = nullptr, *hist = nullptr, *tile_sums = nullptr;
   uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
