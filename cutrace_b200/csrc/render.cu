@@ -437,7 +437,7 @@ __global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restri
   o[0] = r; o[1] = g; o[2] = b;
   if (gsrc.depth) {
     // peer frame: the level-0 G-buffer was written to the local tile-major buffers (small 8x4-block stores are slow
-    // over NVLink); it travels here together with the colour, one 32-pixel tile row (128..384 contiguous bytes) per warp
+    // over NVLink); it travels here together with the colour, 16-pixel tile rows (64..192 contiguous bytes) per half warp
     out.depth[gi] = gsrc.depth[pix];
     out.hit_id[gi] = gsrc.hit_id[pix];
     out.normal[3 * gi] = gsrc.normal[3 * (size_t)pix]; out.normal[3 * gi + 1] = gsrc.normal[3 * (size_t)pix + 1];
@@ -446,7 +446,7 @@ __global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restri
 }
 
 // forwards the level-0 G-buffer of this rank's tiles (tile-major, local) to a row-major frame in peer memory: one
-// 32-pixel tile row per warp -> 128 / 384-byte contiguous NVLink stores.  Runs on an auxiliary stream right after
+// 16-pixel tile row per half warp -> 64 / 192-byte contiguous NVLink stores.  Runs on an auxiliary stream right after
 // trace(0), i.e. the transfer overlaps the remaining bounce levels.
 __global__ void export_gbuffer_kernel(const TileMap tm, uint32_t px_base, uint32_t n_px, FrameTargets src, FrameTargets out) {
   // a SMALL grid-stride grid: the kernel is bound by the NVLink stores (all ranks push into rank 0 at the same moment),

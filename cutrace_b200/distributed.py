@@ -2,9 +2,11 @@
 
 This is the only place the render path shards: pixels are independent
 (/root/reference/inc/kernel.hpp:37-59 has no inter-thread communication), so rank r renders the
-32x32 tiles t with t % world == r into a tile-major local buffer; ONE exchange step follows — an NCCL
-gather of the float framebuffers to rank 0 over NVLink — and rank 0 un-tiles the gathered buffers into
-row-major images on the device (cutrace_untile_device).  torch.distributed is plumbing only.
+16x16 tiles whose slot s (screen tile (s * a) % n_tiles, a multiplicative permutation) has s % world == r.
+ONE exchange step follows.  Default ("peer"): every rank's kernels store their tiles straight into rank 0's
+row-major frame over NVLink (CUDA IPC), so the exchange is fused into the producing kernels and only a
+barrier remains.  Fallback ("gather"): tile-major local buffers, an NCCL gather of the float framebuffers
+to rank 0, and an un-tile kernel there (cutrace_untile_device).  torch.distributed is plumbing only.
 """
 from __future__ import annotations
 
