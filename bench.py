@@ -172,7 +172,7 @@ def run_reference(args, scene, wl):
                     scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", config={"workload": wl["label"]},
                     cpu_baseline=cb, e2e={"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     reference_arm="host build of the reference's device functions (no sm_100a rebuild available)")
-        print(json.dumps(line))
+        emit(line)
         return
     # unique-ray numerator: counted by our renderer on the same frame (identical for every implementation)
     with ct.Renderer(scene, device=0) as r:
@@ -209,7 +209,27 @@ def run_reference(args, scene, wl):
                      "d2h_bytes_per_step": int(28 * n), "what": "cutrace::gpu::render<S,5,256> total bracket (inc/kernel.hpp:88-126)"},
                 cpu_baseline=cb,
                 reference_arm="reference CUDA kernel rebuilt for sm_100a (the comparator north_star names); cpu_baseline is the reference's device code compiled for the host")
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." to fd 1 when
+    NCCL_DEBUG is set on the box), so fd 1 is pointed at stderr for the rest of the process — library banners, child
+    processes, stray prints — and the result line goes to a private duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -225,6 +245,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "gather"],
                     help="N > 1: peer = kernels store into rank 0's frame over NVLink (CUDA IPC), gather = NCCL gather + un-tile")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3:
         args.warmup = 3
 
@@ -412,7 +433,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(scene, wl["label"])
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "absent", "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -67,3 +67,24 @@ def test_jpeg_corner_sizes(tmp_path, w, h):
     assert im.size == (w, h)
     got = np.asarray(im.convert("RGB")).astype(float)
     assert np.abs(got - img).mean() < 12.0
+
+
+def test_bench_stdout_carries_only_the_result_line(tmp_path):
+    """bench.py's contract is ONE JSON line on stdout; library banners on fd 1 (NCCL's version line) must land on stderr."""
+    import json
+    import subprocess
+    import sys
+
+    script = tmp_path / "emit_check.py"
+    script.write_text(
+        "import os, sys, subprocess\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "bench.claim_stdout()\n"
+        "print('stray python print')\n"
+        "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n')\n"
+        "subprocess.run(['echo', 'stray child output'])\n"
+        "bench.emit({'metric': 'x', 'value': 1})\n")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, check=True)
+    assert json.loads(r.stdout) == {"metric": "x", "value": 1} and r.stdout.count("\n") == 1
+    assert "NCCL version" in r.stderr and "stray python print" in r.stderr and "stray child output" in r.stderr
