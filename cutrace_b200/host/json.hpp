@@ -104,6 +104,7 @@ class JsonParser {
           default: err = at("bad escape in string"); return false;
         }
       } else {
+        if ((unsigned char)c < 0x20) { err = at("control character in string"); return false; }   // as picojson and RFC 8259
         out += c;
       }
     }
@@ -157,11 +158,16 @@ class JsonParser {
     if (lit("false")) { v.kind = JsonValue::Bool; v.b = false; return true; }
     if (lit("null")) { v.kind = JsonValue::Null; return true; }
     if (c == '-' || (c >= '0' && c <= '9')) {
-      const char *start = s_.c_str() + p_;
+      // picojson's number rule (the reference's JSON library, CMakeLists.txt:14-17), restated: take the longest run of
+      // [0-9+-.eE], and strtod must consume all of it.  Lenient where strict JSON is not ("041", "0.", "1.e5") and strict
+      // where a bare strtod is not ("0x10", "-inf": the run ends at 'x' / 'i').
+      size_t q = p_;
+      while (q < s_.size() && ((s_[q] >= '0' && s_[q] <= '9') || s_[q] == '+' || s_[q] == '-' || s_[q] == '.' || s_[q] == 'e' || s_[q] == 'E')) q++;
+      const std::string run = s_.substr(p_, q - p_);
       char *end = nullptr;
-      double d = strtod(start, &end);
-      if (end == start) { err = at("bad number"); return false; }
-      p_ += (size_t)(end - start);
+      double d = strtod(run.c_str(), &end);
+      if (run.empty() || end != run.c_str() + run.size()) { err = at("bad number"); return false; }
+      p_ = q;
       v.kind = JsonValue::Number;
       v.num = d;
       return true;

@@ -2,6 +2,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cctype>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -56,6 +57,32 @@ void look_at(const float pos[3], const float up_in[3], const float look[3], floa
 }
 
 // ---- STL ---------------------------------------------------------------------------------------------
+
+// a whole token must be one number ("0.5x" or "1e" is malformed, not 0.5 / 1): same rule as the Python mirror's float()
+// grammar: [+-] ( digits [. digits] | . digits ) [ (e|E) [+-] digits ]  |  [+-] inf | infinity | nan   (no hex floats)
+static bool parse_number(const std::string &tok, double &out) {
+  size_t i = 0;
+  const size_t n = tok.size();
+  if (i < n && (tok[i] == '+' || tok[i] == '-')) i++;
+  std::string rest;
+  for (size_t k = i; k < n; k++) rest.push_back((char)tolower((unsigned char)tok[k]));
+  if (rest != "inf" && rest != "infinity" && rest != "nan") {
+    size_t digits = 0;
+    while (i < n && isdigit((unsigned char)tok[i])) { i++; digits++; }
+    if (i < n && tok[i] == '.') { i++; while (i < n && isdigit((unsigned char)tok[i])) { i++; digits++; } }
+    if (!digits) return false;
+    if (i < n && (tok[i] == 'e' || tok[i] == 'E')) {
+      i++;
+      if (i < n && (tok[i] == '+' || tok[i] == '-')) i++;
+      size_t ed = 0;
+      while (i < n && isdigit((unsigned char)tok[i])) { i++; ed++; }
+      if (!ed) return false;
+    }
+    if (i != n) return false;
+  }
+  out = strtod(tok.c_str(), nullptr);
+  return true;
+}
 bool read_stl(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err) {
   std::ifstream f(path, std::ios::binary);
   if (!f) { err = "cannot open mesh file '" + path + "'"; return false; }
@@ -77,9 +104,12 @@ bool read_stl(const std::string &path, std::vector<float> &p1, std::vector<float
   std::vector<float> verts;
   while (in >> tok) {
     if (tok == "vertex") {
-      double x, y, z;
-      if (!(in >> x >> y >> z)) { err = "bad vertex in ASCII STL '" + path + "'"; return false; }
-      verts.push_back((float)x); verts.push_back((float)y); verts.push_back((float)z);
+      double c[3];
+      for (double &x : c) {
+        std::string num;
+        if (!(in >> num) || !parse_number(num, x)) { err = "bad vertex in ASCII STL '" + path + "'"; return false; }
+      }
+      verts.push_back((float)c[0]); verts.push_back((float)c[1]); verts.push_back((float)c[2]);
     }
   }
   if (verts.empty() || verts.size() % 9) { err = "cannot read STL file '" + path + "'"; return false; }
@@ -105,14 +135,20 @@ bool read_obj(const std::string &path, std::vector<float> &p1, std::vector<float
     std::string tag;
     if (!(in >> tag)) continue;
     if (tag == "v") {
-      double x, y, z;
-      if (!(in >> x >> y >> z)) { err = "bad vertex in OBJ '" + path + "'"; return false; }
-      v.push_back((float)x); v.push_back((float)y); v.push_back((float)z);
+      double c[3];
+      for (double &x : c) {
+        std::string num;
+        if (!(in >> num) || !parse_number(num, x)) { err = "bad vertex in OBJ '" + path + "'"; return false; }
+      }
+      v.push_back((float)c[0]); v.push_back((float)c[1]); v.push_back((float)c[2]);
     } else if (tag == "f") {
       std::vector<long> idx;
       std::string tok;
       while (in >> tok) {
-        long i = strtol(tok.c_str(), nullptr, 10);   // the part before the first '/'
+        char *end = nullptr;
+        long i = strtol(tok.c_str(), &end, 10);   // the part before the first '/'
+        const bool whole = end == tok.c_str() + tok.size();   // not `*end == 0`: a token may hold an embedded NUL byte
+        if (end == tok.c_str() || (!whole && *end != '/')) { err = "bad face index in OBJ '" + path + "'"; return false; }
         const long nv = (long)(v.size() / 3);
         if (i < 0) i = nv + i + 1;
         if (i < 1 || i > nv) { err = "face index out of range in OBJ '" + path + "'"; return false; }

@@ -17,6 +17,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import re
 import struct
 from dataclasses import dataclass, field
 
@@ -78,6 +79,17 @@ def look_at(pos, up, look):
     return forward, right, up2
 
 
+_NUMBER = re.compile(rb"[+-]?((\d+\.?\d*|\.\d+)([eE][+-]?\d+)?|inf|infinity|nan)\Z", re.IGNORECASE)
+_INDEX = re.compile(rb"[+-]?\d+\Z")
+
+
+def _mesh_number(tok):
+    """One whole token (bytes) = one number, same grammar as parse_number() in cutrace_b200/host/scene_loader.cpp."""
+    if not _NUMBER.match(tok):
+        raise ValueError(tok)
+    return float(tok)
+
+
 def read_stl(path):
     """Binary or ASCII STL -> (n,3,3) float32 vertex array in file order.
 
@@ -98,10 +110,17 @@ def read_stl(path):
             return rec[:, 12:48].copy().view("<f4").reshape(n, 3, 3).astype(np.float32)
     # ASCII
     verts = []
-    for line in data.decode("ascii", errors="replace").splitlines():
-        p = line.split()
-        if len(p) == 4 and p[0] == "vertex":
-            verts.append([float(p[1]), float(p[2]), float(p[3])])
+    toks = data.split()      # bytes: ASCII white space only.  A token stream, like the C++ reader: "vertex" + three numbers
+    k = 0
+    while k < len(toks):
+        if toks[k] == b"vertex":
+            try:
+                verts.append([_mesh_number(toks[k + 1]), _mesh_number(toks[k + 2]), _mesh_number(toks[k + 3])])
+            except (IndexError, ValueError) as e:
+                raise SceneError(f"bad vertex in ASCII STL {path!r}") from e
+            k += 4
+        else:
+            k += 1
     if not verts or len(verts) % 3:
         raise SceneError(f"cannot read STL file {path!r}")
     return np.asarray(verts, dtype=np.float64).astype(np.float32).reshape(-1, 3, 3)
@@ -111,8 +130,8 @@ def read_obj(path):
     """Wavefront OBJ -> (n,3,3) float32: `v` and `f` records only, a/b/c index forms, negative indices, polygons
     fan-triangulated from their first vertex (mirror of cutrace_b200/host/scene_loader.cpp read_obj)."""
     try:
-        with open(path, "r", errors="replace") as f:
-            lines = f.readlines()
+        with open(path, "rb") as f:
+            lines = f.read().split(b"\n")      # bytes: lines end at LF only and tokens at ASCII white space, like std::getline / operator>>
     except OSError as e:
         raise SceneError(f"cannot open mesh file {path!r}") from e
     v, tris = [], []
@@ -120,14 +139,18 @@ def read_obj(path):
         p = line.split()
         if not p:
             continue
-        if p[0] == "v":
-            if len(p) < 4:
-                raise SceneError(f"bad vertex in OBJ {path!r}")
-            v.append([float(p[1]), float(p[2]), float(p[3])])
-        elif p[0] == "f":
+        if p[0] == b"v":
+            try:
+                v.append([_mesh_number(p[1]), _mesh_number(p[2]), _mesh_number(p[3])])
+            except (IndexError, ValueError) as e:
+                raise SceneError(f"bad vertex in OBJ {path!r}") from e
+        elif p[0] == b"f":
             idx = []
             for tok in p[1:]:
-                i = int(tok.split("/")[0])
+                head = tok.split(b"/")[0]
+                if not _INDEX.match(head):
+                    raise SceneError(f"bad face index in OBJ {path!r}")
+                i = int(head)
                 if i < 0:
                     i = len(v) + i + 1
                 if not 1 <= i <= len(v):

@@ -183,3 +183,66 @@ def test_synthetic_grid_as_json_and_stl_files(host, tmp_path):
     path = synth.write_scene_files(soup, str(tmp_path), [0, 0.3, -5], [0, 1, 0], [0, 0, 0], name="soup")
     assert _same(soup, load_scene_json(path, base_dir=str(tmp_path))) == []
     assert _same(soup, host.load_scene(path, base_dir=str(tmp_path))) == []
+
+
+def test_json_numbers_follow_picojson_rule(host, tmp_path):
+    """The reference parses scene files with picojson: a number is the longest run of [0-9+-.eE] that strtod consumes
+    entirely.  So "041" and "0." load (strict JSON would refuse them), "0x10" / "-inf" / a raw control character in a
+    string do not."""
+    from cutrace_b200.scene import SceneError
+
+    src = open(os.path.join(ROOT, "scenes", "solids.json")).read()
+    assert '"near_plane": 0.1' in src and '"ambient"' in src
+
+    def load(text):
+        p = tmp_path / "s.json"
+        p.write_text(text)
+        return host.load_scene(str(p), base_dir=ROOT)
+
+    base = load(src)
+    assert _same(base, load(src.replace('"near_plane": 0.1', '"near_plane": 041'))) == []      # near_plane is dead on the path
+    assert _same(base, load(src.replace('"near_plane": 0.1', '"near_plane": 0.'))) == []
+    assert _same(base, load(src.replace('"near_plane": 0.1', '"near_plane": 1.e-1'))) == []
+    for bad in ('0x10', '-inf', 'nan', '1e', '--1', '.5'):
+        with pytest.raises(SceneError):
+            load(src.replace('"near_plane": 0.1', f'"near_plane": {bad}'))
+    with pytest.raises(SceneError):
+        load(src.replace('"near_plane"', '"near\tplane"'))
+
+
+def test_mesh_tokens_must_be_whole_numbers(host, tmp_path):
+    """Both front-ends read ASCII STL / OBJ as byte tokens split at ASCII white space, and a coordinate or index token has to
+    be one number in full — "0.5x", a hex float or an embedded NUL is a malformed file, not a truncated value."""
+    from cutrace_b200.scene import SceneError, read_mesh
+
+    stl = open(os.path.join(ROOT, "scenes", "tetra.stl"), "rb").read()
+    obj = open(os.path.join(ROOT, "scenes", "cube.obj"), "rb").read()
+    assert b"vertex" in stl and b"\nf " in obj
+    doc = json.load(open(os.path.join(ROOT, "scenes", "solids.json")))
+
+    def both(name, data):
+        path = tmp_path / name
+        path.write_bytes(data)
+        scene = {"objects": [{"type": "mesh", "file": str(path), "material": 0}], "lights": doc["lights"],
+                 "materials": doc["materials"], "camera": doc["camera"]}
+        sp = tmp_path / "s.json"
+        sp.write_text(json.dumps(scene))
+        out = []
+        for fn in (lambda: host.load_scene(str(sp), base_dir="/").n_triangles, lambda: len(read_mesh(str(path)))):
+            try:
+                out.append(fn())
+            except SceneError:
+                out.append(None)
+        return out
+
+    assert both("ok.stl", stl) == [4, 4] and both("ok.obj", obj) == [12, 12]
+    first = stl.index(b"vertex") + len(b"vertex ")
+    num_end = stl.index(b" ", first)
+    assert both("x.stl", stl[:num_end] + b"x" + stl[num_end:]) == [None, None]                 # "0.000000x"
+    assert both("hex.stl", stl[:first] + b"0x1p0" + stl[num_end:]) == [None, None]
+    assert both("nel.stl", stl[:num_end] + b"\x85" + stl[num_end:]) == [None, None]            # NEL is not white space
+    assert both("split.stl", stl.replace(b"vertex ", b"vertex\n", 1)) == [4, 4]               # a token stream, not lines
+    face = obj.index(b"\nf ") + 3
+    assert both("idx.obj", obj[:face] + b"1x " + obj[face:]) == [None, None]
+    assert both("nul.obj", obj[:face + 1] + b"\x00" + obj[face + 1:]) == [None, None]
+    assert both("cr.obj", obj.replace(b"\n", b"\r\n")) == [12, 12]                             # CR is white space
