@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    "triangle": dict(scene="triangle", width=20, height=20, label="scene/triangle.json@20x20"),
     "bunny4k": dict(scene="bunny", width=3840, height=2160, label="scene/bunny.json@3840x2160"),
     "mirror1080": dict(scene="mirror", width=1920, height=1080, label="scene/mirror.json@1920x1080"),
     "spheres1080": dict(scene="sphere_plane", width=1920, height=1080, label="scene/sphere_plane.json@1920x1080"),

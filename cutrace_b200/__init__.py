@@ -72,6 +72,13 @@ class Renderer:
         _lib.check(self._lib.cutrace_get_stats(self._ctx, C.byref(st)))
         return st.as_dict()
 
+    def phase_ms(self):
+        """cutrace_get_phase_ms: when each bounce level's rays were all traced / the frame was assembled (ms from kernel start)."""
+        buf = (C.c_float * 18)()
+        n = C.c_uint32()
+        _lib.check(self._lib.cutrace_get_phase_ms(self._ctx, buf, 18, C.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
+
     def download(self, into=None, want=("depth", "normal", "color", "hit_id")):
         n = self.width * self.height
         out = into or {}

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("CUTRACE_B200_LIB") or os.path.join(HERE, "lib", "libc
 # every symbol include/cutrace.h declares
 SYMBOLS = (
     "cutrace_default_opts", "cutrace_upload_scene", "cutrace_render", "cutrace_download", "cutrace_render_download", "cutrace_download_bytes", "cutrace_free",
-    "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_device_buffers", "cutrace_frame_device",
+    "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_get_phase_ms", "cutrace_device_buffers", "cutrace_frame_device",
     "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach", "cutrace_enable_peer_access",
     "cutrace_set_frame_max_depth",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free",
@@ -80,6 +80,7 @@ def load():
     lib.cutrace_set_camera.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                        C.POINTER(C.c_float), C.c_float, C.c_uint32, C.c_uint32]
     lib.cutrace_get_stats.argtypes = [P, C.POINTER(cutrace_stats)]
+    lib.cutrace_get_phase_ms.argtypes = [P, C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint32)]
     lib.cutrace_device_buffers.argtypes = [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(C.c_uint64)]
     lib.cutrace_frame_device.argtypes = [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P)]
     lib.cutrace_frame_ipc_export.argtypes = [P, P]

@@ -9,6 +9,7 @@
 //                         (inc/kernel.hpp:110-125) with one device un-tile + one copy per image.
 // There is NO CPU fallback anywhere in this library: without a CUDA device every entry point
 // fails with CUTRACE_ERR_NO_DEVICE.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -69,7 +70,7 @@ static FrameCounters *pinned_counters_get() {
     if (!g_pinned_free.empty()) { FrameCounters *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
   }
   FrameCounters *p = nullptr;
-  if (cudaHostAlloc(&p, sizeof(FrameCounters), cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  if (cudaHostAlloc(&p, sizeof(FrameCounters), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return nullptr;
   return p;
 }
 static void pinned_counters_put(FrameCounters *p) {
@@ -175,7 +176,13 @@ struct cutrace_ctx {
   uint64_t batch_px = 0, cap = 0;
   uint32_t factor = 1;
   FrameCounters *d_ctr = nullptr;
-  FrameCounters *h_ctr = nullptr;   // pinned
+  FrameCounters *h_ctr = nullptr;   // pinned + mapped: the frame kernel publishes its counters here
+  FrameCounters *h_ctr_dev = nullptr;   // device address of h_ctr
+  float phase_ms[18] = {};          // frame kernel: when trace(p) was complete / the frame ended, relative to its start (last batch)
+  uint32_t phase_count = 0;
+  bool ctr_dirty = true;            // d_ctr may hold values of an earlier (multi-launch or failed) frame: clear before a frame kernel
+  bool frame_kernel_failed = false; // a cooperative launch was refused: this ctx stays on the multi-launch path
+  bool env_no_frame_kernel = false, env_export_with_color = false;
   LaunchCfg cfg{};
   // download staging (row-major full frame), lazily allocated
   float *st_depth = nullptr;         // staging frame block (same layout as `frame`)
@@ -300,10 +307,11 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   batch = (batch / 1024ull) * 1024ull;
   if (batch < 1024) batch = 1024;
   if (batch > c->n_local_px) batch = c->n_local_px;
-  while (batch * c->factor >= (1ull << 31) - (1ull << 24) && batch > 1024) batch = ((batch / 2) / 1024ull) * 1024ull;
+  while (batch * c->factor >= (1ull << 31) - (1ull << 25) && batch > 1024) batch = ((batch / 2) / 1024ull) * 1024ull;
   c->batch_px = batch;
   // every producer warp may leave one partly used slot block per queue behind
-  const uint64_t slack = (uint64_t)c->cfg.grid_trace * (TRACE_THREADS / 32) * SLOT_BLOCK;
+  // (reserve_slots in render.cu: the tail of a warp's last block of a level is the only thing it ever leaves unused)
+  const uint64_t slack = (uint64_t)std::max(c->cfg.grid_trace, c->cfg.grid_frame) * (TRACE_THREADS / 32) * SLOT_BLOCK;
   c->cap = batch * c->factor + slack;
 
   cudaStream_t st = c->stream;
@@ -466,6 +474,8 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   if (!guard.ok) { delete c; return fail(CUTRACE_ERR_CUDA, "cudaSetDevice failed"); }
   pool_keep_memory(dev);
   c->env_no_graph = getenv("CUTRACE_NO_GRAPH") != nullptr;
+  c->env_no_frame_kernel = getenv("CUTRACE_NO_FRAME_KERNEL") != nullptr;          // developer toggle: one launch per level and kind, as a CUDA graph
+  c->env_export_with_color = getenv("CUTRACE_EXPORT_WITH_COLOR") != nullptr;      // developer toggle: remote G-buffer stores at the end of the frame
   c->env_graph_first = getenv("CUTRACE_GRAPH_FIRST") != nullptr;
   c->env_skip_export = getenv("CUTRACE_DEBUG_SKIP_EXPORT") != nullptr;      // timing experiments of profiles/r01_tuning.md only:
   c->env_local_color = getenv("CUTRACE_DEBUG_LOCAL_COLOR") != nullptr;      // they leave the peer frame incomplete
@@ -573,6 +583,11 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   CUF(dmalloc(&c->d_ctr, sizeof(FrameCounters), c->stream));
   c->h_ctr = pinned_counters_get();
   if (!c->h_ctr) { cutrace_free(c); return fail(CUTRACE_ERR_OUT_OF_MEMORY, "cudaHostAlloc failed"); }
+  {
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, c->h_ctr, 0) == cudaSuccess) c->h_ctr_dev = static_cast<FrameCounters *>(dp);
+    else cudaGetLastError();
+  }
   LAP("ctr alloc");
   {
     // shared-memory plan: everything (nodes + primitives) if it fits next to the SM, else the top of the tree
@@ -674,13 +689,14 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       RayRec *in = c->rays[L & 1], *outq = c->rays[(L + 1) & 1];
       cudaEvent_t e0 = c->events[2 + 3 * L], e1 = c->events[3 + 3 * L], e2 = c->events[4 + 3 * L];
       if (serialize) EQ(cudaEventRecord(e0, st));
-      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, c->shade[L], c->d_ctr, gbuf, c->nlev, (uint32_t)bound, st);
+      launch_trace(c->cfg, c->sv, c->tm, L, bounces, (uint32_t)base, n_px, in, outq, (uint32_t)c->cap, c->shade[L], (uint32_t)c->shade_cap[L], c->d_ctr, gbuf,
+                   c->nlev, (uint32_t)bound, st);
       EQ(cudaEventRecord(e1, st));
       if (L == 0) EQ(cudaEventRecordWithFlags(c->ev_gbuf, st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
       cudaStream_t ss = serialize ? st : c->aux[L & 1];
       if (!serialize) EQ(cudaStreamWaitEvent(ss, e1, 0));
       float *lc = branching ? nullptr : c->level_color + (size_t)L * 3 * c->batch_px;
-      launch_shade(c->cfg, c->sv, L, c->shade[L], c->d_ctr, acc, branching, lc, (uint32_t)base, (uint32_t)bound, ss);
+      launch_shade(c->cfg, c->sv, L, c->shade[L], (uint32_t)c->shade_cap[L], c->d_ctr, acc, branching, lc, (uint32_t)base, (uint32_t)bound, ss);
       EQ(cudaEventRecord(e2, ss));
       launches += 2;
       if (L == 0 && gsrc.depth && !c->env_skip_export) {   // peer frame: ship the G-buffer now, under the remaining levels
@@ -705,12 +721,58 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
 #undef EQ
   };
 
+  // Default path: ONE persistent cooperative kernel per pixel batch runs every bounce level (render.cu: frame_kernel).  It expects
+  // cleared counters and leaves them cleared; its counters arrive in c->h_ctr (mapped pinned memory) without a copy.
+  // With an early G-buffer download pending (cutrace_render_download) trace(0) runs as its own kernel first, so that the
+  // copy engine can start behind it while the frame kernel works on the bounce levels.
+  const bool use_frame = !serialize && !c->env_no_frame_kernel && !c->frame_kernel_failed && c->cfg.grid_frame > 0 && c->h_ctr_dev;
+  auto enqueue_frame = [&](uint64_t base, uint32_t n_px, bool split_primary) -> cudaError_t {
+    cudaError_t e;
+    if (c->ctr_dirty) {
+      if ((e = cudaMemsetAsync(c->d_ctr, 0, sizeof(FrameCounters), st)) != cudaSuccess) return e;
+      c->ctr_dirty = false;
+    }
+    if (branching && base == 0 && (e = cudaMemsetAsync(c->local_color, 0, sizeof(float) * 3 * c->n_local_px, st)) != cudaSuccess) return e;
+    const uint64_t warps = (uint64_t)std::max(c->cfg.grid_trace, c->cfg.grid_frame) * (TRACE_THREADS / 32);
+    FrameArgs fa{};
+    fa.sv = c->sv; fa.tm = c->tm; fa.bounces = bounces; fa.levels = levels; fa.first_level = 0;
+    fa.px_base = (uint32_t)base; fa.n_px = n_px;
+    fa.rays[0] = c->rays[0]; fa.rays[1] = c->rays[1]; fa.ray_cap = (uint32_t)c->cap;
+    uint64_t bound_max = n_px;
+    for (uint32_t L = 0; L < levels; L++) {
+      fa.shade[L] = c->shade[L]; fa.shade_cap[L] = (uint32_t)c->shade_cap[L];
+      uint64_t bound = (uint64_t)n_px * (branching ? (1ull << L) : 1ull) + warps * SLOT_BLOCK;
+      if (bound > c->shade_cap[L]) bound = c->shade_cap[L];
+      bound_max = std::max(bound_max, bound);
+    }
+    fa.ctr = c->d_ctr; fa.host_ctr = c->h_ctr_dev;
+    fa.gbuf = gbuf; fa.out = out; fa.gsrc = gsrc; fa.acc = acc;
+    if (c->env_skip_export) fa.gsrc = FrameTargets{};
+    fa.level_color = branching ? nullptr : c->level_color; fa.level_stride = 3ull * c->batch_px; fa.nlev = c->nlev;
+    fa.local_color = c->local_color; fa.combine_levels = branching ? 0u : levels; fa.atomic_accumulate = branching ? 1 : 0;
+    fa.combine = 1; fa.export_with_color = c->env_export_with_color ? 1 : 0;
+    if (c->peer_frame && c->fb.color && c->env_local_color) { fa.out = c->fb; fa.out.row_major = 0; }   // timing experiment only
+    if (split_primary) {
+      const uint64_t b0 = std::min<uint64_t>((uint64_t)n_px + warps * SLOT_BLOCK, c->shade_cap[0]);
+      launch_trace(c->cfg, c->sv, c->tm, 0, bounces, (uint32_t)base, n_px, c->rays[0], c->rays[1], (uint32_t)c->cap, c->shade[0], (uint32_t)c->shade_cap[0],
+                   c->d_ctr, gbuf, c->nlev, (uint32_t)b0, st);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(c->ev_gbuf, st)) != cudaSuccess) return e;
+      fa.first_level = 1;
+      launches += 1;
+    }
+    c->ctr_dirty = true;   // until the kernel has run to its end
+    if ((e = launch_frame(c->cfg, fa, (uint32_t)std::min<uint64_t>(bound_max, 0xffffffffull), st)) != cudaSuccess) return e;
+    launches += 1;
+    return cudaSuccess;
+  };
+
   // One batch (the normal case): the frame is a CUDA graph, captured from the code above and replayed afterwards — one
   // launch instead of ~40 API calls, which is what a 0.05 .. 2 ms frame is bound by.  The FIRST frame of a ctx is
   // enqueued directly: capture + instantiate cost more than the ~40 calls they replace, and a caller that renders one
   // frame per scene (the reference's main.cu does) never gets that back; the graph is built on the second frame.
   const bool single_batch = c->batch_px >= c->n_local_px;
-  const bool use_graph = single_batch && !serialize && !c->graph_failed && !c->env_no_graph &&
+  const bool use_graph = !use_frame && single_batch && !serialize && !c->graph_failed && !c->env_no_graph &&
                          (c->frames_rendered > 0 || c->env_graph_first);
   if (use_graph && !c->graph) {
     cudaGraph_t g = nullptr;
@@ -732,15 +794,32 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   CU(cudaEventRecord(ev_begin, st));
   for (uint64_t base = 0; base < c->n_local_px; base += c->batch_px) {
     const uint32_t n_px = (uint32_t)std::min<uint64_t>(c->batch_px, c->n_local_px - base);
-    if (c->graph && use_graph) {
-      CU(cudaGraphLaunch(c->graph, st));
-      S.kernel_launches = c->graph_launches;
-    } else {
+    const bool early_gbuf = single_batch && c->frame && !c->peer_frame && (c->dl_depth || c->dl_normal || c->dl_id);
+    bool frame_done = false;
+    if (use_frame) {
       launches = 0;
-      CU(enqueue(base, n_px));
-      S.kernel_launches += launches;
+      cudaError_t fe = enqueue_frame(base, n_px, early_gbuf);
+      if (fe == cudaSuccess) {
+        frame_done = true;
+        S.kernel_launches += launches;
+      } else {   // e.g. cudaErrorCooperativeLaunchTooLarge under MPS limits: stay on the multi-launch path from now on
+        cudaGetLastError();
+        c->frame_kernel_failed = true;
+        CU(cudaStreamSynchronize(st));
+      }
     }
-    if (single_batch && c->frame && !c->peer_frame && (c->dl_depth || c->dl_normal || c->dl_id)) {
+    if (!frame_done) {
+      c->ctr_dirty = true;
+      if (c->graph && use_graph) {
+        CU(cudaGraphLaunch(c->graph, st));
+        S.kernel_launches = c->graph_launches;
+      } else {
+        launches = 0;
+        CU(enqueue(base, n_px));
+        S.kernel_launches += launches;
+      }
+    }
+    if (early_gbuf) {
       // G-buffer -> host underneath the remaining bounce levels (copy engine; the frame is already row-major)
       const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
       const FrameTargets v = frame_views(c->frame, n);
@@ -750,13 +829,21 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       if (c->dl_normal) CU(cudaMemcpyAsync(c->dl_normal, v.normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->copy_stream));
       c->dl_depth = c->dl_normal = nullptr; c->dl_id = nullptr;   // consumed
     }
-    CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+    if (!frame_done) CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     if (base + c->batch_px >= c->n_local_px) CU(cudaEventRecord(ev_end, st));
     LAP("render: enqueue");
     CU(cudaStreamSynchronize(st));
     LAP("render: wait for the frame");
     const FrameCounters &h = *c->h_ctr;
-    if (h.overflow) return fail(CUTRACE_ERR_INTERNAL, "internal: ray queue overflow");
+    if (frame_done) {
+      c->ctr_dirty = false;   // the frame kernel cleared the device counters on its way out
+      c->phase_count = levels + 1;
+      for (uint32_t p = 0; p <= levels; p++)
+        c->phase_ms[p] = h.phase_ns[p] >= h.phase_ns[17] ? (float)((double)(h.phase_ns[p] - h.phase_ns[17]) * 1e-6) : 0.f;
+    } else {
+      c->phase_count = 0;
+    }
+    if (h.overflow) return fail(CUTRACE_ERR_INTERNAL, "internal: ray queue overflow (a queue reservation did not fit; the frame is incomplete)");
     S.rays_reflect += h.rays_reflect;
     S.rays_transmit += h.rays_transmit;
     S.shadow_casts += h.shadow_casts;
@@ -800,6 +887,13 @@ int cutrace_render_download(cutrace_ctx *c, float *depth, float *normal, float *
   CU(cudaStreamSynchronize(c->copy_stream));
   LAP("render_download: G-buffer D2H tail");
   if (max_depth) *max_depth = c->stats.max_depth;
+  return CUTRACE_OK;
+}
+
+int cutrace_get_phase_ms(cutrace_ctx *c, float *out, uint32_t capacity, uint32_t *n_out) {
+  if (!c || (!out && capacity) || !n_out) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  *n_out = c->phase_count;
+  for (uint32_t p = 0; p < c->phase_count && p < capacity; p++) out[p] = c->phase_ms[p];
   return CUTRACE_OK;
 }
 

@@ -114,7 +114,13 @@ struct FrameCounters {
   unsigned int work_shade[18];
   unsigned long long rays_reflect, rays_transmit, shadow_casts, shade_records;
   unsigned int max_depth_bits;  // float bits of the largest finite primary depth
-  unsigned int overflow;        // set if a queue would overflow (cannot happen with worst-case sizing)
+  unsigned int overflow;        // a queue reservation did not fit: the emission was dropped, the frame is reported as failed
+  // ---- persistent frame kernel (render.cu: frame_kernel) ----
+  unsigned int arrive[18];      // grid barrier of phase p: warps that have finished trace(p)   (arrive[levels]: all shading done)
+  unsigned int work_export;     // cursor of the G-buffer export (peer / host frame)
+  unsigned int finished;        // warps that have left the kernel: the last one publishes the counters and clears them
+  unsigned int pad_;
+  unsigned long long phase_ns[18];   // %globaltimer when phase p opened (diagnostics: where a frame's time goes)
 };
 
 // everything a render kernel needs, passed by value (lives in the constant bank)

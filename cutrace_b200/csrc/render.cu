@@ -1,80 +1,140 @@
 // render.cu — the wavefront pipeline that replaces the reference's recursive one-thread-per-pixel
 // kernel (inc/kernel.hpp:35-60 -> inc/shading.hpp:116-154 -> inc/ray_cast.hpp:29-55).
 //
-// Per bounce level L (0 = primary rays) two persistent, work-stealing kernels run:
+// Per bounce level L (0 = primary rays) there are two kinds of work:
 //
-//   trace_kernel  closest hit for every ray of level L (L = 0: rays are generated from the pixel
-//                 index, cam::get_ray inc/default_schema.hpp:376-386).  Level 0 also writes the
-//                 G-buffer (depth / raw normal / object id, inc/kernel.hpp:52-56) and reduces the
-//                 largest finite depth (inc/kernel.hpp:120-125).  Every hit emits one ShadeRec;
-//                 mirror / transparent materials push child rays into the level L+1 queue
-//                 (inc/shading.hpp:130-149), compacted with warp ballot + popc and ONE atomicAdd
-//                 per warp.
-//   shade_kernel  per ShadeRec: all shadow rays (shadow_intensity, inc/shading.hpp:22-45) and the
-//                 Phong sum (inc/shading.hpp:64-99), accumulated into the colour buffer with the
-//                 path weight of the hit.
+//   trace(L)   closest hit for every ray of level L (L = 0: rays are generated from the pixel index,
+//              cam::get_ray inc/default_schema.hpp:376-386).  Level 0 also writes the G-buffer
+//              (depth / raw normal / object id, inc/kernel.hpp:52-56) and reduces the largest finite
+//              depth (inc/kernel.hpp:120-125).  Every hit emits one ShadeRec; mirror / transparent
+//              materials push child rays into the level L+1 queue (inc/shading.hpp:130-149),
+//              compacted with warp ballot + popc into slot blocks a warp reserves with ONE atomicAdd.
+//   shade(L)   per ShadeRec: all shadow rays (shadow_intensity, inc/shading.hpp:22-45) and the Phong
+//              sum (inc/shading.hpp:64-99), stored with the path weight of the hit.
 //
 // The recursion  rgb = (1-t)*(phong + r*R) + t*T  (inc/shading.hpp:138,148) is unrolled into path
 // weights: own Phong term w*(1-t), reflected child w*(1-t)*r, transmitted child w*t; at the last
 // level (bounces exhausted) the blend is skipped exactly like `if constexpr(bounces != 0)`.
 //
-// Kernels are persistent: grid = SM count x resident CTAs; each warp claims WORK_CHUNK rays at a time
-// from a global cursor (work stealing), so cheap and expensive rays balance without a tail.
+// Two schedulers drive the same device functions (trace_chunk / shade_chunk):
+//
+//   frame_kernel   (default) ONE persistent cooperative kernel per frame: the level loop runs on the device.  Phase p
+//                  = trace(p); a warp that runs out of trace(p) work arrives at the phase barrier and, instead of
+//                  spinning, shades records of the levels < p until the barrier opens (all warps arrived), so the
+//                  tail of every trace level is filled with shading.  After the last phase: ordered per-pixel sum of
+//                  the level images, G-buffer / colour stores to wherever the frame lives (own HBM, a peer GPU over
+//                  NVLink, pinned host memory), counters published to mapped host memory and cleared for the next
+//                  frame.  The scene is staged into shared memory once per CTA and frame (cp.async.bulk + mbarrier).
+//   trace_kernel / shade_kernel   one launch per level and kind (CUTRACE_FLAG_SERIALIZE: per-kernel timings; also the
+//                  fallback when a cooperative launch is not possible).
+//
+// All kernels are persistent: each warp claims work from a global cursor (guided chunk sizes).
 #include "render.cuh"
 #include "trace.cuh"
 
 namespace ctb {
+
+#define CTB_FULL 0xffffffffu
 
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
 }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Work stealing with guided chunk sizes: a warp claims `remaining / (2 * warps in flight)` items, at least one
-// warp-iteration (32) and at most WORK_CHUNK_MAX.  Large claims while there is plenty of work keep the cursor
+// warp-iteration (32) and at most `max_chunk`.  Large claims while there is plenty of work keep the cursor
 // atomics rare; 32-item claims at the end keep the tail short — at deep bounce levels of the 10 M-triangle scene a
 // few grazing rays cost milliseconds each and fixed 128-ray claims left the GPU idle behind them
 // (profiles/r01_tuning.md, "tile scaling").
-__device__ __forceinline__ bool claim_work(unsigned *cursor, unsigned n_work, unsigned lane, unsigned &base, unsigned &end) {
+__device__ __forceinline__ bool claim_work(unsigned *cursor, unsigned n_work, unsigned lane, unsigned max_chunk, unsigned &base, unsigned &end) {
   unsigned b = 0, chunk = 0;
   if (lane == 0) {
     const unsigned cur = *reinterpret_cast<volatile unsigned *>(cursor);
-    const unsigned remaining = cur < n_work ? n_work - cur : 0u;
-    const unsigned warps = gridDim.x * (blockDim.x >> 5);
-    chunk = remaining / (2u * warps);
-    chunk = chunk < 32u ? 32u : (chunk > (unsigned)WORK_CHUNK_MAX ? (unsigned)WORK_CHUNK_MAX : chunk);
-    chunk &= ~31u;
-    b = atomicAdd(cursor, chunk);
+    if (cur < n_work) {
+      const unsigned remaining = n_work - cur;
+      const unsigned warps = gridDim.x * (blockDim.x >> 5);
+      chunk = remaining / (2u * warps);
+      chunk = chunk < 32u ? 32u : (chunk > max_chunk ? max_chunk : chunk);
+      chunk &= ~31u;
+      b = atomicAdd(cursor, chunk);
+    } else {
+      b = n_work;   // exhausted: no atomic (the frame kernel polls exhausted cursors while it waits for a phase to open)
+    }
   }
-  base = __shfl_sync(0xffffffffu, b, 0);
-  chunk = __shfl_sync(0xffffffffu, chunk, 0);
+  base = __shfl_sync(CTB_FULL, b, 0);
+  chunk = __shfl_sync(CTB_FULL, chunk, 0);
   end = base + chunk < n_work ? base + chunk : n_work;
   return base < n_work;
 }
 
-// stage the BVH nodes and the primitive store in shared memory (MODE 1) — LDS.128 instead of
-// divergent LDG.128 for the small reference scenes whose whole BVH fits next to the SM
+// ---- scene staging (MODE 1: whole BVH + primitive store, MODE 2: top of the BVH) ------------------------------------------
+// One thread arms an mbarrier with the byte count and issues bulk asynchronous copies global -> shared (cp.async.bulk,
+// SASS UBLKCP): the copy engine of the SM moves the 71 KB of bunny.json's BVH while no thread spends issue slots on
+// LDG/STS pairs (round 1 staged with 4,444 LDG.128 + STS.128 per CTA and launch).  All threads then wait on the barrier.
+#define CTB_BULK_CHUNK 32768u
+__device__ __forceinline__ void bulk_stage(float4 *smem, const float4 *g0, uint32_t bytes0, const float4 *g1, uint32_t bytes1, uint64_t *bar) {
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes0 + bytes1) : "memory");
+    const char *src[2] = {reinterpret_cast<const char *>(g0), reinterpret_cast<const char *>(g1)};
+    const uint32_t len[2] = {bytes0, bytes1};
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+#pragma unroll 1
+      for (uint32_t off = 0; off < len[k]; off += CTB_BULK_CHUNK) {
+        const uint32_t sz = len[k] - off < CTB_BULK_CHUNK ? len[k] - off : CTB_BULK_CHUNK;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src[k] + off),
+                     "r"(sz), "r"(bar_s)
+                     : "memory");
+        dst += sz;
+      }
+    }
+  }
+  // every thread waits for phase 0 of the barrier (all bytes landed)
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar_s) : "memory");
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void stage_scene(const SceneView &sv, float4 *smem, const float4 *&nodes, const float4 *&prims) {
+  const float4 *gn = reinterpret_cast<const float4 *>(sv.nodes);
+  const float4 *gp = reinterpret_cast<const float4 *>(sv.prims);
   if (MODE == 1) {
-    const float4 *gn = reinterpret_cast<const float4 *>(sv.nodes);
-    const float4 *gp = reinterpret_cast<const float4 *>(sv.prims);
-    uint32_t nn = sv.n_nodes * 4u, np = sv.n_prims * 3u;
-    for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) smem[i] = __ldg(gn + i);
-    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) smem[nn + i] = __ldg(gp + i);
-    __syncthreads();
+    const uint32_t nb = sv.n_nodes * (uint32_t)sizeof(Node), pb = sv.n_prims * (uint32_t)sizeof(PrimRec);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(smem) + nb + pb);   // 16-byte aligned: both sizes are multiples of 16
+    bulk_stage(smem, gn, nb, gp, pb, bar);
     nodes = smem;
-    prims = smem + nn;
+    prims = smem + sv.n_nodes * 4u;
   } else {
     if (MODE == 2) {   // top of the BVH (first smem_nodes nodes, breadth-first) -> shared memory
-      const float4 *gn = reinterpret_cast<const float4 *>(sv.nodes);
-      const uint32_t nn = sv.smem_nodes * 4u;
-      for (uint32_t i = threadIdx.x; i < nn; i += blockDim.x) smem[i] = __ldg(gn + i);
-      __syncthreads();
+      const uint32_t nb = sv.smem_nodes * (uint32_t)sizeof(Node);
+      uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(smem) + nb);
+      bulk_stage(smem, gn, nb, gn, 0u, bar);
     }
-    nodes = reinterpret_cast<const float4 *>(sv.nodes);
-    prims = reinterpret_cast<const float4 *>(sv.prims);
+    nodes = gn;
+    prims = gp;
   }
 }
 
@@ -104,152 +164,212 @@ __device__ __forceinline__ void camera_ray(const Camera &c, uint32_t x, uint32_t
   d = vnormalized(vadd(vadd(x_v, y_v), z_v));
 }
 
+// ---- queue slots --------------------------------------------------------------------------------------------------------
+// A warp reserves a block of queue slots with ONE atomicAdd and fills it over the next iterations (ballot + popc
+// compaction inside the warp).  One same-address atomic WITH return per warp-iteration and queue had made the trace
+// kernels wait on the L2 atomic unit (ncu r01: long_scoreboard 11.5 warp-cycles per issue, 45 % issue slots).  An emission
+// that does not fit into the rest of the current block is SPLIT: its first records fill the block to the last slot, the
+// others open the next block — so the only unused slots a warp ever leaves are the tail of its last block of a level
+// (retired as holes, pix = CTB_HOLE, by flush_block).  Hence   reserved(L) <= valid(L) + warps * SLOT_BLOCK,
+// which is exactly the slack the queues are allocated with (api.cu: alloc_frame).  Every reservation is nevertheless
+// checked against the capacity: on overflow the emission is dropped, the part of the failed reservation that lies inside
+// the queue is retired as holes (consumers never read unwritten slots) and FrameCounters.overflow makes the host fail the
+// frame with CUTRACE_ERR_INTERNAL.
+struct SlotBlock { unsigned next, end; };
+struct Emit { unsigned base0, rem, base1; bool fits; };
+
+__device__ __forceinline__ void store_hole(void *rec) {
+  __stcs(reinterpret_cast<float4 *>(rec), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
+}
+
+template <typename Rec>
+__device__ __forceinline__ Emit reserve_slots(SlotBlock &b, unsigned n, unsigned lane, unsigned slot_block, unsigned *counter, unsigned cap,
+                                              Rec *queue, FrameCounters *ctr) {
+  Emit e;
+  e.base0 = b.next; e.rem = b.end - b.next; e.base1 = 0; e.fits = true;
+  if (n <= e.rem) { b.next += n; return e; }
+  const unsigned need = n - e.rem;
+  const unsigned blk = slot_block > need ? slot_block : need;
+  unsigned nb = 0;
+  if (lane == 0) nb = atomicAdd(counter, blk);
+  nb = __shfl_sync(CTB_FULL, nb, 0);
+  if (nb > cap || blk > cap - nb) {                       // does not fit: never write past the queue
+    if (lane == 0) atomicExch(&ctr->overflow, 1u);
+    for (unsigned k = nb + lane; k < cap; k += 32) store_hole(queue + k);
+    e.fits = false;
+    b.next = b.end;                                       // the old block is full (its `rem` slots are used by this emission)
+    return e;
+  }
+  e.base1 = nb;
+  b.next = nb + need; b.end = nb + blk;
+  return e;
+}
+__device__ __forceinline__ bool emit_ok(const Emit &e, unsigned rank) { return rank < e.rem || e.fits; }
+__device__ __forceinline__ unsigned emit_slot(const Emit &e, unsigned rank) { return rank < e.rem ? e.base0 + rank : e.base1 + (rank - e.rem); }
+
+template <typename Rec>
+__device__ __forceinline__ void flush_block(SlotBlock &b, Rec *queue, unsigned lane) {
+  for (unsigned k = b.next + lane; k < b.end; k += 32) store_hole(queue + k);
+  b.next = b.end = 0;
+}
+
+// what one bounce level reads and writes
+struct LevelIO {
+  const RayRec *rays_in;
+  RayRec *rays_out;
+  ShadeRec *shade_out;
+  unsigned ray_cap, shade_cap;   // capacity of rays_out / shade_out in records
+};
+
+struct TraceAcc {   // per-lane tallies of one level, reduced and added to the frame counters by trace_flush
+  unsigned n_refl, n_trans, n_shaded;
+  float max_depth;
+  SlotBlock sq, rq;   // this warp's current slot blocks in the shade / ray queue (warp-uniform)
+};
+__device__ __forceinline__ void trace_acc_reset(TraceAcc &a) {
+  a.n_refl = a.n_trans = a.n_shaded = 0u; a.max_depth = 0.f;
+  a.sq.next = a.sq.end = a.rq.next = a.rq.end = 0u;
+}
+
+// closest hit + G-buffer + queue emission for the work items [base, end) of level `level` (one warp)
+template <int MODE, bool BRUTE>
+__device__ __forceinline__ void trace_chunk(const SceneView &sv, const float4 *nodes, const float4 *prims, const TileMap &tm, uint32_t level,
+                                            uint32_t bounces, uint32_t px_base, unsigned base, unsigned end, unsigned n_work, const LevelIO &io,
+                                            FrameCounters *ctr, const FrameTargets &fb, uint32_t *__restrict__ nlev, unsigned slot_block,
+                                            unsigned lane, unsigned lt_mask, TraceAcc &acc) {
+#pragma unroll 1
+  for (unsigned off = 0; base + off < end; off += 32) {
+    const uint32_t i = base + off + lane;
+    bool active = i < n_work;
+    vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
+    float w = 1.0f;
+    uint32_t pix = 0, gx = 0, gy = 0;
+    if (level == 0) {
+      active = active && work_to_pixel(tm, px_base + i, gx, gy, pix);
+      if (active) camera_ray(sv.cam, gx, gy, o, d);
+    } else if (active) {
+      const float4 *rp = reinterpret_cast<const float4 *>(io.rays_in + i);
+      float4 a = __ldcg(rp), b = __ldcg(rp + 1);   // L2 only: the queue was written by other SMs earlier in this kernel
+      o = mk3(a.x, a.y, a.z); pix = __float_as_uint(a.w);
+      d = mk3(b.x, b.y, b.z); w = b.w;
+      active = pix != CTB_HOLE;
+    }
+    Hit h;
+    hit_reset(h);
+    if (active) closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
+    const bool hit = active && h.kind >= 0;
+    vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
+    uint32_t mat = 0;
+    float reflect = 0.f, transp = 0.f;
+    if (hit) {
+      hit_surface<MODE>(sv, prims, h, o, d, point, nrm);
+      mat = __ldg(sv.obj_material + h.obj);
+      const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
+      float4 m1 = __ldg(mp + 1);
+      reflect = m1.x; transp = m1.z;
+    }
+    if (level == 0 && active) {   // G-buffer, inc/kernel.hpp:52-56
+      const size_t gi = fb.row_major ? (size_t)gy * tm.width + gx : (size_t)pix;   // possibly peer memory (NVLink store)
+      fb.depth[gi] = h.t;
+      fb.normal[3 * gi] = nrm.x; fb.normal[3 * gi + 1] = nrm.y; fb.normal[3 * gi + 2] = nrm.z;
+      fb.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
+      if (hit && isfinite(h.t)) acc.max_depth = fmaxf(acc.max_depth, h.t);
+      if (nlev && !hit) nlev[pix] = 0u;
+    }
+    // number of bounce levels that contributed to this pixel so far (levels run in order)
+    if (nlev && hit) nlev[pix] = level + 1u;
+    // inc/shading.hpp:126-149
+    bool do_refl = false, do_trans = false;
+    float w_own = w;
+    if (hit && level < bounces) {
+      do_refl = (double)reflect >= 1e-6;
+      do_trans = (double)transp >= 1e-6;
+      if (do_trans) w_own = w * (1.0f - transp);
+    }
+    // ---- shade record ----
+    const unsigned m_hit = __ballot_sync(CTB_FULL, hit);
+    if (m_hit) {
+      const Emit e = reserve_slots(acc.sq, __popc(m_hit), lane, slot_block, &ctr->n_shade[level], io.shade_cap, io.shade_out, ctr);
+      const unsigned rank = __popc(m_hit & lt_mask);
+      if (hit && emit_ok(e, rank)) {
+        float4 *sp = reinterpret_cast<float4 *>(io.shade_out + emit_slot(e, rank));
+        __stcs(sp, make_float4(point.x, point.y, point.z, __uint_as_float(pix)));
+        __stcs(sp + 1, make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(mat)));
+        __stcs(sp + 2, make_float4(d.x, d.y, d.z, w_own));
+        acc.n_shaded++;
+      }
+    }
+    // ---- child rays ----
+    const unsigned m_r = __ballot_sync(CTB_FULL, do_refl), m_t = __ballot_sync(CTB_FULL, do_trans);
+    if (m_r | m_t) {
+      const unsigned nr = __popc(m_r), nt = __popc(m_t);
+      const Emit e = reserve_slots(acc.rq, nr + nt, lane, slot_block, &ctr->n_rays[level + 1], io.ray_cap, io.rays_out, ctr);
+      const vec3 origin = vadd(o, vscale(d, h.t));   // incoming->start + distance * incoming->dir
+      if (do_refl) {
+        const unsigned rank = __popc(m_r & lt_mask);
+        if (emit_ok(e, rank)) {
+          vec3 nd = vnormalized(d), nn = vnormalized(nrm);
+          vec3 rd = vreflect(nd, nn);
+          float4 *rp = reinterpret_cast<float4 *>(io.rays_out + emit_slot(e, rank));
+          __stcs(rp, make_float4(origin.x, origin.y, origin.z, __uint_as_float(pix)));
+          __stcs(rp + 1, make_float4(rd.x, rd.y, rd.z, w_own * reflect));
+          acc.n_refl++;
+        }
+      }
+      if (do_trans) {
+        const unsigned rank = nr + __popc(m_t & lt_mask);
+        if (emit_ok(e, rank)) {
+          float4 *rp = reinterpret_cast<float4 *>(io.rays_out + emit_slot(e, rank));
+          __stcs(rp, make_float4(origin.x, origin.y, origin.z, __uint_as_float(pix)));
+          __stcs(rp + 1, make_float4(d.x, d.y, d.z, w * transp));
+          acc.n_trans++;
+        }
+      }
+    }
+  }
+}
+
+// end of a level for this warp: retire the unused tails of its slot blocks, add its tallies to the frame counters
+__device__ __forceinline__ void trace_flush(uint32_t level, const LevelIO &io, FrameCounters *ctr, unsigned lane, TraceAcc &acc) {
+  flush_block(acc.sq, io.shade_out, lane);
+  flush_block(acc.rq, io.rays_out, lane);
+  for (int s = 16; s > 0; s >>= 1) {
+    acc.n_refl += __shfl_xor_sync(CTB_FULL, acc.n_refl, s);
+    acc.n_trans += __shfl_xor_sync(CTB_FULL, acc.n_trans, s);
+    acc.n_shaded += __shfl_xor_sync(CTB_FULL, acc.n_shaded, s);
+    acc.max_depth = fmaxf(acc.max_depth, __shfl_xor_sync(CTB_FULL, acc.max_depth, s));
+  }
+  if (lane == 0) {
+    if (acc.n_refl) atomicAdd(&ctr->rays_reflect, (unsigned long long)acc.n_refl);
+    if (acc.n_shaded) atomicAdd(&ctr->shade_records, (unsigned long long)acc.n_shaded);
+    if (acc.n_trans) atomicAdd(&ctr->rays_transmit, (unsigned long long)acc.n_trans);
+    if (level == 0 && acc.max_depth > 0.f) atomicMax(&ctr->max_depth_bits, __float_as_uint(acc.max_depth));
+  }
+  trace_acc_reset(acc);
+}
+
 template <int MODE, bool BRUTE>
 __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
-trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t bounces, uint32_t px_base, uint32_t n_px,
-             const RayRec *__restrict__ rays_in, RayRec *__restrict__ rays_out, ShadeRec *__restrict__ shade_out,
+trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t bounces, uint32_t px_base, uint32_t n_px, const LevelIO io,
              FrameCounters *ctr, FrameTargets fb, uint32_t *__restrict__ nlev) {
   extern __shared__ float4 smem[];
   const float4 *nodes, *prims;
   stage_scene<MODE>(sv, smem, nodes, prims);
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = lanemask_lt();
-  const uint32_t n_work = level == 0 ? n_px : ctr->n_rays[level];
-  unsigned long long n_refl = 0, n_trans = 0, n_shaded = 0;
-  float max_depth = 0.f;
-  unsigned s_next = 0, s_end = 0, r_next = 0, r_end = 0;   // this warp's reserved slot blocks (warp-uniform)
-  // block size: 1/8 of what a warp is expected to emit over the kernel, 32..SLOT_BLOCK — every warp leaves half a block
-  // of holes behind on average, so small levels (deep bounces, 1/8 shards) fall back to one reservation per iteration
+  uint32_t n_work = level == 0 ? n_px : ctr->n_rays[level];
+  if (level && n_work > io.ray_cap) n_work = io.ray_cap;   // (only after an overflow) rays_in has the capacity of rays_out
+  // block size: 1/8 of what a warp is expected to emit over the kernel, CTB_SLOT_MIN..SLOT_BLOCK
   unsigned slot_block = (n_work / (gridDim.x * (blockDim.x >> 5) * (unsigned)CTB_SLOT_DIV)) & ~31u;
   slot_block = slot_block < (unsigned)CTB_SLOT_MIN ? (unsigned)CTB_SLOT_MIN : (slot_block > (unsigned)SLOT_BLOCK ? (unsigned)SLOT_BLOCK : slot_block);
-
+  TraceAcc acc;
+  trace_acc_reset(acc);
   for (;;) {
     unsigned base, end;
-    if (!claim_work(&ctr->work_trace[level], n_work, lane, base, end)) break;
-#pragma unroll 1
-    for (unsigned off = 0; base + off < end; off += 32) {
-      const uint32_t i = base + off + lane;
-      bool active = i < n_work;
-      vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
-      float w = 1.0f;
-      uint32_t pix = 0, gx = 0, gy = 0;
-      if (level == 0) {
-        active = active && work_to_pixel(tm, px_base + i, gx, gy, pix);
-        if (active) camera_ray(sv.cam, gx, gy, o, d);
-      } else if (active) {
-        const float4 *rp = reinterpret_cast<const float4 *>(rays_in + i);
-        float4 a = __ldcs(rp), b = __ldcs(rp + 1);
-        o = mk3(a.x, a.y, a.z); pix = __float_as_uint(a.w);
-        d = mk3(b.x, b.y, b.z); w = b.w;
-        active = pix != CTB_HOLE;
-      }
-      Hit h;
-      hit_reset(h);
-      if (active) closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
-      const bool hit = active && h.kind >= 0;
-      vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
-      uint32_t mat = 0;
-      float reflect = 0.f, transp = 0.f;
-      if (hit) {
-        hit_surface<MODE>(sv, prims, h, o, d, point, nrm);
-        mat = __ldg(sv.obj_material + h.obj);
-        const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
-        float4 m1 = __ldg(mp + 1);
-        reflect = m1.x; transp = m1.z;
-      }
-      if (level == 0 && active) {   // G-buffer, inc/kernel.hpp:52-56
-        const size_t gi = fb.row_major ? (size_t)gy * tm.width + gx : (size_t)pix;   // possibly peer memory (NVLink store)
-        fb.depth[gi] = h.t;
-        fb.normal[3 * gi] = nrm.x; fb.normal[3 * gi + 1] = nrm.y; fb.normal[3 * gi + 2] = nrm.z;
-        fb.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
-        if (hit && isfinite(h.t)) max_depth = fmaxf(max_depth, h.t);
-        if (nlev && !hit) nlev[pix] = 0u;
-      }
-      // number of bounce levels that contributed to this pixel so far (levels run in order on one stream)
-      if (nlev && hit) nlev[pix] = level + 1u;
-      // inc/shading.hpp:126-149
-      bool do_refl = false, do_trans = false;
-      float w_own = w;
-      if (hit && level < bounces) {
-        do_refl = (double)reflect >= 1e-6;
-        do_trans = (double)transp >= 1e-6;
-        if (do_trans) w_own = w * (1.0f - transp);
-      }
-      // ---- output slots.  A warp reserves SLOT_BLOCK queue slots with ONE atomicAdd and fills them over the next
-      // iterations (ballot + popc compaction inside the warp); the unused tail of a block is retired as holes
-      // (pix = CTB_HOLE).  One same-address atomic WITH return per warp-iteration and queue had made the trace
-      // kernels wait on the L2 atomic unit (ncu: long_scoreboard 11.5 warp-cycles per issue, 45 % issue slots).
-      const unsigned m_hit = __ballot_sync(0xffffffffu, hit);
-      if (m_hit) {
-        const unsigned n_hit = __popc(m_hit);
-        if (s_next + n_hit > s_end) {
-          for (unsigned k = s_next + lane; k < s_end; k += 32)
-            __stcs(reinterpret_cast<float4 *>(shade_out + k), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
-          unsigned b = 0;
-          const unsigned blk = slot_block > n_hit ? slot_block : n_hit;
-          if (lane == 0) b = atomicAdd(&ctr->n_shade[level], blk);
-          s_next = __shfl_sync(0xffffffffu, b, 0);
-          s_end = s_next + blk;
-        }
-        if (hit) {
-          float4 *sp = reinterpret_cast<float4 *>(shade_out + s_next + __popc(m_hit & lt_mask));
-          __stcs(sp, make_float4(point.x, point.y, point.z, __uint_as_float(pix)));
-          __stcs(sp + 1, make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(mat)));
-          __stcs(sp + 2, make_float4(d.x, d.y, d.z, w_own));
-          n_shaded++;
-        }
-        s_next += n_hit;
-      }
-      // ---- child rays ----
-      const unsigned m_r = __ballot_sync(0xffffffffu, do_refl), m_t = __ballot_sync(0xffffffffu, do_trans);
-      if (m_r | m_t) {
-        const unsigned nr = __popc(m_r), nt = __popc(m_t);
-        if (r_next + nr + nt > r_end) {
-          for (unsigned k = r_next + lane; k < r_end; k += 32)
-            __stcs(reinterpret_cast<float4 *>(rays_out + k), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
-          unsigned b = 0;
-          const unsigned blk = slot_block > nr + nt ? slot_block : nr + nt;
-          if (lane == 0) b = atomicAdd(&ctr->n_rays[level + 1], blk);
-          r_next = __shfl_sync(0xffffffffu, b, 0);
-          r_end = r_next + blk;
-        }
-        const vec3 origin = vadd(o, vscale(d, h.t));   // incoming->start + distance * incoming->dir
-        if (do_refl) {
-          vec3 nd = vnormalized(d), nn = vnormalized(nrm);
-          vec3 rd = vreflect(nd, nn);
-          float4 *rp = reinterpret_cast<float4 *>(rays_out + r_next + __popc(m_r & lt_mask));
-          __stcs(rp, make_float4(origin.x, origin.y, origin.z, __uint_as_float(pix)));
-          __stcs(rp + 1, make_float4(rd.x, rd.y, rd.z, w_own * reflect));
-          n_refl++;
-        }
-        if (do_trans) {
-          float4 *rp = reinterpret_cast<float4 *>(rays_out + r_next + nr + __popc(m_t & lt_mask));
-          __stcs(rp, make_float4(origin.x, origin.y, origin.z, __uint_as_float(pix)));
-          __stcs(rp + 1, make_float4(d.x, d.y, d.z, w * transp));
-          n_trans++;
-        }
-        r_next += nr + nt;
-      }
-    }
+    if (!claim_work(&ctr->work_trace[level], n_work, lane, (unsigned)WORK_CHUNK_MAX, base, end)) break;
+    trace_chunk<MODE, BRUTE>(sv, nodes, prims, tm, level, bounces, px_base, base, end, n_work, io, ctr, fb, nlev, slot_block, lane, lt_mask, acc);
   }
-  // retire the unused tails of this warp's last blocks
-  for (unsigned k = s_next + lane; k < s_end; k += 32)
-    __stcs(reinterpret_cast<float4 *>(shade_out + k), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
-  for (unsigned k = r_next + lane; k < r_end; k += 32)
-    __stcs(reinterpret_cast<float4 *>(rays_out + k), make_float4(0.f, 0.f, 0.f, __uint_as_float(CTB_HOLE)));
-  // per-warp totals
-  for (int s = 16; s > 0; s >>= 1) {
-    n_refl += __shfl_xor_sync(0xffffffffu, n_refl, s);
-    n_trans += __shfl_xor_sync(0xffffffffu, n_trans, s);
-    n_shaded += __shfl_xor_sync(0xffffffffu, n_shaded, s);
-    max_depth = fmaxf(max_depth, __shfl_xor_sync(0xffffffffu, max_depth, s));
-  }
-  if (lane == 0) {
-    if (n_refl) atomicAdd(&ctr->rays_reflect, n_refl);
-    if (n_shaded) atomicAdd(&ctr->shade_records, n_shaded);
-    if (n_trans) atomicAdd(&ctr->rays_transmit, n_trans);
-    if (level == 0 && max_depth > 0.f) atomicMax(&ctr->max_depth_bits, __float_as_uint(max_depth));
-  }
+  trace_flush(level, io, ctr, lane, acc);
 }
 
 // shadow_intensity, inc/shading.hpp:22-45
@@ -259,7 +379,7 @@ trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t boun
 
 template <int MODE, bool BRUTE, bool OPAQUE>
 __device__ __forceinline__ float shadow_intensity(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 o, vec3 d,
-                                                  float max_dist, unsigned long long &casts) {
+                                                  float max_dist, unsigned &casts) {
   if (OPAQUE) {
     // every crossing adds 1 - 0 = 1 -> the first march step saturates: any surface in (1e-3, max_dist) shadows fully
     casts++;
@@ -280,189 +400,331 @@ __device__ __forceinline__ float shadow_intensity(const SceneView &sv, const flo
   return intensity;
 }
 
+// shadow rays + Phong for the shade records [base, end) of one level (one warp)
+template <int MODE, bool BRUTE, bool OPAQUE>
+__device__ __forceinline__ void shade_chunk(const SceneView &sv, const float4 *nodes, const float4 *prims, unsigned base, unsigned end,
+                                            unsigned n_work, const ShadeRec *__restrict__ shade, const FrameTargets &fb, int atomic_accumulate,
+                                            float *__restrict__ level_color, uint32_t px_base, unsigned lane, unsigned &casts) {
+#pragma unroll 1
+  for (unsigned off = 0; base + off < end; off += 32) {
+    const uint32_t i = base + off + lane;
+    if (i < n_work) {
+      const float4 *sp = reinterpret_cast<const float4 *>(shade + i);
+      const float4 s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2);
+      const vec3 hit = mk3(s0.x, s0.y, s0.z), normal = mk3(s1.x, s1.y, s1.z), in_dir = mk3(s2.x, s2.y, s2.z);
+      const uint32_t pix = __float_as_uint(s0.w), mat = __float_as_uint(s1.w);
+      const float weight = s2.w;
+      if (pix == CTB_HOLE) continue;   // retired tail of a producer warp's slot block
+      // phong, inc/shading.hpp:64-99
+      const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
+      const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+      const vec3 diffuse = mk3(m0.x, m0.y, m0.z);
+      const vec3 specular = vscale(diffuse, m0.w);        // *spec = specular * color
+      const float phong_exp = m1.y;
+      vec3 final = vscale(diffuse, sv.cam.ambient);
+      const vec3 nn = vnormalized(normal);
+      const vec3 in_n = vscale(vnormalized(in_dir), -1.0f);
+      if (OPAQUE) {
+        // every material is opaque: the shadow march saturates on its first step, so the K shadow rays
+        // of this hit are any-hit queries and walk the BVH as one packet
+        for (uint32_t l0 = 0; l0 < sv.n_lights; l0 += SHADOW_PACKET) {
+          vec3 sd[SHADOW_PACKET];
+          float md[SHADOW_PACKET];
+          vec3 lcol[SHADOW_PACKET];
+          unsigned valid = 0;
+#pragma unroll
+          for (int k = 0; k < SHADOW_PACKET; k++) {
+            sd[k] = mk3(0.f, 0.f, 1.f); md[k] = 0.f; lcol[k] = mk3(0.f, 0.f, 0.f);
+            if (l0 + k < sv.n_lights) {
+              const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l0 + k);
+              const float4 l0v = __ldg(lp), l1v = __ldg(lp + 1);
+              vec3 direction;
+              float distance;
+              if (__float_as_uint(l0v.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
+                direction = vscale(mk3(l0v.x, l0v.y, l0v.z), -1.0f);
+                distance = INFINITY;
+              } else {                                               // inc/default_schema.hpp:305-308
+                vec3 P = mk3(l0v.x, l0v.y, l0v.z);
+                direction = vnormalized(vsub(P, hit));
+                distance = vnorm(vsub(P, hit));
+              }
+              sd[k] = vnormalized(direction);
+              md[k] = distance * vnorm(direction);
+              lcol[k] = mk3(l1v.x, l1v.y, l1v.z);
+              valid |= 1u << k;
+            }
+          }
+          casts += __popc(valid);
+          const unsigned occ = any_hit_packet<MODE, SHADOW_PACKET, BRUTE>(sv, nodes, prims, hit, sd, md, valid);
+#pragma unroll
+          for (int k = 0; k < SHADOW_PACKET; k++) {
+            if ((valid & ~occ) & (1u << k)) {        // shadow_fac = 0 < 1
+              const vec3 nd = sd[k];
+              float fd = fmaxf(0.0f, vdot(nn, nd));
+              vec3 ld = vmul(diffuse, lcol[k]);
+              vec3 hv = vnormalized(vadd(in_n, nd));
+              float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+              vec3 ls = vmul(specular, lcol[k]);
+              vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - 0.0f);
+              final.x += term.x; final.y += term.y; final.z += term.z;
+            }
+          }
+        }
+      } else {
+        for (uint32_t l = 0; l < sv.n_lights; l++) {
+          const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l);
+          const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
+          vec3 direction;
+          float distance;
+          if (__float_as_uint(l0.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
+            direction = vscale(mk3(l0.x, l0.y, l0.z), -1.0f);
+            distance = INFINITY;
+          } else {                                              // inc/default_schema.hpp:305-308
+            vec3 P = mk3(l0.x, l0.y, l0.z);
+            direction = vnormalized(vsub(P, hit));
+            distance = vnorm(vsub(P, hit));
+          }
+          const vec3 sdir = vnormalized(direction);
+          const float light_dist = distance * vnorm(direction);
+          const vec3 color = mk3(l1.x, l1.y, l1.z);
+          const vec3 nd = sdir;
+          const float shadow_fac = shadow_intensity<MODE, BRUTE, false>(sv, nodes, prims, hit, sdir, light_dist, casts);
+          if (shadow_fac < 1.0f) {
+            float fd = fmaxf(0.0f, vdot(nn, nd));
+            vec3 ld = vmul(diffuse, color);
+            vec3 hv = vnormalized(vadd(in_n, nd));
+            float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+            vec3 ls = vmul(specular, color);
+            vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - shadow_fac);
+            final.x += term.x; final.y += term.y; final.z += term.z;
+          }
+        }
+      }
+      if (level_color) {   // one hit per pixel and level: plain store into this level's partial image
+        float *lp = level_color + 3 * (size_t)(pix - px_base);
+        lp[0] = weight * final.x; lp[1] = weight * final.y; lp[2] = weight * final.z;
+        continue;
+      }
+      float *cp = fb.color + 3 * (size_t)pix;
+      if (atomic_accumulate) {
+        atomicAdd(cp, weight * final.x); atomicAdd(cp + 1, weight * final.y); atomicAdd(cp + 2, weight * final.z);
+      } else {
+        cp[0] += weight * final.x; cp[1] += weight * final.y; cp[2] += weight * final.z;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void casts_flush(FrameCounters *ctr, unsigned lane, unsigned &casts) {
+  unsigned long long c = casts;
+  for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(CTB_FULL, c, s);
+  if (lane == 0 && c) atomicAdd(&ctr->shadow_casts, c);
+  casts = 0;
+}
+
 template <int MODE, bool BRUTE, bool OPAQUE>
 __global__ void __launch_bounds__(TRACE_THREADS, CTB_SHADE_MIN_BLOCKS)
-shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ shade, FrameCounters *ctr, FrameTargets fb,
+shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ shade, uint32_t shade_cap, FrameCounters *ctr, FrameTargets fb,
              int atomic_accumulate, float *__restrict__ level_color, uint32_t px_base) {
   extern __shared__ float4 smem[];
   const float4 *nodes, *prims;
   stage_scene<MODE>(sv, smem, nodes, prims);
   const unsigned lane = threadIdx.x & 31u;
-  const uint32_t n_work = ctr->n_shade[level];
-  unsigned long long casts = 0;
-
+  uint32_t n_work = ctr->n_shade[level];
+  if (n_work > shade_cap) n_work = shade_cap;
+  unsigned casts = 0;
   for (;;) {
     unsigned base, end;
-    if (!claim_work(&ctr->work_shade[level], n_work, lane, base, end)) break;
-#pragma unroll 1
-    for (unsigned off = 0; base + off < end; off += 32) {
-      const uint32_t i = base + off + lane;
-      if (i < n_work) {
-        const float4 *sp = reinterpret_cast<const float4 *>(shade + i);
-        const float4 s0 = __ldcs(sp), s1 = __ldcs(sp + 1), s2 = __ldcs(sp + 2);
-        const vec3 hit = mk3(s0.x, s0.y, s0.z), normal = mk3(s1.x, s1.y, s1.z), in_dir = mk3(s2.x, s2.y, s2.z);
-        const uint32_t pix = __float_as_uint(s0.w), mat = __float_as_uint(s1.w);
-        const float weight = s2.w;
-        if (pix == CTB_HOLE) continue;   // retired tail of a producer warp's slot block
-        // phong, inc/shading.hpp:64-99
-        const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
-        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-        const vec3 diffuse = mk3(m0.x, m0.y, m0.z);
-        const vec3 specular = vscale(diffuse, m0.w);        // *spec = specular * color
-        const float phong_exp = m1.y;
-        vec3 final = vscale(diffuse, sv.cam.ambient);
-        const vec3 nn = vnormalized(normal);
-        const vec3 in_n = vscale(vnormalized(in_dir), -1.0f);
-        if (OPAQUE) {
-          // every material is opaque: the shadow march saturates on its first step, so the K shadow rays
-          // of this hit are any-hit queries and walk the BVH as one packet
-          for (uint32_t l0 = 0; l0 < sv.n_lights; l0 += SHADOW_PACKET) {
-            vec3 sd[SHADOW_PACKET];
-            float md[SHADOW_PACKET];
-            vec3 lcol[SHADOW_PACKET];
-            unsigned valid = 0;
-#pragma unroll
-            for (int k = 0; k < SHADOW_PACKET; k++) {
-              sd[k] = mk3(0.f, 0.f, 1.f); md[k] = 0.f; lcol[k] = mk3(0.f, 0.f, 0.f);
-              if (l0 + k < sv.n_lights) {
-                const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l0 + k);
-                const float4 l0v = __ldg(lp), l1v = __ldg(lp + 1);
-                vec3 direction;
-                float distance;
-                if (__float_as_uint(l0v.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
-                  direction = vscale(mk3(l0v.x, l0v.y, l0v.z), -1.0f);
-                  distance = INFINITY;
-                } else {                                               // inc/default_schema.hpp:305-308
-                  vec3 P = mk3(l0v.x, l0v.y, l0v.z);
-                  direction = vnormalized(vsub(P, hit));
-                  distance = vnorm(vsub(P, hit));
-                }
-                sd[k] = vnormalized(direction);
-                md[k] = distance * vnorm(direction);
-                lcol[k] = mk3(l1v.x, l1v.y, l1v.z);
-                valid |= 1u << k;
-              }
-            }
-            casts += __popc(valid);
-            const unsigned occ = any_hit_packet<MODE, SHADOW_PACKET, BRUTE>(sv, nodes, prims, hit, sd, md, valid);
-#pragma unroll
-            for (int k = 0; k < SHADOW_PACKET; k++) {
-              if ((valid & ~occ) & (1u << k)) {        // shadow_fac = 0 < 1
-                const vec3 nd = sd[k];
-                float fd = fmaxf(0.0f, vdot(nn, nd));
-                vec3 ld = vmul(diffuse, lcol[k]);
-                vec3 hv = vnormalized(vadd(in_n, nd));
-                float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
-                vec3 ls = vmul(specular, lcol[k]);
-                vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - 0.0f);
-                final.x += term.x; final.y += term.y; final.z += term.z;
-              }
-            }
-          }
-        } else {
-          for (uint32_t l = 0; l < sv.n_lights; l++) {
-            const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l);
-            const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
-            vec3 direction;
-            float distance;
-            if (__float_as_uint(l0.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
-              direction = vscale(mk3(l0.x, l0.y, l0.z), -1.0f);
-              distance = INFINITY;
-            } else {                                              // inc/default_schema.hpp:305-308
-              vec3 P = mk3(l0.x, l0.y, l0.z);
-              direction = vnormalized(vsub(P, hit));
-              distance = vnorm(vsub(P, hit));
-            }
-            const vec3 sdir = vnormalized(direction);
-            const float light_dist = distance * vnorm(direction);
-            const vec3 color = mk3(l1.x, l1.y, l1.z);
-            const vec3 nd = sdir;
-            const float shadow_fac = shadow_intensity<MODE, BRUTE, false>(sv, nodes, prims, hit, sdir, light_dist, casts);
-            if (shadow_fac < 1.0f) {
-              float fd = fmaxf(0.0f, vdot(nn, nd));
-              vec3 ld = vmul(diffuse, color);
-              vec3 hv = vnormalized(vadd(in_n, nd));
-              float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
-              vec3 ls = vmul(specular, color);
-              vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - shadow_fac);
-              final.x += term.x; final.y += term.y; final.z += term.z;
-            }
-          }
-        }
-        if (level_color) {   // one hit per pixel and level: plain store into this level's partial image
-          float *lp = level_color + 3 * (size_t)(pix - px_base);
-          lp[0] = weight * final.x; lp[1] = weight * final.y; lp[2] = weight * final.z;
-          continue;
-        }
-        float *cp = fb.color + 3 * (size_t)pix;
-        if (atomic_accumulate) {
-          atomicAdd(cp, weight * final.x); atomicAdd(cp + 1, weight * final.y); atomicAdd(cp + 2, weight * final.z);
-        } else {
-          cp[0] += weight * final.x; cp[1] += weight * final.y; cp[2] += weight * final.z;
-        }
-      }
-    }
+    if (!claim_work(&ctr->work_shade[level], n_work, lane, (unsigned)WORK_CHUNK_MAX, base, end)) break;
+    shade_chunk<MODE, BRUTE, OPAQUE>(sv, nodes, prims, base, end, n_work, shade, fb, atomic_accumulate, level_color, px_base, lane, casts);
   }
-  for (int s = 16; s > 0; s >>= 1) casts += __shfl_xor_sync(0xffffffffu, casts, s);
-  if (lane == 0 && casts) atomicAdd(&ctr->shadow_casts, casts);
+  casts_flush(ctr, lane, casts);
 }
 
 // -------------------------------------------------------------------------------------------------
-// host side
+// frame assembly
 // -------------------------------------------------------------------------------------------------
-// colour of a pixel = sum of its per-level partial images in level order (same order as a serial accumulation),
-// stored where the frame lives: tile-major local buffer, own row-major frame, or a peer GPU's frame over NVLink
-__global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restrict__ nlev, const float *__restrict__ level_color,
-                                      uint64_t level_stride, uint32_t levels, const float *__restrict__ local_color,
-                                      uint32_t px_base, uint32_t n_px, FrameTargets out, FrameTargets gsrc) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_px) return;
+// colour of local pixel `pix` = sum of its per-level partial images in level order (same order as a serial accumulation),
+// stored where the frame lives: tile-major local buffer, own row-major frame, a peer GPU's frame over NVLink, or pinned
+// host memory.  gsrc.depth != NULL: the level-0 G-buffer (tile-major, local) travels with it.
+__device__ __forceinline__ void combine_pixel(const TileMap &tm, uint32_t i, uint32_t px_base, const uint32_t *__restrict__ nlev,
+                                              const float *__restrict__ level_color, uint64_t level_stride, uint32_t levels,
+                                              const float *__restrict__ local_color, const FrameTargets &out, const FrameTargets &gsrc) {
   const uint32_t pix = px_base + i;
   uint32_t x, y;
   if (!pixel_of_local(tm, pix, x, y)) return;
   float r = 0.f, g = 0.f, b = 0.f;
   if (levels == 0) {
     const float *p = local_color + 3 * (size_t)pix;
-    r = p[0]; g = p[1]; b = p[2];
+    r = __ldcg(p); g = __ldcg(p + 1); b = __ldcg(p + 2);
   } else {
-    uint32_t n = nlev[pix];
+    uint32_t n = __ldcg(nlev + pix);
     n = n < levels ? n : levels;
     for (uint32_t l = 0; l < n; l++) {
       const float *p = level_color + l * level_stride + 3 * (size_t)i;
-      r += p[0]; g += p[1]; b += p[2];
+      r += __ldcg(p); g += __ldcg(p + 1); b += __ldcg(p + 2);
     }
   }
   const size_t gi = out.row_major ? (size_t)y * tm.width + x : (size_t)pix;
   float *o = out.color + 3 * gi;
   o[0] = r; o[1] = g; o[2] = b;
   if (gsrc.depth) {
-    // peer frame: the level-0 G-buffer was written to the local tile-major buffers (small 8x4-block stores are slow
-    // over NVLink); it travels here together with the colour, 16-pixel tile rows (64..192 contiguous bytes) per half warp
-    out.depth[gi] = gsrc.depth[pix];
-    out.hit_id[gi] = gsrc.hit_id[pix];
-    out.normal[3 * gi] = gsrc.normal[3 * (size_t)pix]; out.normal[3 * gi + 1] = gsrc.normal[3 * (size_t)pix + 1];
-    out.normal[3 * gi + 2] = gsrc.normal[3 * (size_t)pix + 2];
+    out.depth[gi] = __ldcg(gsrc.depth + pix);
+    out.hit_id[gi] = __ldcg(gsrc.hit_id + pix);
+    out.normal[3 * gi] = __ldcg(gsrc.normal + 3 * (size_t)pix); out.normal[3 * gi + 1] = __ldcg(gsrc.normal + 3 * (size_t)pix + 1);
+    out.normal[3 * gi + 2] = __ldcg(gsrc.normal + 3 * (size_t)pix + 2);
   }
 }
 
-// forwards the level-0 G-buffer of this rank's tiles (tile-major, local) to a row-major frame in peer memory: one
-// 16-pixel tile row per half warp -> 64 / 192-byte contiguous NVLink stores.  Runs on an auxiliary stream right after
-// trace(0), i.e. the transfer overlaps the remaining bounce levels.
+// forwards the level-0 G-buffer of one local pixel (tile-major, local) to a row-major frame elsewhere: one 16-pixel tile row
+// per half warp -> 64 / 192-byte contiguous NVLink (or PCIe) stores
+__device__ __forceinline__ void export_pixel(const TileMap &tm, uint32_t pix, const FrameTargets &src, const FrameTargets &out) {
+  uint32_t x, y;
+  if (!pixel_of_local(tm, pix, x, y)) return;
+  const size_t gi = (size_t)y * tm.width + x;
+  out.depth[gi] = __ldcg(src.depth + pix);
+  out.hit_id[gi] = __ldcg(src.hit_id + pix);
+  out.normal[3 * gi] = __ldcg(src.normal + 3 * (size_t)pix); out.normal[3 * gi + 1] = __ldcg(src.normal + 3 * (size_t)pix + 1);
+  out.normal[3 * gi + 2] = __ldcg(src.normal + 3 * (size_t)pix + 2);
+}
+
+__global__ void combine_levels_kernel(const TileMap tm, const uint32_t *__restrict__ nlev, const float *__restrict__ level_color,
+                                      uint64_t level_stride, uint32_t levels, const float *__restrict__ local_color,
+                                      uint32_t px_base, uint32_t n_px, FrameTargets out, FrameTargets gsrc) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  combine_pixel(tm, i, px_base, nlev, level_color, level_stride, levels, local_color, out, gsrc);
+}
+
+// Runs on an auxiliary stream right after trace(0) (multi-launch path), i.e. the transfer overlaps the remaining levels.
 __global__ void export_gbuffer_kernel(const TileMap tm, uint32_t px_base, uint32_t n_px, FrameTargets src, FrameTargets out) {
   // a SMALL grid-stride grid: the kernel is bound by the NVLink stores (all ranks push into rank 0 at the same moment),
   // and every resident CTA of it takes SM slots away from the persistent trace/shade CTAs it is supposed to run under
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += gridDim.x * blockDim.x) {
-    const uint32_t pix = px_base + i;
-    uint32_t x, y;
-    if (!pixel_of_local(tm, pix, x, y)) continue;
-    const size_t gi = (size_t)y * tm.width + x;
-    out.depth[gi] = src.depth[pix];
-    out.hit_id[gi] = src.hit_id[pix];
-    out.normal[3 * gi] = src.normal[3 * (size_t)pix]; out.normal[3 * gi + 1] = src.normal[3 * (size_t)pix + 1];
-    out.normal[3 * gi + 2] = src.normal[3 * (size_t)pix + 2];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += gridDim.x * blockDim.x) export_pixel(tm, px_base + i, src, out);
+}
+
+// -------------------------------------------------------------------------------------------------
+// the persistent frame kernel
+// -------------------------------------------------------------------------------------------------
+#define CTB_EXPORT_CHUNK 256u
+
+template <int MODE, bool BRUTE, bool OPAQUE>
+__global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(const FrameArgs a) {
+  extern __shared__ float4 smem[];
+  const float4 *nodes, *prims;
+  stage_scene<MODE>(a.sv, smem, nodes, prims);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = lanemask_lt();
+  const unsigned warps_total = gridDim.x * (blockDim.x >> 5);
+  FrameCounters *ctr = a.ctr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctr->phase_ns[17] = globaltimer_ns();   // diagnostics: start of the frame on the device
+  unsigned casts = 0;
+  unsigned shade_lo = 0;                      // lowest shade level this warp still expects unclaimed records in
+  bool export_left = a.gsrc.depth != nullptr && !a.export_with_color;   // G-buffer export to a remote frame pending
+  TraceAcc acc;
+  trace_acc_reset(acc);
+
+  for (uint32_t p = a.first_level; p <= a.levels; p++) {
+    // ---- trace(p): the critical path, every warp drains it first ----
+    if (p < a.levels) {
+      LevelIO io;
+      io.rays_in = a.rays[p & 1]; io.rays_out = a.rays[(p + 1) & 1]; io.shade_out = a.shade[p];
+      io.ray_cap = a.ray_cap; io.shade_cap = a.shade_cap[p];
+      uint32_t n_work = a.n_px;
+      if (p) { n_work = __ldcg(&ctr->n_rays[p]); if (n_work > a.ray_cap) n_work = a.ray_cap; }
+      unsigned slot_block = (n_work / (warps_total * (unsigned)CTB_SLOT_DIV)) & ~31u;
+      slot_block = slot_block < (unsigned)CTB_SLOT_MIN ? (unsigned)CTB_SLOT_MIN : (slot_block > (unsigned)SLOT_BLOCK ? (unsigned)SLOT_BLOCK : slot_block);
+      for (;;) {
+        unsigned base, end;
+        if (!claim_work(&ctr->work_trace[p], n_work, lane, (unsigned)WORK_CHUNK_MAX, base, end)) break;
+        trace_chunk<MODE, BRUTE>(a.sv, nodes, prims, a.tm, p, a.bounces, a.px_base, base, end, n_work, io, ctr, a.gbuf, a.nlev, slot_block, lane,
+                                 lt_mask, acc);
+      }
+      trace_flush(p, io, ctr, lane, acc);
+      // arrive at the phase barrier: everything this warp wrote for level p (queue records, holes, counters) is released
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) red_release_add(&ctr->arrive[p], 1u);
+    }
+    // ---- while the phase is still closed (other warps are tracing): fill the time with work that is off the critical path ----
+    for (;;) {
+      unsigned open = 1;
+      if (p < a.levels) {
+        unsigned v = 0;
+        if (lane == 0) v = ld_acquire_u32(&ctr->arrive[p]);
+        open = __shfl_sync(CTB_FULL, v, 0) >= warps_total;
+        if (open) break;
+      }
+      if (export_left && p >= 1) {     // G-buffer of this rank's tiles -> remote frame, under the remaining levels
+        unsigned b = 0;
+        if (lane == 0) b = atomicAdd(&ctr->work_export, CTB_EXPORT_CHUNK);
+        b = __shfl_sync(CTB_FULL, b, 0);
+        if (b < a.n_px) {
+          const unsigned e = b + CTB_EXPORT_CHUNK < a.n_px ? b + CTB_EXPORT_CHUNK : a.n_px;
+          for (unsigned i = b + lane; i < e; i += 32) export_pixel(a.tm, a.px_base + i, a.gsrc, a.out);
+          continue;
+        }
+        export_left = false;
+      }
+      if (shade_lo < p) {              // records of levels < p are complete
+        uint32_t n_sw = 0;
+        if (lane == 0) { n_sw = __ldcg(&ctr->n_shade[shade_lo]); if (n_sw > a.shade_cap[shade_lo]) n_sw = a.shade_cap[shade_lo]; }
+        n_sw = __shfl_sync(CTB_FULL, n_sw, 0);
+        unsigned base, end;
+        if (!claim_work(&ctr->work_shade[shade_lo], n_sw, lane, p < a.levels ? (unsigned)CTB_FILL_CHUNK_MAX : (unsigned)WORK_CHUNK_MAX, base, end)) {
+          shade_lo++;
+          continue;
+        }
+        float *lc = a.level_color ? a.level_color + (size_t)shade_lo * a.level_stride : nullptr;
+        shade_chunk<MODE, BRUTE, OPAQUE>(a.sv, nodes, prims, base, end, n_sw, a.shade[shade_lo], a.acc, a.atomic_accumulate, lc, a.px_base, lane, casts);
+        continue;
+      }
+      if (p == a.levels) break;        // last phase: nothing left to claim
+      __nanosleep(128);                // nothing to fill with: wait for the phase to open
+    }
+    if (p < a.levels && lane == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->phase_ns[p] = globaltimer_ns();
+  }
+  // ---- all records are claimed; wait until every warp has finished shading ----
+  casts_flush(ctr, lane, casts);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) {
+    red_release_add(&ctr->arrive[a.levels], 1u);
+    while (ld_acquire_u32(&ctr->arrive[a.levels]) < warps_total) __nanosleep(64);
+  }
+  __syncwarp();
+  __threadfence();
+  // ---- frame assembly: ordered sum of the level images (+ G-buffer) -> the frame ----
+  if (a.combine) {
+    const FrameTargets g = a.export_with_color ? a.gsrc : FrameTargets{};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_px; i += gridDim.x * blockDim.x)
+      combine_pixel(a.tm, i, a.px_base, a.nlev, a.level_color, a.level_stride, a.combine_levels, a.local_color, a.out, g);
+  }
+  // ---- the last warp out publishes the counters to mapped host memory and clears them for the next frame ----
+  __threadfence();
+  __syncwarp();
+  unsigned last = 0;
+  if (lane == 0) last = atomicAdd(&ctr->finished, 1u) == warps_total - 1u;
+  last = __shfl_sync(CTB_FULL, last, 0);
+  if (last) {
+    __threadfence();
+    if (lane == 0) ctr->phase_ns[a.levels] = globaltimer_ns();
+    __syncwarp();
+    unsigned *src = reinterpret_cast<unsigned *>(ctr);
+    volatile unsigned *dst = reinterpret_cast<volatile unsigned *>(a.host_ctr);
+    constexpr unsigned NW = sizeof(FrameCounters) / 4;
+    for (unsigned k = lane; k < NW; k += 32) {
+      const unsigned v = __ldcg(src + k);
+      if (dst) dst[k] = v;
+      src[k] = 0u;
+    }
+    __threadfence_system();
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
 void launch_export_gbuffer(const TileMap &tm, uint32_t px_base, uint32_t n_px, const FrameTargets &src, const FrameTargets &out,
                            cudaStream_t st) {
   if (!n_px) return;
@@ -478,9 +740,10 @@ void launch_combine(const TileMap &tm, const uint32_t *nlev, const float *level_
   combine_levels_kernel<<<(n_px + 255) / 256, 256, 0, st>>>(tm, nlev, level_color, level_stride, levels, local_color, px_base, n_px, out, gsrc);
 }
 
-typedef void (*trace_fn)(const SceneView, const TileMap, uint32_t, uint32_t, uint32_t, uint32_t, const RayRec *, RayRec *, ShadeRec *,
-                         FrameCounters *, FrameTargets, uint32_t *);
-typedef void (*shade_fn)(const SceneView, uint32_t, const ShadeRec *, FrameCounters *, FrameTargets, int, float *, uint32_t);
+typedef void (*trace_fn)(const SceneView, const TileMap, uint32_t, uint32_t, uint32_t, uint32_t, const LevelIO, FrameCounters *, FrameTargets,
+                         uint32_t *);
+typedef void (*shade_fn)(const SceneView, uint32_t, const ShadeRec *, uint32_t, FrameCounters *, FrameTargets, int, float *, uint32_t);
+typedef void (*frame_fn)(const FrameArgs);
 
 static trace_fn pick_trace(int mode, bool brute) {
   if (brute) return trace_kernel<0, true>;
@@ -493,36 +756,47 @@ static shade_fn pick_shade(int mode, bool brute, bool opaque) {
   if (mode == 2) return opaque ? shade_kernel<2, false, true> : shade_kernel<2, false, false>;
   return opaque ? shade_kernel<0, false, true> : shade_kernel<0, false, false>;
 }
+static frame_fn pick_frame(int mode, bool brute, bool opaque) {
+  if (brute) return opaque ? frame_kernel<0, true, true> : frame_kernel<0, true, false>;
+  if (mode == 1) return opaque ? frame_kernel<1, false, true> : frame_kernel<1, false, false>;
+  if (mode == 2) return opaque ? frame_kernel<2, false, true> : frame_kernel<2, false, false>;
+  return opaque ? frame_kernel<0, false, true> : frame_kernel<0, false, false>;
+}
 
 cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
-  int dev = 0, sms = 0, smem_optin = 0;
+  int dev = 0, sms = 0, smem_optin = 0, coop = 0;
   cudaError_t e;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev)) != cudaSuccess) return e;
   size_t need = (size_t)sv.n_nodes * sizeof(Node) + (size_t)sv.n_prims * sizeof(PrimRec);
   cfg->mode = 0;
   cfg->smem_bytes = 0;
   if (allow_smem && !sv.brute_force && sv.n_prims > 0 && need + 1024 <= (size_t)smem_optin) {
     cfg->mode = 1;
-    cfg->smem_bytes = need;
+    cfg->smem_bytes = need + 16;   // + the staging mbarrier
   } else if (allow_smem && !sv.brute_force && sv.smem_nodes > 0) {
     cfg->mode = 2;   // api.cu moved the top sv.smem_nodes nodes (breadth-first) to the front of the node array
-    cfg->smem_bytes = (size_t)sv.smem_nodes * sizeof(Node);
+    cfg->smem_bytes = (size_t)sv.smem_nodes * sizeof(Node) + 16;
   }
   trace_fn tf = pick_trace(cfg->mode, sv.brute_force != 0);
   shade_fn sf = pick_shade(cfg->mode, sv.brute_force != 0, sv.all_opaque != 0);
-  int occ_t = 1, occ_s = 1;
+  frame_fn ff = pick_frame(cfg->mode, sv.brute_force != 0, sv.all_opaque != 0);
+  int occ_t = 1, occ_s = 1, occ_f = 1;
   if (cfg->mode != 0) {
     if ((e = cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem_bytes)) != cudaSuccess) return e;
   }
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, tf, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, sf, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, ff, TRACE_THREADS, cfg->smem_bytes)) != cudaSuccess) return e;
   if (occ_t < 1) occ_t = 1;
   if (occ_s < 1) occ_s = 1;
   cfg->grid_trace = sms * occ_t;
   cfg->grid_shade = sms * occ_s;
+  cfg->grid_frame = occ_f >= 1 && coop ? sms * occ_f : 0;   // 0: no cooperative launch on this device -> multi-launch path
   return cudaSuccess;
 }
 
@@ -533,19 +807,28 @@ static inline int clamp_grid(int persistent, uint32_t work_bound) {
 }
 
 void launch_trace(const LaunchCfg &cfg, const SceneView &sv, const TileMap &tm, uint32_t level, uint32_t bounces,
-                  uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, ShadeRec *shade_out,
-                  FrameCounters *ctr, const FrameTargets &fb, uint32_t *nlev, uint32_t work_bound, cudaStream_t st) {
+                  uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, uint32_t ray_cap, ShadeRec *shade_out,
+                  uint32_t shade_cap, FrameCounters *ctr, const FrameTargets &fb, uint32_t *nlev, uint32_t work_bound, cudaStream_t st) {
   int grid = clamp_grid(cfg.grid_trace, work_bound);
-  pick_trace(cfg.mode, sv.brute_force != 0)<<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(sv, tm, level, bounces, px_base, n_px, rays_in,
-                                                                                         rays_out, shade_out, ctr, fb, nlev);
+  LevelIO io;
+  io.rays_in = rays_in; io.rays_out = rays_out; io.shade_out = shade_out; io.ray_cap = ray_cap; io.shade_cap = shade_cap;
+  pick_trace(cfg.mode, sv.brute_force != 0)<<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(sv, tm, level, bounces, px_base, n_px, io, ctr, fb, nlev);
 }
 
-void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, FrameCounters *ctr,
+void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, uint32_t shade_cap, FrameCounters *ctr,
                   const FrameTargets &fb, bool atomic_accumulate, float *level_color, uint32_t px_base, uint32_t work_bound,
                   cudaStream_t st) {
   int grid = clamp_grid(cfg.grid_shade, work_bound);
   pick_shade(cfg.mode, sv.brute_force != 0, sv.all_opaque != 0)<<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(
-      sv, level, shade, ctr, fb, atomic_accumulate ? 1 : 0, level_color, px_base);
+      sv, level, shade, shade_cap, ctr, fb, atomic_accumulate ? 1 : 0, level_color, px_base);
+}
+
+cudaError_t launch_frame(const LaunchCfg &cfg, const FrameArgs &args, uint32_t work_bound, cudaStream_t st) {
+  if (cfg.grid_frame <= 0) return cudaErrorNotSupported;
+  int grid = clamp_grid(cfg.grid_frame, work_bound);
+  frame_fn f = pick_frame(cfg.mode, args.sv.brute_force != 0, args.sv.all_opaque != 0);
+  void *params[] = {const_cast<FrameArgs *>(&args)};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(f), dim3(grid), dim3(TRACE_THREADS), params, cfg.smem_bytes, st);
 }
 
 }  // namespace ctb

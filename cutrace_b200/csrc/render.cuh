@@ -44,6 +44,39 @@ struct LaunchCfg {
   int mode;             // 0 global, 1 BVH staged in shared memory
   size_t smem_bytes;
   int grid_trace, grid_shade;   // persistent grid sizes (multiples of the SM count)
+  int grid_frame;               // co-resident CTAs of the cooperative frame kernel (0: not available on this device)
+};
+
+#ifndef CTB_FILL_CHUNK_MAX
+#define CTB_FILL_CHUNK_MAX 128   // shade records a warp claims at a time while it is only filling the tail of a trace phase
+#endif
+
+// Everything the persistent frame kernel needs (one kernel = all bounce levels of one pixel batch), passed by value.
+struct FrameArgs {
+  SceneView sv;
+  TileMap tm;
+  uint32_t bounces, levels;      // levels = bounces + 1 when some material spawns secondary rays, else 1
+  uint32_t first_level;          // 0, or 1 when trace(0) already ran as its own kernel (cutrace_render_download: the G-buffer
+                                 // copy to the host starts behind that kernel)
+  uint32_t px_base, n_px;        // local pixel range of this batch
+  RayRec *rays[2];               // ping-pong ray queues
+  uint32_t ray_cap;
+  ShadeRec *shade[16];           // one shade queue per level
+  uint32_t shade_cap[16];
+  FrameCounters *ctr;            // device counters: zero on entry, published to host_ctr and cleared again on exit
+  FrameCounters *host_ctr;       // mapped pinned host memory (device pointer), may be NULL
+  FrameTargets gbuf;             // where trace(0) stores the G-buffer
+  FrameTargets out;              // where the finished frame lives (own HBM / peer GPU / pinned host memory)
+  FrameTargets gsrc;             // != NULL: local tile-major G-buffer that has to travel to `out`
+  FrameTargets acc;              // branching scenes: local colour accumulator (float atomics)
+  float *level_color;            // non-branching scenes: levels x level_stride floats of per-level partial images
+  uint64_t level_stride;
+  uint32_t *nlev;
+  const float *local_color;      // branching scenes: what the frame assembly copies
+  uint32_t combine_levels;       // levels of the ordered sum; 0 = copy local_color
+  int atomic_accumulate;
+  int combine;                   // run the frame assembly inside the kernel
+  int export_with_color;         // 1: the G-buffer travels with the colour at the end, 0: as filler work under the bounce levels
 };
 
 // fills cfg for a scene on the current device; smem budget from the device attributes
@@ -52,12 +85,14 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg);
 // One bounce level of the wavefront. Level 0 generates primary rays for local pixel indices
 // [px_base, px_base + n_px) itself; deeper levels read rays_in (count in ctr->n_rays[level]).
 void launch_trace(const LaunchCfg &cfg, const SceneView &sv, const TileMap &tm, uint32_t level, uint32_t bounces,
-                  uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, ShadeRec *shade_out,
-                  FrameCounters *ctr, const FrameTargets &fb, uint32_t *nlev, uint32_t work_bound, cudaStream_t st);
+                  uint32_t px_base, uint32_t n_px, const RayRec *rays_in, RayRec *rays_out, uint32_t ray_cap, ShadeRec *shade_out,
+                  uint32_t shade_cap, FrameCounters *ctr, const FrameTargets &fb, uint32_t *nlev, uint32_t work_bound, cudaStream_t st);
 // shadow rays + Phong for the shade records of one level; accumulates into fb.color
-void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, FrameCounters *ctr,
+void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, const ShadeRec *shade, uint32_t shade_cap, FrameCounters *ctr,
                   const FrameTargets &fb, bool atomic_accumulate, float *level_color, uint32_t px_base, uint32_t work_bound,
                   cudaStream_t st);
+// all levels of one pixel batch in ONE cooperative persistent kernel (device-side level loop, see render.cu)
+cudaError_t launch_frame(const LaunchCfg &cfg, const FrameArgs &args, uint32_t work_bound, cudaStream_t st);
 // colour[px] = sum over levels l < nlev[px] of level_color[l][px - px_base], in level order; levels == 0: copy the
 // locally accumulated colour (branching scenes) instead.  Writes into `out` in its layout; gsrc.depth != NULL: also
 // forwards the tile-major G-buffer gsrc to `out` (peer frame).

@@ -214,6 +214,12 @@ int cutrace_set_camera(cutrace_ctx *ctx, const float pos[3], const float up[3], 
 /* stats of the last upload/render */
 int cutrace_get_stats(cutrace_ctx *ctx, cutrace_stats *stats);
 
+/* Diagnostics of the last frame when it ran as one persistent kernel (the default): out[p] = milliseconds from the start
+ * of the kernel until every ray of bounce level p was traced (p < levels), out[levels] = until the frame was assembled.
+ * Taken from %globaltimer on the device.  *n_out = number of valid entries (0 when the frame ran as separate launches,
+ * CUTRACE_FLAG_SERIALIZE).  The reference has no counterpart (one opaque kernel, inc/kernel.hpp:103-108). */
+int cutrace_get_phase_ms(cutrace_ctx *ctx, float *out, uint32_t capacity, uint32_t *n_out);
+
 /* Device-resident results of the last render, tile-major local layout: pixel j of local tile i is
  * at (i*CUTRACE_TILE_PIXELS + j).  Pointers stay valid until the next set_camera/free.
  * Used by the multi-GPU gather (NCCL over the caller's communicator, or peer copies). */

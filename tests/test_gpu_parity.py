@@ -117,6 +117,9 @@ def test_edge_cases_vs_oracle(ct, oracle):
         out, st = gpu_render(ct, s)
         ref = oracle.oracle_render(s)
         assert_parity(compare(out, ref, s.width, s.height), what, oracle_is_host=True, chaotic=True)
+        if oracle.have_ref_gpu() and what != "empty scene":   # the tight yardstick: same FMA contraction, same libm
+            gref = oracle.ref_gpu_render(s)
+            assert_parity(compare(out, gref, s.width, s.height), what + " vs reference sm_100a kernel")
         if what == "empty scene":
             assert np.all(out["hit_id"] == 0xFFFFFFFF) and np.all(np.isposinf(out["depth"])) and not out["color"].any()
             assert st["max_depth"] == 0.0
@@ -135,8 +138,11 @@ def test_bounce_budget_and_fudge(ct, oracle):
 
 
 # ---- (3) the reference's own kernel rebuilt for sm_100a ---------------------------------------------
-@pytest.mark.parametrize("name,res", [("triangle", None), ("sphere_plane", (1920, 1080)), ("mirror", (960, 540)), ("bunny", (480, 270))])
+@pytest.mark.parametrize("name,res", [("triangle", None), ("sphere_plane", (1920, 1080)), ("mirror", (1920, 1080)), ("bunny", (480, 270)),
+                                      ("bunny", (3840, 2160))])
 def test_vs_reference_cuda_kernel(ct, oracle, name, res):
+    """BASELINE configs 1-4 at their full resolutions, FULL frames, against the reference's own kernel launched like
+    /root/reference/inc/kernel.hpp:103-106 (bunny.json at 4K costs the reference ~0.9 s)."""
     if not oracle.have_ref_gpu():
         pytest.skip("oracle/_ref/libcutrace_ref_gpu.so was not built (reference tree absent at build time)")
     s = load_golden_scene(name)
@@ -164,6 +170,119 @@ def test_bunny_4k_subset_vs_reference_cuda_kernel(ct, oracle):
     # four shadow rays per shaded hit; a ray that leaks through a crack between triangles shades nothing
     assert st["rays_shadow"] % 4 == 0
     assert 0.9999 * 4 * (st["rays_primary"] + st["rays_reflect"]) <= st["rays_shadow"] <= 4 * (st["rays_primary"] + st["rays_reflect"])
+
+
+def test_config5_full_size_subset_vs_reference_cuda_kernel(ct, oracle):
+    """BASELINE config 5 at FULL size: the 106 x 106 instance hall (10,112,400 triangles) at 7680x4320 rendered
+    completely by this path; a seeded 4096-pixel subset of it against the reference's ray_cast / ray_color run by the
+    oracle-side subset kernel (brute force cannot render 33 M pixels: SURVEY.md 8d "Reference on config 5")."""
+    if not oracle.have_ref_gpu():
+        pytest.skip("reference CUDA oracle not built")
+    from cutrace_b200 import synth
+
+    meshes = synth.meshes_from_scenes(load_golden_scene("bunny"), load_golden_scene("mirror"))[:2]
+    s = synth.grid_scene(meshes, grid=106, width=7680, height=4320)
+    assert s.n_triangles == 10_112_400
+    px = np.random.default_rng(0).choice(s.width * s.height, 4096, replace=False).astype(np.uint64)
+    ref = oracle.ref_gpu_render(s, px=px)
+    with ct.Renderer(s) as r:      # no FLAG_VALIDATE_BVH here: the validation walk of 3.6 M nodes is covered at G = 24
+        st = r.render()
+        out = r.download(want=("depth", "normal", "color", "hit_id"))
+    sub = {k: out[k][px.astype(np.int64)] for k in ("depth", "normal", "color", "hit_id")}
+    m = compare(sub, ref)
+    assert_parity(m, "config 5 (10.1 M triangles @ 7680x4320) subset vs reference sm_100a kernel")
+    assert m["id_mismatch"] == 0, m
+    assert np.all(out["hit_id"] != 0xFFFFFFFF)        # closed hall: every primary ray hits
+    assert st["rays_primary"] == 7680 * 4320 and st["rays_shadow"] % 3 == 0
+
+
+def test_mesh_deviations_documented_in_design_8(ct, oracle):
+    """DESIGN.md 8 lists two places where the LBVH walk is not the reference's mesh::intersect; both are constructed
+    here and compared with the reference's own kernel.
+    (1) per-mesh AABB pre-test (inc/default_schema.hpp:99-114): a FLAT mesh (all vertices in the plane z = 0, so its
+        box has zero thickness) seen by rays that travel inside that plane and by axis-parallel rays through box faces.
+        The reference's slab test produces 0 * inf = NaN there; fminf/fmaxf drop the NaN, so the mesh is still entered
+        and the Cramer test decides (alpha = 0 -> non-finite -> miss).  Same image expected.
+    (2) a mesh whose nearest triangle sits at exactly t == min_dist is rejected as a WHOLE by the reference
+        (mesh::intersect keeps the closest triangle, ray_cast then drops it); here only that triangle is dropped.
+        Constructed with fudge = 1.0 and an axis-aligned quad at distance exactly 1.0 in front of a second quad of the
+        same mesh: a measure-zero case in which the two paths are allowed to differ, recorded rather than asserted equal."""
+    if not oracle.have_ref_gpu():
+        pytest.skip("reference CUDA oracle not built")
+    from cutrace_b200.scene import FlatScene, LIGHT_POINT, OBJ_MESH
+
+    def scene(tris, eye, look, fudge_scene=None, width=64, height=48):
+        tris = np.asarray(tris, np.float32)
+        fwd, right, up = ct.look_at(np.asarray(eye, np.float32), [0, 1, 0], np.asarray(look, np.float32))
+        return FlatScene(cam_pos=np.asarray(eye, np.float32), cam_up=up, cam_forward=fwd, cam_right=right, ambient=0.1, width=width,
+                         height=height, tri_p1=tris[:, 0], tri_p2=tris[:, 1], tri_p3=tris[:, 2], tri_object=np.zeros(len(tris), np.uint32),
+                         obj_material=np.zeros(1, np.uint32), obj_kind=np.asarray([OBJ_MESH], np.uint32),
+                         mat_color=np.asarray([[0.8, 0.5, 0.2]], np.float32), mat_specular=np.asarray([0.3], np.float32),
+                         mat_reflect=np.asarray([0.2], np.float32), mat_phong=np.asarray([32], np.float32),
+                         mat_transparency=np.zeros(1, np.float32), light_kind=np.asarray([LIGHT_POINT], np.uint32),
+                         light_vec=np.asarray([[1, 3, -4]], np.float32), light_color=np.ones((1, 3), np.float32))
+
+    flat = [[[-1, -1, 0], [1, -1, 0], [1, 1, 0]], [[-1, -1, 0], [1, 1, 0], [-1, 1, 0]], [[1, -1, 0], [3, -1, 0], [3, 1, 0]]]
+    views = {
+        "flat mesh, camera IN its plane (grazing: every ray with d.z = 0 lies in the box's zero-thickness slab)": ([-4, 0, 0], [0, 0, 0]),
+        "flat mesh, axis-parallel central ray": ([0, 0, -3], [0, 0, 0]),
+        "flat mesh, camera on the box's x = 3 face plane": ([3, 0, -3], [3, 0, 0]),
+        "flat mesh, oblique": ([2, 1.5, -3], [0.5, 0, 0]),
+    }
+    for what, (eye, look) in views.items():
+        s = scene(flat, eye, look)
+        out, _ = gpu_render(ct, s)
+        gref = oracle.ref_gpu_render(s)
+        m = compare(out, gref, s.width, s.height)
+        assert_parity(m, what)
+        assert m["id_mismatch"] == 0, (what, m)
+    # (2) t == min_dist: camera at z = -1 looking down +z at two parallel quads of ONE mesh at z = 0 (t = 1 on the central
+    # axis-parallel ray only) and z = 1; fudge = 1.0
+    quads = [[[-1, -1, 0], [1, -1, 0], [1, 1, 0]], [[-1, -1, 0], [1, 1, 0], [-1, 1, 0]],
+             [[-2, -2, 1], [2, -2, 1], [2, 2, 1]], [[-2, -2, 1], [2, 2, 1], [-2, 2, 1]]]
+    s = scene(quads, [0, 0, -1], [0, 0, 0], width=65, height=49)
+    with ct.Renderer(s, fudge=1.0) as r:
+        r.render()
+        out = r.download()
+    gref = oracle.ref_gpu_render(s, fudge=1.0)
+    m = compare(out, gref, s.width, s.height)
+    # pixels whose nearest triangle is at t <= 1 exactly may differ (reference: whole mesh missed; here: the far quad is hit)
+    assert m["id_mismatch"] <= 4 and m["sentinel_mismatch"] <= 4, m
+    same = out["hit_id"] == gref["hit_id"]
+    assert np.array_equal(out["depth"][same].view(np.uint32), gref["depth"][same].view(np.uint32))
+
+
+def test_closed_mirror_box_at_15_bounces_does_not_overflow_the_queues(ct, oracle):
+    """queue capacity.  A closed box of 0.999 mirrors at the maximum bounce budget and an odd resolution keeps
+    every ray alive for 16 levels, so the retired slot-block tails (holes) compound level after level; the kernels
+    check every reservation against the queue capacity (FrameCounters.overflow -> CUTRACE_ERR_INTERNAL) and the
+    capacity carries one slot block per producer warp AND level.  The frame must render, twice with the same bits."""
+    from cutrace_b200.scene import FlatScene, LIGHT_POINT, OBJ_PLANE
+
+    eye = np.asarray([0.1, 0.2, -0.3], np.float32)
+    fwd, right, up = ct.look_at(eye, [0, 1, 0], np.asarray([0.3, 0.1, 1.0], np.float32))
+    pts = np.asarray([[0, -1, 0], [0, 1, 0], [-1, 0, 0], [1, 0, 0], [0, 0, -1], [0, 0, 1]], np.float32)
+    s = FlatScene(cam_pos=eye, cam_up=up, cam_forward=fwd, cam_right=right, ambient=0.1, width=1021, height=577,
+                  pl_point=pts, pl_normal=-pts, pl_object=np.arange(6, dtype=np.uint32), obj_material=np.zeros(6, np.uint32),
+                  obj_kind=np.full(6, OBJ_PLANE, np.uint32), mat_color=np.asarray([[0.9, 0.8, 0.7]], np.float32),
+                  mat_specular=np.asarray([0.3], np.float32), mat_reflect=np.asarray([0.999], np.float32),
+                  mat_phong=np.asarray([50], np.float32), mat_transparency=np.zeros(1, np.float32),
+                  light_kind=np.asarray([LIGHT_POINT], np.uint32), light_vec=np.asarray([[0.2, 0.5, 0.1]], np.float32),
+                  light_color=np.ones((1, 3), np.float32))
+    with ct.Renderer(s, bounces=15) as r:
+        st = r.render()
+        a = r.download()
+        st2 = r.render()
+        b = r.download()
+    n = s.width * s.height
+    assert st["rays_primary"] == n and st["rays_reflect"] == 15 * n and st["rays_shadow"] == 16 * n
+    assert st2["rays_total"] == st["rays_total"]
+    for k in ("depth", "normal", "color", "hit_id"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    small = s.with_resolution(101, 57)
+    out, _ = gpu_render(ct, small, bounces=15)
+    ref = oracle.oracle_render(small, bounces=15)
+    assert_parity(compare(out, ref, small.width, small.height), "mirror box, 15 bounces", oracle_is_host=True, chaotic=True)
 
 
 # ---- size-independent properties at full size ----------------------------------------------------------
@@ -447,9 +566,44 @@ def test_overlapped_and_serialized_frames_are_bit_identical(ct):
         assert sa["rays_total"] == sb["rays_total"] and sb["trace_ms"] > 0 and sb["shade_ms"] > 0
 
 
-def test_direct_first_frame_and_graph_replays_are_bit_identical(ct):
-    """The first frame of a ctx is enqueued stream by stream, the second captures the CUDA graph, later ones replay it:
-    same bits and same counters every time (bunny.json: one ray per pixel and level, deterministic sum)."""
+def test_frame_kernel_equals_the_multi_launch_paths(ct, monkeypatch):
+    """The persistent frame kernel (device-side level loop, default) against the two multi-launch schedulers that drive the
+    same device functions: CUTRACE_NO_FRAME_KERNEL (one launch per level and kind on three streams, captured as a CUDA graph
+    from the second frame on) and CUTRACE_FLAG_SERIALIZE (one stream).  Same bits, same counters; the frame kernel is ONE
+    launch and reports when each bounce level was complete."""
+    for name, res in (("bunny", (640, 360)), ("mirror", (333, 205)), ("triangle", None)):
+        s = load_golden_scene(name)
+        if res:
+            s = s.with_resolution(*res)
+        with ct.Renderer(s) as r:
+            sa = r.render()
+            sa = r.render()
+            a = r.download()
+            ph = r.phase_ms()
+        assert sa["kernel_launches"] == 1
+        levels = 6 if name != "triangle" else 1
+        assert len(ph) == levels + 1 and all(b >= a_ for a_, b in zip(ph, ph[1:])) and ph[-1] <= sa["render_ms"] * 1.5 + 0.05, ph
+        monkeypatch.setenv("CUTRACE_NO_FRAME_KERNEL", "1")
+        with ct.Renderer(s) as r:
+            frames = []
+            for _ in range(3):     # direct, graph capture, graph replay
+                sb = r.render()
+                frames.append(r.download())
+            assert r.phase_ms() == []
+        monkeypatch.delenv("CUTRACE_NO_FRAME_KERNEL")
+        assert sb["kernel_launches"] == 2 * levels + 1
+        for b in frames:
+            for k in ("depth", "normal", "color", "hit_id"):
+                assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (name, k)
+        for k in ("rays_total", "rays_shadow", "rays_reflect", "shadow_casts", "max_depth"):
+            assert sa[k] == sb[k], (name, k)
+
+
+def test_direct_first_frame_and_graph_replays_are_bit_identical(ct, monkeypatch):
+    """Multi-launch scheduler (CUTRACE_NO_FRAME_KERNEL): the first frame of a ctx is enqueued stream by stream, the second
+    captures the CUDA graph, later ones replay it: same bits and same counters every time (bunny.json: one ray per pixel
+    and level, deterministic sum)."""
+    monkeypatch.setenv("CUTRACE_NO_FRAME_KERNEL", "1")
     s = load_golden_scene("bunny").with_resolution(320, 180)
     with ct.Renderer(s) as r:
         frames = []
@@ -594,5 +748,10 @@ def test_integration_binding_against_the_reference_operator(ct):
     r = subprocess.run([exe, "640", "360"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout, r.stderr)
     m = json.loads(r.stdout.strip().splitlines()[-1])
-    assert m["sentinel_mismatch"] == 0 and m["depth_off_pixels"] <= 2 and m["normal_max_abs"] <= 1e-5 or m["depth_off_pixels"] > 0
+    # depth differing on a pixel = another object won an edge tie there (normals then differ too): at most 2 of them
+    assert m["sentinel_mismatch"] == 0, m
+    assert m["depth_off_pixels"] <= 2, m
+    if m["depth_off_pixels"] == 0:
+        assert m["normal_max_abs"] <= 1e-5 and m["depth_max_rel"] <= 1e-6, m
+    assert m["color_max_abs"] < 5e-2, m
     assert m["max_ref"] == m["max_new"]
