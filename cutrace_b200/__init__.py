@@ -19,11 +19,12 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import CutraceError, FLAG_BRUTE_FORCE, FLAG_NO_SMEM_TOP, FLAG_SERIALIZE, FLAG_VALIDATE_BVH, cutrace_opts, cutrace_stats
+from ._lib import (CutraceError, FLAG_BRUTE_FORCE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, FLAG_NO_SMEM_TOP, FLAG_SERIALIZE, FLAG_VALIDATE_BVH,
+                   cutrace_opts, cutrace_stats)
 from .scene import FlatScene, SceneError, load_scene_json, look_at
 
 __all__ = ["Renderer", "render", "FlatScene", "SceneError", "CutraceError", "load_scene_json", "look_at",
-           "FLAG_BRUTE_FORCE", "FLAG_NO_SMEM_TOP", "FLAG_VALIDATE_BVH", "FLAG_SERIALIZE"]
+           "FLAG_BRUTE_FORCE", "FLAG_NO_SMEM_TOP", "FLAG_VALIDATE_BVH", "FLAG_SERIALIZE", "FLAG_FRAME_KERNEL", "FLAG_LAUNCHES"]
 
 
 class Renderer:
@@ -146,15 +147,18 @@ class Renderer:
         return [x.value for x in p]
 
     def frame_ipc_export(self) -> bytes:
-        buf = C.create_string_buffer(64)
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
         _lib.check(self._lib.cutrace_frame_ipc_export(self._ctx, buf))
         return buf.raw
 
     def frame_ipc_import(self, handle: bytes):
-        _lib.check(self._lib.cutrace_frame_ipc_import(self._ctx, C.create_string_buffer(handle, 64)))
+        _lib.check(self._lib.cutrace_frame_ipc_import(self._ctx, C.create_string_buffer(handle, _lib.IPC_HANDLE_BYTES)))
 
-    def frame_attach(self, block_ptr):
-        _lib.check(self._lib.cutrace_frame_attach(self._ctx, block_ptr))
+    def frame_attach(self, block_ptr, width=None, height=None):
+        """Kernels of this ctx store their tiles into the row-major frame block at ``block_ptr`` (another ctx's frame, or
+        pinned / registered host memory); ``None`` detaches.  width/height describe the block (default: this ctx's)."""
+        _lib.check(self._lib.cutrace_frame_attach(self._ctx, block_ptr, self.width if width is None else width,
+                                                  self.height if height is None else height))
 
     def untile_device(self, world, g_depth, g_normal, g_color, g_id, stride_px, depth, normal, color, hit_id):
         _lib.check(self._lib.cutrace_untile_device(self._ctx, world, g_depth, g_normal, g_color, g_id, stride_px,

@@ -17,11 +17,12 @@ SYMBOLS = (
     "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_get_phase_ms", "cutrace_device_buffers", "cutrace_frame_device",
     "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach", "cutrace_enable_peer_access",
     "cutrace_set_frame_max_depth",
-    "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free",
+    "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free", "cutrace_host_register", "cutrace_host_unregister",
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version", "cutrace_tile_size",
 )
 
-FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE = 1, 2, 4, 8
+FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES = 1, 2, 4, 8, 16, 32
+IPC_HANDLE_BYTES = 80
 
 
 class cutrace_opts(C.Structure):
@@ -85,7 +86,9 @@ def load():
     lib.cutrace_frame_device.argtypes = [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P)]
     lib.cutrace_frame_ipc_export.argtypes = [P, P]
     lib.cutrace_frame_ipc_import.argtypes = [P, P]
-    lib.cutrace_frame_attach.argtypes = [P, P]
+    lib.cutrace_frame_attach.argtypes = [P, P, C.c_uint32, C.c_uint32]
+    lib.cutrace_host_register.argtypes = [P, C.c_size_t]
+    lib.cutrace_host_unregister.argtypes = [P]
     lib.cutrace_enable_peer_access.argtypes = [C.c_int, C.c_int]
     lib.cutrace_set_frame_max_depth.argtypes = [P, C.c_float]
     lib.cutrace_untile_device.argtypes = [P, C.c_uint32, P, P, P, P, C.c_uint64, P, P, P, P]

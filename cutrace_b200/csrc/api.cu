@@ -63,17 +63,17 @@ static int fail(int code, const std::string &msg) {
 // needs for its frame counters is therefore recycled through a process-wide free list.
 #include <mutex>
 static std::mutex g_pinned_mu;
-static std::vector<FrameCounters *> g_pinned_free;
-static FrameCounters *pinned_counters_get() {
+static std::vector<FrameStats *> g_pinned_free;
+static FrameStats *pinned_counters_get() {
   {
     std::lock_guard<std::mutex> lk(g_pinned_mu);
-    if (!g_pinned_free.empty()) { FrameCounters *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
+    if (!g_pinned_free.empty()) { FrameStats *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
   }
-  FrameCounters *p = nullptr;
-  if (cudaHostAlloc(&p, sizeof(FrameCounters), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return nullptr;
+  FrameStats *p = nullptr;
+  if (cudaHostAlloc(&p, sizeof(FrameStats), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return nullptr;
   return p;
 }
-static void pinned_counters_put(FrameCounters *p) {
+static void pinned_counters_put(FrameStats *p) {
   if (!p) return;
   std::lock_guard<std::mutex> lk(g_pinned_mu);
   g_pinned_free.push_back(p);
@@ -153,6 +153,7 @@ struct cutrace_ctx {
   MaterialRec *materials = nullptr;
   LightRec *lights = nullptr;
   uint32_t *obj_material = nullptr;
+  ObjBound *obj_bounds = nullptr;    // per-object AABB + mesh flag (the reference's mesh pre-test, trace.cuh: mesh_gate)
   SceneView sv{};
   int max_children = 0;
   // frame
@@ -176,13 +177,13 @@ struct cutrace_ctx {
   uint64_t batch_px = 0, cap = 0;
   uint32_t factor = 1;
   FrameCounters *d_ctr = nullptr;
-  FrameCounters *h_ctr = nullptr;   // pinned + mapped: the frame kernel publishes its counters here
-  FrameCounters *h_ctr_dev = nullptr;   // device address of h_ctr
+  FrameStats *h_ctr = nullptr;      // pinned + mapped: the frame kernel publishes its statistics here
+  FrameStats *h_ctr_dev = nullptr;  // device address of h_ctr
   float phase_ms[18] = {};          // frame kernel: when trace(p) was complete / the frame ended, relative to its start (last batch)
   uint32_t phase_count = 0;
   bool ctr_dirty = true;            // d_ctr may hold values of an earlier (multi-launch or failed) frame: clear before a frame kernel
   bool frame_kernel_failed = false; // a cooperative launch was refused: this ctx stays on the multi-launch path
-  bool env_no_frame_kernel = false, env_export_with_color = false;
+  bool env_export_with_color = false;
   LaunchCfg cfg{};
   // download staging (row-major full frame), lazily allocated
   float *st_depth = nullptr;         // staging frame block (same layout as `frame`)
@@ -435,6 +436,7 @@ void cutrace_free(cutrace_ctx *c) {
   LAP("free: frame + graph");
   dfree(c->bvh.nodes, c->stream); dfree(c->bvh.prims, c->stream);
   dfree(c->planes, c->stream); dfree(c->materials, c->stream); dfree(c->lights, c->stream); dfree(c->obj_material, c->stream);
+  dfree(c->obj_bounds, c->stream);
   dfree(c->d_ctr, c->stream);
   LAP("free: scene buffers");
   if (c->stream) cudaStreamSynchronize(c->stream);
@@ -474,7 +476,11 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   if (!guard.ok) { delete c; return fail(CUTRACE_ERR_CUDA, "cudaSetDevice failed"); }
   pool_keep_memory(dev);
   c->env_no_graph = getenv("CUTRACE_NO_GRAPH") != nullptr;
-  c->env_no_frame_kernel = getenv("CUTRACE_NO_FRAME_KERNEL") != nullptr;          // developer toggle: one launch per level and kind, as a CUDA graph
+  if (const char *e = getenv("CUTRACE_SCHEDULER")) {   // developer override of cutrace_opts.flags: "frame" | "launches"
+    c->opts.flags &= ~(CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES);
+    if (!strcmp(e, "frame")) c->opts.flags |= CUTRACE_FLAG_FRAME_KERNEL;
+    else if (!strcmp(e, "launches")) c->opts.flags |= CUTRACE_FLAG_LAUNCHES;
+  }
   c->env_export_with_color = getenv("CUTRACE_EXPORT_WITH_COLOR") != nullptr;      // developer toggle: remote G-buffer stores at the end of the frame
   c->env_graph_first = getenv("CUTRACE_GRAPH_FIRST") != nullptr;
   c->env_skip_export = getenv("CUTRACE_DEBUG_SKIP_EXPORT") != nullptr;      // timing experiments of profiles/r01_tuning.md only:
@@ -548,6 +554,17 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
     CUT(cudaMemcpyAsync(d_so, s->sph_object, sizeof(uint32_t) * ns, cudaMemcpyHostToDevice, c->stream));
   }
   LAP("primitive H2D");
+  {
+    uint32_t *d_kind = nullptr;
+    if (s->obj_kind && s->n_objects) {
+      CUT(dmalloc(&d_kind, sizeof(uint32_t) * s->n_objects, c->stream));
+      CUT(cudaMemcpyAsync(d_kind, s->obj_kind, sizeof(uint32_t) * s->n_objects, cudaMemcpyHostToDevice, c->stream));
+    }
+    std::string oerr;
+    rc = build_object_bounds(d_p1, d_p2, d_p3, d_to, (uint32_t)nt, s->n_objects, d_kind, &c->obj_bounds, c->stream, oerr);
+    dfree(d_kind, c->stream);
+    if (rc) { free_tmp(); cutrace_free(c); return fail(rc, oerr); }
+  }
   BvhInput bi;
   bi.d_p1 = d_p1; bi.d_p2 = d_p2; bi.d_p3 = d_p3; bi.d_tri_obj = d_to; bi.n_tri = (uint32_t)nt;
   bi.d_sph_center = d_sc; bi.d_sph_radius = d_sr; bi.d_sph_obj = d_so; bi.n_sph = (uint32_t)ns;
@@ -569,7 +586,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
 
   SceneView &sv = c->sv;
   sv.nodes = c->bvh.nodes; sv.prims = c->bvh.prims; sv.planes = c->planes; sv.materials = c->materials;
-  sv.lights = c->lights; sv.obj_material = c->obj_material;
+  sv.lights = c->lights; sv.obj_material = c->obj_material; sv.obj_bounds = c->obj_bounds;
   sv.n_prims = c->bvh.n_prims; sv.n_nodes = c->bvh.n_nodes; sv.n_planes = (uint32_t)s->n_planes;
   sv.n_lights = s->n_lights; sv.n_materials = s->n_materials; sv.n_objects = s->n_objects;
   sv.root = c->bvh.root;
@@ -585,7 +602,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   if (!c->h_ctr) { cutrace_free(c); return fail(CUTRACE_ERR_OUT_OF_MEMORY, "cudaHostAlloc failed"); }
   {
     void *dp = nullptr;
-    if (cudaHostGetDevicePointer(&dp, c->h_ctr, 0) == cudaSuccess) c->h_ctr_dev = static_cast<FrameCounters *>(dp);
+    if (cudaHostGetDevicePointer(&dp, c->h_ctr, 0) == cudaSuccess) c->h_ctr_dev = static_cast<FrameStats *>(dp);
     else cudaGetLastError();
   }
   LAP("ctr alloc");
@@ -725,7 +742,11 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   // cleared counters and leaves them cleared; its counters arrive in c->h_ctr (mapped pinned memory) without a copy.
   // With an early G-buffer download pending (cutrace_render_download) trace(0) runs as its own kernel first, so that the
   // copy engine can start behind it while the frame kernel works on the bounce levels.
-  const bool use_frame = !serialize && !c->env_no_frame_kernel && !c->frame_kernel_failed && c->cfg.grid_frame > 0 && c->h_ctr_dev;
+  // which scheduler: see CUTRACE_FLAG_FRAME_KERNEL in cutrace.h
+  const bool want_frame = (c->opts.flags & CUTRACE_FLAG_FRAME_KERNEL) ? true
+                          : (c->opts.flags & CUTRACE_FLAG_LAUNCHES) ? false
+                                                                    : (c->tm.world > 1 && c->n_local_px >= (1ull << 19));
+  const bool use_frame = want_frame && !serialize && !c->frame_kernel_failed && c->cfg.grid_frame > 0 && c->h_ctr_dev;
   auto enqueue_frame = [&](uint64_t base, uint32_t n_px, bool split_primary) -> cudaError_t {
     cudaError_t e;
     if (c->ctr_dirty) {
@@ -745,7 +766,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       if (bound > c->shade_cap[L]) bound = c->shade_cap[L];
       bound_max = std::max(bound_max, bound);
     }
-    fa.ctr = c->d_ctr; fa.host_ctr = c->h_ctr_dev;
+    fa.ctr = c->d_ctr; fa.host_stats = c->h_ctr_dev;
     fa.gbuf = gbuf; fa.out = out; fa.gsrc = gsrc; fa.acc = acc;
     if (c->env_skip_export) fa.gsrc = FrameTargets{};
     fa.level_color = branching ? nullptr : c->level_color; fa.level_stride = 3ull * c->batch_px; fa.nlev = c->nlev;
@@ -829,12 +850,12 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
       if (c->dl_normal) CU(cudaMemcpyAsync(c->dl_normal, v.normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->copy_stream));
       c->dl_depth = c->dl_normal = nullptr; c->dl_id = nullptr;   // consumed
     }
-    if (!frame_done) CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+    if (!frame_done) CU(cudaMemcpyAsync(c->h_ctr, &c->d_ctr->st, sizeof(FrameStats), cudaMemcpyDeviceToHost, st));
     if (base + c->batch_px >= c->n_local_px) CU(cudaEventRecord(ev_end, st));
     LAP("render: enqueue");
     CU(cudaStreamSynchronize(st));
     LAP("render: wait for the frame");
-    const FrameCounters &h = *c->h_ctr;
+    const FrameStats &h = *c->h_ctr;
     if (frame_done) {
       c->ctr_dirty = false;   // the frame kernel cleared the device counters on its way out
       c->phase_count = levels + 1;
@@ -981,7 +1002,7 @@ int cutrace_frame_device(cutrace_ctx *c, float **depth, float **normal, float **
 
 int cutrace_frame_ipc_export(cutrace_ctx *c, void *handle) {
   if (!c || !handle) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
-  static_assert(sizeof(cudaIpcMemHandle_t) == CUTRACE_IPC_HANDLE_BYTES, "IPC handle size");
+  static_assert(sizeof(cudaIpcMemHandle_t) + 16 == CUTRACE_IPC_HANDLE_BYTES, "IPC handle size");
   DeviceGuard g(c->device);
   CU(cudaStreamSynchronize(c->stream));
   if (!c->frame_is_ipc) {   // pool memory cannot be exported: give the frame its own cudaMalloc block
@@ -995,18 +1016,26 @@ int cutrace_frame_ipc_export(cutrace_ctx *c, void *handle) {
   }
   cudaIpcMemHandle_t h;
   CU(cudaIpcGetMemHandle(&h, c->frame));
+  memset(handle, 0, CUTRACE_IPC_HANDLE_BYTES);
   memcpy(handle, &h, sizeof h);
+  const uint32_t dims[2] = {c->tm.width, c->tm.height};
+  memcpy(static_cast<char *>(handle) + sizeof h, dims, sizeof dims);
   return CUTRACE_OK;
 }
 
 int cutrace_frame_ipc_import(cutrace_ctx *c, const void *handle) {
   if (!c || !handle) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
   DeviceGuard g(c->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  uint32_t dims[2];
+  memcpy(dims, static_cast<const char *>(handle) + sizeof h, sizeof dims);
+  if (dims[0] != c->tm.width || dims[1] != c->tm.height)
+    return fail(CUTRACE_ERR_INVALID_ARG, "the exported frame is " + std::to_string(dims[0]) + "x" + std::to_string(dims[1]) + ", this ctx renders " +
+                                             std::to_string(c->tm.width) + "x" + std::to_string(c->tm.height));
   CU(cudaStreamSynchronize(c->stream));
   if (c->peer_frame && c->peer_is_ipc) cudaIpcCloseMemHandle(c->peer_frame);
   c->peer_frame = nullptr;
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle, sizeof h);
   void *p = nullptr;
   CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   c->peer_frame = p;
@@ -1035,15 +1064,42 @@ int cutrace_set_frame_max_depth(cutrace_ctx *c, float max_depth) {
   return CUTRACE_OK;
 }
 
-int cutrace_frame_attach(cutrace_ctx *c, void *frame_block) {
+int cutrace_frame_attach(cutrace_ctx *c, void *frame_block, uint32_t width, uint32_t height) {
   if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
   DeviceGuard g(c->device);
+  void *dev_ptr = frame_block;
+  if (frame_block) {
+    if (width != c->tm.width || height != c->tm.height)
+      return fail(CUTRACE_ERR_INVALID_ARG, "the frame block is " + std::to_string(width) + "x" + std::to_string(height) + ", this ctx renders " +
+                                               std::to_string(c->tm.width) + "x" + std::to_string(c->tm.height));
+    cudaPointerAttributes at{};
+    cudaError_t e = cudaPointerGetAttributes(&at, frame_block);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(CUTRACE_ERR_INVALID_ARG, "frame_block is not memory CUDA knows (device, or registered / pinned host memory)"); }
+    if (at.type == cudaMemoryTypeHost) {
+      if (!at.devicePointer) return fail(CUTRACE_ERR_INVALID_ARG, "host frame_block is not mapped into the device address space");
+      dev_ptr = at.devicePointer;
+    } else if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+      return fail(CUTRACE_ERR_INVALID_ARG, "frame_block is unregistered host memory: register it with cutrace_host_register first");
+    }
+  }
   CU(cudaStreamSynchronize(c->stream));
   if (c->peer_frame && c->peer_is_ipc) cudaIpcCloseMemHandle(c->peer_frame);
-  c->peer_frame = frame_block;   // NULL detaches
+  c->peer_frame = dev_ptr;   // NULL detaches
   c->peer_is_ipc = false;
   c->rendered = false;
   drop_graph(c);
+  return CUTRACE_OK;
+}
+
+int cutrace_host_register(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+  return CUTRACE_OK;
+}
+
+int cutrace_host_unregister(void *ptr) {
+  if (!ptr) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  CU(cudaHostUnregister(ptr));
   return CUTRACE_OK;
 }
 
@@ -1086,7 +1142,7 @@ int cutrace_encode_bytes_device(cutrace_ctx *c, const float *depth, const float 
 
 void *cutrace_host_alloc(size_t bytes) {
   void *p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
   return p;
 }
 

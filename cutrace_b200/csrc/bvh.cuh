@@ -35,6 +35,10 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err);
 int reorder_top(BvhResult &bvh, uint32_t S, cudaStream_t stream, uint32_t *n_top_out, std::string &err);
 // device-side self check, see cutrace_validate_bvh()
 int validate_bvh(const BvhResult &bvh, cudaStream_t stream, std::string &err);
+// per-object AABB (min / max over the vertices of the object's triangles, like cutrace's host code) + "is a mesh" flag for the
+// reference's mesh pre-test (trace.cuh: mesh_gate).  d_obj_kind may be NULL (an object with more than one triangle is a mesh).
+int build_object_bounds(const float *d_p1, const float *d_p2, const float *d_p3, const uint32_t *d_tri_obj, uint32_t n_tri, uint32_t n_objects,
+                        const uint32_t *d_obj_kind, ObjBound **out, cudaStream_t st, std::string &err);
 // radix sort entry point (exposed for the sort unit test): sorts n (key,value) pairs ascending, stable.
 // d_keys/d_vals are overwritten with the result; tmp buffers are allocated internally.
 int radix_sort_pairs(uint64_t *d_keys, uint32_t *d_vals, uint32_t n, cudaStream_t stream, std::string &err);

@@ -693,6 +693,87 @@ done:
 }
 
 // ---------------------------------------------------------------------------------------------
+// per-object boxes for the reference's mesh pre-test (trace.cuh: mesh_gate)
+// ---------------------------------------------------------------------------------------------
+// acc: n_objects x 8 words = lo.xyz (ordered), hi.xyz (ordered), triangle count, unused
+__global__ void object_bounds_init_kernel(unsigned int *acc, uint32_t n_objects) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_objects * 8u) return;
+  const uint32_t w = i & 7u;
+  acc[i] = w < 3u ? 0xffffffffu : 0u;
+}
+// min / max over the vertices of every triangle of an object — exactly cpu::schema::mesh::bounding_box
+// (inc/default_schema.hpp:573-586; min and max are exact in float).  A warp whose 32 triangles belong to one object (the
+// normal case: meshes are contiguous) reduces first and issues one set of atomics.
+__global__ void object_bounds_kernel(const float *__restrict__ p1, const float *__restrict__ p2, const float *__restrict__ p3,
+                                     const uint32_t *__restrict__ tri_obj, uint32_t n_tri, uint32_t n_objects, unsigned int *acc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n_tri;
+  uint32_t obj = valid ? tri_obj[i] : 0xffffffffu;
+  if (obj >= n_objects) obj = 0xffffffffu;   // reported by prim_bounds_kernel
+  float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (obj != 0xffffffffu) {
+    for (int c = 0; c < 3; c++) {
+      const float a = p1[3 * (size_t)i + c], b = p2[3 * (size_t)i + c], d = p3[3 * (size_t)i + c];
+      l[c] = fminf(fminf(a, b), d);
+      h[c] = fmaxf(fmaxf(a, b), d);
+    }
+  }
+  const uint32_t obj0 = __shfl_sync(0xffffffffu, obj, 0);
+  if (__all_sync(0xffffffffu, obj == obj0)) {
+    if (obj0 == 0xffffffffu) return;
+    for (int c = 0; c < 3; c++)
+      for (int o = 16; o > 0; o >>= 1) {
+        l[c] = fminf(l[c], __shfl_xor_sync(0xffffffffu, l[c], o));
+        h[c] = fmaxf(h[c], __shfl_xor_sync(0xffffffffu, h[c], o));
+      }
+    if ((threadIdx.x & 31) == 0) {
+      unsigned int *a = acc + 8 * (size_t)obj0;
+      for (int c = 0; c < 3; c++) { atomicMin(a + c, f2ord(l[c])); atomicMax(a + 3 + c, f2ord(h[c])); }
+      atomicAdd(a + 6, 32u);
+    }
+  } else if (obj != 0xffffffffu) {
+    unsigned int *a = acc + 8 * (size_t)obj;
+    for (int c = 0; c < 3; c++) { atomicMin(a + c, f2ord(l[c])); atomicMax(a + 3 + c, f2ord(h[c])); }
+    atomicAdd(a + 6, 1u);
+  }
+}
+__device__ __forceinline__ float ord2f(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__global__ void object_bounds_finish_kernel(const unsigned int *__restrict__ acc, const uint32_t *__restrict__ obj_kind, uint32_t n_objects,
+                                            ObjBound *out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_objects) return;
+  const unsigned int *a = acc + 8 * (size_t)i;
+  ObjBound b;
+  const bool any = a[6] != 0u;
+  for (int c = 0; c < 3; c++) { b.lo[c] = any ? ord2f(a[c]) : INFINITY; b.hi[c] = any ? ord2f(a[3 + c]) : -INFINITY; }
+  // a mesh gets the pre-test, a loose triangle does not; without obj_kind an object with exactly one triangle is a loose triangle
+  b.is_mesh = obj_kind ? (obj_kind[i] == CUTRACE_OBJ_MESH ? 1u : 0u) : (a[6] > 1u ? 1u : 0u);
+  b.pad = 0u;
+  out[i] = b;
+}
+
+int build_object_bounds(const float *d_p1, const float *d_p2, const float *d_p3, const uint32_t *d_tri_obj, uint32_t n_tri, uint32_t n_objects,
+                        const uint32_t *d_obj_kind, ObjBound **out, cudaStream_t st, std::string &err) {
+  int rc = CUTRACE_OK;
+  unsigned int *acc = nullptr;
+  *out = nullptr;
+  if (n_objects == 0) return rc;
+  CK(dmalloc(out, sizeof(ObjBound) * n_objects, st));
+  CK(dmalloc(&acc, sizeof(unsigned int) * 8 * (size_t)n_objects, st));
+  object_bounds_init_kernel<<<(n_objects * 8u + 255u) / 256u, 256, 0, st>>>(acc, n_objects);
+  if (n_tri) object_bounds_kernel<<<(n_tri + 255u) / 256u, 256, 0, st>>>(d_p1, d_p2, d_p3, d_tri_obj, n_tri, n_objects, acc);
+  object_bounds_finish_kernel<<<(n_objects + 255u) / 256u, 256, 0, st>>>(acc, d_obj_kind, n_objects, *out);
+  CK(cudaGetLastError());
+done:
+  dfree(acc, st);
+  if (rc) { dfree(*out, st); *out = nullptr; }
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // driver
 // ---------------------------------------------------------------------------------------------
 int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {

@@ -107,20 +107,32 @@ struct __align__(16) ShadeRec {     // 48 B: one shaded hit = n_lights shadow ra
 static_assert(sizeof(RayRec) == 32 && sizeof(ShadeRec) == 48, "queue record sizes");
 
 // device-side counters of one frame
-struct FrameCounters {
-  unsigned int n_rays[18];      // ray-queue slots reserved for level L (valid rays + retired holes)
-  unsigned int n_shade[18];     // shade-queue slots reserved by level L (valid records + retired holes)
-  unsigned int work_trace[18];  // work-stealing cursors
-  unsigned int work_shade[18];
+// Words that many warps hit with atomics at the same time each sit on their own 128-byte line: same-address atomics
+// retire at ~0.67 ns each on B200 whatever the SM count, and atomics to ONE line from every warp of the grid (cursor,
+// queue tails, barrier) had made a nearly empty bounce level cost 40 us (profiles/r02_tuning.md).
+struct __align__(128) HotWord { unsigned int v; unsigned int pad_[31]; };
+struct FrameStats {               // what the host reads after a frame
   unsigned long long rays_reflect, rays_transmit, shadow_casts, shade_records;
-  unsigned int max_depth_bits;  // float bits of the largest finite primary depth
-  unsigned int overflow;        // a queue reservation did not fit: the emission was dropped, the frame is reported as failed
-  // ---- persistent frame kernel (render.cu: frame_kernel) ----
-  unsigned int arrive[18];      // grid barrier of phase p: warps that have finished trace(p)   (arrive[levels]: all shading done)
-  unsigned int work_export;     // cursor of the G-buffer export (peer / host frame)
-  unsigned int finished;        // warps that have left the kernel: the last one publishes the counters and clears them
-  unsigned int pad_;
-  unsigned long long phase_ns[18];   // %globaltimer when phase p opened (diagnostics: where a frame's time goes)
+  unsigned int max_depth_bits;    // float bits of the largest finite primary depth
+  unsigned int overflow;          // a queue reservation did not fit: the emission was dropped, the frame is reported as failed
+  unsigned long long phase_ns[19];   // frame kernel: %globaltimer when phase p opened; [17] start, [levels] end of the frame
+};
+struct FrameCounters {
+  HotWord n_rays[18];       // ray-queue slots reserved for level L (valid rays + retired holes)
+  HotWord n_shade[18];      // shade-queue slots reserved by level L (valid records + retired holes)
+  HotWord work_trace[18];   // work-stealing cursors
+  HotWord work_shade[18];
+  HotWord arrive[19];       // frame kernel: CTAs that have finished trace(p)   (arrive[levels]: all shading done)
+  HotWord work_export;      // cursor of the G-buffer export (peer / host frame)
+  HotWord finished;         // CTAs that have left the frame kernel: the last one publishes the stats and clears everything
+  FrameStats st;
+};
+
+// Per-object data for the reference's mesh pre-test (inc/default_schema.hpp:99-114): the AABB cutrace computes on the host
+// for every mesh (inc/default_schema.hpp:573-586) and whether the object is a mesh at all.
+struct __align__(16) ObjBound {
+  float lo[3]; uint32_t is_mesh;
+  float hi[3]; uint32_t pad;
 };
 
 // everything a render kernel needs, passed by value (lives in the constant bank)
@@ -131,6 +143,7 @@ struct SceneView {
   const MaterialRec *materials;
   const LightRec *lights;
   const uint32_t *obj_material;
+  const ObjBound *obj_bounds;   // n_objects
   uint32_t n_prims, n_nodes, n_planes, n_lights, n_materials, n_objects;
   int root;                 // node index, leaf code, or CTB_SENTINEL (empty BVH)
   uint32_t smem_nodes;      // nodes [0, smem_nodes) are staged in shared memory

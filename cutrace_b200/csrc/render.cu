@@ -29,6 +29,7 @@
 //                  fallback when a cooperative launch is not possible).
 //
 // All kernels are persistent: each warp claims work from a global cursor (guided chunk sizes).
+#include <cstddef>
 #include "render.cuh"
 #include "trace.cuh"
 
@@ -55,22 +56,52 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+#ifdef CTB_PHASE_DEBUG   // developer instrumentation (tools/build_variant.sh dbg -DCTB_PHASE_DEBUG): where a phase's time goes
+// [0] first / [1] last warp out of trace(p) work, [2] last warp arrived (after flush), [3] first / [4] last warp that saw the phase open,
+// [5][0] last CTA staged
+__device__ unsigned long long g_dbg_ns[6][18];
+#define DBG_MIN(k, p) do { if (lane == 0) atomicMin(&g_dbg_ns[k][p], globaltimer_ns()); } while (0)
+#define DBG_MAX(k, p) do { if (lane == 0) atomicMax(&g_dbg_ns[k][p], globaltimer_ns()); } while (0)
+#else
+#define DBG_MIN(k, p)
+#define DBG_MAX(k, p)
+#endif
+
 // Work stealing with guided chunk sizes: a warp claims `remaining / (2 * warps in flight)` items, at least one
 // warp-iteration (32) and at most `max_chunk`.  Large claims while there is plenty of work keep the cursor
 // atomics rare; 32-item claims at the end keep the tail short — at deep bounce levels of the 10 M-triangle scene a
 // few grazing rays cost milliseconds each and fixed 128-ray claims left the GPU idle behind them
 // (profiles/r01_tuning.md, "tile scaling").
-__device__ __forceinline__ bool claim_work(unsigned *cursor, unsigned n_work, unsigned lane, unsigned max_chunk, unsigned &base, unsigned &end) {
+// `first` (warp-uniform; trace phases, which every warp enters at the same moment): the first chunk of a warp is its
+// STATIC slot gw * c0 — no atomic at all; the cursor then hands out what lies behind warps * c0.  A bounce level with fewer
+// than 32 rays per warp costs no cursor atomics whatsoever (4,736 warps hitting one address at the start of every phase took
+// 3 us by themselves, profiles/r02_tuning.md).
+__device__ __forceinline__ unsigned guided_chunk(unsigned remaining, unsigned warps, unsigned max_chunk) {
+  unsigned chunk = remaining / (2u * warps);
+  chunk = chunk < 32u ? 32u : (chunk > max_chunk ? max_chunk : chunk);
+  return chunk & ~31u;
+}
+__device__ __forceinline__ bool claim_work(unsigned *cursor, unsigned n_work, unsigned lane, unsigned max_chunk, bool static_first, bool first,
+                                           unsigned &base, unsigned &end) {
+  const unsigned warps = gridDim.x * (blockDim.x >> 5);
+  unsigned dyn0 = 0;
+  if (static_first) {
+    const unsigned c0 = guided_chunk(n_work, warps, max_chunk);
+    if (first) {
+      const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+      base = gw * c0;
+      end = base + c0 < n_work ? base + c0 : n_work;
+      return base < n_work;
+    }
+    dyn0 = warps * c0;
+    if (dyn0 >= n_work) return false;
+  }
   unsigned b = 0, chunk = 0;
   if (lane == 0) {
-    const unsigned cur = *reinterpret_cast<volatile unsigned *>(cursor);
+    const unsigned cur = dyn0 + *reinterpret_cast<volatile unsigned *>(cursor);
     if (cur < n_work) {
-      const unsigned remaining = n_work - cur;
-      const unsigned warps = gridDim.x * (blockDim.x >> 5);
-      chunk = remaining / (2u * warps);
-      chunk = chunk < 32u ? 32u : (chunk > max_chunk ? max_chunk : chunk);
-      chunk &= ~31u;
-      b = atomicAdd(cursor, chunk);
+      chunk = guided_chunk(n_work - cur, warps, max_chunk);
+      b = dyn0 + atomicAdd(cursor, chunk);
     } else {
       b = n_work;   // exhausted: no atomic (the frame kernel polls exhausted cursors while it waits for a phase to open)
     }
@@ -194,7 +225,7 @@ __device__ __forceinline__ Emit reserve_slots(SlotBlock &b, unsigned n, unsigned
   if (lane == 0) nb = atomicAdd(counter, blk);
   nb = __shfl_sync(CTB_FULL, nb, 0);
   if (nb > cap || blk > cap - nb) {                       // does not fit: never write past the queue
-    if (lane == 0) atomicExch(&ctr->overflow, 1u);
+    if (lane == 0) atomicExch(&ctr->st.overflow, 1u);
     for (unsigned k = nb + lane; k < cap; k += 32) store_hole(queue + k);
     e.fits = false;
     b.next = b.end;                                       // the old block is full (its `rem` slots are used by this emission)
@@ -289,7 +320,7 @@ __device__ __forceinline__ void trace_chunk(const SceneView &sv, const float4 *n
     // ---- shade record ----
     const unsigned m_hit = __ballot_sync(CTB_FULL, hit);
     if (m_hit) {
-      const Emit e = reserve_slots(acc.sq, __popc(m_hit), lane, slot_block, &ctr->n_shade[level], io.shade_cap, io.shade_out, ctr);
+      const Emit e = reserve_slots(acc.sq, __popc(m_hit), lane, slot_block, &ctr->n_shade[level].v, io.shade_cap, io.shade_out, ctr);
       const unsigned rank = __popc(m_hit & lt_mask);
       if (hit && emit_ok(e, rank)) {
         float4 *sp = reinterpret_cast<float4 *>(io.shade_out + emit_slot(e, rank));
@@ -303,7 +334,7 @@ __device__ __forceinline__ void trace_chunk(const SceneView &sv, const float4 *n
     const unsigned m_r = __ballot_sync(CTB_FULL, do_refl), m_t = __ballot_sync(CTB_FULL, do_trans);
     if (m_r | m_t) {
       const unsigned nr = __popc(m_r), nt = __popc(m_t);
-      const Emit e = reserve_slots(acc.rq, nr + nt, lane, slot_block, &ctr->n_rays[level + 1], io.ray_cap, io.rays_out, ctr);
+      const Emit e = reserve_slots(acc.rq, nr + nt, lane, slot_block, &ctr->n_rays[level + 1].v, io.ray_cap, io.rays_out, ctr);
       const vec3 origin = vadd(o, vscale(d, h.t));   // incoming->start + distance * incoming->dir
       if (do_refl) {
         const unsigned rank = __popc(m_r & lt_mask);
@@ -329,47 +360,28 @@ __device__ __forceinline__ void trace_chunk(const SceneView &sv, const float4 *n
   }
 }
 
-// end of a level for this warp: retire the unused tails of its slot blocks, add its tallies to the frame counters
-__device__ __forceinline__ void trace_flush(uint32_t level, const LevelIO &io, FrameCounters *ctr, unsigned lane, TraceAcc &acc) {
+// end of a level for this warp: retire the unused tails of its slot blocks
+__device__ __forceinline__ void trace_flush(const LevelIO &io, unsigned lane, TraceAcc &acc) {
   flush_block(acc.sq, io.shade_out, lane);
   flush_block(acc.rq, io.rays_out, lane);
+}
+// adds a warp's tallies to the frame statistics (once per kernel and warp)
+__device__ __forceinline__ void tallies_flush(FrameCounters *ctr, unsigned lane, TraceAcc &acc, unsigned casts) {
+  unsigned long long c = casts;
   for (int s = 16; s > 0; s >>= 1) {
     acc.n_refl += __shfl_xor_sync(CTB_FULL, acc.n_refl, s);
     acc.n_trans += __shfl_xor_sync(CTB_FULL, acc.n_trans, s);
     acc.n_shaded += __shfl_xor_sync(CTB_FULL, acc.n_shaded, s);
     acc.max_depth = fmaxf(acc.max_depth, __shfl_xor_sync(CTB_FULL, acc.max_depth, s));
+    c += __shfl_xor_sync(CTB_FULL, c, s);
   }
   if (lane == 0) {
-    if (acc.n_refl) atomicAdd(&ctr->rays_reflect, (unsigned long long)acc.n_refl);
-    if (acc.n_shaded) atomicAdd(&ctr->shade_records, (unsigned long long)acc.n_shaded);
-    if (acc.n_trans) atomicAdd(&ctr->rays_transmit, (unsigned long long)acc.n_trans);
-    if (level == 0 && acc.max_depth > 0.f) atomicMax(&ctr->max_depth_bits, __float_as_uint(acc.max_depth));
+    if (acc.n_refl) atomicAdd(&ctr->st.rays_reflect, (unsigned long long)acc.n_refl);
+    if (acc.n_shaded) atomicAdd(&ctr->st.shade_records, (unsigned long long)acc.n_shaded);
+    if (acc.n_trans) atomicAdd(&ctr->st.rays_transmit, (unsigned long long)acc.n_trans);
+    if (acc.max_depth > 0.f) atomicMax(&ctr->st.max_depth_bits, __float_as_uint(acc.max_depth));
+    if (c) atomicAdd(&ctr->st.shadow_casts, c);
   }
-  trace_acc_reset(acc);
-}
-
-template <int MODE, bool BRUTE>
-__global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
-trace_kernel(const SceneView sv, const TileMap tm, uint32_t level, uint32_t bounces, uint32_t px_base, uint32_t n_px, const LevelIO io,
-             FrameCounters *ctr, FrameTargets fb, uint32_t *__restrict__ nlev) {
-  extern __shared__ float4 smem[];
-  const float4 *nodes, *prims;
-  stage_scene<MODE>(sv, smem, nodes, prims);
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = lanemask_lt();
-  uint32_t n_work = level == 0 ? n_px : ctr->n_rays[level];
-  if (level && n_work > io.ray_cap) n_work = io.ray_cap;   // (only after an overflow) rays_in has the capacity of rays_out
-  // block size: 1/8 of what a warp is expected to emit over the kernel, CTB_SLOT_MIN..SLOT_BLOCK
-  unsigned slot_block = (n_work / (gridDim.x * (blockDim.x >> 5) * (unsigned)CTB_SLOT_DIV)) & ~31u;
-  slot_block = slot_block < (unsigned)CTB_SLOT_MIN ? (unsigned)CTB_SLOT_MIN : (slot_block > (unsigned)SLOT_BLOCK ? (unsigned)SLOT_BLOCK : slot_block);
-  TraceAcc acc;
-  trace_acc_reset(acc);
-  for (;;) {
-    unsigned base, end;
-    if (!claim_work(&ctr->work_trace[level], n_work, lane, (unsigned)WORK_CHUNK_MAX, base, end)) break;
-    trace_chunk<MODE, BRUTE>(sv, nodes, prims, tm, level, bounces, px_base, base, end, n_work, io, ctr, fb, nlev, slot_block, lane, lt_mask, acc);
-  }
-  trace_flush(level, io, ctr, lane, acc);
 }
 
 // shadow_intensity, inc/shading.hpp:22-45
@@ -398,6 +410,16 @@ __device__ __forceinline__ float shadow_intensity(const SceneView &sv, const flo
     last_hit = h.t;
   }
   return intensity;
+}
+
+// final += (1 - shadow_fac) * (fd * ld + fs * ls), inc/shading.hpp:95.  Written with explicit roundings — fma(fd, ld, fs * ls),
+// then fma(keep, ., final), the forms nvcc's contraction picks for the reference's expression — because the compiler's own
+// choice depends on the surrounding code: the same source inlined into the frame kernel and into shade_kernel differed in the
+// last bit of 0.4 % of the pixels (profiles/r02_tuning.md), and the schedulers are supposed to agree bit for bit.
+__device__ __forceinline__ void phong_add(vec3 &final, vec3 ld, float fd, vec3 ls, float fs, float keep) {
+  final.x = __fmaf_rn(keep, __fmaf_rn(fd, ld.x, __fmul_rn(fs, ls.x)), final.x);
+  final.y = __fmaf_rn(keep, __fmaf_rn(fd, ld.y, __fmul_rn(fs, ls.y)), final.y);
+  final.z = __fmaf_rn(keep, __fmaf_rn(fd, ld.z, __fmul_rn(fs, ls.z)), final.z);
 }
 
 // shadow rays + Phong for the shade records [base, end) of one level (one warp)
@@ -465,8 +487,7 @@ __device__ __forceinline__ void shade_chunk(const SceneView &sv, const float4 *n
               vec3 hv = vnormalized(vadd(in_n, nd));
               float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
               vec3 ls = vmul(specular, lcol[k]);
-              vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - 0.0f);
-              final.x += term.x; final.y += term.y; final.z += term.z;
+              phong_add(final, ld, fd, ls, fs, 1.0f);
             }
           }
         }
@@ -495,8 +516,7 @@ __device__ __forceinline__ void shade_chunk(const SceneView &sv, const float4 *n
             vec3 hv = vnormalized(vadd(in_n, nd));
             float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
             vec3 ls = vmul(specular, color);
-            vec3 term = vscale(vadd(vscale(ld, fd), vscale(ls, fs)), 1 - shadow_fac);
-            final.x += term.x; final.y += term.y; final.z += term.z;
+            phong_add(final, ld, fd, ls, fs, 1 - shadow_fac);
           }
         }
       }
@@ -515,30 +535,127 @@ __device__ __forceinline__ void shade_chunk(const SceneView &sv, const float4 *n
   }
 }
 
-__device__ __forceinline__ void casts_flush(FrameCounters *ctr, unsigned lane, unsigned &casts) {
-  unsigned long long c = casts;
-  for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(CTB_FULL, c, s);
-  if (lane == 0 && c) atomicAdd(&ctr->shadow_casts, c);
-  casts = 0;
+// -------------------------------------------------------------------------------------------------
+// the two kinds of work as callable units
+// -------------------------------------------------------------------------------------------------
+// trace_chunk / shade_chunk are entered through these two functions from the per-level kernels AND from the frame kernel.
+// nvcc chooses FMA contractions (and everything else) per compilation context: the same source inlined into two kernels gives
+// hit points and colours that differ in the last bit (0.4 % of the pixels, profiles/r02_tuning.md).  Built with
+// -DCTB_SHARED_BODIES=1 the two functions are __noinline__: one compiled body per kind of work, every scheduler executes the
+// same SASS for a ray and all of them agree bit for bit by construction (checked: identical md5 of the colour image) — but the
+// calling convention (SceneView through a generic pointer instead of constant-bank operands, registers saved around the call)
+// costs 10-12 % of the frame (bunny.json 4K 9.83 -> 11.05 ms), so the product build inlines them and the schedulers are allowed
+// to differ in the last bits (tests/parity.py: assert_same_frame(color_ulps=...)).
+#ifndef CTB_SHARED_BODIES
+#define CTB_SHARED_BODIES 0
+#endif
+#if CTB_SHARED_BODIES
+#define CTB_CHUNK_LINKAGE __noinline__
+#else
+#define CTB_CHUNK_LINKAGE __forceinline__
+#endif
+struct TraceCall {
+  const SceneView *sv;   // kernel parameter space (__grid_constant__)
+  const TileMap *tm;
+  uint32_t level, bounces, px_base;
+  unsigned base, end, n_work, slot_block;
+  LevelIO io;
+  FrameCounters *ctr;
+  FrameTargets fb;
+  uint32_t *nlev;
+};
+struct ShadeCall {
+  const SceneView *sv;
+  unsigned base, end, n_work;
+  const ShadeRec *shade;
+  FrameTargets fb;
+  int atomic_accumulate;
+  float *level_color;
+  uint32_t px_base;
+};
+
+// node / primitive pointers as the staged kernels see them (MODE 1: the shared-memory copy made by stage_scene)
+template <int MODE>
+__device__ __forceinline__ void scene_ptrs(const SceneView &sv, const float4 *&nodes, const float4 *&prims) {
+  extern __shared__ float4 ctb_dyn_smem[];
+  if (MODE == 1) {
+    nodes = ctb_dyn_smem;
+    prims = ctb_dyn_smem + sv.n_nodes * 4u;
+  } else {
+    nodes = reinterpret_cast<const float4 *>(sv.nodes);
+    prims = reinterpret_cast<const float4 *>(sv.prims);
+  }
+}
+
+template <int MODE, bool BRUTE>
+__device__ CTB_CHUNK_LINKAGE void trace_chunk_fn(const TraceCall *c, TraceAcc *acc_io) {
+  const SceneView &sv = *c->sv;
+  const float4 *nodes, *prims;
+  scene_ptrs<MODE>(sv, nodes, prims);
+  TraceAcc acc = *acc_io;
+  trace_chunk<MODE, BRUTE>(sv, nodes, prims, *c->tm, c->level, c->bounces, c->px_base, c->base, c->end, c->n_work, c->io, c->ctr, c->fb, c->nlev,
+                           c->slot_block, threadIdx.x & 31u, lanemask_lt(), acc);
+  *acc_io = acc;
 }
 
 template <int MODE, bool BRUTE, bool OPAQUE>
-__global__ void __launch_bounds__(TRACE_THREADS, CTB_SHADE_MIN_BLOCKS)
-shade_kernel(const SceneView sv, uint32_t level, const ShadeRec *__restrict__ shade, uint32_t shade_cap, FrameCounters *ctr, FrameTargets fb,
-             int atomic_accumulate, float *__restrict__ level_color, uint32_t px_base) {
+__device__ CTB_CHUNK_LINKAGE unsigned shade_chunk_fn(const ShadeCall *c) {
+  const SceneView &sv = *c->sv;
+  const float4 *nodes, *prims;
+  scene_ptrs<MODE>(sv, nodes, prims);
+  unsigned casts = 0;
+  shade_chunk<MODE, BRUTE, OPAQUE>(sv, nodes, prims, c->base, c->end, c->n_work, c->shade, c->fb, c->atomic_accumulate, c->level_color, c->px_base,
+                                   threadIdx.x & 31u, casts);
+  return casts;
+}
+
+template <int MODE, bool BRUTE>
+__global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS)
+trace_kernel(const __grid_constant__ SceneView sv, const __grid_constant__ TileMap tm, uint32_t level, uint32_t bounces, uint32_t px_base,
+             uint32_t n_px, const LevelIO io, FrameCounters *ctr, FrameTargets fb, uint32_t *__restrict__ nlev) {
   extern __shared__ float4 smem[];
   const float4 *nodes, *prims;
   stage_scene<MODE>(sv, smem, nodes, prims);
   const unsigned lane = threadIdx.x & 31u;
-  uint32_t n_work = ctr->n_shade[level];
+  uint32_t n_work = level == 0 ? n_px : ctr->n_rays[level].v;
+  if (level && n_work > io.ray_cap) n_work = io.ray_cap;   // (only after an overflow) rays_in has the capacity of rays_out
+  // block size: 1/8 of what a warp is expected to emit over the kernel, CTB_SLOT_MIN..SLOT_BLOCK
+  unsigned slot_block = (n_work / (gridDim.x * (blockDim.x >> 5) * (unsigned)CTB_SLOT_DIV)) & ~31u;
+  slot_block = slot_block < (unsigned)CTB_SLOT_MIN ? (unsigned)CTB_SLOT_MIN : (slot_block > (unsigned)SLOT_BLOCK ? (unsigned)SLOT_BLOCK : slot_block);
+  TraceAcc acc;
+  trace_acc_reset(acc);
+  TraceCall tc;
+  tc.sv = &sv; tc.tm = &tm; tc.level = level; tc.bounces = bounces; tc.px_base = px_base; tc.n_work = n_work; tc.slot_block = slot_block;
+  tc.io = io; tc.ctr = ctr; tc.fb = fb; tc.nlev = nlev;
+  for (bool first = true;; first = false) {
+    if (!claim_work(&ctr->work_trace[level].v, n_work, lane, (unsigned)WORK_CHUNK_MAX, true, first, tc.base, tc.end)) { if (first) continue; break; }
+    trace_chunk_fn<MODE, BRUTE>(&tc, &acc);
+  }
+  trace_flush(io, lane, acc);
+  tallies_flush(ctr, lane, acc, 0u);
+}
+
+template <int MODE, bool BRUTE, bool OPAQUE>
+__global__ void __launch_bounds__(TRACE_THREADS, CTB_SHADE_MIN_BLOCKS)
+shade_kernel(const __grid_constant__ SceneView sv, uint32_t level, const ShadeRec *__restrict__ shade, uint32_t shade_cap, FrameCounters *ctr,
+             FrameTargets fb, int atomic_accumulate, float *__restrict__ level_color, uint32_t px_base) {
+  extern __shared__ float4 smem[];
+  const float4 *nodes, *prims;
+  stage_scene<MODE>(sv, smem, nodes, prims);
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t n_work = ctr->n_shade[level].v;
   if (n_work > shade_cap) n_work = shade_cap;
   unsigned casts = 0;
-  for (;;) {
-    unsigned base, end;
-    if (!claim_work(&ctr->work_shade[level], n_work, lane, (unsigned)WORK_CHUNK_MAX, base, end)) break;
-    shade_chunk<MODE, BRUTE, OPAQUE>(sv, nodes, prims, base, end, n_work, shade, fb, atomic_accumulate, level_color, px_base, lane, casts);
+  ShadeCall sc;
+  sc.sv = &sv; sc.n_work = n_work; sc.shade = shade; sc.fb = fb; sc.atomic_accumulate = atomic_accumulate; sc.level_color = level_color;
+  sc.px_base = px_base;
+  for (bool first = true;; first = false) {
+    if (!claim_work(&ctr->work_shade[level].v, n_work, lane, (unsigned)WORK_CHUNK_MAX, true, first, sc.base, sc.end)) { if (first) continue; break; }
+    casts += shade_chunk_fn<MODE, BRUTE, OPAQUE>(&sc);
   }
-  casts_flush(ctr, lane, casts);
+  TraceAcc none;
+  trace_acc_reset(none);
+  tallies_flush(ctr, lane, none, casts);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -608,56 +725,100 @@ __global__ void export_gbuffer_kernel(const TileMap tm, uint32_t px_base, uint32
 // -------------------------------------------------------------------------------------------------
 #define CTB_EXPORT_CHUNK 256u
 
+// Grid barrier of the frame kernel, two-level.  Warps of a CTA count themselves in shared memory; the LAST warp of a CTA
+// to arrive publishes the CTA to the global counter (one release-RMW per CTA and phase instead of one per warp) and then
+// becomes the CTA's poller: it alone spins on the global counter (ld.acquire.gpu) and raises a shared-memory flag when
+// every CTA has arrived.  The other warps keep doing filler work and only look at the shared flag between chunks.
+//   fence protocol: writer warp: stores ... __threadfence(); smem arrive.   last warp: smem arrive; __threadfence();
+//   red.release.gpu.  poller: ld.acquire.gpu; __threadfence(); smem flag.  reader: smem flag; __threadfence(); loads (.cg).
+struct CtaSync {
+  unsigned arrived;              // warps of this CTA that have arrived, monotonic over the phases
+  volatile unsigned open;        // phases known to be open, monotonic
+  unsigned long long refl, trans, shaded, casts;   // CTA-wide tallies, added to the frame statistics once per CTA
+  unsigned max_depth_bits;
+};
+
 template <int MODE, bool BRUTE, bool OPAQUE>
-__global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(const FrameArgs a) {
+__global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(const __grid_constant__ FrameArgs a) {
   extern __shared__ float4 smem[];
+  __shared__ CtaSync cs;
+  if (threadIdx.x == 0) { cs.arrived = 0u; cs.open = 0u; cs.refl = cs.trans = cs.shaded = cs.casts = 0ull; cs.max_depth_bits = 0u; }
   const float4 *nodes, *prims;
   stage_scene<MODE>(a.sv, smem, nodes, prims);
+  if (MODE == 0) __syncthreads();   // (the staging paths synchronise the CTA themselves)
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = lanemask_lt();
-  const unsigned warps_total = gridDim.x * (blockDim.x >> 5);
+  const unsigned wpc = blockDim.x >> 5;
   FrameCounters *ctr = a.ctr;
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctr->phase_ns[17] = globaltimer_ns();   // diagnostics: start of the frame on the device
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctr->st.phase_ns[17] = globaltimer_ns();   // diagnostics: start of the frame on the device
+  DBG_MAX(5, 0);
   unsigned casts = 0;
   unsigned shade_lo = 0;                      // lowest shade level this warp still expects unclaimed records in
   bool export_left = a.gsrc.depth != nullptr && !a.export_with_color;   // G-buffer export to a remote frame pending
+  unsigned k_phase = 0;                       // barriers passed so far
   TraceAcc acc;
   trace_acc_reset(acc);
+  TraceCall tc;
+  tc.sv = &a.sv; tc.tm = &a.tm; tc.bounces = a.bounces; tc.px_base = a.px_base; tc.ctr = ctr; tc.fb = a.gbuf; tc.nlev = a.nlev;
+  ShadeCall sc;
+  sc.sv = &a.sv; sc.fb = a.acc; sc.atomic_accumulate = a.atomic_accumulate; sc.px_base = a.px_base;
 
+  // arrive at barrier number k_phase (global counter `gctr`); returns true for the warp that became the CTA's poller.
+  // A grid of one CTA (tiny frames) never touches the global counter.
+  auto cta_arrive = [&](unsigned *gctr) -> bool {
+    __threadfence();
+    __syncwarp();
+    unsigned last = 0;
+    if (lane == 0) {
+      last = atomicAdd(&cs.arrived, 1u) == (k_phase + 1u) * wpc - 1u;
+      if (last && gridDim.x > 1) red_release_add(gctr, 1u);   // release: orders the whole CTA's writes (fence cumulativity) before the count
+    }
+    return __shfl_sync(CTB_FULL, last, 0) != 0;
+  };
+  auto poll_until_open = [&](unsigned *gctr) {
+    if (lane == 0) {
+      if (gridDim.x > 1) while (ld_acquire_u32(gctr) < gridDim.x) __nanosleep(100);
+      __threadfence_block();
+      cs.open = k_phase + 1u;
+    }
+    __syncwarp();
+  };
   for (uint32_t p = a.first_level; p <= a.levels; p++) {
+    bool poller = false;
     // ---- trace(p): the critical path, every warp drains it first ----
     if (p < a.levels) {
       LevelIO io;
       io.rays_in = a.rays[p & 1]; io.rays_out = a.rays[(p + 1) & 1]; io.shade_out = a.shade[p];
       io.ray_cap = a.ray_cap; io.shade_cap = a.shade_cap[p];
       uint32_t n_work = a.n_px;
-      if (p) { n_work = __ldcg(&ctr->n_rays[p]); if (n_work > a.ray_cap) n_work = a.ray_cap; }
-      unsigned slot_block = (n_work / (warps_total * (unsigned)CTB_SLOT_DIV)) & ~31u;
+      if (p) { n_work = __ldcg(&ctr->n_rays[p].v); if (n_work > a.ray_cap) n_work = a.ray_cap; }
+      unsigned slot_block = (n_work / (gridDim.x * wpc * (unsigned)CTB_SLOT_DIV)) & ~31u;
       slot_block = slot_block < (unsigned)CTB_SLOT_MIN ? (unsigned)CTB_SLOT_MIN : (slot_block > (unsigned)SLOT_BLOCK ? (unsigned)SLOT_BLOCK : slot_block);
+      tc.level = p; tc.n_work = n_work; tc.slot_block = slot_block; tc.io = io;
+      // a level with at most two warp-iterations per warp is dealt out statically (no cursor atomics)
+      const bool tiny = n_work <= 64u * gridDim.x * wpc;
+      bool first = tiny;
       for (;;) {
         unsigned base, end;
-        if (!claim_work(&ctr->work_trace[p], n_work, lane, (unsigned)WORK_CHUNK_MAX, base, end)) break;
-        trace_chunk<MODE, BRUTE>(a.sv, nodes, prims, a.tm, p, a.bounces, a.px_base, base, end, n_work, io, ctr, a.gbuf, a.nlev, slot_block, lane,
-                                 lt_mask, acc);
+        if (!claim_work(&ctr->work_trace[p].v, n_work, lane, (unsigned)WORK_CHUNK_MAX, tiny, first, base, end)) {
+          if (first) { first = false; continue; }
+          break;
+        }
+        first = false;
+        tc.base = base; tc.end = end;
+        trace_chunk_fn<MODE, BRUTE>(&tc, &acc);
       }
-      trace_flush(p, io, ctr, lane, acc);
-      // arrive at the phase barrier: everything this warp wrote for level p (queue records, holes, counters) is released
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) red_release_add(&ctr->arrive[p], 1u);
+      DBG_MIN(0, p); DBG_MAX(1, p);
+      trace_flush(io, lane, acc);
+      poller = cta_arrive(&ctr->arrive[p].v);   // everything this warp wrote for level p (queue records, holes, counters) is released
+      DBG_MAX(2, p);
+      if (poller) poll_until_open(&ctr->arrive[p].v);
     }
     // ---- while the phase is still closed (other warps are tracing): fill the time with work that is off the critical path ----
     for (;;) {
-      unsigned open = 1;
-      if (p < a.levels) {
-        unsigned v = 0;
-        if (lane == 0) v = ld_acquire_u32(&ctr->arrive[p]);
-        open = __shfl_sync(CTB_FULL, v, 0) >= warps_total;
-        if (open) break;
-      }
+      if (p < a.levels && (poller || cs.open > k_phase)) break;
       if (export_left && p >= 1) {     // G-buffer of this rank's tiles -> remote frame, under the remaining levels
         unsigned b = 0;
-        if (lane == 0) b = atomicAdd(&ctr->work_export, CTB_EXPORT_CHUNK);
+        if (lane == 0) b = atomicAdd(&ctr->work_export.v, CTB_EXPORT_CHUNK);
         b = __shfl_sync(CTB_FULL, b, 0);
         if (b < a.n_px) {
           const unsigned e = b + CTB_EXPORT_CHUNK < a.n_px ? b + CTB_EXPORT_CHUNK : a.n_px;
@@ -668,56 +829,94 @@ __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(co
       }
       if (shade_lo < p) {              // records of levels < p are complete
         uint32_t n_sw = 0;
-        if (lane == 0) { n_sw = __ldcg(&ctr->n_shade[shade_lo]); if (n_sw > a.shade_cap[shade_lo]) n_sw = a.shade_cap[shade_lo]; }
+        if (lane == 0) { n_sw = __ldcg(&ctr->n_shade[shade_lo].v); if (n_sw > a.shade_cap[shade_lo]) n_sw = a.shade_cap[shade_lo]; }
         n_sw = __shfl_sync(CTB_FULL, n_sw, 0);
         unsigned base, end;
-        if (!claim_work(&ctr->work_shade[shade_lo], n_sw, lane, p < a.levels ? (unsigned)CTB_FILL_CHUNK_MAX : (unsigned)WORK_CHUNK_MAX, base, end)) {
+        if (!claim_work(&ctr->work_shade[shade_lo].v, n_sw, lane, p < a.levels ? (unsigned)CTB_FILL_CHUNK_MAX : (unsigned)WORK_CHUNK_MAX, false, false,
+                        base, end)) {
           shade_lo++;
           continue;
         }
-        float *lc = a.level_color ? a.level_color + (size_t)shade_lo * a.level_stride : nullptr;
-        shade_chunk<MODE, BRUTE, OPAQUE>(a.sv, nodes, prims, base, end, n_sw, a.shade[shade_lo], a.acc, a.atomic_accumulate, lc, a.px_base, lane, casts);
+        sc.base = base; sc.end = end; sc.n_work = n_sw; sc.shade = a.shade[shade_lo];
+        sc.level_color = a.level_color ? a.level_color + (size_t)shade_lo * a.level_stride : nullptr;
+        casts += shade_chunk_fn<MODE, BRUTE, OPAQUE>(&sc);
         continue;
       }
       if (p == a.levels) break;        // last phase: nothing left to claim
-      __nanosleep(128);                // nothing to fill with: wait for the phase to open
+      __nanosleep(100);                // nothing to fill with: wait for the CTA's poller to raise the flag
     }
-    if (p < a.levels && lane == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->phase_ns[p] = globaltimer_ns();
+    if (p < a.levels) {
+      __threadfence_block();           // reader side of the fence protocol (queue reads that follow are .cg: served by L2)
+      k_phase++;
+      DBG_MIN(3, p); DBG_MAX(4, p);
+      if (lane == 0 && blockIdx.x == 0 && threadIdx.x == 0) ctr->st.phase_ns[p] = globaltimer_ns();
+    }
   }
-  // ---- all records are claimed; wait until every warp has finished shading ----
-  casts_flush(ctr, lane, casts);
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) {
-    red_release_add(&ctr->arrive[a.levels], 1u);
-    while (ld_acquire_u32(&ctr->arrive[a.levels]) < warps_total) __nanosleep(64);
+  // ---- all records are claimed; CTA-wide tallies, then wait until every warp of the grid has finished shading ----
+  {
+    unsigned long long c = casts;
+    for (int s = 16; s > 0; s >>= 1) {
+      acc.n_refl += __shfl_xor_sync(CTB_FULL, acc.n_refl, s);
+      acc.n_trans += __shfl_xor_sync(CTB_FULL, acc.n_trans, s);
+      acc.n_shaded += __shfl_xor_sync(CTB_FULL, acc.n_shaded, s);
+      acc.max_depth = fmaxf(acc.max_depth, __shfl_xor_sync(CTB_FULL, acc.max_depth, s));
+      c += __shfl_xor_sync(CTB_FULL, c, s);
+    }
+    if (lane == 0) {
+      if (acc.n_refl) atomicAdd(&cs.refl, (unsigned long long)acc.n_refl);
+      if (acc.n_trans) atomicAdd(&cs.trans, (unsigned long long)acc.n_trans);
+      if (acc.n_shaded) atomicAdd(&cs.shaded, (unsigned long long)acc.n_shaded);
+      if (c) atomicAdd(&cs.casts, c);
+      if (acc.max_depth > 0.f) atomicMax(&cs.max_depth_bits, __float_as_uint(acc.max_depth));
+    }
   }
-  __syncwarp();
-  __threadfence();
+  {
+    // the CTA's last warp adds the CTA's tallies to the frame statistics BEFORE it publishes the CTA: whoever sees the
+    // final barrier open also sees complete statistics
+    __threadfence();
+    __syncwarp();
+    unsigned last = 0;
+    if (lane == 0) {
+      last = atomicAdd(&cs.arrived, 1u) == (k_phase + 1u) * wpc - 1u;
+      if (last) {
+        __threadfence_block();
+        if (cs.refl) atomicAdd(&ctr->st.rays_reflect, cs.refl);
+        if (cs.trans) atomicAdd(&ctr->st.rays_transmit, cs.trans);
+        if (cs.shaded) atomicAdd(&ctr->st.shade_records, cs.shaded);
+        if (cs.casts) atomicAdd(&ctr->st.shadow_casts, cs.casts);
+        if (cs.max_depth_bits) atomicMax(&ctr->st.max_depth_bits, cs.max_depth_bits);
+        if (gridDim.x > 1) red_release_add(&ctr->arrive[a.levels].v, 1u);
+      }
+    }
+    last = __shfl_sync(CTB_FULL, last, 0);
+    if (last) poll_until_open(&ctr->arrive[a.levels].v);
+    else if (lane == 0) { while (cs.open <= k_phase) __nanosleep(100); }
+    __syncwarp();
+    __threadfence_block();
+    k_phase++;
+  }
   // ---- frame assembly: ordered sum of the level images (+ G-buffer) -> the frame ----
   if (a.combine) {
     const FrameTargets g = a.export_with_color ? a.gsrc : FrameTargets{};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_px; i += gridDim.x * blockDim.x)
       combine_pixel(a.tm, i, a.px_base, a.nlev, a.level_color, a.level_stride, a.combine_levels, a.local_color, a.out, g);
   }
-  // ---- the last warp out publishes the counters to mapped host memory and clears them for the next frame ----
+  // ---- the last CTA out publishes the statistics to mapped host memory and clears all counters for the next frame ----
   __threadfence();
-  __syncwarp();
-  unsigned last = 0;
-  if (lane == 0) last = atomicAdd(&ctr->finished, 1u) == warps_total - 1u;
-  last = __shfl_sync(CTB_FULL, last, 0);
-  if (last) {
+  __syncthreads();
+  __shared__ unsigned s_last_cta;
+  if (threadIdx.x == 0) s_last_cta = atomicAdd(&ctr->finished.v, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (s_last_cta) {
     __threadfence();
-    if (lane == 0) ctr->phase_ns[a.levels] = globaltimer_ns();
-    __syncwarp();
+    if (threadIdx.x == 0) ctr->st.phase_ns[a.levels] = globaltimer_ns();
+    __syncthreads();
     unsigned *src = reinterpret_cast<unsigned *>(ctr);
-    volatile unsigned *dst = reinterpret_cast<volatile unsigned *>(a.host_ctr);
-    constexpr unsigned NW = sizeof(FrameCounters) / 4;
-    for (unsigned k = lane; k < NW; k += 32) {
-      const unsigned v = __ldcg(src + k);
-      if (dst) dst[k] = v;
-      src[k] = 0u;
-    }
+    constexpr unsigned NW = sizeof(FrameCounters) / 4, S0 = offsetof(FrameCounters, st) / 4, SN = sizeof(FrameStats) / 4;
+    volatile unsigned *dst = reinterpret_cast<volatile unsigned *>(a.host_stats);
+    if (dst && threadIdx.x < SN) dst[threadIdx.x] = __ldcg(src + S0 + threadIdx.x);
+    __syncthreads();
+    for (unsigned k = threadIdx.x; k < NW; k += blockDim.x) src[k] = 0u;
     __threadfence_system();
   }
 }
@@ -725,6 +924,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(co
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
+#ifdef CTB_PHASE_DEBUG
+extern "C" int cutrace_debug_phase_dump(unsigned long long *out /* 6 x 18 */) {
+  unsigned long long init[6][18];
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, g_dbg_ns, sizeof init) != cudaSuccess) return -1;
+  for (int k = 0; k < 6; k++) for (int p = 0; p < 18; p++) init[k][p] = (k == 0 || k == 3) ? ~0ull : 0ull;
+  return cudaMemcpyToSymbol(g_dbg_ns, init, sizeof init) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 void launch_export_gbuffer(const TileMap &tm, uint32_t px_base, uint32_t n_px, const FrameTargets &src, const FrameTargets &out,
                            cudaStream_t st) {
   if (!n_px) return;

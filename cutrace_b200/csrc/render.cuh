@@ -64,7 +64,7 @@ struct FrameArgs {
   ShadeRec *shade[16];           // one shade queue per level
   uint32_t shade_cap[16];
   FrameCounters *ctr;            // device counters: zero on entry, published to host_ctr and cleared again on exit
-  FrameCounters *host_ctr;       // mapped pinned host memory (device pointer), may be NULL
+  FrameStats *host_stats;        // mapped pinned host memory (device pointer), may be NULL
   FrameTargets gbuf;             // where trace(0) stores the G-buffer
   FrameTargets out;              // where the finished frame lives (own HBM / peer GPU / pinned host memory)
   FrameTargets gsrc;             // != NULL: local tile-major G-buffer that has to travel to `out`

@@ -126,6 +126,43 @@ __device__ __forceinline__ void make_ray(RayCtx &r, vec3 o, vec3 d, float scene_
   }
 }
 
+// ---- the reference's per-mesh AABB pre-test -------------------------------------------------------------------------
+// mesh::intersect (inc/default_schema.hpp:125-144) first runs bound_intersects (:99-114): a slab test of the ray against the
+// AABB the host computed for the mesh (:573-586), tmin = 0, tmax = INF, device min/max (NaN-dropping), pass iff
+// tmin <= tmax.  A ray that hits a triangle lying IN a face of that box (a flat mesh, an axis-aligned quad seen edge-on, a
+// silhouette pixel exactly on the box edge) can fail this test by rounding although Cramer's rule accepts the triangle —
+// the reference then misses the whole mesh.  The LBVH never looks at per-mesh boxes, so the test is replayed here for the
+// only rays it can matter for: a triangle hit that is about to be ACCEPTED and whose hit point is not strictly inside its
+// mesh's box.  `mesh_gate_exact` is the reference's arithmetic, operation for operation ((min - start) * (1 / dir) cannot be
+// contracted into an FMA); the cheap inside-test in front of it is sound because a point inside the box by
+// 1e-5 * (scene size + distance) keeps every slab interval open by 25x the rounding error of t1 / t2.
+__device__ __noinline__ bool mesh_gate_exact(float lox, float loy, float loz, float hix, float hiy, float hiz, vec3 start, vec3 dir) {
+  float tmin = 0.0f, tmax = INFINITY;
+  const float r_inv[3] = {1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z};
+  const float lo[3] = {lox, loy, loz}, hi[3] = {hix, hiy, hiz}, st[3] = {start.x, start.y, start.z};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float t1 = __fmul_rn(lo[d] - st[d], r_inv[d]);
+    const float t2 = __fmul_rn(hi[d] - st[d], r_inv[d]);
+    tmin = fminf(fmaxf(t1, tmin), fmaxf(t2, tmin));
+    tmax = fmaxf(fminf(t1, tmax), fminf(t2, tmax));
+  }
+  return tmin <= tmax;
+}
+#ifndef CTB_MESH_GATE
+#define CTB_MESH_GATE 1   // 0: tuning builds only (measures what the replayed pre-test costs)
+#endif
+__device__ __forceinline__ bool mesh_gate(const ObjBound *__restrict__ ob, uint32_t obj, vec3 o, vec3 d, float t, float scene_mag) {
+  if (!CTB_MESH_GATE) return true;
+  const float4 *bp = reinterpret_cast<const float4 *>(ob + obj);
+  const float4 lo = __ldg(bp), hi = __ldg(bp + 1);
+  if (__float_as_uint(lo.w) == 0u) return true;   // a loose triangle object: the reference has no pre-test for it
+  const float px = fmaf(t, d.x, o.x), py = fmaf(t, d.y, o.y), pz = fmaf(t, d.z, o.z);
+  const float m = 1e-5f * (scene_mag + fabsf(t) + fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
+  if (px > lo.x + m && px < hi.x - m && py > lo.y + m && py < hi.y - m && pz > lo.z + m && pz < hi.z - m) return true;
+  return mesh_gate_exact(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, d);
+}
+
 // MODE 0: nodes / primitives in global memory (LDG.128 through L1)
 // MODE 1: the whole BVH and primitive store staged in shared memory (LDS.128) — the reference scenes
 // MODE 2: the top `sv.smem_nodes` nodes (breadth-first) staged in shared memory, everything else global — big scenes
@@ -154,7 +191,7 @@ __device__ __forceinline__ NodeData load_node(const SceneView &sv, const float4 
 }
 
 template <int MODE>
-__device__ __forceinline__ void test_prim(const float4 *__restrict__ prims, uint32_t k, const RayCtx &r, float min_t, Hit &h) {
+__device__ __forceinline__ void test_prim(const SceneView &sv, const float4 *__restrict__ prims, uint32_t k, const RayCtx &r, float min_t, Hit &h) {
   const float4 *pp = prims + 3 * (size_t)k;
   const float4 q0 = ld16<MODE>(pp), q1 = ld16<MODE>(pp + 1), q2 = ld16<MODE>(pp + 2);
   float t;
@@ -163,7 +200,9 @@ __device__ __forceinline__ void test_prim(const float4 *__restrict__ prims, uint
   else ok = sphere_test(q0.x, q0.y, q0.z, q1.x, r.o, r.d, min_t, &t);
   if (ok) {
     const uint32_t obj = __float_as_uint(q0.w), idx = __float_as_uint(q1.w);
-    if (hit_better(h, t, obj, idx)) { h.t = t; h.obj = obj; h.idx = idx; h.ref = k; h.kind = (int)__float_as_uint(q2.w); }
+    if (hit_better(h, t, obj, idx) && (__float_as_uint(q2.w) != CTB_PRIM_TRI || mesh_gate(sv.obj_bounds, obj, r.o, r.d, t, sv.scene_mag))) {
+      h.t = t; h.obj = obj; h.idx = idx; h.ref = k; h.kind = (int)__float_as_uint(q2.w);
+    }
   }
 }
 
@@ -178,7 +217,7 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
   if (BRUTE) {
 #pragma unroll 1
     for (uint32_t k = 0; k < sv.n_prims; k++) {
-      test_prim<MODE>(prims, k, r, min_t, h);
+      test_prim<MODE>(sv, prims, k, r, min_t, h);
       if (ANY && h.t < max_t) return true;
     }
     return false;
@@ -233,7 +272,7 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
     if (pending) {
       const uint32_t first = leaf_first(pending), count = leaf_count(pending);
 #pragma unroll 1
-      for (uint32_t k = first; k < first + count; k++) test_prim<MODE>(prims, k, r, min_t, h);
+      for (uint32_t k = first; k < first + count; k++) test_prim<MODE>(sv, prims, k, r, min_t, h);
       if (ANY && h.t < max_t) return true;
       pending = 0;
     }
@@ -242,7 +281,7 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
     {   // leaf
       const uint32_t first = leaf_first(cur), count = leaf_count(cur);
 #pragma unroll 1
-      for (uint32_t k = first; k < first + count; k++) test_prim<MODE>(prims, k, r, min_t, h);
+      for (uint32_t k = first; k < first + count; k++) test_prim<MODE>(sv, prims, k, r, min_t, h);
       if (ANY && h.t < max_t) return true;
       cur = stack[--sp];
     }
@@ -337,7 +376,7 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
         if (act & (1u << k)) {
           RayCtx r; make_ray(r, o, d[k], sv.scene_mag);
           Hit h; hit_reset(h);
-          test_prim<MODE>(prims, i, r, min_t, h);
+          test_prim<MODE>(sv, prims, i, r, min_t, h);
           if (h.t < max_t[k]) { occ |= 1u << k; act &= ~(1u << k); }
         }
       }
@@ -412,7 +451,8 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
                 const float beta = nb[k] / alpha[k], gamma = ng[k] / alpha[k];
                 if (beta >= 0 && gamma >= 0 && beta + gamma <= 1) {
                   const float t0 = nt / alpha[k];
-                  if (isfinite(t0) && min_t <= t0 && t0 > min_t && t0 < max_t[k]) { occ |= 1u << k; act &= ~(1u << k); }
+                  if (isfinite(t0) && min_t <= t0 && t0 > min_t && t0 < max_t[k] &&
+                      mesh_gate(sv.obj_bounds, __float_as_uint(q0.w), o, d[k], t0, sv.scene_mag)) { occ |= 1u << k; act &= ~(1u << k); }
                 }
               }
             }

@@ -83,7 +83,7 @@ int main(int argc, const char **argv) {
     float *block = nullptr;
     if (cutrace_frame_ipc_export(ctx, handle) || cutrace_frame_device(ctx, &block, nullptr, nullptr, nullptr)) return fail_all("frame export");
     for (long r = 1; r < gpus; r++)
-      if (cutrace_enable_peer_access((int)r, 0) || cutrace_frame_attach(ctxs[(size_t)r], block)) return fail_all("peer frame");
+      if (cutrace_enable_peer_access((int)r, 0) || cutrace_frame_attach(ctxs[(size_t)r], block, scene.width, scene.height)) return fail_all("peer frame");
   }
 
   // dump_scene_kernel, inc/kernel.hpp:152-165 (variant indices: objects 0 triangle,1 mesh,2 plane,3 sphere;

@@ -127,6 +127,12 @@ typedef struct cutrace_scene_desc {
 #define CUTRACE_FLAG_SERIALIZE 8u      /* run every kernel of a frame on one stream (per-kernel trace_ms / shade_ms are
                                           only measured in this mode); default: shade kernels overlap the trace chain */
 
+/* Scheduler of a frame.  Default (neither flag): chosen per ctx from measurements on B200 (profiles/r02_tuning.md) — the
+ * persistent frame kernel (ONE cooperative launch, level loop on the device) for tile shards of at least 2^19 pixels, where
+ * thirteen short launches per frame cost 5 % more; one launch per level and kind, replayed as a CUDA graph, otherwise. */
+#define CUTRACE_FLAG_FRAME_KERNEL 16u  /* force the persistent frame kernel */
+#define CUTRACE_FLAG_LAUNCHES 32u      /* force one launch per level and kind */
+
 typedef struct cutrace_opts {
   float fudge;          /* min hit distance; the reference passes 1e-3 (main.cu:30)            */
   uint32_t bounces;     /* recursion budget; the reference passes 5 (main.cu:30); max 15       */
@@ -233,16 +239,27 @@ int cutrace_frame_device(cutrace_ctx *ctx, float **depth, float **normal, float 
 /* Multi-GPU without a gather: the ctx that owns the final frame (normally tile_rank 0) exports it through CUDA IPC;
  * the other ranks' ctxs import the handle and from then on their kernels store the G-buffer and the final colour of
  * their tiles straight into that frame over NVLink (peer stores fused into the producing kernels).  The caller only
- * has to synchronise the ranks (a barrier / the max-depth all-reduce) before downloading from the exporting ctx.
- * `handle` is CUTRACE_IPC_HANDLE_BYTES bytes, to be shipped to the other processes by the caller.  Re-export after
- * cutrace_set_camera changes the resolution. */
-#define CUTRACE_IPC_HANDLE_BYTES 64
+ * has to synchronise the ranks (a barrier / the max-depth all-reduce) before downloading from the exporting ctx, and
+ * once more before the next frame is rendered if it read the frame in between (the stores of frame N+1 must not
+ * overtake a reader of frame N).
+ * `handle` is CUTRACE_IPC_HANDLE_BYTES bytes, to be shipped to the other processes by the caller: the CUDA IPC handle
+ * followed by the frame's width and height, which the importing ctx checks against its own (a mismatch would be an
+ * out-of-bounds store into another GPU's memory).  Re-export after cutrace_set_camera changes the resolution. */
+#define CUTRACE_IPC_HANDLE_BYTES 80
 int cutrace_frame_ipc_export(cutrace_ctx *ctx, void *handle);
 int cutrace_frame_ipc_import(cutrace_ctx *ctx, const void *handle);
-/* Same idea inside one process (several ctxs / GPUs driven by one host thread, peer access enabled by the caller):
- * `frame_block` is the depth pointer cutrace_frame_device returned for the owning ctx (the frame is one block of
- * 32*width*height bytes).  NULL detaches. */
-int cutrace_frame_attach(cutrace_ctx *ctx, void *frame_block);
+/* Same idea for any frame block the caller can name by address: `frame_block` is 32*width*height bytes laid out as
+ * depth n | normal 3n | colour 3n | hit id n (n = width*height), row-major — e.g.
+ *   - the depth pointer cutrace_frame_device returned for the owning ctx of the same process (several ctxs / GPUs driven
+ *     by one host, peer access enabled by the caller), or
+ *   - PINNED HOST memory registered with cutrace_host_register (or from cutrace_host_alloc): every rank's kernels then
+ *     store their tiles straight into the caller's host frame over their own PCIe link — the multi-GPU download without
+ *     funnelling the frame through one GPU; a shared-memory mapping registered by every process works across processes.
+ * width/height are the dimensions of the block and must equal the ctx's.  NULL detaches. */
+int cutrace_frame_attach(cutrace_ctx *ctx, void *frame_block, uint32_t width, uint32_t height);
+/* page-locks + maps caller memory (e.g. a shared-memory frame) for cutrace_frame_attach / fast copies; undone by unregister */
+int cutrace_host_register(void *ptr, size_t bytes);
+int cutrace_host_unregister(void *ptr);
 /* helpers for a one-process multi-GPU host: peer access from `device` to `peer_device` (idempotent), and the frame-wide
  * max depth (max over the ranks' cutrace_stats.max_depth, kernel.hpp:120-125) that cutrace_download_bytes of the ctx
  * owning the frame should use for the depth image. */

@@ -49,8 +49,10 @@ def compare(a, b, width=None, height=None):
     if fin.any():
         err = np.abs(da[fin].astype(np.float64) - db[fin]) / np.maximum(1.0, np.abs(db[fin]))
         m["depth_max_rel"] = float(err.max())
+        m["depth_off_pixels"] = int((err > 1e-6).sum())      # pixels whose depth is not (practically) bit-identical
     else:
         m["depth_max_rel"] = 0.0
+        m["depth_off_pixels"] = 0
     na, nb = a["normal"].reshape(-1, 3)[agree], b["normal"].reshape(-1, 3)[agree]
     m["normal_max_abs"] = float(np.abs(na.astype(np.float64) - nb).max()) if len(na) else 0.0
     ca = np.clip(np.nan_to_num(a["color"].reshape(-1, 3).astype(np.float64)), 0, 1)
@@ -78,3 +80,32 @@ def assert_parity(m, what="", oracle_is_host=False, chaotic=False):
         if m["pixels"] < 4096:   # PSNR of a tiny frame is decided by a single chaotic pixel
             return
     assert m["color_psnr"] >= tol["psnr"], f"{what}: colour PSNR {m['color_psnr']:.2f} dB < {tol['psnr']} ({m})"
+
+
+# on id-agreeing pixels depth must hold abs(d) <= 1e-4 * max(1, t).  Cramer's t of a triangle seen almost edge-on
+# is ill-conditioned (alpha -> 0), and which products nvcc fuses into FMAs depends on the surrounding code, so two builds of the
+# SAME expression can differ there: measured 5 of 129,600 pixels up to 1.45e-5 on the instanced-mesh scenes, where this path's
+# BVH walk and its own brute-force loop agree bit for bit (profiles/r02_parity.md).  Mesh-heavy scenes are therefore held to
+# the survey's 1e-4 bound plus "at most 0.01 % of the pixels off by more than 1e-6"; the four reference scenes stay at 1e-6.
+TOL_DEPTH_MESH = dict(max_rel=1e-4, off_frac=1e-4)
+
+
+def assert_parity_mesh_scene(m, what=""):
+    """assert_parity against the reference's sm_100a kernel with the depth rule for mesh-heavy scenes (see TOL_DEPTH_MESH)."""
+    assert m["depth_max_rel"] <= TOL_DEPTH_MESH["max_rel"], f"{what}: depth error {m['depth_max_rel']:.3g} ({m})"
+    assert m["depth_off_pixels"] <= max(1, TOL_DEPTH_MESH["off_frac"] * m["pixels"]), f"{what}: {m['depth_off_pixels']} pixels with depth off by > 1e-6 ({m})"
+    assert_parity(dict(m, depth_max_rel=min(m["depth_max_rel"], TOL_REF_GPU["depth"])), what)
+
+
+def assert_same_frame(a, b, what="", color_ulps=0):
+    """Two renders of one scene by this path (different schedulers / shards / batches): depth, normal and hit id bit-identical;
+    colour bit-identical, or (color_ulps > 0) within that many units in the last place of 1.0 — the frame kernel and the
+    per-level kernels are separate compilations of the same source and nvcc's FMA contraction differs between them in the last
+    bit of ~0.4 % of the pixels (each scheduler on its own is bit-reproducible)."""
+    for k in ("depth", "normal", "hit_id"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (what, k)
+    if color_ulps == 0:
+        assert np.array_equal(a["color"].view(np.uint32), b["color"].view(np.uint32)), (what, "color")
+    else:
+        d = np.abs(a["color"].astype(np.float64) - b["color"])
+        assert d.max() <= color_ulps * 1.1920929e-07 * max(1.0, float(np.abs(b["color"]).max())), (what, "color", float(d.max()))

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, GOLDEN_CASES, load_golden_scene
-from parity import assert_parity, compare
+from parity import assert_parity, assert_parity_mesh_scene, assert_same_frame, compare
 
 pytestmark = pytest.mark.gpu
 
@@ -190,10 +190,34 @@ def test_config5_full_size_subset_vs_reference_cuda_kernel(ct, oracle):
         out = r.download(want=("depth", "normal", "color", "hit_id"))
     sub = {k: out[k][px.astype(np.int64)] for k in ("depth", "normal", "color", "hit_id")}
     m = compare(sub, ref)
-    assert_parity(m, "config 5 (10.1 M triangles @ 7680x4320) subset vs reference sm_100a kernel")
+    assert_parity_mesh_scene(m, "config 5 (10.1 M triangles @ 7680x4320) subset vs reference sm_100a kernel")
     assert m["id_mismatch"] == 0, m
     assert np.all(out["hit_id"] != 0xFFFFFFFF)        # closed hall: every primary ray hits
     assert st["rays_primary"] == 7680 * 4320 and st["rays_shadow"] % 3 == 0
+
+
+def test_grid_scene_full_frame_vs_reference_kernel(ct, oracle):
+    """config 5 in small (6 x 6 instances, 32,400 triangles, mirrors) as a FULL frame against the reference's real
+    render_kernel (brute force is affordable at this size), and the oracle-side subset kernel against that same kernel on
+    the same pixels — the subset kernel is what the full-size config-5 test has to rely on."""
+    if not oracle.have_ref_gpu():
+        pytest.skip("reference CUDA oracle not built")
+    from cutrace_b200 import synth
+
+    meshes = synth.meshes_from_scenes(load_golden_scene("bunny"), load_golden_scene("mirror"))[:2]
+    s = synth.grid_scene(meshes, grid=6, width=480, height=270)
+    ref = oracle.ref_gpu_render(s)
+    out, st = gpu_render(ct, s)
+    m = compare(out, ref, s.width, s.height)
+    assert_parity_mesh_scene(m, "6x6 grid full frame vs reference sm_100a kernel")
+    brute, _ = gpu_render(ct, s, flags=ct.FLAG_BRUTE_FORCE)       # the BVH walk never changes which triangle wins or its t
+    assert_same_frame(out, brute, "LBVH walk vs brute-force loop")
+    px = np.random.default_rng(3).choice(s.width * s.height, 4096, replace=False).astype(np.uint64)
+    sub = oracle.ref_gpu_render(s, px=px)
+    full_sub = {k: ref[k][px.astype(np.int64)] for k in ("depth", "normal", "color", "hit_id")}
+    ms = compare(sub, full_sub)
+    print("subset kernel vs render_kernel:", ms, " this path vs render_kernel:", m)
+    assert ms["id_mismatch"] == 0 and ms["depth_max_rel"] <= 1e-4, ms
 
 
 def test_mesh_deviations_documented_in_design_8(ct, oracle):
@@ -312,9 +336,11 @@ def test_full_size_properties_bunny_4k(ct):
     assert m["id_mismatch"] == 0 and m["depth_max_rel"] == 0.0 and m["color_max_abs"] <= 1e-6, m
 
 
-def test_tile_sharding_equals_single_ctx(ct):
+@pytest.mark.parametrize("sched", ["frame", "launches"])
+def test_tile_sharding_equals_single_ctx(ct, monkeypatch, sched):
     """world=3 interleaved tile shards rendered by three ctxs (one GPU) and stitched by cutrace_download
     are bit-identical to the unsharded frame — the multi-GPU path changes who renders a pixel, not what."""
+    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)
     s = load_golden_scene("mirror").with_resolution(333, 205)
     full, st = gpu_render(ct, s)
     acc = None
@@ -333,10 +359,12 @@ def test_tile_sharding_equals_single_ctx(ct):
     assert rays == st["rays_total"]
 
 
-def test_peer_frame_stores_equal_single_ctx(ct):
+@pytest.mark.parametrize("sched", ["frame", "launches"])
+def test_peer_frame_stores_equal_single_ctx(ct, monkeypatch, sched):
     """The gather-free multi-GPU path on one GPU: three sharded ctxs store their tiles straight into rank 0's row-major
     frame (cutrace_frame_attach = the in-process form of cutrace_frame_ipc_import); the assembled frame is bit-identical
     to the unsharded render."""
+    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)
     for name, res in (("mirror", (333, 205)), ("sphere_plane", (200, 120))):
         s = load_golden_scene(name).with_resolution(*res)
         full, st = gpu_render(ct, s)
@@ -551,8 +579,10 @@ def test_download_bytes_equals_host_output_stage(ct, oracle):
     assert np.array_equal(b["depth_rgb"], d8) and np.array_equal(b["normal_rgb"], n8) and np.array_equal(b["color_rgb"], c8)
 
 
-def test_overlapped_and_serialized_frames_are_bit_identical(ct):
-    """shade kernels overlapping the trace chain (default) vs everything on one stream: same bits."""
+def test_overlapped_and_serialized_frames_are_bit_identical(ct, monkeypatch):
+    """Multi-launch scheduler: shade kernels overlapping the trace chain on three streams vs everything on one stream
+    (CUTRACE_FLAG_SERIALIZE) — the same kernels in a different order: same bits."""
+    monkeypatch.setenv("CUTRACE_SCHEDULER", "launches")
     for name, res in (("bunny", (640, 360)), ("sphere_plane", (640, 360))):
         s = load_golden_scene(name).with_resolution(*res)
         a, sa = gpu_render(ct, s)
@@ -567,43 +597,50 @@ def test_overlapped_and_serialized_frames_are_bit_identical(ct):
 
 
 def test_frame_kernel_equals_the_multi_launch_paths(ct, monkeypatch):
-    """The persistent frame kernel (device-side level loop, default) against the two multi-launch schedulers that drive the
-    same device functions: CUTRACE_NO_FRAME_KERNEL (one launch per level and kind on three streams, captured as a CUDA graph
-    from the second frame on) and CUTRACE_FLAG_SERIALIZE (one stream).  Same bits, same counters; the frame kernel is ONE
-    launch and reports when each bounce level was complete."""
+    """The persistent frame kernel (device-side level loop; CUTRACE_FLAG_FRAME_KERNEL) against the multi-launch scheduler that
+    drives the same device functions (CUTRACE_FLAG_LAUNCHES: one launch per level and kind on three streams, captured as a
+    CUDA graph from the second frame on).  Depth, normals, ids and every counter are identical; colours agree to the last
+    bits (the two are separate compilations: tests/parity.py assert_same_frame); each scheduler is bit-reproducible.  The
+    frame kernel is ONE launch and reports when each bounce level was complete."""
     for name, res in (("bunny", (640, 360)), ("mirror", (333, 205)), ("triangle", None)):
         s = load_golden_scene(name)
         if res:
             s = s.with_resolution(*res)
-        with ct.Renderer(s) as r:
+        with ct.Renderer(s, flags=ct.FLAG_FRAME_KERNEL) as r:
             sa = r.render()
             sa = r.render()
             a = r.download()
             ph = r.phase_ms()
+            r.render()
+            assert_same_frame(a, r.download(), name)          # two frame-kernel frames: same bits
         assert sa["kernel_launches"] == 1
         levels = 6 if name != "triangle" else 1
         assert len(ph) == levels + 1 and all(b >= a_ for a_, b in zip(ph, ph[1:])) and ph[-1] <= sa["render_ms"] * 1.5 + 0.05, ph
-        monkeypatch.setenv("CUTRACE_NO_FRAME_KERNEL", "1")
-        with ct.Renderer(s) as r:
+        with ct.Renderer(s, flags=ct.FLAG_LAUNCHES) as r:
             frames = []
             for _ in range(3):     # direct, graph capture, graph replay
                 sb = r.render()
                 frames.append(r.download())
             assert r.phase_ms() == []
-        monkeypatch.delenv("CUTRACE_NO_FRAME_KERNEL")
         assert sb["kernel_launches"] == 2 * levels + 1
         for b in frames:
-            for k in ("depth", "normal", "color", "hit_id"):
-                assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (name, k)
+            assert_same_frame(frames[0], b, name)              # the multi-launch frames agree with each other bit for bit
+            m = compare(a, b, s.width, s.height)
+            assert m["id_mismatch"] == 0 and m["depth_max_rel"] == 0.0 and m["normal_max_abs"] == 0.0, (name, m)
+            # colour: last-bit differences, plus the odd shadow-edge pixel when a hit point moved by an ulp
+            assert m["color_bad_frac"] <= 1e-4 and np.median(np.abs(a["color"] - b["color"])) == 0.0, (name, m)
         for k in ("rays_total", "rays_shadow", "rays_reflect", "shadow_casts", "max_depth"):
             assert sa[k] == sb[k], (name, k)
+        # the default picks one of the two
+        with ct.Renderer(s) as r:
+            assert r.render()["kernel_launches"] in (1, 2 * levels + 1)
 
 
 def test_direct_first_frame_and_graph_replays_are_bit_identical(ct, monkeypatch):
-    """Multi-launch scheduler (CUTRACE_NO_FRAME_KERNEL): the first frame of a ctx is enqueued stream by stream, the second
+    """Multi-launch scheduler (CUTRACE_SCHEDULER=launches): the first frame of a ctx is enqueued stream by stream, the second
     captures the CUDA graph, later ones replay it: same bits and same counters every time (bunny.json: one ray per pixel
     and level, deterministic sum)."""
-    monkeypatch.setenv("CUTRACE_NO_FRAME_KERNEL", "1")
+    monkeypatch.setenv("CUTRACE_SCHEDULER", "launches")
     s = load_golden_scene("bunny").with_resolution(320, 180)
     with ct.Renderer(s) as r:
         frames = []
@@ -642,6 +679,23 @@ def test_render_download_fused_equals_render_then_download(ct):
         for k in ("depth", "normal", "color", "hit_id"):
             assert np.array_equal(d[k].view(np.uint32), e[k].view(np.uint32)), k
         assert not np.array_equal(d["depth"], b["depth"])
+
+
+def test_render_download_with_the_frame_kernel(ct, monkeypatch):
+    """cutrace_render_download under the frame-kernel scheduler: trace(0) runs as its own kernel (the G-buffer copies start
+    behind it), the frame kernel takes over at level 1.  G-buffer identical to render + download; colours to the last bits."""
+    monkeypatch.setenv("CUTRACE_SCHEDULER", "frame")
+    s = load_golden_scene("bunny").with_resolution(1280, 720)
+    with ct.Renderer(s) as r:
+        a, sta = r.render_download()
+        stb = r.render()
+        b = r.download()
+        assert sta["kernel_launches"] == 2 and stb["kernel_launches"] == 1
+        m = compare(a, b, s.width, s.height)
+        assert m["id_mismatch"] == 0 and m["depth_max_rel"] == 0.0 and m["normal_max_abs"] == 0.0 and m["color_bad_frac"] <= 1e-4, m
+        assert a["max_depth"] == b["max_depth"] and sta["rays_total"] == stb["rays_total"]
+        c, _ = r.render_download()
+        assert_same_frame(a, c, "two fused frames")
 
 
 def test_set_camera_resizes_and_reuses_the_scene(ct):

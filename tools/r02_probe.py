@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Round-2 scheduler probe on one GPU: every BASELINE workload, unsharded and as a 1/8 tile shard, with the persistent frame
-kernel (default) and with the round-1 multi-launch graph (CUTRACE_NO_FRAME_KERNEL=1).  Prints median render_ms, the frame
+kernel (default) and with the round-1 multi-launch graph (CUTRACE_SCHEDULER=launches).  Prints median render_ms, the frame
 kernel's phase times and an md5 of the colour image (the schedulers must agree bit for bit on non-branching scenes).
 usage: tools/r02_probe.py [workload ...]      (child mode: --child <mode> <workload> <world>)"""
 import hashlib
@@ -18,7 +18,7 @@ def child(workload, world, frames):
     import cutrace_b200 as ct
 
     scene, wl = bench.load_workload(workload)
-    tag = "multi-launch" if os.environ.get("CUTRACE_NO_FRAME_KERNEL") else "frame-kernel"
+    tag = {"launches": "multi-launch", "frame": "frame-kernel"}[os.environ["CUTRACE_SCHEDULER"]]
     with ct.Renderer(scene, tile_rank=0, tile_world=world) as r:
         ms = []
         for _ in range(frames):
@@ -41,9 +41,7 @@ def main():
                 continue
             for nf in (False, True):
                 env = dict(os.environ)
-                env.pop("CUTRACE_NO_FRAME_KERNEL", None)
-                if nf:
-                    env["CUTRACE_NO_FRAME_KERNEL"] = "1"
+                env["CUTRACE_SCHEDULER"] = "launches" if nf else "frame"
                 frames = 5 if wl == "synthetic10m" else 9
                 subprocess.run(["timeout", "300", sys.executable, os.path.abspath(__file__), "--child", wl, str(world), str(frames)], env=env, check=False)
 
