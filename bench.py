@@ -8,23 +8,28 @@ Metric (BASELINE.json): Mrays/s (primary + secondary) on scene/bunny.json at 384
 `ms_per_step`.  Unique rays = primaries + reflection + transmission + shadow rays (one per light per
 shaded hit); the same numerator is used for every implementation.
 
-A step = one frame.  `value` times cutrace_render (+ the NCCL tile gather when N > 1) with the scene
-already resident in HBM; `e2e` times upload (H2D + LBVH build) + render + download into pinned host
-buffers through the C-ABI, every step.  One process per GPU; under torchrun each rank renders its
-interleaved 32x32 tiles, rank 0 gathers.  Timing: CUDA events / device time, max over ranks.
+A step = one frame.  `value` times cutrace_render (+ the rank barrier when N > 1: the ranks' kernels store
+their tiles into rank 0's frame over NVLink) with the scene already resident in HBM.  `e2e` times the whole
+call sequence with host buffers, every step: upload (H2D + LBVH build) + render + results in pinned host
+memory — N = 1: cutrace_render_download (copy engine), N > 1: every rank's kernels store their tiles into ONE
+shared pinned host frame over their own PCIe link (cutrace_frame_attach on registered shared memory).
+One process per GPU; timing: CUDA events / device time, max over ranks.
 
-The reference arm runs the UNMODIFIED reference kernel `render_kernel<default_gpu_scene,5>` rebuilt
-for sm_100a from the reference headers in place (oracle/_ref/libcutrace_ref_gpu.so, built by
-oracle/Makefile in the container) — the comparator BASELINE.json's north_star names.  The reference has
-no CPU renderer; its device functions compiled for the host through a qualifier-erasing shim
-(oracle/_ref/libcutrace_ref_host.so) are timed on a bounded pixel sample as `cpu_baseline`.
+Besides the headline workload the line carries `extra_workloads` (BASELINE configs 1-3 and 5, same
+measurements, fewer frames) and, for N > 1, `parity_check`: the assembled N-GPU frame against the same frame
+rendered by one GPU, bit for bit.
+
+The reference arm runs the UNMODIFIED reference kernel `render_kernel<default_gpu_scene,5>` rebuilt for
+sm_100a from the reference headers in place (oracle/_ref/libcutrace_ref_gpu.so, built by oracle/Makefile in
+the container) — the comparator BASELINE.json's north_star names.  It never loads this repo's CUDA library.
+The reference has no CPU renderer; its device functions compiled for the host through a qualifier-erasing
+shim (oracle/_ref/libcutrace_ref_host.so) are timed on a bounded pixel sample as `cpu_baseline`.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -39,13 +44,18 @@ WORKLOADS = {
     "spheres1080": dict(scene="sphere_plane", width=1920, height=1080, label="scene/sphere_plane.json@1920x1080"),
     "synthetic10m": dict(scene="grid106", width=7680, height=4320, label="synthetic grid 106x106 (10,112,400 triangles)@7680x4320"),
 }
+# Unique rays per frame, a property of scene + resolution, identical for every implementation.  The reference arm
+# uses these constants (it must not run this repo's renderer); tests/test_gpu_parity.py::test_bench_ray_constants pins them to what
+# the renderer counts.
+RAYS_PER_FRAME = {"triangle": 438, "bunny4k": 248_825_266, "mirror1080": 6_638_544, "spheres1080": 10_524_880, "synthetic10m": 406_265_452}
+BOUNCES = 5
 
 
 def load_workload(name):
     from cutrace_b200 import synth
     from cutrace_b200.scene import FlatScene
 
-    w = WORKLOADS[name]
+    w = dict(WORKLOADS[name], name=name)
     gold = os.path.join(ROOT, "tests", "golden", "scenes")
     if w["scene"].startswith("grid"):
         meshes = synth.meshes_from_scenes(FlatScene.load(os.path.join(gold, "bunny.npz")), FlatScene.load(os.path.join(gold, "mirror.npz")))[:2]
@@ -57,8 +67,15 @@ def n_primitives(scene):
     return scene.n_triangles + scene.n_spheres + scene.n_planes
 
 
-def algorithmic_bytes_per_ray(n_prims):
-    """64 B queue traffic + one 64-byte two-child node per level of a balanced tree + one 48-byte triangle."""
+def config_of(scene, wl):
+    """The `config` object — the SAME keys and values in both arms."""
+    n_px = scene.width * scene.height
+    return {"workload": wl["label"], "rays_per_frame": RAYS_PER_FRAME[wl["name"]], "primitives": n_primitives(scene), "bounces": BOUNCES,
+            "l2": "queues + framebuffer per frame > L2 (126 MB)" if n_px * 28 > 126e6 else "working set < L2; frames are re-rendered back to back"}
+
+
+def survey_bytes_per_ray(n_prims):
+    """SURVEY.md §8d's model figure: 64 B queue traffic + one 64-byte two-child node per level of a balanced tree + one 48-byte triangle."""
     import math
 
     return 64 + 64 * math.ceil(math.log2(max(n_prims, 2))) + 48
@@ -119,13 +136,13 @@ def cpu_baseline(scene, label, seconds_target=12.0):
     w, h = scene.width, scene.height
     render = (lambda px: po.ref_host_render(scene, px=px, threads=cores)) if kind == "reference" else \
         (lambda px: po.oracle_render(scene, px=px, threads=cores))
-    # calibrate on a 64x36 strided grid, then size the sample for ~seconds_target
-    def grid(nx, ny):
+
+    def grid(nx, ny):   # a strided nx x ny grid of pixels of the frame
         xs = (np.arange(nx) * w) // nx
         ys = (np.arange(ny) * h) // ny
         return (ys[:, None] * w + xs[None, :]).reshape(-1).astype(np.uint64)
 
-    px = grid(64, 36)
+    px = grid(min(64, w), min(36, h))   # calibrate, then size the sample for ~seconds_target
     t = time.perf_counter(); render(px); dt = time.perf_counter() - t
     per_px = dt / len(px)
     n = int(min(w * h, max(len(px), seconds_target / max(per_px, 1e-9))))
@@ -157,60 +174,86 @@ def ensure_library():
             last = size
 
 
-def run_reference(args, scene, wl):
-    """--impl reference: the reference's own CUDA kernel rebuilt for sm_100a, rank 0 only."""
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CUDA kernel rebuilt for sm_100a, rank 0 only.  Scene arrays come from the same
+    fixture (pure numpy host code); this repo's CUDA library is never loaded in this arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyoracle as po
-    import cutrace_b200 as ct
+    import ctypes as C
 
+    from oracle import pyoracle as po
+
+    scene, wl = load_workload(args.workload)
     base = {"impl": "reference", "metric": "Mrays/s (primary+secondary)", "unit": "Mrays/s", "higher_is_better": True}
+    cfg = config_of(scene, wl)
+    rays = RAYS_PER_FRAME[wl["name"]]
     if not po.have_ref_gpu():
         # the reference could not be compiled in the container: fall back to its host build / the port
         cb = cpu_baseline(scene, wl["label"], seconds_target=20.0)
-        line = dict(base, value=cb["value"], n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=None,
-                    scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", config={"workload": wl["label"]},
-                    cpu_baseline=cb, e2e={"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                    reference_arm="host build of the reference's device functions (no sm_100a rebuild available)")
-        emit(line)
+        emit(dict(base, value=cb["value"], n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=None, scaling="strong",
+                  vs_baseline=None, dtype="f32", data="synthetic", config=cfg, cpu_baseline=cb,
+                  e2e={"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                  reference_arm="host build of the reference's device functions (no sm_100a rebuild available)"))
         return
-    # unique-ray numerator: counted by our renderer on the same frame (identical for every implementation)
-    with ct.Renderer(scene, device=0) as r:
-        rays = r.render()["rays_total"]
-    import ctypes as C
-
     lib = po._load(po.REF_GPU_SO)
-    with ClockSampler(0) as clk:
-        ref = po.ref_gpu_render(scene, iters=args.steps, warmup=args.warmup)
-        # e2e: the reference's whole operator gpu::render<S,5,256> (managed allocs, launch+sync, 3*h row copies, max scan)
-        fn = lib.cutrace_ref_gpu_render_e2e
-        fn.restype = C.c_int
-        fn.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        n = scene.width * scene.height
+    fn = lib.cutrace_ref_gpu_render_e2e
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def ref_e2e(s, frames):
+        """the reference's whole operator gpu::render<S,5,256>: managed allocs, launch + sync, 3*h row copies, host max scan"""
+        n = s.width * s.height
         d, nm, c = np.empty(n, np.float32), np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
         tot = C.c_float(); rms = C.c_float(); mx = C.c_float()
-        desc = scene.as_desc()
-        e2e_ms = []
-        for i in range(1 + max(1, min(args.steps, 3))):
+        desc = s.as_desc()
+        out = []
+        for i in range(1 + frames):
             rc = fn(C.byref(desc), 1e-3, d.ctypes.data, nm.ctypes.data, c.ctypes.data, C.byref(rms), C.byref(tot), C.byref(mx))
             if rc:
                 raise RuntimeError(f"reference e2e failed: {rc}")
             if i:
-                e2e_ms.append(tot.value)
+                out.append(tot.value)
+        return float(np.mean(out))
+
+    with ClockSampler(0) as clk:
+        ref = po.ref_gpu_render(scene, iters=args.steps, warmup=args.warmup)
+        e2e = ref_e2e(scene, max(1, min(args.steps, 3)))
     ms = ref["render_ms"]
-    e2e = float(np.mean(e2e_ms))
+    # BASELINE configs 1-3 on the reference kernel (full frames) and config 5 on the oracle-side subset kernel
+    extra = {}
+    if not args.no_extra:
+        for name in ("triangle", "spheres1080", "mirror1080"):
+            if name == wl["name"]:
+                continue
+            s2, w2 = load_workload(name)
+            r2 = po.ref_gpu_render(s2, iters=5, warmup=2)
+            extra[name] = {"workload": w2["label"], "ms_per_frame": r2["render_ms"], "value": RAYS_PER_FRAME[name] / r2["render_ms"] / 1e3, "unit": "Mrays/s",
+                           "e2e_ms_per_frame": ref_e2e(s2, 3)}
+        if wl["name"] != "synthetic10m":
+            s5, w5 = load_workload("synthetic10m")
+            px = np.random.default_rng(0).choice(s5.width * s5.height, 4096, replace=False).astype(np.uint64)
+            r5 = po.ref_gpu_render(s5, px=px)
+            ms5 = r5["render_ms"] / 4096 * s5.width * s5.height
+            extra["synthetic10m"] = {"workload": w5["label"], "ms_per_frame": ms5, "value": RAYS_PER_FRAME["synthetic10m"] / ms5 / 1e3, "unit": "Mrays/s",
+                                     "extrapolated": f"brute force cannot render 33 M pixels: the reference's ray_cast / ray_color on a seeded 4096-pixel subset took "
+                                                     f"{r5['render_ms']:.1f} ms, scaled linearly in the pixel count (4096 threads fill 16 of 148 SMs: an upper bound, up to ~9x high)"}
     cb = cpu_baseline(scene, wl["label"], seconds_target=10.0)
-    scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in __import__("cutrace_b200.scene", fromlist=["_ARRAY_FIELDS"])._ARRAY_FIELDS)
-    line = dict(base, value=rays / ms / 1e3, n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms, scaling="strong",
-                vs_baseline=None, dtype="f32", data="synthetic (reference scene geometry, fixture tests/golden/scenes)",
-                config={"workload": wl["label"], "rays_per_frame": int(rays), "launch": "<<<w*h/256+1,256>>> render_kernel<S,5>, sm_100a rebuild"},
-                clocks=clk.summary(), gpu_launches=args.steps,
-                e2e={"value": rays / e2e / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e, "h2d_bytes_per_step": int(scene_bytes),
-                     "d2h_bytes_per_step": int(28 * n), "what": "cutrace::gpu::render<S,5,256> total bracket (inc/kernel.hpp:88-126)"},
-                cpu_baseline=cb,
-                reference_arm="reference CUDA kernel rebuilt for sm_100a (the comparator north_star names); cpu_baseline is the reference's device code compiled for the host")
-    emit(line)
+    import cutrace_b200._lib as product_lib
+    from cutrace_b200.scene import _ARRAY_FIELDS
+
+    scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in _ARRAY_FIELDS)
+    n = scene.width * scene.height
+    emit(dict(base, value=rays / ms / 1e3, n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms, scaling="strong",
+              vs_baseline=None, dtype="f32", data="synthetic (reference scene geometry, fixture tests/golden/scenes)", config=cfg,
+              launch="<<<w*h/256+1,256>>> render_kernel<S,5>, sm_100a rebuild", clocks=clk.summary(), gpu_launches=args.steps,
+              e2e={"value": rays / e2e / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e, "h2d_bytes_per_step": int(scene_bytes),
+                   "d2h_bytes_per_step": int(28 * n), "what": "cutrace::gpu::render<S,5,256> total bracket (inc/kernel.hpp:88-126)"},
+              extra_workloads=extra, cpu_baseline=cb, product_library_loaded=product_lib._lib is not None,
+              reference_arm="reference CUDA kernel rebuilt for sm_100a (the comparator north_star names); cpu_baseline is the reference's device code compiled for the host"))
 
 
 _RESULT_OUT = None
@@ -233,6 +276,213 @@ def emit(line):
     out.flush()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        ensure_library()
+        import cutrace_b200 as ct
+
+        self.torch, self.dist, self.ct, self.args = torch, dist, ct, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.failed = False
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: cutrace_b200 has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        if self.world != args.gpus and self.rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={self.world}; using WORLD_SIZE", file=sys.stderr)
+        # the ctx launches its trace chain on this (high-priority) stream; torch events see its kernels
+        self.stream = torch.cuda.Stream(device=self.local_rank, priority=-1)
+        torch.cuda.set_stream(self.stream)
+        self.lib = ct._lib.load()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op):
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN}[op])
+        return [float(x) for x in t]
+
+    # ---- device-resident frames: K frames between two CUDA events on the launching stream ----
+    def resident(self, scene, steps, warmup, sampler=False):
+        from cutrace_b200.distributed import TileShardedRenderer
+
+        torch, args = self.torch, self.args
+        tsr = TileShardedRenderer(scene, rank=self.rank, world=self.world, device=self.local_rank, flags=args.flags, stream=self.stream.cuda_stream,
+                                  exchange=args.exchange)
+
+        def step():
+            st = tsr.render()
+            if self.world > 1:
+                tsr.gather()
+            return st
+
+        for _ in range(warmup):
+            st = step()
+        self.barrier()
+        dev_ms = []
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(self.local_rank, enabled=(sampler and self.rank == 0)) as clk:
+            if sampler:
+                self.barrier()   # rank 0 spent 0.25 s starting the sampler: line the ranks up again before the timed region
+            ev0.record(self.stream)
+            for _ in range(steps):
+                st = step()
+                dev_ms.append(st["render_ms"])
+            ev1.record(self.stream)
+            self.barrier()
+        ms_local = ev0.elapsed_time(ev1) / steps
+        if args.verbose:
+            print(f"[rank {self.rank}] step {ms_local:.3f} ms  render {np.mean(dev_ms):.3f}  rays {st['rays_total']}  px {st['local_pixels']}  "
+                  f"scheduler {st['scheduler']}  phases {' '.join(f'{x:.3f}' for x in tsr.r.phase_ms())}", file=sys.stderr, flush=True)
+        ms_step, render_dev_ms = self.reduce([ms_local, float(np.mean(dev_ms))], "max")
+        rays, rays_shadow = self.reduce([st["rays_total"], st["rays_shadow"]], "sum")
+        launches = int(st["kernel_launches"]) + (1 if self.world > 1 and self.rank == 0 and tsr.exchange == "gather" else 0)
+        res = dict(ms_per_step=ms_step, render_device_ms=render_dev_ms, rays=rays, rays_shadow=rays_shadow, launches_per_step=launches,
+                   scheduler="frame kernel" if st["scheduler"] else "one launch per level and kind (CUDA graph)", exchange=tsr.exchange,
+                   clocks=clk.summary() if sampler else None)
+        # ---- the N-GPU frame against the same frame rendered by ONE GPU, bit for bit (pixels are independent in the reference,
+        # /root/reference/inc/kernel.hpp:37-59: sharding changes who renders a pixel, not what) ----
+        if self.world > 1 and not args.no_parity_check:
+            res["parity_check"] = self.parity_check(scene, tsr, st)
+        tsr.close()
+        return res
+
+    def parity_check(self, scene, tsr, st, host_frame=None):
+        ct = self.ct
+        ok = 1
+        info = {}
+        if self.rank == 0:
+            if host_frame is not None:
+                got = host_frame.as_dict()
+            elif tsr.exchange == "gather":
+                got = {k: getattr(tsr, "out_" + a).cpu().numpy() for k, a in (("depth", "depth"), ("normal", "normal"), ("color", "color"), ("hit_id", "id"))}
+            else:
+                got = tsr.r.download()
+            # same scheduler as the shards used: the frame kernel and the per-level kernels are separate compilations (last-bit colours)
+            flags = (self.args.flags & ~(ct.FLAG_FRAME_KERNEL | ct.FLAG_LAUNCHES)) | (ct.FLAG_FRAME_KERNEL if st["scheduler"] else ct.FLAG_LAUNCHES)
+            with ct.Renderer(scene, device=self.local_rank, flags=flags) as r1:
+                r1.render()
+                one = r1.download()
+            branching = scene.max_children() >= 2   # a material reflects AND transmits: float atomics, order-dependent last bits
+            info = {"pixels": int(scene.width * scene.height), "world": self.world,
+                    "source": "shared pinned host frame" if host_frame is not None else "rank 0's device frame"}
+            for k in ("depth", "normal", "hit_id", "color"):
+                a, b = np.asarray(got[k]).reshape(-1), np.asarray(one[k]).reshape(-1)
+                same = bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
+                if k == "color" and branching and not same:
+                    same = bool(np.abs(a - b).max() < 1e-5)
+                    info["color_note"] = "branching scene: float atomics, compared to 1e-5"
+                info[k + "_equal"] = same
+                if not same:
+                    info[k + "_differing"] = int((a.view(np.uint32) != b.view(np.uint32)).sum())
+                    ok = 0
+            info["n_gpu_equals_1_gpu"] = bool(ok)
+        ok = self.reduce([ok], "min")[0] >= 1   # every rank learns the verdict
+        self.failed = self.failed or not ok
+        return info
+
+    # ---- per-kernel times: two extra frames with CUTRACE_FLAG_SERIALIZE (one stream, CUDA events around every kernel) ----
+    def kernel_ms(self, scene):
+        from cutrace_b200.distributed import TileShardedRenderer
+
+        ser = TileShardedRenderer(scene, rank=self.rank, world=self.world, device=self.local_rank, flags=self.args.flags | self.ct.FLAG_SERIALIZE,
+                                  stream=self.stream.cuda_stream, exchange="gather")
+        ser.render()
+        sst = ser.render()
+        ser.close()
+        shade, trace, serial = self.reduce([sst["shade_ms"], sst["trace_ms"], sst["render_ms"]], "max")
+        return {"trace": trace, "shade": shade, "serialized_frame": serial,
+                "note": "a frame rendered with CUTRACE_FLAG_SERIALIZE (one launch per level and kind on one stream); the timed frames overlap shading with the trace chain"}
+
+    # ---- end to end: host scene in, host frame out, every step ----
+    def e2e(self, scene, steps, check_parity=False):
+        import ctypes as C
+
+        from cutrace_b200.distributed import SharedHostFrame, TileShardedRenderer
+        from cutrace_b200.scene import _ARRAY_FIELDS
+
+        ct, lib, args = self.ct, self.lib, self.args
+        n_px = scene.width * scene.height
+        scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in _ARRAY_FIELDS if k != "obj_kind") + 64
+        ms, parity = [], None
+        if self.world == 1:
+            pinned, ptrs = {}, []
+            for k, m in (("depth", 1), ("normal", 3), ("color", 3)):
+                p = lib.cutrace_host_alloc(n_px * m * 4)
+                ptrs.append(p)
+                pinned[k] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n_px * m,))
+            for i in range(2 + steps):
+                self.barrier()
+                t0 = time.perf_counter()
+                r = ct.Renderer(scene, device=self.local_rank, flags=args.flags, stream=self.stream.cuda_stream)
+                md = C.c_float()
+                ct._lib.check(lib.cutrace_render_download(r._ctx, pinned["depth"].ctypes.data, pinned["normal"].ctypes.data, pinned["color"].ctypes.data,
+                                                          None, C.byref(md), None))
+                r.close()
+                self.barrier()
+                if i >= 2:
+                    ms.append((time.perf_counter() - t0) * 1e3)
+            del pinned
+            for p in ptrs:
+                lib.cutrace_host_free(p)
+            what = ("cutrace_upload_scene (H2D + LBVH build) + cutrace_render_download (render; depth/normal D2H under the bounce levels, colour D2H at "
+                    "the end) into pinned host buffers + cutrace_free, every frame")
+            d2h = 28 * n_px
+        else:
+            frame = SharedHostFrame(scene.width, scene.height, self.rank, self.world, self.local_rank)
+            for i in range(2 + steps):
+                self.barrier()
+                t0 = time.perf_counter()
+                tr = TileShardedRenderer(scene, rank=self.rank, world=self.world, device=self.local_rank, flags=args.flags, stream=self.stream.cuda_stream,
+                                         exchange="host", host_frame=frame)
+                st = tr.render()                      # returns when this rank's tiles are in the host frame
+                tr.max_depth(st["max_depth"])         # 1-float all-reduce (kernel.hpp:120-125); doubles as the "frame complete" barrier
+                if i >= 2:
+                    ms.append((time.perf_counter() - t0) * 1e3)
+                if check_parity and i == 1 + steps:   # outside the timed part of the last frame
+                    parity = self.parity_check(scene, tr, st, host_frame=frame)
+                tr.close()
+                self.barrier()
+            frame.close()
+            what = ("per rank: cutrace_upload_scene (H2D + LBVH build) + cutrace_frame_attach(shared pinned host frame) + cutrace_render — every rank's "
+                    "kernels store their tiles (G-buffer under the bounce levels, colour at the end) straight into ONE host frame over their own PCIe link — "
+                    "+ max-depth all-reduce, every frame (cutrace_free of the frame's ctx follows outside the bracket)")
+            d2h = 32 * n_px
+            scene_bytes *= self.world
+        med, mean, mx = self.reduce([float(np.median(ms)), float(np.mean(ms)), float(np.max(ms))], "max")
+        out = {"ms_per_frame": med, "ms_per_frame_mean": mean, "ms_per_frame_max": mx, "frames": len(ms), "statistic": "median",
+               "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(d2h), "what": what}
+        if parity is not None:
+            out["parity_check"] = parity
+        return out
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def compulsory_bytes_per_frame(n_px, rays_total, rays_shadow, n_lights):
+    """DRAM bytes a frame cannot avoid with this data layout: per traced ray a 32-byte ray record in (levels >= 1), a 48-byte
+    shade record and a 32-byte child ray out; per shaded hit 48 B in, 12 B level colour out and 12 B read again by the ordered sum; per
+    pixel 20 B G-buffer, 4 B level count, 12 B final colour."""
+    traced = rays_total - rays_shadow
+    shaded = rays_shadow / max(1, n_lights)
+    return traced * (32 + 48 + 32) - n_px * 32 + shaded * (48 + 12 + 12) + n_px * (20 + 4 + 12)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -241,202 +491,111 @@ def main():
     ap.add_argument("--impl", default="cutrace_b200", choices=["cutrace_b200", "reference"])
     ap.add_argument("--workload", default="bunny4k", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads (BASELINE configs 1-3 and 5)")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--verbose", action="store_true", help="per-rank timing lines on stderr")
     ap.add_argument("--exchange", default="peer", choices=["peer", "gather"],
-                    help="N > 1: peer = kernels store into rank 0's frame over NVLink (CUDA IPC), gather = NCCL gather + un-tile")
+                    help="N > 1, device-resident frames: peer = kernels store into rank 0's frame over NVLink (CUDA IPC), gather = NCCL gather + un-tile")
     args = ap.parse_args()
     claim_stdout()
     if args.warmup < 3:
         args.warmup = 3
-
-    scene, wl = load_workload(args.workload)
     if args.impl == "reference":
-        run_reference(args, scene, wl)
+        run_reference(args)
         return
 
-    import torch
-    import torch.distributed as dist
-
-    ensure_library()
-    import cutrace_b200 as ct
-    from cutrace_b200.distributed import TileShardedRenderer
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: cutrace_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world != args.gpus and rank == 0:
-        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    b = Bench(args)
+    scene, wl = load_workload(args.workload)
     n_px = scene.width * scene.height
-    stream = torch.cuda.Stream(device=local_rank, priority=-1)   # the ctx launches its trace chain on this (high-priority) stream; torch events see its kernels
-    torch.cuda.set_stream(stream)
-    tsr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream,
-                              exchange=args.exchange)
-    exchange = tsr.exchange
+    main_res = b.resident(scene, args.steps, args.warmup, sampler=True)
+    kms = b.kernel_ms(scene)
+    e2e = b.e2e(scene, max(5, min(args.steps, 20)), check_parity=not args.no_parity_check)
+    rays, ms_step = main_res["rays"], main_res["ms_per_step"]
 
-    def step():
-        st = tsr.render()
-        if world > 1:
-            tsr.gather()
-        return st
+    extra = {}
+    if not args.no_extra:
+        for name in ("triangle", "spheres1080", "mirror1080", "synthetic10m"):
+            if name == wl["name"]:
+                continue
+            s2, w2 = load_workload(name)
+            big = name == "synthetic10m"
+            r2 = b.resident(s2, 5 if big else 10, 3)
+            e2 = b.e2e(s2, 3 if big else 5, check_parity=(big and not args.no_parity_check))
+            extra[name] = {"workload": w2["label"], "ms_per_frame": r2["ms_per_step"], "value": r2["rays"] / r2["ms_per_step"] / 1e3, "unit": "Mrays/s",
+                           "rays_per_frame": int(r2["rays"]), "scheduler": r2["scheduler"], "render_device_ms": r2["render_device_ms"],
+                           "e2e_ms_per_frame": e2["ms_per_frame"], "e2e_value": r2["rays"] / e2["ms_per_frame"] / 1e3}
+            if "parity_check" in r2:
+                extra[name]["parity_check"] = r2["parity_check"]
+            if "parity_check" in e2:
+                extra[name]["e2e_parity_check"] = e2["parity_check"]
+            del s2
 
-    for _ in range(args.warmup):
-        st = step()
-    barrier()
-    dev_ms, trace_ms, shade_ms = [], [], []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
-        barrier()   # rank 0 spent 0.25 s starting the sampler: line the ranks up again before the timed region
-        ev0.record(stream)
-        for _ in range(args.steps):
-            st = step()
-            dev_ms.append(st["render_ms"]); trace_ms.append(st["trace_ms"]); shade_ms.append(st["shade_ms"])
-        ev1.record(stream)
-        barrier()
-    # exactly K steps between two CUDA events on the launching stream, barrier + synchronize on both sides
-    ms_local = ev0.elapsed_time(ev1) / args.steps
-    rays_local = st["rays_total"]
-    if args.verbose:
-        print(f"[rank {rank}] step {ms_local:.3f} ms  render {np.mean(dev_ms):.3f} (trace {np.mean(trace_ms):.3f} shade {np.mean(shade_ms):.3f})  "
-              f"rays {rays_local}  px {st['local_pixels']}", file=sys.stderr, flush=True)
-    t = torch.tensor([ms_local, float(rays_local), float(np.mean(shade_ms)), float(np.mean(trace_ms)), float(st["rays_shadow"]),
-                      float(np.mean(dev_ms))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_step, rays = float(tmax[0]), float(tsum[1])
-        shade, trace, rays_shadow, render_dev_ms = float(tmax[2]), float(tmax[3]), float(tsum[4]), float(tmax[5])
-    else:
-        ms_step, rays, shade, trace, rays_shadow, render_dev_ms = (float(x) for x in t)
-    launches_per_step = int(st["kernel_launches"]) + (1 if world > 1 and rank == 0 and exchange == "gather" else 0)
-
-    # per-kernel times need a serialised frame (by default the shade kernels overlap the trace chain): two extra
-    # frames with CUTRACE_FLAG_SERIALIZE, outside the timed region, CUDA events on the launching stream
-    tsr.close()
-    ser = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags | ct.FLAG_SERIALIZE, stream=stream.cuda_stream,
-                              exchange="gather")
-    ser.render()
-    sst = ser.render()
-    ser.close()
-    ks = torch.tensor([sst["shade_ms"], sst["trace_ms"], sst["render_ms"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ks, op=dist.ReduceOp.MAX)
-    shade, trace, serial_ms = float(ks[0]), float(ks[1]), float(ks[2])
-    # ---- e2e: upload (H2D + LBVH build) + render + download to pinned host, through the C-ABI ----
-    barrier()
-    import ctypes as C
-
-    lib = ct._lib.load()
-    pinned = {}
-    if rank == 0:
-        for k, (m, dt) in {"depth": (1, np.float32), "normal": (3, np.float32), "color": (3, np.float32)}.items():
-            p = lib.cutrace_host_alloc(n_px * m * 4)
-            pinned[k] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n_px * m,))
-    e2e_steps = max(5, min(args.steps, 20))
-    e2e_ms = []
-    for i in range(2 + e2e_steps):
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            r = ct.Renderer(scene, device=local_rank, flags=args.flags, stream=stream.cuda_stream)
-            md = C.c_float()
-            ct._lib.check(lib.cutrace_render_download(r._ctx, pinned["depth"].ctypes.data, pinned["normal"].ctypes.data,
-                                                      pinned["color"].ctypes.data, None, C.byref(md), None))
-            r.close()
-        else:
-            tr = TileShardedRenderer(scene, rank=rank, world=world, device=local_rank, flags=args.flags, stream=stream.cuda_stream,
-                                     exchange=args.exchange)
-            stl = tr.render()
-            tr.gather()
-            tr.max_depth(stl["max_depth"])
-            if rank == 0:
-                for k, src in (("depth", tr.out_depth), ("normal", tr.out_normal), ("color", tr.out_color)):
-                    torch.from_numpy(pinned[k]).copy_(src, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-            tr.close()
-        barrier()
-        if i >= 2:
-            e2e_ms.append((time.perf_counter() - t0) * 1e3)
-    if args.verbose:
-        print(f"[rank {rank}] e2e frames (ms): " + " ".join(f"{x:.2f}" for x in e2e_ms), file=sys.stderr, flush=True)
-    # per-frame wall time of the whole call sequence; the MEDIAN is reported (one frame in ~10 shows a 30-100 ms host
-    # hiccup in cudaFree/stream teardown on these boxes), mean and max are kept next to it
-    e2e_t = torch.tensor([float(np.median(e2e_ms)), float(np.mean(e2e_ms)), float(np.max(e2e_ms))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e, e2e_mean, e2e_max = (float(x) for x in e2e_t)
-    from cutrace_b200.scene import _ARRAY_FIELDS
-
-    scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in _ARRAY_FIELDS if k != "obj_kind") + 64
-
-    if rank == 0:
+    if b.rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:  # noqa: BLE001
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        bpr = algorithmic_bytes_per_ray(n_primitives(scene))
-        dominant = "shade_kernel (shadow rays + Phong)" if shade >= trace else "trace_kernel (closest hit)"
-        dom_ms = max(shade, trace)
-        dom_rays = rays_shadow if shade >= trace else (rays - rays_shadow)
-        achieved = dom_rays * bpr / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        ncu_facts = {}
-        traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        clocks = main_res["clocks"]
+        comp = compulsory_bytes_per_frame(n_px, rays, main_res["rays_shadow"], scene.n_lights)
+        achieved = comp / (ms_step * 1e-3) / 1e9
+        # what ncu measured for one frame of this workload (committed: profiles/ncu_frame.json, written by tools/ncu_frame.py)
+        ncu = {}
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(wl["label"], {})
-            key = "shade_kernel" if shade >= trace else "trace_kernel"
-            traffic = tr[key]["mean_traffic_bytes"] if world == 1 and key in tr else None
-            ncu_facts = {k: tr[key][k] for k in ("issue_slots_busy_pct", "active_threads_per_warp_instruction", "dram_throughput_pct") if k in tr.get(key, {})}
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_frame.json"))).get(wl["label"], {}).get(f"n{b.world}", {})
         except Exception:  # noqa: BLE001
             pass
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        sms = b.torch.cuda.get_device_properties(b.local_rank).multi_processor_count
+        issue = None
+        if ncu.get("thread_inst_per_frame"):
+            lanes_peak = sms * 4 * 32 * sm_hz    # thread-instructions per second the SMs can issue
+            issue = {"thread_inst_per_frame": ncu["thread_inst_per_frame"], "warp_inst_per_frame": ncu.get("warp_inst_per_frame"),
+                     "active_lanes_per_warp_inst": ncu.get("active_lanes"), "frac": ncu["thread_inst_per_frame"] / (ms_step * 1e-3) / lanes_peak,
+                     "peak": "SMs x 4 schedulers x 32 lanes x SM clock", "sms": sms, "sm_mhz": sm_hz / 1e6,
+                     "source": "instruction counts: committed ncu capture of the same (deterministic) frame; time: this run"}
+        bpr = survey_bytes_per_ray(n_primitives(scene))
         line = {
-            "metric": "Mrays/s (primary+secondary)", "value": rays / ms_step / 1e3, "unit": "Mrays/s", "n_gpus": world,
+            "metric": "Mrays/s (primary+secondary)", "value": rays / ms_step / 1e3, "unit": "Mrays/s", "n_gpus": b.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (reference scene geometry from the committed fixture tests/golden/scenes; no image inputs)",
-            "config": {"workload": wl["label"], "rays_per_frame": int(rays), "primitives": n_primitives(scene), "bounces": 5,
-                       "parallelism": f"tiles{world}/{exchange}" if world > 1 else "single", "l2": "queues+framebuffer per frame > L2 (126 MB)"
-                       if n_px * 28 > 126e6 else "working set < L2; frames are re-rendered back to back",
-                       "timed": "K frames between two CUDA events on the launching stream" + ("" if world == 1 else (", incl. the rank barrier (tiles are stored into rank 0's frame over NVLink by the kernels)" if exchange == "peer" else ", incl. NCCL gather + un-tile")),
-                       "render_device_ms": render_dev_ms},
-            "clocks": clk.summary(),
-            "e2e": {"value": rays / e2e / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e, "ms_per_frame_mean": e2e_mean, "ms_per_frame_max": e2e_max,
-                    "frames": len(e2e_ms), "statistic": "median", "h2d_bytes_per_step": int(scene_bytes),
-                    "d2h_bytes_per_step": int(28 * n_px),
-                    "what": "cutrace_upload_scene (H2D + LBVH build) + cutrace_render_download (render; depth/normal D2H under the bounce levels, colour D2H at the end) into pinned host buffers + cutrace_free, every frame"},
-            "gpu_launches": launches_per_step * args.steps,
+            "config": config_of(scene, wl),
+            "details": {"parallelism": f"tiles{b.world}/{main_res['exchange']}" if b.world > 1 else "single", "scheduler": main_res["scheduler"],
+                        "timed": "K frames between two CUDA events on the launching stream" + (
+                            "" if b.world == 1 else ", incl. the rank barrier (tiles are stored into rank 0's frame over NVLink by the kernels)"
+                            if main_res["exchange"] == "peer" else ", incl. NCCL gather + un-tile"),
+                        "render_device_ms": main_res["render_device_ms"], "rays_counted": int(rays)},
+            "clocks": clocks,
+            "e2e": dict(e2e, value=rays / e2e["ms_per_frame"] / 1e3, unit="Mrays/s"),
+            "gpu_launches": main_res["launches_per_step"] * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                         "algorithmic_bytes_per_launch": dom_rays * bpr / max(1, int(st["kernel_launches"]) // 2),
-                         "kernel": dominant, "bytes_per_ray": bpr,
-                         "ncu": dict(ncu_facts, source="profiles/ncu_traffic.json (committed ncu --set full capture of this kernel)",
-                                     reading="the kernel is issue-bound, not DRAM-bound: see issue_slots_busy_pct / active_threads_per_warp_instruction (of 32) / dram_throughput_pct"),
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                         "note": "algorithmic bytes/ray (SURVEY §8d) x rays of the dominant kernel / its CUDA-event time; the scene is cache-resident, "
-                                 "so issue-slot utilisation and divergence (profiles/) explain the kernel, not DRAM"},
-            "kernel_ms": {"trace": trace, "shade": shade, "serialized_frame": serial_ms,
-                          "note": "measured on a frame rendered with CUTRACE_FLAG_SERIALIZE (one stream); the timed frames overlap shade(L) with trace(L+1..)"},
+                         "what": "compulsory DRAM bytes of one frame (queue records in/out, level colours, framebuffer: DESIGN.md 3) / ms_per_step",
+                         "compulsory_bytes_per_frame": comp, "traffic": ncu.get("dram_bytes_per_frame"),
+                         "traffic_unit": "bytes per frame, all kernels (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "binding_resource": "issue slots x active lanes (the BVH is cache-resident; DRAM runs at `frac` of its peak)", "issue": issue,
+                         "kernels": ncu.get("kernels"),
+                         "survey_model": {"bytes_per_ray": bpr, "achieved": rays * bpr / (ms_step * 1e-3) / 1e9, "frac": rays * bpr / (ms_step * 1e-3) / 1e9 / peak,
+                                          "note": "SURVEY 8d's model (one 64-byte node per level of a balanced tree per ray, as if from HBM): these bytes are served "
+                                                  "from shared memory / L1, so this is NOT a bandwidth measurement and can exceed 1"},
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "kernel_ms": kms,
+            "extra_workloads": extra,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if "parity_check" in main_res:
+            line["parity_check"] = main_res["parity_check"]
+        if not args.no_cpu_baseline and b.world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline(scene, wl["label"])
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "absent", "sample": f"failed: {e}"}
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    failed = b.failed
+    b.finish()
+    if failed:
+        raise SystemExit("parity_check failed: the N-GPU frame differs from the 1-GPU frame")
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ SYMBOLS = (
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version", "cutrace_tile_size",
 )
 
-FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES = 1, 2, 4, 8, 16, 32
+FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, FLAG_PIXEL_KERNEL = 1, 2, 4, 8, 16, 32, 64
 IPC_HANDLE_BYTES = 80
 
 
@@ -39,7 +39,7 @@ class cutrace_stats(C.Structure):
         ("rays_primary", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_transmit", C.c_uint64),
         ("rays_shadow", C.c_uint64), ("shadow_casts", C.c_uint64), ("local_pixels", C.c_uint64),
         ("kernel_launches", C.c_uint32), ("bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("smem_nodes", C.c_uint32),
-        ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("reserved", C.c_uint32 * 6),
+        ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("scheduler", C.c_uint32), ("reserved", C.c_uint32 * 5),
     ]
 
     def as_dict(self):

@@ -181,6 +181,7 @@ struct cutrace_ctx {
   FrameStats *h_ctr_dev = nullptr;  // device address of h_ctr
   float phase_ms[18] = {};          // frame kernel: when trace(p) was complete / the frame ended, relative to its start (last batch)
   uint32_t phase_count = 0;
+  bool queues_ready = false;        // rays / shade queues, level images (alloc_queues)
   bool ctr_dirty = true;            // d_ctr may hold values of an earlier (multi-launch or failed) frame: clear before a frame kernel
   bool frame_kernel_failed = false; // a cooperative launch was refused: this ctx stays on the multi-launch path
   bool env_export_with_color = false;
@@ -253,6 +254,7 @@ void free_frame(cutrace_ctx *c) {
   dfree(c->st_bytes, st); c->st_bytes = nullptr; c->st_bytes_px = 0;
   c->fb = FrameTargets{};
   c->rays[0] = c->rays[1] = nullptr;
+  c->queues_ready = false;
   c->st_depth = nullptr;
   c->st_px = 0;
   c->rendered = false;
@@ -324,19 +326,29 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   } else {                 // one GPU: results are written row-major, no un-tile pass
     CU(dmalloc(&c->frame, 32ull * width * height, st));
   }
+  for (uint32_t L = 0; L < levels; L++) c->shade_cap[L] = batch * (branching ? (1ull << L) : 1ull) + slack;
+  c->queues_ready = false;   // the wavefront's queues are allocated by the first frame that needs them (the pixel kernel has none)
+  return CUTRACE_OK;
+}
+
+// queue memory of the wavefront schedulers, sized by alloc_frame
+int alloc_queues(cutrace_ctx *c) {
+  if (c->queues_ready) return CUTRACE_OK;
+  cudaStream_t st = c->stream;
+  const uint32_t b = c->opts.bounces;
+  const bool branching = c->max_children >= 2 && b > 0;
+  const uint32_t levels = c->max_children > 0 ? b + 1 : 1;
   if (branching) CU(dmalloc(&c->local_color, sizeof(float) * 3 * c->n_local_px, st));
   if (c->max_children > 0 && b > 0) {
     CU(dmalloc(&c->rays[0], sizeof(RayRec) * c->cap, st));
     CU(dmalloc(&c->rays[1], sizeof(RayRec) * c->cap, st));
   }
-  for (uint32_t L = 0; L < levels; L++) {
-    c->shade_cap[L] = batch * (branching ? (1ull << L) : 1ull) + slack;
-    CU(dmalloc(&c->shade[L], sizeof(ShadeRec) * c->shade_cap[L], st));
-  }
+  for (uint32_t L = 0; L < levels; L++) CU(dmalloc(&c->shade[L], sizeof(ShadeRec) * c->shade_cap[L], st));
   if (!branching) {
-    CU(dmalloc(&c->level_color, sizeof(float) * 3 * batch * levels, st));
+    CU(dmalloc(&c->level_color, sizeof(float) * 3 * c->batch_px * levels, st));
     CU(dmalloc(&c->nlev, sizeof(uint32_t) * c->n_local_px, st));
   }
+  c->queues_ready = true;
   return CUTRACE_OK;
 }
 
@@ -477,9 +489,10 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   pool_keep_memory(dev);
   c->env_no_graph = getenv("CUTRACE_NO_GRAPH") != nullptr;
   if (const char *e = getenv("CUTRACE_SCHEDULER")) {   // developer override of cutrace_opts.flags: "frame" | "launches"
-    c->opts.flags &= ~(CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES);
+    c->opts.flags &= ~(CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES | CUTRACE_FLAG_PIXEL_KERNEL);
     if (!strcmp(e, "frame")) c->opts.flags |= CUTRACE_FLAG_FRAME_KERNEL;
     else if (!strcmp(e, "launches")) c->opts.flags |= CUTRACE_FLAG_LAUNCHES;
+    else if (!strcmp(e, "pixel")) c->opts.flags |= CUTRACE_FLAG_PIXEL_KERNEL;
   }
   c->env_export_with_color = getenv("CUTRACE_EXPORT_WITH_COLOR") != nullptr;      // developer toggle: remote G-buffer stores at the end of the frame
   c->env_graph_first = getenv("CUTRACE_GRAPH_FIRST") != nullptr;
@@ -680,6 +693,12 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   }
   PhaseTimer ptimer; (void)ptimer;
   cudaEvent_t ev_begin = c->events[0], ev_end = c->events[1];
+  {
+    const uint32_t forced_ = c->opts.flags & (CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES | CUTRACE_FLAG_PIXEL_KERNEL);
+    const bool tiny_ = c->n_local_px <= (1ull << 14) || (c->sv.n_prims <= 16u && c->sv.n_planes <= 16u);
+    const bool pixel_ = !(c->opts.flags & CUTRACE_FLAG_SERIALIZE) && c->h_ctr_dev && (forced_ ? (forced_ & CUTRACE_FLAG_PIXEL_KERNEL) != 0 : tiny_);
+    if (!pixel_) { int rc_ = alloc_queues(c); if (rc_) return rc_; }
+  }
   const bool branching = c->max_children >= 2 && bounces > 0;
   const bool serialize = (c->opts.flags & CUTRACE_FLAG_SERIALIZE) != 0;
   const FrameTargets out = frame_targets(c);
@@ -694,7 +713,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   //   trace(L) -> trace(L+1) (ray queue)   and   trace(L) -> shade(L) (shade queue L)
   // The trace chain runs on the ctx stream; shade(L) runs on one of two auxiliary streams behind an event, so the
   // persistent CTAs of later kernels fill the SMs that the tail of an earlier kernel leaves idle.
-  bool capturing = false;
+  bool capturing = false, early_event = false;
   auto enqueue = [&](uint64_t base, uint32_t n_px) -> cudaError_t {
     cudaError_t e;
 #define EQ(call) do { e = (call); if (e != cudaSuccess) return e; } while (0)
@@ -742,10 +761,11 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   // cleared counters and leaves them cleared; its counters arrive in c->h_ctr (mapped pinned memory) without a copy.
   // With an early G-buffer download pending (cutrace_render_download) trace(0) runs as its own kernel first, so that the
   // copy engine can start behind it while the frame kernel works on the bounce levels.
-  // which scheduler: see CUTRACE_FLAG_FRAME_KERNEL in cutrace.h
-  const bool want_frame = (c->opts.flags & CUTRACE_FLAG_FRAME_KERNEL) ? true
-                          : (c->opts.flags & CUTRACE_FLAG_LAUNCHES) ? false
-                                                                    : (c->tm.world > 1 && c->n_local_px >= (1ull << 19));
+  // which scheduler: see CUTRACE_FLAG_FRAME_KERNEL / CUTRACE_FLAG_PIXEL_KERNEL in cutrace.h
+  const uint32_t forced = c->opts.flags & (CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES | CUTRACE_FLAG_PIXEL_KERNEL);
+  const bool tiny = c->n_local_px <= (1ull << 14) || (c->sv.n_prims <= 16u && c->sv.n_planes <= 16u);
+  const bool use_pixel = !serialize && c->h_ctr_dev && (forced ? (forced & CUTRACE_FLAG_PIXEL_KERNEL) != 0 : tiny);
+  const bool want_frame = !use_pixel && (forced ? (forced & CUTRACE_FLAG_FRAME_KERNEL) != 0 : (c->tm.world > 1 && c->n_local_px >= (1ull << 19)));
   const bool use_frame = want_frame && !serialize && !c->frame_kernel_failed && c->cfg.grid_frame > 0 && c->h_ctr_dev;
   auto enqueue_frame = [&](uint64_t base, uint32_t n_px, bool split_primary) -> cudaError_t {
     cudaError_t e;
@@ -788,12 +808,30 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     return cudaSuccess;
   };
 
+  auto enqueue_pixel = [&](uint64_t base, uint32_t n_px) -> cudaError_t {
+    cudaError_t e;
+    if (c->ctr_dirty) {
+      if ((e = cudaMemsetAsync(c->d_ctr, 0, sizeof(FrameCounters), st)) != cudaSuccess) return e;
+      c->ctr_dirty = false;
+    }
+    PixelArgs pa{};
+    pa.sv = c->sv; pa.tm = c->tm; pa.bounces = bounces; pa.px_base = (uint32_t)base; pa.n_px = n_px;
+    pa.ctr = c->d_ctr; pa.host_stats = c->h_ctr_dev; pa.out = out;
+    c->ctr_dirty = true;   // until the kernel has run to its end
+    if ((e = launch_pixel(pa, st)) != cudaSuccess) return e;
+    if (early_event) {   // cutrace_render_download: the G-buffer is complete when the kernel is
+      if ((e = cudaEventRecord(c->ev_gbuf, st)) != cudaSuccess) return e;
+    }
+    launches += 1;
+    return cudaSuccess;
+  };
+
   // One batch (the normal case): the frame is a CUDA graph, captured from the code above and replayed afterwards — one
   // launch instead of ~40 API calls, which is what a 0.05 .. 2 ms frame is bound by.  The FIRST frame of a ctx is
   // enqueued directly: capture + instantiate cost more than the ~40 calls they replace, and a caller that renders one
   // frame per scene (the reference's main.cu does) never gets that back; the graph is built on the second frame.
   const bool single_batch = c->batch_px >= c->n_local_px;
-  const bool use_graph = !use_frame && single_batch && !serialize && !c->graph_failed && !c->env_no_graph &&
+  const bool use_graph = !use_frame && !use_pixel && single_batch && !serialize && !c->graph_failed && !c->env_no_graph &&
                          (c->frames_rendered > 0 || c->env_graph_first);
   if (use_graph && !c->graph) {
     cudaGraph_t g = nullptr;
@@ -817,11 +855,20 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     const uint32_t n_px = (uint32_t)std::min<uint64_t>(c->batch_px, c->n_local_px - base);
     const bool early_gbuf = single_batch && c->frame && !c->peer_frame && (c->dl_depth || c->dl_normal || c->dl_id);
     bool frame_done = false;
-    if (use_frame) {
+    uint32_t sched = 0;
+    if (use_pixel) {
+      launches = 0;
+      early_event = early_gbuf;
+      CU(enqueue_pixel(base, n_px));
+      frame_done = true;
+      sched = 2;
+      S.kernel_launches += launches;
+    } else if (use_frame) {
       launches = 0;
       cudaError_t fe = enqueue_frame(base, n_px, early_gbuf);
       if (fe == cudaSuccess) {
         frame_done = true;
+        sched = 1;
         S.kernel_launches += launches;
       } else {   // e.g. cudaErrorCooperativeLaunchTooLarge under MPS limits: stay on the multi-launch path from now on
         cudaGetLastError();
@@ -856,10 +903,11 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     CU(cudaStreamSynchronize(st));
     LAP("render: wait for the frame");
     const FrameStats &h = *c->h_ctr;
+    S.scheduler = sched;
     if (frame_done) {
       c->ctr_dirty = false;   // the frame kernel cleared the device counters on its way out
-      c->phase_count = levels + 1;
-      for (uint32_t p = 0; p <= levels; p++)
+      c->phase_count = sched == 1 ? levels + 1 : 0;
+      for (uint32_t p = 0; p <= levels && sched == 1; p++)
         c->phase_ms[p] = h.phase_ns[p] >= h.phase_ns[17] ? (float)((double)(h.phase_ns[p] - h.phase_ns[17]) * 1e-6) : 0.f;
     } else {
       c->phase_count = 0;

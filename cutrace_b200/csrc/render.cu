@@ -422,6 +422,96 @@ __device__ __forceinline__ void phong_add(vec3 &final, vec3 ld, float fd, vec3 l
   final.z = __fmaf_rn(keep, __fmaf_rn(fd, ld.z, __fmul_rn(fs, ls.z)), final.z);
 }
 
+// phong (inc/shading.hpp:64-99) of one shaded hit: all its shadow rays (shadow_intensity, :22-45) and the sum over the lights
+template <int MODE, bool BRUTE, bool OPAQUE>
+__device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 hit, vec3 normal, vec3 in_dir,
+                                             uint32_t mat, unsigned &casts) {
+  // phong, inc/shading.hpp:64-99
+  const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
+  const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+  const vec3 diffuse = mk3(m0.x, m0.y, m0.z);
+  const vec3 specular = vscale(diffuse, m0.w);        // *spec = specular * color
+  const float phong_exp = m1.y;
+  vec3 final = vscale(diffuse, sv.cam.ambient);
+  const vec3 nn = vnormalized(normal);
+  const vec3 in_n = vscale(vnormalized(in_dir), -1.0f);
+  if (OPAQUE) {
+    // every material is opaque: the shadow march saturates on its first step, so the K shadow rays
+    // of this hit are any-hit queries and walk the BVH as one packet
+    for (uint32_t l0 = 0; l0 < sv.n_lights; l0 += SHADOW_PACKET) {
+      vec3 sd[SHADOW_PACKET];
+      float md[SHADOW_PACKET];
+      vec3 lcol[SHADOW_PACKET];
+      unsigned valid = 0;
+#pragma unroll
+      for (int k = 0; k < SHADOW_PACKET; k++) {
+        sd[k] = mk3(0.f, 0.f, 1.f); md[k] = 0.f; lcol[k] = mk3(0.f, 0.f, 0.f);
+        if (l0 + k < sv.n_lights) {
+          const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l0 + k);
+          const float4 l0v = __ldg(lp), l1v = __ldg(lp + 1);
+          vec3 direction;
+          float distance;
+          if (__float_as_uint(l0v.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
+            direction = vscale(mk3(l0v.x, l0v.y, l0v.z), -1.0f);
+            distance = INFINITY;
+          } else {                                               // inc/default_schema.hpp:305-308
+            vec3 P = mk3(l0v.x, l0v.y, l0v.z);
+            direction = vnormalized(vsub(P, hit));
+            distance = vnorm(vsub(P, hit));
+          }
+          sd[k] = vnormalized(direction);
+          md[k] = distance * vnorm(direction);
+          lcol[k] = mk3(l1v.x, l1v.y, l1v.z);
+          valid |= 1u << k;
+        }
+      }
+      casts += __popc(valid);
+      const unsigned occ = any_hit_packet<MODE, SHADOW_PACKET, BRUTE>(sv, nodes, prims, hit, sd, md, valid);
+#pragma unroll
+      for (int k = 0; k < SHADOW_PACKET; k++) {
+        if ((valid & ~occ) & (1u << k)) {        // shadow_fac = 0 < 1
+          const vec3 nd = sd[k];
+          float fd = fmaxf(0.0f, vdot(nn, nd));
+          vec3 ld = vmul(diffuse, lcol[k]);
+          vec3 hv = vnormalized(vadd(in_n, nd));
+          float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+          vec3 ls = vmul(specular, lcol[k]);
+          phong_add(final, ld, fd, ls, fs, 1.0f);
+        }
+      }
+    }
+  } else {
+    for (uint32_t l = 0; l < sv.n_lights; l++) {
+      const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l);
+      const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
+      vec3 direction;
+      float distance;
+      if (__float_as_uint(l0.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
+        direction = vscale(mk3(l0.x, l0.y, l0.z), -1.0f);
+        distance = INFINITY;
+      } else {                                              // inc/default_schema.hpp:305-308
+        vec3 P = mk3(l0.x, l0.y, l0.z);
+        direction = vnormalized(vsub(P, hit));
+        distance = vnorm(vsub(P, hit));
+      }
+      const vec3 sdir = vnormalized(direction);
+      const float light_dist = distance * vnorm(direction);
+      const vec3 color = mk3(l1.x, l1.y, l1.z);
+      const vec3 nd = sdir;
+      const float shadow_fac = shadow_intensity<MODE, BRUTE, false>(sv, nodes, prims, hit, sdir, light_dist, casts);
+      if (shadow_fac < 1.0f) {
+        float fd = fmaxf(0.0f, vdot(nn, nd));
+        vec3 ld = vmul(diffuse, color);
+        vec3 hv = vnormalized(vadd(in_n, nd));
+        float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+        vec3 ls = vmul(specular, color);
+        phong_add(final, ld, fd, ls, fs, 1 - shadow_fac);
+      }
+    }
+  }
+  return final;
+}
+
 // shadow rays + Phong for the shade records [base, end) of one level (one warp)
 template <int MODE, bool BRUTE, bool OPAQUE>
 __device__ __forceinline__ void shade_chunk(const SceneView &sv, const float4 *nodes, const float4 *prims, unsigned base, unsigned end,
@@ -437,89 +527,7 @@ __device__ __forceinline__ void shade_chunk(const SceneView &sv, const float4 *n
       const uint32_t pix = __float_as_uint(s0.w), mat = __float_as_uint(s1.w);
       const float weight = s2.w;
       if (pix == CTB_HOLE) continue;   // retired tail of a producer warp's slot block
-      // phong, inc/shading.hpp:64-99
-      const float4 *mp = reinterpret_cast<const float4 *>(sv.materials + mat);
-      const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-      const vec3 diffuse = mk3(m0.x, m0.y, m0.z);
-      const vec3 specular = vscale(diffuse, m0.w);        // *spec = specular * color
-      const float phong_exp = m1.y;
-      vec3 final = vscale(diffuse, sv.cam.ambient);
-      const vec3 nn = vnormalized(normal);
-      const vec3 in_n = vscale(vnormalized(in_dir), -1.0f);
-      if (OPAQUE) {
-        // every material is opaque: the shadow march saturates on its first step, so the K shadow rays
-        // of this hit are any-hit queries and walk the BVH as one packet
-        for (uint32_t l0 = 0; l0 < sv.n_lights; l0 += SHADOW_PACKET) {
-          vec3 sd[SHADOW_PACKET];
-          float md[SHADOW_PACKET];
-          vec3 lcol[SHADOW_PACKET];
-          unsigned valid = 0;
-#pragma unroll
-          for (int k = 0; k < SHADOW_PACKET; k++) {
-            sd[k] = mk3(0.f, 0.f, 1.f); md[k] = 0.f; lcol[k] = mk3(0.f, 0.f, 0.f);
-            if (l0 + k < sv.n_lights) {
-              const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l0 + k);
-              const float4 l0v = __ldg(lp), l1v = __ldg(lp + 1);
-              vec3 direction;
-              float distance;
-              if (__float_as_uint(l0v.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
-                direction = vscale(mk3(l0v.x, l0v.y, l0v.z), -1.0f);
-                distance = INFINITY;
-              } else {                                               // inc/default_schema.hpp:305-308
-                vec3 P = mk3(l0v.x, l0v.y, l0v.z);
-                direction = vnormalized(vsub(P, hit));
-                distance = vnorm(vsub(P, hit));
-              }
-              sd[k] = vnormalized(direction);
-              md[k] = distance * vnorm(direction);
-              lcol[k] = mk3(l1v.x, l1v.y, l1v.z);
-              valid |= 1u << k;
-            }
-          }
-          casts += __popc(valid);
-          const unsigned occ = any_hit_packet<MODE, SHADOW_PACKET, BRUTE>(sv, nodes, prims, hit, sd, md, valid);
-#pragma unroll
-          for (int k = 0; k < SHADOW_PACKET; k++) {
-            if ((valid & ~occ) & (1u << k)) {        // shadow_fac = 0 < 1
-              const vec3 nd = sd[k];
-              float fd = fmaxf(0.0f, vdot(nn, nd));
-              vec3 ld = vmul(diffuse, lcol[k]);
-              vec3 hv = vnormalized(vadd(in_n, nd));
-              float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
-              vec3 ls = vmul(specular, lcol[k]);
-              phong_add(final, ld, fd, ls, fs, 1.0f);
-            }
-          }
-        }
-      } else {
-        for (uint32_t l = 0; l < sv.n_lights; l++) {
-          const float4 *lp = reinterpret_cast<const float4 *>(sv.lights + l);
-          const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
-          vec3 direction;
-          float distance;
-          if (__float_as_uint(l0.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
-            direction = vscale(mk3(l0.x, l0.y, l0.z), -1.0f);
-            distance = INFINITY;
-          } else {                                              // inc/default_schema.hpp:305-308
-            vec3 P = mk3(l0.x, l0.y, l0.z);
-            direction = vnormalized(vsub(P, hit));
-            distance = vnorm(vsub(P, hit));
-          }
-          const vec3 sdir = vnormalized(direction);
-          const float light_dist = distance * vnorm(direction);
-          const vec3 color = mk3(l1.x, l1.y, l1.z);
-          const vec3 nd = sdir;
-          const float shadow_fac = shadow_intensity<MODE, BRUTE, false>(sv, nodes, prims, hit, sdir, light_dist, casts);
-          if (shadow_fac < 1.0f) {
-            float fd = fmaxf(0.0f, vdot(nn, nd));
-            vec3 ld = vmul(diffuse, color);
-            vec3 hv = vnormalized(vadd(in_n, nd));
-            float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
-            vec3 ls = vmul(specular, color);
-            phong_add(final, ld, fd, ls, fs, 1 - shadow_fac);
-          }
-        }
-      }
+      const vec3 final = phong_record<MODE, BRUTE, OPAQUE>(sv, nodes, prims, hit, normal, in_dir, mat, casts);
       if (level_color) {   // one hit per pixel and level: plain store into this level's partial image
         float *lp = level_color + 3 * (size_t)(pix - px_base);
         lp[0] = weight * final.x; lp[1] = weight * final.y; lp[2] = weight * final.z;
@@ -922,6 +930,134 @@ __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(co
 }
 
 // -------------------------------------------------------------------------------------------------
+// the pixel kernel: one thread per pixel walks its whole path — for tiny scenes and tiny frames
+// -------------------------------------------------------------------------------------------------
+// The wavefront exists to keep 32 lanes busy on deep BVHs.  A scene of a handful of analytic primitives (sphere_plane.json:
+// three spheres and a plane) or a frame of a few hundred pixels (triangle.json is 20 x 20) has nothing to regroup: queue
+// records, a launch per level and the phase barriers are pure overhead there (the reference's own kernel, one launch, beat
+// the round-1 wavefront on triangle.json: 11.5 us against 33 us).  This kernel keeps the reference's shape — a thread per
+// pixel — without its cost: the recursion of ray_color (inc/shading.hpp:116-154) is a loop with an explicit stack of at
+// most one deferred child per level, the primary ray is cast once (the reference casts it twice, inc/kernel.hpp:52 and
+// inc/shading.hpp:123), path weights replace the nested blend, and the colour is summed in depth-first order — for
+// non-branching scenes exactly the level order of the wavefront's ordered sum.  Counters arrive in mapped host memory and
+// are cleared by the last block, like in the frame kernel: the frame is ONE launch, no memset, no copy.
+template <bool BRUTE, bool OPAQUE>
+__global__ void __launch_bounds__(256, 4) pixel_kernel(const __grid_constant__ PixelArgs a) {
+  const SceneView &sv = a.sv;
+  const float4 *nodes = reinterpret_cast<const float4 *>(sv.nodes), *prims = reinterpret_cast<const float4 *>(sv.prims);
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t gx = 0, gy = 0, pix = 0;
+  const bool active = i < a.n_px && work_to_pixel(a.tm, a.px_base + i, gx, gy, pix);
+  TraceAcc acc;
+  trace_acc_reset(acc);
+  unsigned casts = 0;
+  if (active) {
+    struct Pending { vec3 o, d; float w; uint32_t level; } stack[16];
+    int sp = 0;
+    vec3 o, d;
+    camera_ray(sv.cam, gx, gy, o, d);
+    float w = 1.0f;
+    uint32_t level = 0;
+    float r = 0.f, g = 0.f, b = 0.f;
+    const size_t gi = a.out.row_major ? (size_t)gy * a.tm.width + gx : (size_t)pix;
+    for (;;) {
+      Hit h;
+      closest_hit<0, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
+      const bool hit = h.kind >= 0;
+      vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
+      if (hit) hit_surface<0>(sv, prims, h, o, d, point, nrm);
+      if (level == 0) {   // G-buffer, inc/kernel.hpp:52-56
+        a.out.depth[gi] = h.t;
+        a.out.normal[3 * gi] = nrm.x; a.out.normal[3 * gi + 1] = nrm.y; a.out.normal[3 * gi + 2] = nrm.z;
+        a.out.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
+        if (hit && isfinite(h.t)) acc.max_depth = h.t;
+      }
+      bool next = false;
+      if (hit) {
+        const uint32_t mat = __ldg(sv.obj_material + h.obj);
+        const float4 m1 = __ldg(reinterpret_cast<const float4 *>(sv.materials + mat) + 1);
+        const float reflect = m1.x, transp = m1.z;
+        // inc/shading.hpp:126-149
+        const bool deeper = level < a.bounces;
+        const bool do_refl = deeper && (double)reflect >= 1e-6, do_trans = deeper && (double)transp >= 1e-6;
+        const float w_own = do_trans ? w * (1.0f - transp) : w;
+        const vec3 final = phong_record<0, BRUTE, OPAQUE>(sv, nodes, prims, point, nrm, d, mat, casts);
+        acc.n_shaded++;
+        // product and sum rounded separately, like the wavefront's level image + ordered sum
+        r = __fadd_rn(r, __fmul_rn(w_own, final.x)); g = __fadd_rn(g, __fmul_rn(w_own, final.y)); b = __fadd_rn(b, __fmul_rn(w_own, final.z));
+        const vec3 origin = vadd(o, vscale(d, h.t));   // incoming->start + distance * incoming->dir
+        if (do_trans) {
+          acc.n_trans++;
+          if (do_refl) { stack[sp].o = origin; stack[sp].d = d; stack[sp].w = w * transp; stack[sp].level = level + 1; sp++; }
+          else { o = origin; w = w * transp; level++; next = true; }
+        }
+        if (do_refl) {
+          acc.n_refl++;
+          const vec3 nd = vnormalized(d), nn = vnormalized(nrm);
+          d = vreflect(nd, nn);
+          o = origin; w = w_own * reflect; level++; next = true;
+        }
+      }
+      if (!next) {
+        if (sp == 0) break;
+        sp--;
+        o = stack[sp].o; d = stack[sp].d; w = stack[sp].w; level = stack[sp].level;
+      }
+    }
+    float *cp = a.out.color + 3 * gi;
+    cp[0] = r; cp[1] = g; cp[2] = b;
+  }
+  // ---- tallies: warp -> block -> frame statistics; the last block publishes them and clears the counters ----
+  __shared__ unsigned long long s_t[4];
+  __shared__ unsigned s_md, s_last;
+  if (threadIdx.x == 0) { s_t[0] = s_t[1] = s_t[2] = s_t[3] = 0ull; s_md = 0u; }
+  __syncthreads();
+  {
+    unsigned long long c = casts;
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      acc.n_refl += __shfl_xor_sync(CTB_FULL, acc.n_refl, sft);
+      acc.n_trans += __shfl_xor_sync(CTB_FULL, acc.n_trans, sft);
+      acc.n_shaded += __shfl_xor_sync(CTB_FULL, acc.n_shaded, sft);
+      acc.max_depth = fmaxf(acc.max_depth, __shfl_xor_sync(CTB_FULL, acc.max_depth, sft));
+      c += __shfl_xor_sync(CTB_FULL, c, sft);
+    }
+    if (lane == 0) {
+      if (acc.n_refl) atomicAdd(&s_t[0], (unsigned long long)acc.n_refl);
+      if (acc.n_trans) atomicAdd(&s_t[1], (unsigned long long)acc.n_trans);
+      if (acc.n_shaded) atomicAdd(&s_t[2], (unsigned long long)acc.n_shaded);
+      if (c) atomicAdd(&s_t[3], c);
+      if (acc.max_depth > 0.f) atomicMax(&s_md, __float_as_uint(acc.max_depth));
+    }
+  }
+  __syncthreads();
+  FrameCounters *ctr = a.ctr;
+  if (threadIdx.x == 0) {
+    if (s_t[0]) atomicAdd(&ctr->st.rays_reflect, s_t[0]);
+    if (s_t[1]) atomicAdd(&ctr->st.rays_transmit, s_t[1]);
+    if (s_t[2]) atomicAdd(&ctr->st.shade_records, s_t[2]);
+    if (s_t[3]) atomicAdd(&ctr->st.shadow_casts, s_t[3]);
+    if (s_md) atomicMax(&ctr->st.max_depth_bits, s_md);
+    __threadfence();
+    s_last = atomicAdd(&ctr->finished.v, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    unsigned *src = reinterpret_cast<unsigned *>(ctr);
+    constexpr unsigned S0 = offsetof(FrameCounters, st) / 4, SN = sizeof(FrameStats) / 4;
+    volatile unsigned *dst = reinterpret_cast<volatile unsigned *>(a.host_stats);
+    if (threadIdx.x < SN) {
+      const unsigned v = __ldcg(src + S0 + threadIdx.x);
+      if (dst) dst[threadIdx.x] = v;
+      src[S0 + threadIdx.x] = 0u;
+    }
+    if (threadIdx.x == 0) ctr->finished.v = 0u;
+    __threadfence_system();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
 #ifdef CTB_PHASE_DEBUG
@@ -1030,6 +1166,14 @@ void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, con
   int grid = clamp_grid(cfg.grid_shade, work_bound);
   pick_shade(cfg.mode, sv.brute_force != 0, sv.all_opaque != 0)<<<grid, TRACE_THREADS, cfg.smem_bytes, st>>>(
       sv, level, shade, shade_cap, ctr, fb, atomic_accumulate ? 1 : 0, level_color, px_base);
+}
+
+cudaError_t launch_pixel(const PixelArgs &args, cudaStream_t st) {
+  if (!args.n_px) return cudaSuccess;
+  const bool brute = args.sv.brute_force != 0, opaque = args.sv.all_opaque != 0;
+  void (*f)(const PixelArgs) = brute ? (opaque ? pixel_kernel<true, true> : pixel_kernel<true, false>) : (opaque ? pixel_kernel<false, true> : pixel_kernel<false, false>);
+  f<<<(args.n_px + 255u) / 256u, 256, 0, st>>>(args);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_frame(const LaunchCfg &cfg, const FrameArgs &args, uint32_t work_bound, cudaStream_t st) {

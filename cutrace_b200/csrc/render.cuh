@@ -79,6 +79,18 @@ struct FrameArgs {
   int export_with_color;         // 1: the G-buffer travels with the colour at the end, 0: as filler work under the bounce levels
 };
 
+// the per-pixel kernel (render.cu: pixel_kernel)
+struct PixelArgs {
+  SceneView sv;
+  TileMap tm;
+  uint32_t bounces;
+  uint32_t px_base, n_px;
+  FrameCounters *ctr;        // zero on entry; the statistics are published to host_stats and cleared again on exit
+  FrameStats *host_stats;    // mapped pinned host memory (device pointer), may be NULL
+  FrameTargets out;          // where the frame lives (any layout FrameTargets describes)
+};
+cudaError_t launch_pixel(const PixelArgs &args, cudaStream_t st);
+
 // fills cfg for a scene on the current device; smem budget from the device attributes
 cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg);
 

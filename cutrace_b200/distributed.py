@@ -64,6 +64,86 @@ def untile_host(parts, width, height, channels):
     return out
 
 
+class SharedHostFrame:
+    """One row-major frame block (depth n | normal 3n | colour 3n | hit id n, 32 bytes per pixel) in host memory that every
+    rank process of one box maps and registers with CUDA (cutrace_host_register): the ranks' kernels store their tiles
+    straight into it over their own PCIe links (cutrace_frame_attach), so a multi-GPU frame reaches the host without being
+    funnelled through GPU 0.  Rank 0 creates an anonymous memory file (memfd; /dev/shm as a fallback), the other ranks open it
+    through /proc/<pid>/fd/<n> — torch.distributed only carries the path."""
+
+    def __init__(self, width, height, rank, world, device=None, register=True):
+        import ctypes as C
+        import mmap
+        import os
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.width, self.height, self.rank = width, height, rank
+        n = width * height
+        self.n = n
+        self.nbytes = 32 * n
+        self._unlink = None
+        path = [None]
+        if rank == 0:
+            try:
+                self._fd = os.memfd_create("cutrace_b200_frame")
+                os.ftruncate(self._fd, self.nbytes)
+                path[0] = f"/proc/{os.getpid()}/fd/{self._fd}"
+            except (AttributeError, OSError):
+                import tempfile
+
+                fd, name = tempfile.mkstemp(prefix="cutrace_b200_frame_", dir="/dev/shm")
+                os.ftruncate(fd, self.nbytes)
+                self._fd, path[0], self._unlink = fd, name, name
+        if world > 1:
+            dist.broadcast_object_list(path, src=0, **({"device": torch.device("cuda", device)} if device is not None else {}))
+        if rank != 0:
+            self._fd = os.open(path[0], os.O_RDWR)
+        self._map = mmap.mmap(self._fd, self.nbytes)
+        self._buf = (C.c_char * self.nbytes).from_buffer(self._map)
+        self.ptr = C.addressof(self._buf)
+        self._registered = False
+        if register:   # (register=False: host-side logic only, for the CPU tests)
+            self._lib = _lib.load()
+            torch.cuda.set_device(device)
+            _lib.check(self._lib.cutrace_host_register(self.ptr, self.nbytes))
+            self._registered = True
+        base = np.frombuffer(self._map, dtype=np.float32)
+        self.depth = base[:n]
+        self.normal = base[n:4 * n].reshape(n, 3)
+        self.color = base[4 * n:7 * n].reshape(n, 3)
+        self.hit_id = base[7 * n:8 * n].view(np.uint32)
+        if world > 1:
+            dist.barrier()   # every rank has the file open before rank 0 may drop the name
+
+    def as_dict(self):
+        return dict(depth=self.depth, normal=self.normal, color=self.color, hit_id=self.hit_id)
+
+    def close(self):
+        import os
+
+        if getattr(self, "_registered", False):
+            self._lib.cutrace_host_unregister(self.ptr)
+            self._registered = False
+        for k in ("depth", "normal", "color", "hit_id", "_buf"):
+            self.__dict__.pop(k, None)
+        try:
+            self._map.close()
+        except (BufferError, AttributeError):
+            pass   # numpy views still alive somewhere: the mapping goes away with them
+        if getattr(self, "_fd", None) is not None:
+            os.close(self._fd)
+            self._fd = None
+        if self._unlink and self.rank == 0:
+            try:
+                os.unlink(self._unlink)
+            except OSError:
+                pass
+
+
 class _DevArray:
     """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it (no copy)."""
 
@@ -75,6 +155,8 @@ class TileShardedRenderer:
     """Rank-local renderer of a tile-sharded frame.  Requires an initialised torch.distributed process group when
     world > 1.
 
+    exchange="host": every rank's kernels store their tiles into a SharedHostFrame over their own PCIe link (the
+    multi-GPU download path: nothing is funnelled through GPU 0).
     Default exchange ("peer"): rank 0 exports its row-major frame through CUDA IPC, the other ranks import it and
     their kernels store the G-buffer / final colour of their tiles straight into rank 0's HBM over NVLink — the
     transfer is fused into the producing kernels, and the only collective left is the 1-float max-depth all-reduce,
@@ -82,7 +164,7 @@ class TileShardedRenderer:
     to rank 0 followed by the device un-tile kernel.
     """
 
-    def __init__(self, scene, rank, world, device, exchange="peer", **kw):
+    def __init__(self, scene, rank, world, device, exchange="peer", host_frame=None, **kw):
         import torch
 
         self.torch = torch
@@ -93,6 +175,13 @@ class TileShardedRenderer:
         self.exchange = "none" if world == 1 else exchange
         n = scene.width * scene.height
         as_t = lambda p, cnt, ts: torch.as_tensor(_DevArray(p, cnt, ts), device=self.device)  # noqa: E731
+        if self.exchange == "host":
+            # every rank (rank 0 included) stores its tiles into the shared pinned host frame; nothing to set up per ctx
+            # beyond the attach, so a ctx per frame costs no IPC round trip
+            if host_frame is None:
+                raise ValueError('exchange="host" needs a SharedHostFrame')
+            self.host_frame = host_frame
+            self.r.frame_attach(host_frame.ptr, host_frame.width, host_frame.height)
         if self.exchange == "peer":
             self.exchange = "peer" if self._setup_peer() else "gather"
         if self.exchange == "gather":
@@ -152,7 +241,7 @@ class TileShardedRenderer:
         torch = self.torch
         if self.world == 1:
             return
-        if self.exchange == "peer":
+        if self.exchange in ("peer", "host"):
             dist.barrier()
             return
         pairs = [(self.depth, getattr(self, "g_depth", None), 1), (self.normal, getattr(self, "g_normal", None), 3),
@@ -174,6 +263,14 @@ class TileShardedRenderer:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def release(self):
+        """Collective: the owner of the frame has finished reading it.  In the peer / host exchanges the other ranks' kernels
+        store straight into the frame, so the next render() must not start before its reader is done."""
+        import torch.distributed as dist
+
+        if self.world > 1 and self.exchange in ("peer", "host"):
+            dist.barrier()
 
     def close(self):
         self.r.close()

@@ -132,6 +132,9 @@ typedef struct cutrace_scene_desc {
  * thirteen short launches per frame cost 5 % more; one launch per level and kind, replayed as a CUDA graph, otherwise. */
 #define CUTRACE_FLAG_FRAME_KERNEL 16u  /* force the persistent frame kernel */
 #define CUTRACE_FLAG_LAUNCHES 32u      /* force one launch per level and kind */
+#define CUTRACE_FLAG_PIXEL_KERNEL 64u  /* force the per-pixel kernel (one thread walks a pixel's whole path).  Default: used for
+                                          frames of at most 2^14 pixels and for scenes of at most 16 primitives and 16 planes,
+                                          where the wavefront has nothing to regroup and its queues and launches are overhead */
 
 typedef struct cutrace_opts {
   float fudge;          /* min hit distance; the reference passes 1e-3 (main.cu:30)            */
@@ -169,7 +172,9 @@ typedef struct cutrace_stats {
   uint32_t smem_nodes;      /* BVH nodes staged in shared memory                               */
   float trace_ms;           /* device time in closest-hit kernels (sum over bounce levels)     */
   float shade_ms;           /* device time in shadow+phong kernels                             */
-  uint32_t reserved[6];
+  uint32_t scheduler;       /* how the last frame ran: 0 = one launch per level and kind, 1 = the persistent frame kernel,
+                               2 = the per-pixel kernel */
+  uint32_t reserved[5];
 } cutrace_stats;
 
 typedef struct cutrace_ctx cutrace_ctx;

@@ -82,3 +82,51 @@ def test_tile_ownership_is_a_partition():
         n = ((w + TILE - 1) // TILE) * ((h + TILE - 1) // TILE)
         assert allt == list(range(n))
         assert all(len(tiles_of_rank(w, h, r, world)) <= local_tile_count(w, h, world) for r in range(world))
+
+
+def _host_frame_worker(rank, world, port, w, h, out_path):
+    """exchange="host" without a GPU: every rank writes the oracle's pixels of ITS tiles straight into the shared host frame
+    (what the kernels do over PCIe after cutrace_frame_attach), a barrier, rank 0 reads the assembled frame."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    from cutrace_b200.distributed import SharedHostFrame, tiles_of_rank
+    from cutrace_b200.scene import TILE, FlatScene
+    from oracle import pyoracle as po
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    s = FlatScene.load(os.path.join(ROOT, "tests", "golden", "scenes", "sphere_plane.npz")).with_resolution(w, h)
+    frame = SharedHostFrame(w, h, rank, world, device=None, register=False)
+    tx = (w + TILE - 1) // TILE
+    px = []
+    for gt in tiles_of_rank(w, h, rank, world):
+        ty, txi = divmod(gt, tx)
+        for py in range(TILE):
+            for pxx in range(TILE):
+                x, y = txi * TILE + pxx, ty * TILE + py
+                if x < w and y < h:
+                    px.append(y * w + x)
+    px = np.asarray(px, np.uint64)
+    o = po.oracle_render(s, px=px, threads=2)
+    idx = px.astype(np.int64)
+    frame.depth[idx] = o["depth"]; frame.normal[idx] = o["normal"]; frame.color[idx] = o["color"]; frame.hit_id[idx] = o["hit_id"]
+    dist.barrier()
+    if rank == 0:
+        np.savez(out_path, **{k: np.array(v) for k, v in frame.as_dict().items()})
+    dist.barrier()
+    frame.close()
+    dist.destroy_process_group()
+
+
+def test_world2_shared_host_frame(tmp_path, oracle):
+    import torch.multiprocessing as mp
+
+    w, h = 70, 45
+    out = str(tmp_path / "hostframe.npz")
+    port = _free_port()
+    mp.spawn(_host_frame_worker, args=(2, port, w, h, out), nprocs=2, join=True)
+    got = np.load(out)
+    ref = oracle.oracle_render(load_golden_scene("sphere_plane").with_resolution(w, h))
+    for k in ("depth", "normal", "color", "hit_id"):
+        assert np.array_equal(got[k].reshape(-1).view(np.uint32), ref[k].reshape(-1).view(np.uint32)), k

@@ -43,9 +43,14 @@ def gpu_render(ct, scene, **kw):
 
 
 # ---- (1) reference goldens -------------------------------------------------------------------------
+SCHEDULERS = ["launches", "frame", "pixel"]   # CUTRACE_SCHEDULER: per-level launches, the persistent frame kernel, the per-pixel kernel
+
+
+@pytest.mark.parametrize("sched", SCHEDULERS)
 @pytest.mark.parametrize("name", list(GOLDEN_CASES))
 @pytest.mark.parametrize("mode", ["smem", "global", "brute"])
-def test_reference_goldens(ct, name, mode):
+def test_reference_goldens(ct, name, mode, sched, monkeypatch):
+    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)
     g = dict(np.load(os.path.join(GOLDEN, GOLDEN_CASES[name])))
     s = load_golden_scene(name).with_resolution(int(g["width"]), int(g["height"]))
     flags = {"smem": 0, "global": ct.FLAG_NO_SMEM_TOP, "brute": ct.FLAG_BRUTE_FORCE}[mode]
@@ -56,11 +61,13 @@ def test_reference_goldens(ct, name, mode):
 
 
 # ---- (2) C oracle on seeded inputs -------------------------------------------------------------------
+@pytest.mark.parametrize("sched", SCHEDULERS)
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 @pytest.mark.parametrize("translucent", [False, True])
-def test_random_soup_vs_oracle(ct, oracle, seed, translucent):
+def test_random_soup_vs_oracle(ct, oracle, seed, translucent, sched, monkeypatch):
     from cutrace_b200 import synth
 
+    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)
     s = synth.random_soup(n_tri=300, n_sph=6, n_planes=2, n_lights=3, width=128, height=96, seed=seed, translucent=translucent,
                           duplicates=True)
     out, st = gpu_render(ct, s)
@@ -87,9 +94,11 @@ def _empty_like(s, **kw):
     return e
 
 
-def test_edge_cases_vs_oracle(ct, oracle):
+@pytest.mark.parametrize("sched", SCHEDULERS)
+def test_edge_cases_vs_oracle(ct, oracle, sched, monkeypatch):
     from cutrace_b200 import synth
 
+    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)
     base = synth.random_soup(n_tri=8, n_sph=1, n_planes=1, n_lights=2, width=97, height=61, seed=5)
     z3, zu = np.zeros((0, 3), np.float32), np.zeros(0, np.uint32)
     cases = {
@@ -125,9 +134,10 @@ def test_edge_cases_vs_oracle(ct, oracle):
             assert st["max_depth"] == 0.0
 
 
-def test_bounce_budget_and_fudge(ct, oracle):
+@pytest.mark.parametrize("sched", SCHEDULERS)
+def test_bounce_budget_and_fudge(ct, oracle, sched, monkeypatch):
     """bounces = 0..3 and a different fudge go through the same code as the reference's template arguments."""
-    s = load_golden_scene("sphere_plane").with_resolution(96, 54)
+    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)    s = load_golden_scene("sphere_plane").with_resolution(96, 54)
     for b in (0, 1, 3):
         out, _ = gpu_render(ct, s, bounces=b)
         ref = oracle.oracle_render(s, bounces=b)
@@ -141,6 +151,17 @@ def test_bounce_budget_and_fudge(ct, oracle):
 @pytest.mark.parametrize("name,res", [("triangle", None), ("sphere_plane", (1920, 1080)), ("mirror", (1920, 1080)), ("bunny", (480, 270)),
                                       ("bunny", (3840, 2160))])
 def test_vs_reference_cuda_kernel(ct, oracle, name, res):
+    _vs_reference_cuda_kernel(ct, oracle, name, res)
+
+
+@pytest.mark.parametrize("sched", ["frame", "pixel"])
+@pytest.mark.parametrize("name,res", [("triangle", None), ("sphere_plane", (1920, 1080)), ("mirror", (640, 360)), ("bunny", (480, 270))])
+def test_vs_reference_cuda_kernel_other_schedulers(ct, oracle, name, res, sched, monkeypatch):
+    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)
+    _vs_reference_cuda_kernel(ct, oracle, name, res)
+
+
+def _vs_reference_cuda_kernel(ct, oracle, name, res):
     """BASELINE configs 1-4 at their full resolutions, FULL frames, against the reference's own kernel launched like
     /root/reference/inc/kernel.hpp:103-106 (bunny.json at 4K costs the reference ~0.9 s)."""
     if not oracle.have_ref_gpu():
@@ -194,6 +215,9 @@ def test_config5_full_size_subset_vs_reference_cuda_kernel(ct, oracle):
     assert m["id_mismatch"] == 0, m
     assert np.all(out["hit_id"] != 0xFFFFFFFF)        # closed hall: every primary ray hits
     assert st["rays_primary"] == 7680 * 4320 and st["rays_shadow"] % 3 == 0
+    import bench
+
+    assert st["rays_total"] == bench.RAYS_PER_FRAME["synthetic10m"]
 
 
 def test_grid_scene_full_frame_vs_reference_kernel(ct, oracle):
@@ -307,6 +331,18 @@ def test_closed_mirror_box_at_15_bounces_does_not_overflow_the_queues(ct, oracle
     out, _ = gpu_render(ct, small, bounces=15)
     ref = oracle.oracle_render(small, bounces=15)
     assert_parity(compare(out, ref, small.width, small.height), "mirror box, 15 bounces", oracle_is_host=True, chaotic=True)
+
+
+def test_bench_ray_constants(ct):
+    """bench.py's reference arm takes the unique-ray numerator from constants (it must not run this repo's renderer): they are what
+    the renderer counts on the same frames."""
+    import bench
+
+    for name in ("triangle", "spheres1080", "mirror1080", "bunny4k"):
+        scene, wl = bench.load_workload(name)
+        with ct.Renderer(scene) as r:
+            st = r.render()
+        assert st["rays_total"] == bench.RAYS_PER_FRAME[name], (name, st["rays_total"])
 
 
 # ---- size-independent properties at full size ----------------------------------------------------------
@@ -631,9 +667,20 @@ def test_frame_kernel_equals_the_multi_launch_paths(ct, monkeypatch):
             assert m["color_bad_frac"] <= 1e-4 and np.median(np.abs(a["color"] - b["color"])) == 0.0, (name, m)
         for k in ("rays_total", "rays_shadow", "rays_reflect", "shadow_casts", "max_depth"):
             assert sa[k] == sb[k], (name, k)
-        # the default picks one of the two
+        # the per-pixel kernel: same G-buffer and counters, colours to the last bits
+        with ct.Renderer(s, flags=ct.FLAG_PIXEL_KERNEL) as r:
+            sp = r.render()
+            p = r.download()
+            r.render()
+            assert_same_frame(p, r.download(), name)          # bit-reproducible
+        assert sp["kernel_launches"] == 1 and sp["scheduler"] == 2
+        m = compare(p, a, s.width, s.height)
+        assert m["id_mismatch"] == 0 and m["depth_max_rel"] == 0.0 and m["normal_max_abs"] == 0.0 and m["color_bad_frac"] <= 1e-4, (name, m)
+        for k in ("rays_total", "rays_shadow", "rays_reflect", "shadow_casts", "max_depth"):
+            assert sa[k] == sp[k], (name, k)
+        # the default picks one of the three
         with ct.Renderer(s) as r:
-            assert r.render()["kernel_launches"] in (1, 2 * levels + 1)
+            assert r.render()["scheduler"] in (0, 1, 2)
 
 
 def test_direct_first_frame_and_graph_replays_are_bit_identical(ct, monkeypatch):

@@ -37,10 +37,17 @@ def test_random_soup_is_well_formed(oracle):
 def test_bench_helpers():
     import bench
 
-    assert bench.algorithmic_bytes_per_ray(1005) == 64 + 64 * 10 + 48 == 752          # SURVEY.md §8d, bunny.json
-    assert bench.algorithmic_bytes_per_ray(10_112_406) == 64 + 64 * 24 + 48 == 1648   # 10 M-triangle scene
+    assert bench.survey_bytes_per_ray(1005) == 64 + 64 * 10 + 48 == 752          # SURVEY.md §8d, bunny.json
+    assert bench.survey_bytes_per_ray(10_112_406) == 64 + 64 * 24 + 48 == 1648   # 10 M-triangle scene
     scene, wl = bench.load_workload("bunny4k")
     assert (scene.width, scene.height) == (3840, 2160) and bench.n_primitives(scene) == 1005
+    # both arms print the same `config` object; the unique-ray numerator is a constant of (scene, resolution)
+    cfg = bench.config_of(scene, wl)
+    assert cfg["rays_per_frame"] == bench.RAYS_PER_FRAME["bunny4k"] == 248_825_266 and set(cfg) == {"workload", "rays_per_frame", "primitives", "bounces", "l2"}
+    # compulsory DRAM bytes of a bunny.json frame: ~9 GB, i.e. well under the HBM roofline at 10 ms/frame
+    n_px = 3840 * 2160
+    comp = bench.compulsory_bytes_per_frame(n_px, 248_825_266, 4 * 6 * n_px, 4)
+    assert 8e9 < comp < 11e9
     cs = bench.ClockSampler(0, enabled=False)
     cs.lines = ["1965, 1965, Not Active, Not Active, Not Active, Active", "1950, 1965, Not Active, Not Active, Not Active, Not Active"]
     s = cs.summary()
