@@ -185,14 +185,16 @@ __device__ __forceinline__ bool work_to_pixel(const TileMap &tm, uint32_t i, uin
   return x < tm.width && y < tm.height;
 }
 
-// cam::get_ray, inc/default_schema.hpp:376-386
+// cam::get_ray, inc/default_schema.hpp:376-386 (roundings pinned, see common.cuh)
 __device__ __forceinline__ void camera_ray(const Camera &c, uint32_t x, uint32_t y, vec3 &o, vec3 &d) {
-  float aspect = (float)c.w / (float)c.h;
-  vec3 x_v = vscale(c.right, (((float)x / (float)c.w) - 0.5f) * aspect);
-  vec3 y_v = vscale(c.up, 0.5f - ((float)y / (float)c.h));
-  vec3 z_v = c.forward;
+  const float aspect = CTB_DIV((float)c.w, (float)c.h);
+  const float sx = CTB_MUL(CTB_SUB(CTB_DIV((float)x, (float)c.w), 0.5f), aspect);   // ((x / w) - 0.5) * aspect
+  const float sy = CTB_SUB(0.5f, CTB_DIV((float)y, (float)c.h));                   // 0.5 - y / h
+  // x_v + y_v + z_v with x_v = sx * right, y_v = sy * up, z_v = forward
+  const vec3 v = mk3(CTB_ADD(CTB_FMA(sx, c.right.x, CTB_MUL(sy, c.up.x)), c.forward.x), CTB_ADD(CTB_FMA(sx, c.right.y, CTB_MUL(sy, c.up.y)), c.forward.y),
+                     CTB_ADD(CTB_FMA(sx, c.right.z, CTB_MUL(sy, c.up.z)), c.forward.z));
   o = c.pos;
-  d = vnormalized(vadd(vadd(x_v, y_v), z_v));
+  d = vnormalized(v);
 }
 
 // ---- queue slots --------------------------------------------------------------------------------------------------------
@@ -335,7 +337,7 @@ __device__ __forceinline__ void trace_chunk(const SceneView &sv, const float4 *n
     if (m_r | m_t) {
       const unsigned nr = __popc(m_r), nt = __popc(m_t);
       const Emit e = reserve_slots(acc.rq, nr + nt, lane, slot_block, &ctr->n_rays[level + 1].v, io.ray_cap, io.rays_out, ctr);
-      const vec3 origin = vadd(o, vscale(d, h.t));   // incoming->start + distance * incoming->dir
+      const vec3 origin = vmad(o, d, h.t);   // incoming->start + distance * incoming->dir
       if (do_refl) {
         const unsigned rank = __popc(m_r & lt_mask);
         if (emit_ok(e, rank)) {
@@ -986,7 +988,7 @@ __global__ void __launch_bounds__(256, 4) pixel_kernel(const __grid_constant__ P
         acc.n_shaded++;
         // product and sum rounded separately, like the wavefront's level image + ordered sum
         r = __fadd_rn(r, __fmul_rn(w_own, final.x)); g = __fadd_rn(g, __fmul_rn(w_own, final.y)); b = __fadd_rn(b, __fmul_rn(w_own, final.z));
-        const vec3 origin = vadd(o, vscale(d, h.t));   // incoming->start + distance * incoming->dir
+        const vec3 origin = vmad(o, d, h.t);   // incoming->start + distance * incoming->dir
         if (do_trans) {
           acc.n_trans++;
           if (do_refl) { stack[sp].o = origin; stack[sp].d = d; stack[sp].w = w * transp; stack[sp].level = level + 1; sp++; }

@@ -62,12 +62,12 @@ __device__ __forceinline__ bool tri_test(vec3 p1, vec3 p2, vec3 p3, vec3 o, vec3
   const float tiny = 1e-30f;
   bool neg_b = (__float_as_uint(nb) ^ __float_as_uint(alpha)) >> 31;   // quotient negative (or -0)
   bool neg_g = (__float_as_uint(ng) ^ __float_as_uint(alpha)) >> 31;
-  float aa = fabsf(alpha);
-  if ((neg_b && fabsf(nb) > tiny * aa) || (neg_g && fabsf(ng) > tiny * aa)) return false;
-  float beta = nb / alpha;
-  float gamma = ng / alpha;
-  if (!(beta >= 0 && gamma >= 0 && beta + gamma <= 1)) return false;
-  float t0 = det3(a, b, d) / alpha;
+  float aa = CTB_MUL(tiny, fabsf(alpha));
+  if ((neg_b && fabsf(nb) > aa) || (neg_g && fabsf(ng) > aa)) return false;
+  float beta = CTB_DIV(nb, alpha);
+  float gamma = CTB_DIV(ng, alpha);
+  if (!(beta >= 0 && gamma >= 0 && CTB_ADD(beta, gamma) <= 1)) return false;
+  float t0 = CTB_DIV(det3_t(a, b, d), alpha);
   t = t0;
   // `min_t <= t0` is the primitive's own test, `t0 > min_t` is ray_cast's `dist > min_dist`
   return isfinite(t0) && min_t <= t0 && t0 > min_t;
@@ -78,8 +78,9 @@ __device__ __noinline__ bool sphere_test(float cx, float cy, float cz, float R, 
   vec3 c = mk3(cx, cy, cz);
   vec3 d = vnormalized(dir);
   float dec = -vdot(d, vsub(e, c));
-  float sub = dec * dec - vdot(d, d) * (vdot(vsub(e, c), vsub(e, c)) - R * R);
-  float t0 = (dec - sqrtf(sub)) / vdot(d, d), t1 = (dec + sqrtf(sub)) / vdot(d, d);
+  // dec^2 - (d.d) * ((e-c).(e-c) - R^2), inc/default_schema.hpp:231
+  float sub = CTB_FMA(dec, dec, -CTB_MUL(vdot(d, d), CTB_FMA(-R, R, vdot(vsub(e, c), vsub(e, c)))));
+  float t0 = CTB_DIV(CTB_SUB(dec, CTB_SQRT(sub)), vdot(d, d)), t1 = CTB_DIV(CTB_ADD(dec, CTB_SQRT(sub)), vdot(d, d));
   bool t0v = isfinite(t0) && min_t <= t0, t1v = isfinite(t1) && min_t <= t1;
   if (!t0v && !t1v) return false;
   float t = (t0v && t1v) ? fminf(t0, t1) : (t0v ? t0 : t1);
@@ -89,7 +90,7 @@ __device__ __noinline__ bool sphere_test(float cx, float cy, float cz, float R, 
 
 // plane::intersect, inc/default_schema.hpp:189-192
 __device__ __forceinline__ bool plane_test(vec3 point, vec3 n, vec3 o, vec3 dir, float min_t, float &t) {
-  float t0 = vdot(vsub(point, o), n) / vdot(dir, n);
+  float t0 = CTB_DIV(vdot(n, vsub(point, o)), vdot(dir, n));
   t = t0;
   return isfinite(t0) && min_t <= t0 && t0 > min_t;
 }
@@ -354,13 +355,13 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
     const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + p);
     const float4 a = __ldg(pp), b = __ldg(pp + 1);
     const vec3 n = mk3(b.x, b.y, b.z);
-    const float num = vdot(vsub(mk3(a.x, a.y, a.z), o), n);
+    const float num = vdot(n, vsub(mk3(a.x, a.y, a.z), o));
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const float den = vdot(d[k], n);
       // t0 > 1e-3 needs num and den of equal sign; then the exact IEEE quotient decides (plane::intersect)
-      if (!((__float_as_uint(num) ^ __float_as_uint(den)) >> 31) && fabsf(num) < max_t[k] * fabsf(den) * 1.0001f) {
-        const float t0 = num / den;
+      if (!((__float_as_uint(num) ^ __float_as_uint(den)) >> 31) && fabsf(num) < CTB_MUL(CTB_MUL(max_t[k], fabsf(den)), 1.0001f)) {
+        const float t0 = CTB_DIV(num, den);
         if (isfinite(t0) && min_t <= t0 && t0 > min_t && t0 < max_t[k]) occ |= (act & (1u << k));
       }
     }
@@ -437,20 +438,20 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
             alpha[k] = det3(a, b, d[k]);
             nb[k] = det3(dd, b, d[k]);
             ng[k] = det3(a, dd, d[k]);
-            const float aa = fabsf(alpha[k]) * 1e-30f;
+            const float aa = CTB_MUL(fabsf(alpha[k]), 1e-30f);
             const bool neg_b = (__float_as_uint(nb[k]) ^ __float_as_uint(alpha[k])) >> 31;
             const bool neg_g = (__float_as_uint(ng[k]) ^ __float_as_uint(alpha[k])) >> 31;
             if (!((neg_b && fabsf(nb[k]) > aa) || (neg_g && fabsf(ng[k]) > aa))) cand |= 1u << k;
           }
           cand &= act;
           if (cand) {   // exact path of triangle::intersect for the few rays that pass the sign test
-            const float nt = det3(a, b, dd);
+            const float nt = det3_t(a, b, dd);
 #pragma unroll
             for (int k = 0; k < K; k++) {
               if (cand & (1u << k)) {
-                const float beta = nb[k] / alpha[k], gamma = ng[k] / alpha[k];
-                if (beta >= 0 && gamma >= 0 && beta + gamma <= 1) {
-                  const float t0 = nt / alpha[k];
+                const float beta = CTB_DIV(nb[k], alpha[k]), gamma = CTB_DIV(ng[k], alpha[k]);
+                if (beta >= 0 && gamma >= 0 && CTB_ADD(beta, gamma) <= 1) {
+                  const float t0 = CTB_DIV(nt, alpha[k]);
                   if (isfinite(t0) && min_t <= t0 && t0 > min_t && t0 < max_t[k] &&
                       mesh_gate(sv.obj_bounds, __float_as_uint(q0.w), o, d[k], t0, sv.scene_mag)) { occ |= 1u << k; act &= ~(1u << k); }
                 }
@@ -479,7 +480,7 @@ __device__ __forceinline__ void hit_surface(const SceneView &sv, const float4 *p
   if (h.kind == CTB_KIND_PLANE) {
     const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + h.ref);
     const float4 b = __ldg(pp + 1);
-    point = vadd(o, vscale(d, h.t));                    // inc/default_schema.hpp:194
+    point = vmad(o, d, h.t);                            // inc/default_schema.hpp:194
     normal = mk3(b.x, b.y, b.z);                        // :195 stored normal, not normalised
     return;
   }
@@ -487,11 +488,11 @@ __device__ __forceinline__ void hit_surface(const SceneView &sv, const float4 *p
   const float4 q0 = ld16<MODE>(pp), q1 = ld16<MODE>(pp + 1), q2 = ld16<MODE>(pp + 2);
   if (h.kind == CTB_KIND_TRI) {
     vec3 p1 = mk3(q0.x, q0.y, q0.z), p2 = mk3(q1.x, q1.y, q1.z), p3 = mk3(q2.x, q2.y, q2.z);
-    point = vadd(o, vscale(d, h.t));                                              // :71
+    point = vmad(o, d, h.t);                                                      // :71
     normal = vscale(vnormalized(vcross(vsub(p2, p3), vsub(p1, p3))), -1.0f);      // :72
   } else {
     vec3 c = mk3(q0.x, q0.y, q0.z);
-    point = vadd(o, vscale(vnormalized(d), h.t));                                 // :245
+    point = vmad(o, vnormalized(d), h.t);                                         // :245
     normal = vnormalized(vsub(point, c));                                         // :246
   }
 }

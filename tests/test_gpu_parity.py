@@ -137,7 +137,8 @@ def test_edge_cases_vs_oracle(ct, oracle, sched, monkeypatch):
 @pytest.mark.parametrize("sched", SCHEDULERS)
 def test_bounce_budget_and_fudge(ct, oracle, sched, monkeypatch):
     """bounces = 0..3 and a different fudge go through the same code as the reference's template arguments."""
-    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)    s = load_golden_scene("sphere_plane").with_resolution(96, 54)
+    monkeypatch.setenv("CUTRACE_SCHEDULER", sched)
+    s = load_golden_scene("sphere_plane").with_resolution(96, 54)
     for b in (0, 1, 3):
         out, _ = gpu_render(ct, s, bounces=b)
         ref = oracle.oracle_render(s, bounces=b)
@@ -340,9 +341,10 @@ def test_bench_ray_constants(ct):
 
     for name in ("triangle", "spheres1080", "mirror1080", "bunny4k"):
         scene, wl = bench.load_workload(name)
-        with ct.Renderer(scene) as r:
-            st = r.render()
-        assert st["rays_total"] == bench.RAYS_PER_FRAME[name], (name, st["rays_total"])
+        for flags in (0, ct.FLAG_LAUNCHES, ct.FLAG_FRAME_KERNEL, ct.FLAG_PIXEL_KERNEL):
+            with ct.Renderer(scene, flags=flags) as r:
+                st = r.render()
+            assert st["rays_total"] == bench.RAYS_PER_FRAME[name], (name, flags, st["rays_total"])
 
 
 # ---- size-independent properties at full size ----------------------------------------------------------

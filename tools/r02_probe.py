@@ -18,7 +18,7 @@ def child(workload, world, frames):
     import cutrace_b200 as ct
 
     scene, wl = bench.load_workload(workload)
-    tag = {"launches": "multi-launch", "frame": "frame-kernel"}[os.environ["CUTRACE_SCHEDULER"]]
+    tag = {"launches": "multi-launch", "frame": "frame-kernel", "pixel": "pixel-kernel"}[os.environ["CUTRACE_SCHEDULER"]]
     with ct.Renderer(scene, tile_rank=0, tile_world=world) as r:
         ms = []
         for _ in range(frames):
@@ -39,9 +39,9 @@ def main():
         for world in (1, 8):
             if wl == "triangle" and world > 1:
                 continue
-            for nf in (False, True):
+            for sched in os.environ.get("PROBE_SCHEDS", "frame,launches,pixel").split(","):
                 env = dict(os.environ)
-                env["CUTRACE_SCHEDULER"] = "launches" if nf else "frame"
+                env["CUTRACE_SCHEDULER"] = sched
                 frames = 5 if wl == "synthetic10m" else 9
                 subprocess.run(["timeout", "300", sys.executable, os.path.abspath(__file__), "--child", wl, str(world), str(frames)], env=env, check=False)
 
