@@ -323,15 +323,22 @@ class Bench:
         tsr = TileShardedRenderer(scene, rank=self.rank, world=self.world, device=self.local_rank, flags=args.flags, stream=self.stream.cuda_stream,
                                   exchange=args.exchange)
 
+        host = {"render": 0.0, "gather": 0.0}
+
         def step():
+            t0 = time.perf_counter()
             st = tsr.render()
+            t1 = time.perf_counter()
             if self.world > 1:
                 tsr.gather()
+            host["render"] += t1 - t0
+            host["gather"] += time.perf_counter() - t1
             return st
 
         for _ in range(warmup):
             st = step()
         self.barrier()
+        host["render"] = host["gather"] = 0.0
         dev_ms = []
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(self.local_rank, enabled=(sampler and self.rank == 0)) as clk:
@@ -346,7 +353,8 @@ class Bench:
         ms_local = ev0.elapsed_time(ev1) / steps
         if args.verbose:
             print(f"[rank {self.rank}] step {ms_local:.3f} ms  render {np.mean(dev_ms):.3f}  rays {st['rays_total']}  px {st['local_pixels']}  "
-                  f"scheduler {st['scheduler']}  phases {' '.join(f'{x:.3f}' for x in tsr.r.phase_ms())}", file=sys.stderr, flush=True)
+                  f"scheduler {st['scheduler']}  host ms/step: render call {host['render'] / steps * 1e3:.3f} gather {host['gather'] / steps * 1e3:.3f}  "
+                  f"phases {' '.join(f'{x:.3f}' for x in tsr.r.phase_ms())}", file=sys.stderr, flush=True)
         ms_step, render_dev_ms = self.reduce([ms_local, float(np.mean(dev_ms))], "max")
         rays, rays_shadow = self.reduce([st["rays_total"], st["rays_shadow"]], "sum")
         launches = int(st["kernel_launches"]) + (1 if self.world > 1 and self.rank == 0 and tsr.exchange == "gather" else 0)

@@ -159,6 +159,7 @@ struct cutrace_ctx {
   // frame
   TileMap tm{};
   uint64_t n_local_px = 0;   // padded: n_local_tiles * CUTRACE_TILE_PIXELS
+  uint64_t local_pixels = 0; // pixels of this ctx that are inside the image
   FrameTargets fb{};                 // tile-major local buffers (sharded ctx without a peer frame: NCCL-gather path)
   float *frame = nullptr;            // own row-major full frame: depth n | normal 3n | colour 3n | id n (one block)
   bool frame_is_ipc = false;         // allocated with cudaMalloc and exported through CUDA IPC
@@ -275,8 +276,19 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   tm.n_local_tiles = (total_tiles + tm.world - 1) / tm.world;
   tm.n_tiles = total_tiles;
   tile_permutation(total_tiles, tm.world, &tm.perm_a, &tm.perm_ainv);
+  tm.wide_warps = 0u;   // set by cutrace_frame_attach for a frame in host memory   // a sharded ctx usually stores into a remote frame: 16 x 2 warps give 64 / 192-byte row segments
   c->tm = tm;
   c->n_local_px = (uint64_t)tm.n_local_tiles * CUTRACE_TILE_PIXELS;
+  {
+    uint64_t px = 0;
+    for (uint32_t lt = 0; lt < tm.n_local_tiles; lt++) {
+      uint32_t tx, ty;
+      if (!tile_of_slot(tm, lt * tm.world + tm.rank, tx, ty)) continue;
+      uint32_t w = std::min(CUTRACE_TILE, tm.width - tx * CUTRACE_TILE), h = std::min(CUTRACE_TILE, tm.height - ty * CUTRACE_TILE);
+      px += (uint64_t)w * h;
+    }
+    c->local_pixels = px;
+  }
   c->sv.cam.w = width; c->sv.cam.h = height;
 
   uint32_t b = c->opts.bounces;
@@ -329,6 +341,14 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   for (uint32_t L = 0; L < levels; L++) c->shade_cap[L] = batch * (branching ? (1ull << L) : 1ull) + slack;
   c->queues_ready = false;   // the wavefront's queues are allocated by the first frame that needs them (the pixel kernel has none)
   return CUTRACE_OK;
+}
+
+// Scheduler of a ctx (see CUTRACE_FLAG_PIXEL_KERNEL in cutrace.h): the persistent per-pixel kernel unless the caller forces one of
+// the wavefront schedulers; CUTRACE_FLAG_SERIALIZE (per-kernel timings) implies one launch per level and kind.
+bool wants_pixel_kernel(const cutrace_ctx *c) {
+  const uint32_t forced = c->opts.flags & (CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES | CUTRACE_FLAG_PIXEL_KERNEL);
+  if ((c->opts.flags & CUTRACE_FLAG_SERIALIZE) || !c->h_ctr_dev) return false;
+  return forced ? (forced & CUTRACE_FLAG_PIXEL_KERNEL) != 0 : true;
 }
 
 // queue memory of the wavefront schedulers, sized by alloc_frame
@@ -678,27 +698,11 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   S.rays_primary = S.rays_reflect = S.rays_transmit = S.rays_shadow = S.shadow_casts = 0;
   S.kernel_launches = 0; S.max_depth = 0.f; S.trace_ms = S.shade_ms = 0.f; S.gather_ms = 0.f;
   S.local_pixels = 0;
-  // pixels of this ctx that are inside the image
-  {
-    const TileMap &tm = c->tm;
-    uint64_t px = 0;
-    for (uint32_t lt = 0; lt < tm.n_local_tiles; lt++) {
-      uint32_t tx, ty;
-      if (!tile_of_slot(tm, lt * tm.world + tm.rank, tx, ty)) continue;
-      uint32_t w = std::min(CUTRACE_TILE, tm.width - tx * CUTRACE_TILE), h = std::min(CUTRACE_TILE, tm.height - ty * CUTRACE_TILE);
-      px += (uint64_t)w * h;
-    }
-    S.local_pixels = px;
-    S.rays_primary = px;
-  }
+  S.local_pixels = c->local_pixels;   // pixels of this ctx that are inside the image (counted once, in alloc_frame)
+  S.rays_primary = c->local_pixels;
   PhaseTimer ptimer; (void)ptimer;
   cudaEvent_t ev_begin = c->events[0], ev_end = c->events[1];
-  {
-    const uint32_t forced_ = c->opts.flags & (CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES | CUTRACE_FLAG_PIXEL_KERNEL);
-    const bool tiny_ = c->n_local_px <= (1ull << 14) || (c->sv.n_prims <= 16u && c->sv.n_planes <= 16u);
-    const bool pixel_ = !(c->opts.flags & CUTRACE_FLAG_SERIALIZE) && c->h_ctr_dev && (forced_ ? (forced_ & CUTRACE_FLAG_PIXEL_KERNEL) != 0 : tiny_);
-    if (!pixel_) { int rc_ = alloc_queues(c); if (rc_) return rc_; }
-  }
+  if (!wants_pixel_kernel(c)) { int rc_ = alloc_queues(c); if (rc_) return rc_; }
   const bool branching = c->max_children >= 2 && bounces > 0;
   const bool serialize = (c->opts.flags & CUTRACE_FLAG_SERIALIZE) != 0;
   const FrameTargets out = frame_targets(c);
@@ -763,9 +767,8 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   // copy engine can start behind it while the frame kernel works on the bounce levels.
   // which scheduler: see CUTRACE_FLAG_FRAME_KERNEL / CUTRACE_FLAG_PIXEL_KERNEL in cutrace.h
   const uint32_t forced = c->opts.flags & (CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES | CUTRACE_FLAG_PIXEL_KERNEL);
-  const bool tiny = c->n_local_px <= (1ull << 14) || (c->sv.n_prims <= 16u && c->sv.n_planes <= 16u);
-  const bool use_pixel = !serialize && c->h_ctr_dev && (forced ? (forced & CUTRACE_FLAG_PIXEL_KERNEL) != 0 : tiny);
-  const bool want_frame = !use_pixel && (forced ? (forced & CUTRACE_FLAG_FRAME_KERNEL) != 0 : (c->tm.world > 1 && c->n_local_px >= (1ull << 19)));
+  const bool use_pixel = wants_pixel_kernel(c);
+  const bool want_frame = !use_pixel && (forced & CUTRACE_FLAG_FRAME_KERNEL) != 0;
   const bool use_frame = want_frame && !serialize && !c->frame_kernel_failed && c->cfg.grid_frame > 0 && c->h_ctr_dev;
   auto enqueue_frame = [&](uint64_t base, uint32_t n_px, bool split_primary) -> cudaError_t {
     cudaError_t e;
@@ -818,7 +821,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     pa.sv = c->sv; pa.tm = c->tm; pa.bounces = bounces; pa.px_base = (uint32_t)base; pa.n_px = n_px;
     pa.ctr = c->d_ctr; pa.host_stats = c->h_ctr_dev; pa.out = out;
     c->ctr_dirty = true;   // until the kernel has run to its end
-    if ((e = launch_pixel(pa, st)) != cudaSuccess) return e;
+    if ((e = launch_pixel(c->cfg, pa, st)) != cudaSuccess) return e;
     if (early_event) {   // cutrace_render_download: the G-buffer is complete when the kernel is
       if ((e = cudaEventRecord(c->ev_gbuf, st)) != cudaSuccess) return e;
     }
@@ -1116,6 +1119,7 @@ int cutrace_frame_attach(cutrace_ctx *c, void *frame_block, uint32_t width, uint
   if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
   DeviceGuard g(c->device);
   void *dev_ptr = frame_block;
+  bool host_frame = false;
   if (frame_block) {
     if (width != c->tm.width || height != c->tm.height)
       return fail(CUTRACE_ERR_INVALID_ARG, "the frame block is " + std::to_string(width) + "x" + std::to_string(height) + ", this ctx renders " +
@@ -1126,6 +1130,7 @@ int cutrace_frame_attach(cutrace_ctx *c, void *frame_block, uint32_t width, uint
     if (at.type == cudaMemoryTypeHost) {
       if (!at.devicePointer) return fail(CUTRACE_ERR_INVALID_ARG, "host frame_block is not mapped into the device address space");
       dev_ptr = at.devicePointer;
+      host_frame = true;
     } else if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
       return fail(CUTRACE_ERR_INVALID_ARG, "frame_block is unregistered host memory: register it with cutrace_host_register first");
     }
@@ -1134,6 +1139,8 @@ int cutrace_frame_attach(cutrace_ctx *c, void *frame_block, uint32_t width, uint
   if (c->peer_frame && c->peer_is_ipc) cudaIpcCloseMemHandle(c->peer_frame);
   c->peer_frame = dev_ptr;   // NULL detaches
   c->peer_is_ipc = false;
+  // per-pixel stores over PCIe: 16 x 2 warps write whole 16-pixel tile rows (64 / 192-byte segments instead of 32 / 96)
+  c->tm.wide_warps = (host_frame && !getenv("CUTRACE_DEBUG_NARROW_WARPS")) ? 1u : 0u;
   c->rendered = false;
   drop_graph(c);
   return CUTRACE_OK;

@@ -214,6 +214,8 @@ struct TileMap {
   uint32_t rank, world;       // this ctx owns slots s with s % world == rank
   uint32_t n_local_tiles;     // ceil(n_tiles / world): the same padded count on every rank
   uint32_t n_tiles, perm_a, perm_ainv;
+  uint32_t wide_warps;        // 0: the 32 pixels of a warp form an 8 x 4 block (most coherent primary rays); 1: a 16 x 2 block — whole
+                              // tile rows, so that per-pixel stores into a remote frame (peer GPU, pinned host memory) are 64 / 192-byte segments
 };
 
 // slot -> screen tile coordinates; false for the padding slots of the last local tile

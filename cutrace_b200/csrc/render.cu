@@ -177,6 +177,10 @@ __device__ __forceinline__ bool work_to_pixel(const TileMap &tm, uint32_t i, uin
   uint32_t lt = i >> (2 * CUTRACE_TILE_SHIFT), w = i & (CUTRACE_TILE_PIXELS - 1u);
   uint32_t b = w >> 5, l = w & 31u;
   uint32_t px = ((b & ((1u << BX_SHIFT) - 1u)) << 3) + (l & 7u), py = ((b >> BX_SHIFT) << 2) + (l >> 3);
+  if (tm.wide_warps) {
+    static_assert(CUTRACE_TILE_SHIFT == 4, "16 x 2 warps assume 16-pixel tile rows");
+    px = l & 15u; py = (b << 1) + (l >> 4);
+  }
   uint32_t tx, ty;
   if (!tile_of_slot(tm, lt * tm.world + tm.rank, tx, ty)) return false;
   x = tx * CUTRACE_TILE + px;
@@ -943,72 +947,84 @@ __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(co
 // inc/shading.hpp:123), path weights replace the nested blend, and the colour is summed in depth-first order — for
 // non-branching scenes exactly the level order of the wavefront's ordered sum.  Counters arrive in mapped host memory and
 // are cleared by the last block, like in the frame kernel: the frame is ONE launch, no memset, no copy.
-template <bool BRUTE, bool OPAQUE>
-__global__ void __launch_bounds__(256, 4) pixel_kernel(const __grid_constant__ PixelArgs a) {
+template <int MODE, bool BRUTE, bool OPAQUE>
+__global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel_kernel(const __grid_constant__ PixelArgs a) {
+  extern __shared__ float4 smem[];
   const SceneView &sv = a.sv;
-  const float4 *nodes = reinterpret_cast<const float4 *>(sv.nodes), *prims = reinterpret_cast<const float4 *>(sv.prims);
+  const float4 *nodes, *prims;
+  stage_scene<MODE>(sv, smem, nodes, prims);
   const unsigned lane = threadIdx.x & 31u;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t gx = 0, gy = 0, pix = 0;
-  const bool active = i < a.n_px && work_to_pixel(a.tm, a.px_base + i, gx, gy, pix);
   TraceAcc acc;
   trace_acc_reset(acc);
   unsigned casts = 0;
-  if (active) {
-    struct Pending { vec3 o, d; float w; uint32_t level; } stack[16];
-    int sp = 0;
-    vec3 o, d;
-    camera_ray(sv.cam, gx, gy, o, d);
-    float w = 1.0f;
-    uint32_t level = 0;
-    float r = 0.f, g = 0.f, b = 0.f;
-    const size_t gi = a.out.row_major ? (size_t)gy * a.tm.width + gx : (size_t)pix;
-    for (;;) {
-      Hit h;
-      closest_hit<0, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
-      const bool hit = h.kind >= 0;
-      vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
-      if (hit) hit_surface<0>(sv, prims, h, o, d, point, nrm);
-      if (level == 0) {   // G-buffer, inc/kernel.hpp:52-56
-        a.out.depth[gi] = h.t;
-        a.out.normal[3 * gi] = nrm.x; a.out.normal[3 * gi + 1] = nrm.y; a.out.normal[3 * gi + 2] = nrm.z;
-        a.out.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
-        if (hit && isfinite(h.t)) acc.max_depth = h.t;
-      }
-      bool next = false;
-      if (hit) {
-        const uint32_t mat = __ldg(sv.obj_material + h.obj);
-        const float4 m1 = __ldg(reinterpret_cast<const float4 *>(sv.materials + mat) + 1);
-        const float reflect = m1.x, transp = m1.z;
-        // inc/shading.hpp:126-149
-        const bool deeper = level < a.bounces;
-        const bool do_refl = deeper && (double)reflect >= 1e-6, do_trans = deeper && (double)transp >= 1e-6;
-        const float w_own = do_trans ? w * (1.0f - transp) : w;
-        const vec3 final = phong_record<0, BRUTE, OPAQUE>(sv, nodes, prims, point, nrm, d, mat, casts);
-        acc.n_shaded++;
-        // product and sum rounded separately, like the wavefront's level image + ordered sum
-        r = __fadd_rn(r, __fmul_rn(w_own, final.x)); g = __fadd_rn(g, __fmul_rn(w_own, final.y)); b = __fadd_rn(b, __fmul_rn(w_own, final.z));
-        const vec3 origin = vmad(o, d, h.t);   // incoming->start + distance * incoming->dir
-        if (do_trans) {
-          acc.n_trans++;
-          if (do_refl) { stack[sp].o = origin; stack[sp].d = d; stack[sp].w = w * transp; stack[sp].level = level + 1; sp++; }
-          else { o = origin; w = w * transp; level++; next = true; }
+  // persistent CTAs: a warp claims 32 .. 128 pixels at a time (paths differ in length by an order of magnitude); frames
+  // with fewer than ~16 claims per warp get the finest grain, or the last claim of a warp is a quarter of its work
+  const unsigned warps_total = gridDim.x * (blockDim.x >> 5);
+  unsigned max_chunk = (a.n_px / (warps_total * 16u)) & ~31u;
+  max_chunk = max_chunk < 32u ? 32u : (max_chunk > 128u ? 128u : max_chunk);
+  for (bool first = true;; first = false) {
+    unsigned base, end;
+    if (!claim_work(&a.ctr->work_trace[0].v, a.n_px, lane, max_chunk, true, first, base, end)) { if (first) continue; break; }
+#pragma unroll 1
+    for (unsigned off = 0; base + off < end; off += 32) {
+      const uint32_t i = base + off + lane;
+      uint32_t gx = 0, gy = 0, pix = 0;
+      if (!(i < a.n_px && work_to_pixel(a.tm, a.px_base + i, gx, gy, pix))) continue;
+      struct Pending { vec3 o, d; float w; uint32_t level; } stack[16];
+      int sp = 0;
+      vec3 o, d;
+      camera_ray(sv.cam, gx, gy, o, d);
+      float w = 1.0f;
+      uint32_t level = 0;
+      float r = 0.f, g = 0.f, b = 0.f;
+      const size_t gi = a.out.row_major ? (size_t)gy * a.tm.width + gx : (size_t)pix;
+      for (;;) {
+        Hit h;
+        closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
+        const bool hit = h.kind >= 0;
+        vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
+        if (hit) hit_surface<MODE>(sv, prims, h, o, d, point, nrm);
+        if (level == 0) {   // G-buffer, inc/kernel.hpp:52-56
+          a.out.depth[gi] = h.t;
+          a.out.normal[3 * gi] = nrm.x; a.out.normal[3 * gi + 1] = nrm.y; a.out.normal[3 * gi + 2] = nrm.z;
+          a.out.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
+          if (hit && isfinite(h.t)) acc.max_depth = fmaxf(acc.max_depth, h.t);
         }
-        if (do_refl) {
-          acc.n_refl++;
-          const vec3 nd = vnormalized(d), nn = vnormalized(nrm);
-          d = vreflect(nd, nn);
-          o = origin; w = w_own * reflect; level++; next = true;
+        bool next = false;
+        if (hit) {
+          const uint32_t mat = __ldg(sv.obj_material + h.obj);
+          const float4 m1 = __ldg(reinterpret_cast<const float4 *>(sv.materials + mat) + 1);
+          const float reflect = m1.x, transp = m1.z;
+          // inc/shading.hpp:126-149
+          const bool deeper = level < a.bounces;
+          const bool do_refl = deeper && (double)reflect >= 1e-6, do_trans = deeper && (double)transp >= 1e-6;
+          const float w_own = do_trans ? w * (1.0f - transp) : w;
+          const vec3 final = phong_record<MODE, BRUTE, OPAQUE>(sv, nodes, prims, point, nrm, d, mat, casts);
+          acc.n_shaded++;
+          // product and sum rounded separately, like the wavefront's level image + ordered sum
+          r = __fadd_rn(r, __fmul_rn(w_own, final.x)); g = __fadd_rn(g, __fmul_rn(w_own, final.y)); b = __fadd_rn(b, __fmul_rn(w_own, final.z));
+          const vec3 origin = vmad(o, d, h.t);   // incoming->start + distance * incoming->dir
+          if (do_trans) {
+            acc.n_trans++;
+            if (do_refl) { stack[sp].o = origin; stack[sp].d = d; stack[sp].w = w * transp; stack[sp].level = level + 1; sp++; }
+            else { o = origin; w = w * transp; level++; next = true; }
+          }
+          if (do_refl) {
+            acc.n_refl++;
+            const vec3 nd = vnormalized(d), nn = vnormalized(nrm);
+            d = vreflect(nd, nn);
+            o = origin; w = w_own * reflect; level++; next = true;
+          }
+        }
+        if (!next) {
+          if (sp == 0) break;
+          sp--;
+          o = stack[sp].o; d = stack[sp].d; w = stack[sp].w; level = stack[sp].level;
         }
       }
-      if (!next) {
-        if (sp == 0) break;
-        sp--;
-        o = stack[sp].o; d = stack[sp].d; w = stack[sp].w; level = stack[sp].level;
-      }
+      float *cp = a.out.color + 3 * gi;
+      cp[0] = r; cp[1] = g; cp[2] = b;
     }
-    float *cp = a.out.color + 3 * gi;
-    cp[0] = r; cp[1] = g; cp[2] = b;
   }
   // ---- tallies: warp -> block -> frame statistics; the last block publishes them and clears the counters ----
   __shared__ unsigned long long s_t[4];
@@ -1054,7 +1070,7 @@ __global__ void __launch_bounds__(256, 4) pixel_kernel(const __grid_constant__ P
       if (dst) dst[threadIdx.x] = v;
       src[S0 + threadIdx.x] = 0u;
     }
-    if (threadIdx.x == 0) ctr->finished.v = 0u;
+    if (threadIdx.x == 0) { ctr->finished.v = 0u; ctr->work_trace[0].v = 0u; }
     __threadfence_system();
   }
 }
@@ -1110,6 +1126,13 @@ static frame_fn pick_frame(int mode, bool brute, bool opaque) {
   return opaque ? frame_kernel<0, false, true> : frame_kernel<0, false, false>;
 }
 
+typedef void (*pixel_fn)(const PixelArgs);
+static pixel_fn pick_pixel(int mode, bool brute, bool opaque) {
+  if (brute) return opaque ? pixel_kernel<0, true, true> : pixel_kernel<0, true, false>;
+  if (mode == 1) return opaque ? pixel_kernel<1, false, true> : pixel_kernel<1, false, false>;
+  return opaque ? pixel_kernel<0, false, true> : pixel_kernel<0, false, false>;
+}
+
 cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
   int dev = 0, sms = 0, smem_optin = 0, coop = 0;
   cudaError_t e;
@@ -1144,6 +1167,15 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
   cfg->grid_trace = sms * occ_t;
   cfg->grid_shade = sms * occ_s;
   cfg->grid_frame = occ_f >= 1 && coop ? sms * occ_f : 0;   // 0: no cooperative launch on this device -> multi-launch path
+  {
+    const int pmode = cfg->mode == 1 ? 1 : 0;
+    pixel_fn pf = pick_pixel(pmode, sv.brute_force != 0, sv.all_opaque != 0);
+    const size_t psmem = pmode == 1 ? cfg->smem_bytes : 0;
+    int occ_p = 1;
+    if (pmode == 1 && (e = cudaFuncSetAttribute(pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pf, CTB_PIXEL_THREADS, psmem)) != cudaSuccess) return e;
+    cfg->grid_pixel = sms * (occ_p < 1 ? 1 : occ_p);
+  }
   return cudaSuccess;
 }
 
@@ -1170,11 +1202,14 @@ void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, con
       sv, level, shade, shade_cap, ctr, fb, atomic_accumulate ? 1 : 0, level_color, px_base);
 }
 
-cudaError_t launch_pixel(const PixelArgs &args, cudaStream_t st) {
+cudaError_t launch_pixel(const LaunchCfg &cfg, const PixelArgs &args, cudaStream_t st) {
   if (!args.n_px) return cudaSuccess;
-  const bool brute = args.sv.brute_force != 0, opaque = args.sv.all_opaque != 0;
-  void (*f)(const PixelArgs) = brute ? (opaque ? pixel_kernel<true, true> : pixel_kernel<true, false>) : (opaque ? pixel_kernel<false, true> : pixel_kernel<false, false>);
-  f<<<(args.n_px + 255u) / 256u, 256, 0, st>>>(args);
+  const int mode = cfg.mode == 1 ? 1 : 0;
+  const size_t smem = mode == 1 ? cfg.smem_bytes : 0;
+  uint64_t need = ((uint64_t)args.n_px + CTB_PIXEL_THREADS - 1) / CTB_PIXEL_THREADS;
+  int grid = (int)(need < (uint64_t)cfg.grid_pixel ? need : (uint64_t)cfg.grid_pixel);
+  if (grid < 1) grid = 1;
+  pick_pixel(mode, args.sv.brute_force != 0, args.sv.all_opaque != 0)<<<grid, CTB_PIXEL_THREADS, smem, st>>>(args);
   return cudaGetLastError();
 }
 

@@ -45,7 +45,16 @@ struct LaunchCfg {
   size_t smem_bytes;
   int grid_trace, grid_shade;   // persistent grid sizes (multiples of the SM count)
   int grid_frame;               // co-resident CTAs of the cooperative frame kernel (0: not available on this device)
+  int grid_pixel;               // persistent grid of the pixel kernel
 };
+// pixel kernel: 512 threads x 2 CTAs per SM (64 registers) measured best on bunny.json 4K — 9.01 ms against 9.44 (256 x 3),
+// 10.3 (256 x 4, where 71 KB of staged scene per CTA caps the SM at 3 CTAs) and 10.7 (256 x 2, 128 registers); profiles/r02_tuning.md
+#ifndef CTB_PIXEL_THREADS
+#define CTB_PIXEL_THREADS 512
+#endif
+#ifndef CTB_PIXEL_MIN_BLOCKS
+#define CTB_PIXEL_MIN_BLOCKS 2
+#endif
 
 #ifndef CTB_FILL_CHUNK_MAX
 #define CTB_FILL_CHUNK_MAX 128   // shade records a warp claims at a time while it is only filling the tail of a trace phase
@@ -89,7 +98,9 @@ struct PixelArgs {
   FrameStats *host_stats;    // mapped pinned host memory (device pointer), may be NULL
   FrameTargets out;          // where the frame lives (any layout FrameTargets describes)
 };
-cudaError_t launch_pixel(const PixelArgs &args, cudaStream_t st);
+
+
+cudaError_t launch_pixel(const LaunchCfg &cfg, const PixelArgs &args, cudaStream_t st);
 
 // fills cfg for a scene on the current device; smem budget from the device attributes
 cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg);

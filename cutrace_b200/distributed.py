@@ -201,7 +201,7 @@ class TileShardedRenderer:
                 self.out_normal = torch.empty(3 * n, dtype=f32, device=self.device)
                 self.out_color = torch.empty(3 * n, dtype=f32, device=self.device)
                 self.out_id = torch.empty(n, dtype=i32, device=self.device)
-        elif rank == 0:
+        elif self.exchange in ("peer", "none") and rank == 0:
             pd, pn, pc, pi = self.r.frame_device()
             self.out_depth, self.out_normal = as_t(pd, n, "<f4"), as_t(pn, 3 * n, "<f4")
             self.out_color, self.out_id = as_t(pc, 3 * n, "<f4"), as_t(pi, n, "<i4")
@@ -211,7 +211,9 @@ class TileShardedRenderer:
         import torch.distributed as dist
 
         torch = self.torch
-        h = torch.zeros(64, dtype=torch.uint8, device=self.device)
+        from ._lib import IPC_HANDLE_BYTES
+
+        h = torch.zeros(IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
         ok = 1
         try:
             if self.rank == 0:
@@ -242,7 +244,13 @@ class TileShardedRenderer:
         if self.world == 1:
             return
         if self.exchange in ("peer", "host"):
-            dist.barrier()
+            # the only collective of these exchanges: the 1-float max-depth all-reduce (kernel.hpp:120-125), which is also the
+            # "every rank's tiles are stored" barrier (each rank's cutrace_render returned before it joined)
+            if not hasattr(self, "_md"):
+                self._md = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self._md.fill_(float(self.r.stats()["max_depth"]))
+            dist.all_reduce(self._md, op=dist.ReduceOp.MAX)
+            self.frame_max_depth = float(self._md.item())
             return
         pairs = [(self.depth, getattr(self, "g_depth", None), 1), (self.normal, getattr(self, "g_normal", None), 3),
                  (self.color, getattr(self, "g_color", None), 3), (self.hit_id, getattr(self, "g_id", None), 1)]

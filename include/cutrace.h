@@ -127,14 +127,14 @@ typedef struct cutrace_scene_desc {
 #define CUTRACE_FLAG_SERIALIZE 8u      /* run every kernel of a frame on one stream (per-kernel trace_ms / shade_ms are
                                           only measured in this mode); default: shade kernels overlap the trace chain */
 
-/* Scheduler of a frame.  Default (neither flag): chosen per ctx from measurements on B200 (profiles/r02_tuning.md) — the
- * persistent frame kernel (ONE cooperative launch, level loop on the device) for tile shards of at least 2^19 pixels, where
- * thirteen short launches per frame cost 5 % more; one launch per level and kind, replayed as a CUDA graph, otherwise. */
-#define CUTRACE_FLAG_FRAME_KERNEL 16u  /* force the persistent frame kernel */
-#define CUTRACE_FLAG_LAUNCHES 32u      /* force one launch per level and kind */
-#define CUTRACE_FLAG_PIXEL_KERNEL 64u  /* force the per-pixel kernel (one thread walks a pixel's whole path).  Default: used for
-                                          frames of at most 2^14 pixels and for scenes of at most 16 primitives and 16 planes,
-                                          where the wavefront has nothing to regroup and its queues and launches are overhead */
+/* Scheduler of a frame.  Default (none of the three flags): the persistent per-pixel kernel — ONE launch per frame, a thread
+ * walks a pixel's whole path (primary ray, shadow rays, reflection / transmission chain) with an explicit stack, warps claim
+ * pixels from a global cursor.  Measured on B200 (profiles/r02_tuning.md) it matches or beats the wavefront on all five
+ * BASELINE configs (bunny.json 4K 9.0 against 9.8 ms; a 1/8 tile shard 1.36 against 1.60 ms) because nothing has to be
+ * regrouped there and the queues cost 9 GB of DRAM traffic per frame.  The two wavefront schedulers stay selectable: */
+#define CUTRACE_FLAG_FRAME_KERNEL 16u  /* wavefront, ONE cooperative launch: level loop and phase barriers on the device */
+#define CUTRACE_FLAG_LAUNCHES 32u      /* wavefront, one launch per bounce level and kind, replayed as a CUDA graph */
+#define CUTRACE_FLAG_PIXEL_KERNEL 64u  /* the per-pixel kernel (the default) */
 
 typedef struct cutrace_opts {
   float fudge;          /* min hit distance; the reference passes 1e-3 (main.cu:30)            */

@@ -374,7 +374,7 @@ def test_full_size_properties_bunny_4k(ct):
     assert m["id_mismatch"] == 0 and m["depth_max_rel"] == 0.0 and m["color_max_abs"] <= 1e-6, m
 
 
-@pytest.mark.parametrize("sched", ["frame", "launches"])
+@pytest.mark.parametrize("sched", SCHEDULERS)
 def test_tile_sharding_equals_single_ctx(ct, monkeypatch, sched):
     """world=3 interleaved tile shards rendered by three ctxs (one GPU) and stitched by cutrace_download
     are bit-identical to the unsharded frame — the multi-GPU path changes who renders a pixel, not what."""
@@ -397,7 +397,7 @@ def test_tile_sharding_equals_single_ctx(ct, monkeypatch, sched):
     assert rays == st["rays_total"]
 
 
-@pytest.mark.parametrize("sched", ["frame", "launches"])
+@pytest.mark.parametrize("sched", SCHEDULERS)
 def test_peer_frame_stores_equal_single_ctx(ct, monkeypatch, sched):
     """The gather-free multi-GPU path on one GPU: three sharded ctxs store their tiles straight into rank 0's row-major
     frame (cutrace_frame_attach = the in-process form of cutrace_frame_ipc_import); the assembled frame is bit-identical
@@ -662,11 +662,7 @@ def test_frame_kernel_equals_the_multi_launch_paths(ct, monkeypatch):
             assert r.phase_ms() == []
         assert sb["kernel_launches"] == 2 * levels + 1
         for b in frames:
-            assert_same_frame(frames[0], b, name)              # the multi-launch frames agree with each other bit for bit
-            m = compare(a, b, s.width, s.height)
-            assert m["id_mismatch"] == 0 and m["depth_max_rel"] == 0.0 and m["normal_max_abs"] == 0.0, (name, m)
-            # colour: last-bit differences, plus the odd shadow-edge pixel when a hit point moved by an ulp
-            assert m["color_bad_frac"] <= 1e-4 and np.median(np.abs(a["color"] - b["color"])) == 0.0, (name, m)
+            assert_same_frame(a, b, name)                      # every rounding is pinned (common.cuh): same bits from every scheduler
         for k in ("rays_total", "rays_shadow", "rays_reflect", "shadow_casts", "max_depth"):
             assert sa[k] == sb[k], (name, k)
         # the per-pixel kernel: same G-buffer and counters, colours to the last bits
@@ -676,13 +672,11 @@ def test_frame_kernel_equals_the_multi_launch_paths(ct, monkeypatch):
             r.render()
             assert_same_frame(p, r.download(), name)          # bit-reproducible
         assert sp["kernel_launches"] == 1 and sp["scheduler"] == 2
-        m = compare(p, a, s.width, s.height)
-        assert m["id_mismatch"] == 0 and m["depth_max_rel"] == 0.0 and m["normal_max_abs"] == 0.0 and m["color_bad_frac"] <= 1e-4, (name, m)
+        assert_same_frame(p, a, name)
         for k in ("rays_total", "rays_shadow", "rays_reflect", "shadow_casts", "max_depth"):
             assert sa[k] == sp[k], (name, k)
-        # the default picks one of the three
-        with ct.Renderer(s) as r:
-            assert r.render()["scheduler"] in (0, 1, 2)
+        with ct.Renderer(s) as r:                              # the default is the per-pixel kernel
+            assert r.render()["scheduler"] == 2
 
 
 def test_direct_first_frame_and_graph_replays_are_bit_identical(ct, monkeypatch):
@@ -740,8 +734,7 @@ def test_render_download_with_the_frame_kernel(ct, monkeypatch):
         stb = r.render()
         b = r.download()
         assert sta["kernel_launches"] == 2 and stb["kernel_launches"] == 1
-        m = compare(a, b, s.width, s.height)
-        assert m["id_mismatch"] == 0 and m["depth_max_rel"] == 0.0 and m["normal_max_abs"] == 0.0 and m["color_bad_frac"] <= 1e-4, m
+        assert_same_frame(a, b, "fused vs render + download")
         assert a["max_depth"] == b["max_depth"] and sta["rays_total"] == stb["rays_total"]
         c, _ = r.render_download()
         assert_same_frame(a, c, "two fused frames")
@@ -768,8 +761,9 @@ def test_set_camera_resizes_and_reuses_the_scene(ct):
 
 
 def test_pixel_batches_equal_one_batch(ct, monkeypatch):
-    """When the worst-case queues do not fit the memory budget the frame is rendered in pixel batches
+    """Wavefront schedulers: when the worst-case queues do not fit the memory budget the frame is rendered in pixel batches
     (CUTRACE_QUEUE_BUDGET_MB forces that here); the result must not change."""
+    monkeypatch.setenv("CUTRACE_SCHEDULER", "launches")
     for name, res in (("bunny", (640, 360)), ("sphere_plane", (320, 180))):
         s = load_golden_scene(name).with_resolution(*res)
         one, st1 = gpu_render(ct, s)

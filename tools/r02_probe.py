@@ -19,7 +19,7 @@ def child(workload, world, frames):
 
     scene, wl = bench.load_workload(workload)
     tag = {"launches": "multi-launch", "frame": "frame-kernel", "pixel": "pixel-kernel"}[os.environ["CUTRACE_SCHEDULER"]]
-    with ct.Renderer(scene, tile_rank=0, tile_world=world) as r:
+    with ct.Renderer(scene, tile_rank=0, tile_world=world, flags=int(os.environ.get("PROBE_FLAGS", "0"))) as r:
         ms = []
         for _ in range(frames):
             st = r.render()
@@ -36,7 +36,7 @@ def main():
         return child(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]))
     wls = sys.argv[1:] or ["triangle", "spheres1080", "mirror1080", "bunny4k", "synthetic10m"]
     for wl in wls:
-        for world in (1, 8):
+        for world in [int(x) for x in os.environ.get("PROBE_WORLDS", "1,8").split(",")]:
             if wl == "triangle" and world > 1:
                 continue
             for sched in os.environ.get("PROBE_SCHEDS", "frame,launches,pixel").split(","):
