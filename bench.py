@@ -359,7 +359,8 @@ class Bench:
         rays, rays_shadow = self.reduce([st["rays_total"], st["rays_shadow"]], "sum")
         launches = int(st["kernel_launches"]) + (1 if self.world > 1 and self.rank == 0 and tsr.exchange == "gather" else 0)
         res = dict(ms_per_step=ms_step, render_device_ms=render_dev_ms, rays=rays, rays_shadow=rays_shadow, launches_per_step=launches,
-                   scheduler="frame kernel" if st["scheduler"] else "one launch per level and kind (CUDA graph)", exchange=tsr.exchange,
+                   scheduler={0: "wavefront: one launch per level and kind (CUDA graph)", 1: "wavefront: persistent frame kernel",
+                              2: "pixel kernel (persistent, one thread per pixel path)"}[int(st["scheduler"])], exchange=tsr.exchange,
                    clocks=clk.summary() if sampler else None)
         # ---- the N-GPU frame against the same frame rendered by ONE GPU, bit for bit (pixels are independent in the reference,
         # /root/reference/inc/kernel.hpp:37-59: sharding changes who renders a pixel, not what) ----
@@ -380,7 +381,8 @@ class Bench:
             else:
                 got = tsr.r.download()
             # same scheduler as the shards used: the frame kernel and the per-level kernels are separate compilations (last-bit colours)
-            flags = (self.args.flags & ~(ct.FLAG_FRAME_KERNEL | ct.FLAG_LAUNCHES)) | (ct.FLAG_FRAME_KERNEL if st["scheduler"] else ct.FLAG_LAUNCHES)
+            forced = {0: ct.FLAG_LAUNCHES, 1: ct.FLAG_FRAME_KERNEL, 2: ct.FLAG_PIXEL_KERNEL}[int(st["scheduler"])]
+            flags = (self.args.flags & ~(ct.FLAG_FRAME_KERNEL | ct.FLAG_LAUNCHES | ct.FLAG_PIXEL_KERNEL)) | forced
             with ct.Renderer(scene, device=self.local_rank, flags=flags) as r1:
                 r1.render()
                 one = r1.download()
@@ -413,7 +415,7 @@ class Bench:
         ser.close()
         shade, trace, serial = self.reduce([sst["shade_ms"], sst["trace_ms"], sst["render_ms"]], "max")
         return {"trace": trace, "shade": shade, "serialized_frame": serial,
-                "note": "a frame rendered with CUTRACE_FLAG_SERIALIZE (one launch per level and kind on one stream); the timed frames overlap shading with the trace chain"}
+                "note": "per-kernel times of the WAVEFRONT scheduler (CUTRACE_FLAG_SERIALIZE: one launch per level and kind on one stream), for comparison; the timed frames run the scheduler named in details.scheduler"}
 
     # ---- end to end: host scene in, host frame out, every step ----
     def e2e(self, scene, steps, check_parity=False):
@@ -490,10 +492,13 @@ class Bench:
             self.dist.destroy_process_group()
 
 
-def compulsory_bytes_per_frame(n_px, rays_total, rays_shadow, n_lights):
-    """DRAM bytes a frame cannot avoid with this data layout: per traced ray a 32-byte ray record in (levels >= 1), a 48-byte
-    shade record and a 32-byte child ray out; per shaded hit 48 B in, 12 B level colour out and 12 B read again by the ordered sum; per
-    pixel 20 B G-buffer, 4 B level count, 12 B final colour."""
+def compulsory_bytes_per_frame(n_px, rays_total, rays_shadow, n_lights, scene_bytes, pixel_kernel=True):
+    """DRAM bytes a frame cannot avoid with this data layout.  Pixel kernel: the 32-byte frame record of every pixel out
+    and the scene in once — a path lives in registers.  Wavefront schedulers: per traced ray a 32-byte ray record in (levels >= 1), a
+    48-byte shade record and a 32-byte child ray out; per shaded hit 48 B in, 12 B level colour out and 12 B read again by the ordered
+    sum; per pixel 20 B G-buffer, 4 B level count, 12 B final colour."""
+    if pixel_kernel:
+        return n_px * 32 + scene_bytes
     traced = rays_total - rays_shadow
     shaded = rays_shadow / max(1, n_lights)
     return traced * (32 + 48 + 32) - n_px * 32 + shaded * (48 + 12 + 12) + n_px * (20 + 4 + 12)
@@ -555,7 +560,11 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         clocks = main_res["clocks"]
-        comp = compulsory_bytes_per_frame(n_px, rays, main_res["rays_shadow"], scene.n_lights)
+        from cutrace_b200.scene import _ARRAY_FIELDS
+
+        scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in _ARRAY_FIELDS if k != "obj_kind")
+        comp = compulsory_bytes_per_frame(n_px, rays, main_res["rays_shadow"], scene.n_lights, scene_bytes,
+                                          pixel_kernel=main_res["scheduler"].startswith("pixel"))
         achieved = comp / (ms_step * 1e-3) / 1e9
         # what ncu measured for one frame of this workload (committed: profiles/ncu_frame.json, written by tools/ncu_frame.py)
         ncu = {}
@@ -588,7 +597,8 @@ def main():
             "e2e": dict(e2e, value=rays / e2e["ms_per_frame"] / 1e3, unit="Mrays/s"),
             "gpu_launches": main_res["launches_per_step"] * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "what": "compulsory DRAM bytes of one frame (queue records in/out, level colours, framebuffer: DESIGN.md 3) / ms_per_step",
+                         "what": "compulsory DRAM bytes of one frame (pixel kernel: the 32-byte frame record per pixel + the scene once; wavefront: plus queue "
+                                 "records and level colours — DESIGN.md 3) / ms_per_step",
                          "compulsory_bytes_per_frame": comp, "traffic": ncu.get("dram_bytes_per_frame"),
                          "traffic_unit": "bytes per frame, all kernels (dram__bytes_read.sum + dram__bytes_write.sum)",
                          "binding_resource": "issue slots x active lanes (the BVH is cache-resident; DRAM runs at `frac` of its peak)", "issue": issue,

@@ -17,7 +17,7 @@ SYMBOLS = (
     "cutrace_last_error", "cutrace_set_camera", "cutrace_get_stats", "cutrace_get_phase_ms", "cutrace_device_buffers", "cutrace_frame_device",
     "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach", "cutrace_enable_peer_access",
     "cutrace_set_frame_max_depth",
-    "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free", "cutrace_host_register", "cutrace_host_unregister",
+    "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free", "cutrace_host_register", "cutrace_host_unregister", "cutrace_trim_memory",
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version", "cutrace_tile_size",
 )
 
@@ -89,6 +89,7 @@ def load():
     lib.cutrace_frame_attach.argtypes = [P, P, C.c_uint32, C.c_uint32]
     lib.cutrace_host_register.argtypes = [P, C.c_size_t]
     lib.cutrace_host_unregister.argtypes = [P]
+    lib.cutrace_trim_memory.argtypes = [C.c_int]
     lib.cutrace_enable_peer_access.argtypes = [C.c_int, C.c_int]
     lib.cutrace_set_frame_max_depth.argtypes = [P, C.c_float]
     lib.cutrace_untile_device.argtypes = [P, C.c_uint32, P, P, P, P, C.c_uint64, P, P, P, P]

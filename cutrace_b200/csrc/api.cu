@@ -203,6 +203,8 @@ struct cutrace_ctx {
   // host destinations of an in-flight cutrace_render_download (NULL otherwise)
   float *dl_depth = nullptr, *dl_normal = nullptr;
   uint32_t *dl_id = nullptr;
+  FrameTargets dl_direct{};          // ... when they are pinned + mapped: device addresses the pixel kernel stores to directly
+  bool dl_direct_on = false;
   std::vector<cudaEvent_t> events;
 };
 
@@ -506,7 +508,6 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   c->opts = o;
   DeviceGuard guard(dev);
   if (!guard.ok) { delete c; return fail(CUTRACE_ERR_CUDA, "cudaSetDevice failed"); }
-  pool_keep_memory(dev);
   c->env_no_graph = getenv("CUTRACE_NO_GRAPH") != nullptr;
   if (const char *e = getenv("CUTRACE_SCHEDULER")) {   // developer override of cutrace_opts.flags: "frame" | "launches"
     c->opts.flags &= ~(CUTRACE_FLAG_FRAME_KERNEL | CUTRACE_FLAG_LAUNCHES | CUTRACE_FLAG_PIXEL_KERNEL);
@@ -820,6 +821,7 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     PixelArgs pa{};
     pa.sv = c->sv; pa.tm = c->tm; pa.bounces = bounces; pa.px_base = (uint32_t)base; pa.n_px = n_px;
     pa.ctr = c->d_ctr; pa.host_stats = c->h_ctr_dev; pa.out = out;
+    if (c->dl_direct_on) { pa.out2 = c->dl_direct; pa.tm.wide_warps = 1u; }   // 16 x 2 warps: whole tile rows per store over PCIe
     c->ctr_dirty = true;   // until the kernel has run to its end
     if ((e = launch_pixel(c->cfg, pa, st)) != cudaSuccess) return e;
     if (early_event) {   // cutrace_render_download: the G-buffer is complete when the kernel is
@@ -940,9 +942,34 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
   return CUTRACE_OK;
 }
 
+// device address of a pinned + mapped host pointer (cutrace_host_alloc / cutrace_host_register), NULL for anything else
+static void *mapped_device_ptr(const void *p) {
+  if (!p) return nullptr;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int cutrace_render_download(cutrace_ctx *c, float *depth, float *normal, float *color, uint32_t *hit_id, float *max_depth,
                             cutrace_stats *stats) {
   if (!c) return fail(CUTRACE_ERR_INVALID_ARG, "ctx is NULL");
+  DeviceGuard g(c->device);
+  // Pixel kernel + pinned, mapped destinations (cutrace_host_alloc / cutrace_host_register): every pixel is stored to the
+  // ctx's frame AND straight into the caller's images as it is finished — the download rides under the render, no copy follows.
+  if (wants_pixel_kernel(c) && c->frame && !c->peer_frame && !getenv("CUTRACE_DEBUG_NO_DIRECT_DOWNLOAD")) {
+    FrameTargets t{};
+    t.depth = static_cast<float *>(mapped_device_ptr(depth)); t.normal = static_cast<float *>(mapped_device_ptr(normal));
+    t.color = static_cast<float *>(mapped_device_ptr(color)); t.hit_id = static_cast<uint32_t *>(mapped_device_ptr(hit_id));
+    t.row_major = 1;
+    if ((!depth || t.depth) && (!normal || t.normal) && (!color || t.color) && (!hit_id || t.hit_id) && (depth || normal || color || hit_id)) {
+      c->dl_direct = t; c->dl_direct_on = true;
+      int rc = cutrace_render(c, stats);
+      c->dl_direct_on = false;
+      if (rc) return rc;
+      if (max_depth) *max_depth = c->stats.max_depth;
+      return CUTRACE_OK;
+    }
+  }
   const bool fused = c->frame && !c->peer_frame && c->batch_px >= c->n_local_px;
   if (fused) { c->dl_depth = depth; c->dl_normal = normal; c->dl_id = hit_id; }
   int rc = cutrace_render(c, stats);
@@ -950,7 +977,6 @@ int cutrace_render_download(cutrace_ctx *c, float *depth, float *normal, float *
   c->dl_depth = c->dl_normal = nullptr; c->dl_id = nullptr;
   if (rc) return rc;
   if (!early) return cutrace_download(c, depth, normal, color, hit_id, max_depth);
-  DeviceGuard g(c->device);
   const uint64_t n = (uint64_t)c->tm.width * c->tm.height;
   PhaseTimer ptimer; (void)ptimer;
   if (color) CU(cudaMemcpyAsync(color, frame_views(c->frame, n).color, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1192,6 +1218,17 @@ int cutrace_encode_bytes_device(cutrace_ctx *c, const float *depth, const float 
   launch_encode_bytes(depth, normal, color, max_depth, n_px, depth_rgb, normal_rgb, color_rgb, c->stream);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
+  return CUTRACE_OK;
+}
+
+int cutrace_trim_memory(int device) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(CUTRACE_ERR_NO_DEVICE, "no CUDA device");
+  if (device < 0) CU(cudaGetDevice(&device));
+  if (device >= n_dev) return fail(CUTRACE_ERR_NO_DEVICE, "requested CUDA device ordinal does not exist");
+  DeviceGuard g(device);
+  CU(cudaDeviceSynchronize());
+  pool_trim(device);
   return CUTRACE_OK;
 }
 

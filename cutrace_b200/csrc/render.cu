@@ -30,6 +30,7 @@
 //
 // All kernels are persistent: each warp claims work from a global cursor (guided chunk sizes).
 #include <cstddef>
+#include <cstdlib>
 #include "render.cuh"
 #include "trace.cuh"
 
@@ -978,6 +979,7 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
       uint32_t level = 0;
       float r = 0.f, g = 0.f, b = 0.f;
       const size_t gi = a.out.row_major ? (size_t)gy * a.tm.width + gx : (size_t)pix;
+      const size_t g2 = (size_t)gy * a.tm.width + gx;
       for (;;) {
         Hit h;
         closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
@@ -988,6 +990,9 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
           a.out.depth[gi] = h.t;
           a.out.normal[3 * gi] = nrm.x; a.out.normal[3 * gi + 1] = nrm.y; a.out.normal[3 * gi + 2] = nrm.z;
           a.out.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
+          if (a.out2.depth) a.out2.depth[g2] = h.t;
+          if (a.out2.normal) { a.out2.normal[3 * g2] = nrm.x; a.out2.normal[3 * g2 + 1] = nrm.y; a.out2.normal[3 * g2 + 2] = nrm.z; }
+          if (a.out2.hit_id) a.out2.hit_id[g2] = hit ? h.obj : CUTRACE_NO_HIT;
           if (hit && isfinite(h.t)) acc.max_depth = fmaxf(acc.max_depth, h.t);
         }
         bool next = false;
@@ -1024,6 +1029,7 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
       }
       float *cp = a.out.color + 3 * gi;
       cp[0] = r; cp[1] = g; cp[2] = b;
+      if (a.out2.color) { float *c2 = a.out2.color + 3 * g2; c2[0] = r; c2[1] = g; c2[2] = b; }
     }
   }
   // ---- tallies: warp -> block -> frame statistics; the last block publishes them and clears the counters ----
@@ -1071,7 +1077,7 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
       src[S0 + threadIdx.x] = 0u;
     }
     if (threadIdx.x == 0) { ctr->finished.v = 0u; ctr->work_trace[0].v = 0u; }
-    __threadfence_system();
+    // (no system fence: the stores to the mapped host block are complete when the kernel is, and nobody reads them earlier)
   }
 }
 
@@ -1204,10 +1210,12 @@ void launch_shade(const LaunchCfg &cfg, const SceneView &sv, uint32_t level, con
 
 cudaError_t launch_pixel(const LaunchCfg &cfg, const PixelArgs &args, cudaStream_t st) {
   if (!args.n_px) return cudaSuccess;
-  const int mode = cfg.mode == 1 ? 1 : 0;
+  // frames of a few thousand pixels read the scene through L1: staging it per CTA (mbarrier round trip) costs more than it saves
+  const int mode = cfg.mode == 1 && args.n_px >= (1u << 16) ? 1 : 0;
   const size_t smem = mode == 1 ? cfg.smem_bytes : 0;
   uint64_t need = ((uint64_t)args.n_px + CTB_PIXEL_THREADS - 1) / CTB_PIXEL_THREADS;
   int grid = (int)(need < (uint64_t)cfg.grid_pixel ? need : (uint64_t)cfg.grid_pixel);
+  if (const char *e = getenv("CUTRACE_DEBUG_PIXEL_GRID")) { int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // tuning experiments
   if (grid < 1) grid = 1;
   pick_pixel(mode, args.sv.brute_force != 0, args.sv.all_opaque != 0)<<<grid, CTB_PIXEL_THREADS, smem, st>>>(args);
   return cudaGetLastError();

@@ -97,6 +97,8 @@ struct PixelArgs {
   FrameCounters *ctr;        // zero on entry; the statistics are published to host_stats and cleared again on exit
   FrameStats *host_stats;    // mapped pinned host memory (device pointer), may be NULL
   FrameTargets out;          // where the frame lives (any layout FrameTargets describes)
+  FrameTargets out2;         // optional second, row-major copy (any pointer may be NULL): the caller's pinned host images of
+                             // cutrace_render_download — the pixels travel over PCIe while the kernel runs, there is no copy afterwards
 };
 
 

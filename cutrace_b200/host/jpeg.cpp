@@ -196,6 +196,7 @@ void encode_jpeg(std::vector<uint8_t> &o, int w, int h, const uint8_t *rgb, int 
 }
 
 bool write_jpeg(const std::string &path, int w, int h, const uint8_t *rgb, int quality) {
+  if (w <= 0 || h <= 0 || w > 65535 || h > 65535) return false;   // baseline JPEG stores the dimensions in 16 bits (SOF0)
   std::vector<uint8_t> buf;
   encode_jpeg(buf, w, h, rgb, quality);
   FILE *f = fopen(path.c_str(), "wb");

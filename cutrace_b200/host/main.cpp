@@ -57,6 +57,7 @@ int main(int argc, const char **argv) {
     fputs(cthost::kSchemaHelp, stdout);
     return -2;
   }
+  if (width > 65535 || height > 65535) { fprintf(stderr, "--width / --height above 65535 cannot be written as baseline JPEG\n"); return -1; }
   if (width > 0) scene.width = (uint32_t)width;
   if (height > 0) scene.height = (uint32_t)height;
 

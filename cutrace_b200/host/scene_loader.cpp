@@ -268,8 +268,9 @@ bool load_scene_text(const std::string &text, const LoadOptions &opt, FlatScene 
       const uint32_t id = (uint32_t)s.obj_material.size();
       double mat_d;
       if (!get_num(o, "material", mat_d, err)) { bad(err); continue; }
-      const size_t mat = (size_t)mat_d;   // (size_t) cast of the double
-      if (mat_d < 0 || mat >= n_mat) { bad("material index " + std::to_string((long long)mat_d) + " out of range"); continue; }
+      // range-check the double BEFORE the (size_t) cast of inc/json_helpers.hpp:88-93: picojson numbers like 1e300 make the cast undefined
+      if (!(mat_d >= 0.0 && mat_d < (double)n_mat)) { bad("material index out of range"); continue; }
+      const size_t mat = (size_t)mat_d;
       if (type == "triangle") {
         float a[3], b[3], c[3];
         const JsonValue *pts = o.find("points");

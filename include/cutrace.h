@@ -262,6 +262,9 @@ int cutrace_frame_ipc_import(cutrace_ctx *ctx, const void *handle);
  *     funnelling the frame through one GPU; a shared-memory mapping registered by every process works across processes.
  * width/height are the dimensions of the block and must equal the ctx's.  NULL detaches. */
 int cutrace_frame_attach(cutrace_ctx *ctx, void *frame_block, uint32_t width, uint32_t height);
+/* Device memory of every ctx comes from a memory pool this library owns (one per device; the device's default pool is not
+ * touched), which keeps freed blocks for the next upload.  Hands the cached blocks of `device` (-1: current) back to the driver. */
+int cutrace_trim_memory(int device);
 /* page-locks + maps caller memory (e.g. a shared-memory frame) for cutrace_frame_attach / fast copies; undone by unregister */
 int cutrace_host_register(void *ptr, size_t bytes);
 int cutrace_host_unregister(void *ptr);

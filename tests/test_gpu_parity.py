@@ -740,6 +740,42 @@ def test_render_download_with_the_frame_kernel(ct, monkeypatch):
         assert_same_frame(a, c, "two fused frames")
 
 
+def test_render_download_straight_into_pinned_host_memory(ct):
+    """cutrace_render_download with pinned + mapped destinations (cutrace_host_alloc): the pixel kernel stores every finished pixel
+    into the ctx's frame AND into the caller's images over PCIe — no copy afterwards.  Same bits as render + download, the
+    device frame stays valid, NULL destinations are skipped, pageable destinations take the copy path."""
+    import ctypes as C
+
+    lib = ct._lib.load()
+    s = load_golden_scene("bunny").with_resolution(1000, 562)     # odd sizes: partial tiles at both edges
+    n = s.width * s.height
+    ptrs, pinned = [], {}
+    for k, m, dt in (("depth", 1, np.float32), ("normal", 3, np.float32), ("color", 3, np.float32), ("hit_id", 1, np.uint32)):
+        p = lib.cutrace_host_alloc(n * m * 4)
+        ptrs.append(p)
+        pinned[k] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float if dt is np.float32 else C.c_uint32)), shape=(n * m,))
+        pinned[k][:] = 0
+    with ct.Renderer(s) as r:
+        md, st = C.c_float(), ct.cutrace_stats()
+        ct._lib.check(lib.cutrace_render_download(r._ctx, pinned["depth"].ctypes.data, pinned["normal"].ctypes.data, pinned["color"].ctypes.data,
+                                                  pinned["hit_id"].ctypes.data, C.byref(md), C.byref(st)))
+        assert st.kernel_launches == 1 and st.scheduler == 2
+        dev = r.download()                                        # the device frame of the same render
+        got = {k: pinned[k].reshape(dev[k].shape).copy() for k in dev if k != "max_depth"}
+        assert_same_frame(got, dev, "pinned destinations vs device frame")
+        assert md.value == dev["max_depth"]
+        r.render()
+        assert_same_frame(got, r.download(), "direct download vs plain render")
+        pinned["color"][:] = 7.0                                  # only depth this time: colour must stay untouched
+        ct._lib.check(lib.cutrace_render_download(r._ctx, pinned["depth"].ctypes.data, None, None, None, C.byref(md), None))
+        assert np.all(pinned["color"] == 7.0) and np.array_equal(pinned["depth"], dev["depth"])
+        pageable, _ = r.render_download()                         # numpy memory: copy path
+        assert_same_frame(pageable, dev, "pageable destinations")
+    del pinned, got
+    for p in ptrs:
+        lib.cutrace_host_free(p)
+
+
 def test_set_camera_resizes_and_reuses_the_scene(ct):
     """cutrace_set_camera: new resolution / view on an uploaded scene (no rebuild) == a fresh ctx."""
     s = load_golden_scene("mirror").with_resolution(320, 180)

@@ -46,8 +46,9 @@ def test_bench_helpers():
     assert cfg["rays_per_frame"] == bench.RAYS_PER_FRAME["bunny4k"] == 248_825_266 and set(cfg) == {"workload", "rays_per_frame", "primitives", "bounces", "l2"}
     # compulsory DRAM bytes of a bunny.json frame: ~9 GB, i.e. well under the HBM roofline at 10 ms/frame
     n_px = 3840 * 2160
-    comp = bench.compulsory_bytes_per_frame(n_px, 248_825_266, 4 * 6 * n_px, 4)
-    assert 8e9 < comp < 11e9
+    comp = bench.compulsory_bytes_per_frame(n_px, 248_825_266, 4 * 6 * n_px, 4, 50_000, pixel_kernel=False)
+    assert 8e9 < comp < 11e9                                                      # wavefront: queues dominate
+    assert bench.compulsory_bytes_per_frame(n_px, 248_825_266, 4 * 6 * n_px, 4, 50_000) == 32 * n_px + 50_000   # pixel kernel: the frame
     cs = bench.ClockSampler(0, enabled=False)
     cs.lines = ["1965, 1965, Not Active, Not Active, Not Active, Active", "1950, 1965, Not Active, Not Active, Not Active, Not Active"]
     s = cs.summary()
