@@ -154,6 +154,7 @@ struct cutrace_ctx {
   LightRec *lights = nullptr;
   uint32_t *obj_material = nullptr;
   ObjBound *obj_bounds = nullptr;    // per-object AABB + mesh flag (the reference's mesh pre-test, trace.cuh: mesh_gate)
+  float *pl_tbl = nullptr, *pl_eps = nullptr;   // light-side table of the planes (trace.cuh: plane_side_prepass)
   SceneView sv{};
   int max_children = 0;
   // frame
@@ -470,7 +471,7 @@ void cutrace_free(cutrace_ctx *c) {
   LAP("free: frame + graph");
   dfree(c->bvh.nodes, c->stream); dfree(c->bvh.prims, c->stream);
   dfree(c->planes, c->stream); dfree(c->materials, c->stream); dfree(c->lights, c->stream); dfree(c->obj_material, c->stream);
-  dfree(c->obj_bounds, c->stream);
+  dfree(c->obj_bounds, c->stream); dfree(c->pl_tbl, c->stream); dfree(c->pl_eps, c->stream);
   dfree(c->d_ctr, c->stream);
   LAP("free: scene buffers");
   if (c->stream) cudaStreamSynchronize(c->stream);
@@ -559,11 +560,40 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
     l.vx = s->light_vec[3 * i]; l.vy = s->light_vec[3 * i + 1]; l.vz = s->light_vec[3 * i + 2]; l.kind = s->light_kind[i];
     l.r = s->light_color[3 * i]; l.g = s->light_color[3 * i + 1]; l.b = s->light_color[3 * i + 2]; l.pad = 0;
   }
+  // side of every light relative to every plane, in double (see plane_side_prepass in trace.cuh); entries too close to the plane are 0
+  std::vector<float> pl_tbl, pl_eps;
+  if (CTB_PLANE_PREPASS) {
+    pl_tbl.resize((size_t)s->n_planes * s->n_lights); pl_eps.resize(2 * s->n_planes);
+    double scale = 1e-30;
+    for (uint64_t i = 0; i < 3 * s->n_planes; i++) scale = std::max(scale, std::fabs((double)s->pl_point[i]));
+    for (uint32_t i = 0; i < 3 * s->n_lights; i++) if (s->light_kind[i / 3] == CUTRACE_LIGHT_POINT) scale = std::max(scale, std::fabs((double)s->light_vec[i]));
+    for (uint64_t p = 0; p < s->n_planes; p++) {
+      const double n[3] = {s->pl_normal[3 * p], s->pl_normal[3 * p + 1], s->pl_normal[3 * p + 2]};
+      const double nn = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      pl_eps[2 * p] = (float)(1e-4 * nn * scale);
+      pl_eps[2 * p + 1] = (float)(1e-5 * nn);
+      for (uint32_t l = 0; l < s->n_lights; l++) {
+        const double v[3] = {s->light_vec[3 * l], s->light_vec[3 * l + 1], s->light_vec[3 * l + 2]};
+        double t, eps;
+        if (s->light_kind[l] == CUTRACE_LIGHT_POINT) {
+          t = n[0] * (s->pl_point[3 * p] - v[0]) + n[1] * (s->pl_point[3 * p + 1] - v[1]) + n[2] * (s->pl_point[3 * p + 2] - v[2]);
+          eps = 1e-4 * nn * scale;
+        } else {                                        // sun: shadow direction d = -direction / |direction|, table = -(d.n)
+          const double vn = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+          t = vn > 0 ? (v[0] * n[0] + v[1] * n[1] + v[2] * n[2]) / vn : 0.0;
+          eps = 1e-4 * nn;
+        }
+        pl_tbl[p * s->n_lights + l] = (std::isfinite(t) && std::fabs(t) > eps) ? (float)t : 0.f;
+      }
+    }
+  }
   std::vector<uint32_t> omat(s->obj_material, s->obj_material + s->n_objects);
   UP(upload(&c->planes, planes, c->stream));
   UP(upload(&c->materials, mats, c->stream));
   UP(upload(&c->lights, lights, c->stream));
   UP(upload(&c->obj_material, omat, c->stream));
+  UP(upload(&c->pl_tbl, pl_tbl, c->stream));
+  UP(upload(&c->pl_eps, pl_eps, c->stream));
   LAP("small record uploads");
 
   // ---- primitives + LBVH ----
@@ -621,6 +651,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   SceneView &sv = c->sv;
   sv.nodes = c->bvh.nodes; sv.prims = c->bvh.prims; sv.planes = c->planes; sv.materials = c->materials;
   sv.lights = c->lights; sv.obj_material = c->obj_material; sv.obj_bounds = c->obj_bounds;
+  sv.pl_tbl = c->pl_tbl; sv.pl_eps = c->pl_eps;
   sv.n_prims = c->bvh.n_prims; sv.n_nodes = c->bvh.n_nodes; sv.n_planes = (uint32_t)s->n_planes;
   sv.n_lights = s->n_lights; sv.n_materials = s->n_materials; sv.n_objects = s->n_objects;
   sv.root = c->bvh.root;

@@ -87,6 +87,14 @@ __host__ __device__ __forceinline__ float det3_t(vec3 c0, vec3 c1, vec3 c2) {
   return t;
 }
 
+// Plane side pre-pass for shadow rays (trace.cuh: plane_side_prepass): one (point - X).n per plane and a sign comparison per
+// light instead of a plane test per (light, plane).  Same images, but MEASURED SLOWER on B200 — bunny.json 4K 9.04 -> 9.94 ms
+// (pixel kernel), 9.86 -> 10.79 (wavefront), hall 81.9 -> 84.1 (profiles/r02_tuning.md): the 20 dependent table loads per
+// shaded hit cost more than the 20 short plane tests they replace.  Off; -DCTB_PLANE_PREPASS=1 builds it.
+#ifndef CTB_PLANE_PREPASS
+#define CTB_PLANE_PREPASS 0
+#endif
+
 // ---- scene records ------------------------------------------------------------------------------
 // One 48-byte record per BVH primitive, stored in BVH-leaf (Morton) order: 3 x LDG.128 / LDS.128.
 // Triangle: p1,p2,p3 = vertices exactly as uploaded (the reference's gpu::schema::triangle is also
@@ -192,6 +200,8 @@ struct SceneView {
   const LightRec *lights;
   const uint32_t *obj_material;
   const ObjBound *obj_bounds;   // n_objects
+  const float *pl_tbl;          // n_planes x n_lights: side of every light relative to every plane (trace.cuh: plane_side_prepass), or NULL
+  const float *pl_eps;          // n_planes x 2: |sX| above eps[0] + eps[1] * |X|_1 is "clearly off the plane"
   uint32_t n_prims, n_nodes, n_planes, n_lights, n_materials, n_objects;
   int root;                 // node index, leaf code, or CTB_SENTINEL (empty BVH)
   uint32_t smem_nodes;      // nodes [0, smem_nodes) are staged in shared memory

@@ -445,6 +445,7 @@ __device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *
   if (OPAQUE) {
     // every material is opaque: the shadow march saturates on its first step, so the K shadow rays
     // of this hit are any-hit queries and walk the BVH as one packet
+    const unsigned plane_maybe = CTB_PLANE_PREPASS ? plane_side_prepass(sv, hit) : 0xffffffffu;
     for (uint32_t l0 = 0; l0 < sv.n_lights; l0 += SHADOW_PACKET) {
       vec3 sd[SHADOW_PACKET];
       float md[SHADOW_PACKET];
@@ -473,7 +474,8 @@ __device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *
         }
       }
       casts += __popc(valid);
-      const unsigned occ = any_hit_packet<MODE, SHADOW_PACKET, BRUTE>(sv, nodes, prims, hit, sd, md, valid);
+      const unsigned occ = any_hit_packet<MODE, SHADOW_PACKET, BRUTE>(sv, nodes, prims, hit, sd, md, valid,
+                                                                      SHADOW_PACKET > 1 || l0 >= 32u || ((plane_maybe >> l0) & 1u));
 #pragma unroll
       for (int k = 0; k < SHADOW_PACKET; k++) {
         if ((valid & ~occ) & (1u << k)) {        // shadow_fac = 0 < 1

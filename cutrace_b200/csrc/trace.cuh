@@ -336,6 +336,39 @@ __device__ __forceinline__ bool any_hit(const SceneView &sv, const float4 *nodes
 }
 
 // -------------------------------------------------------------------------------------------------
+// Which lights can have a PLANE between them and the shaded point X?  plane::intersect (inc/default_schema.hpp:189-192) accepts
+// t0 = ((point - X).n) / (d.n) in (1e-3, light_dist).  For a point light P:  d.n = ((P - X).n) / |P - X| = (sX - sP) / L with
+// sX = (point - X).n and sP = (point - P).n, so t0 = sX L / (sX - sP): negative when sX and sP have the same sign and |sX| < |sP|,
+// beyond the light by the factor 1 / (1 - sP/sX) when |sX| > |sP|, non-finite when they are equal — a plane that has X and P
+// clearly on the same side never shadows.  For a sun the sign of d.n is a constant of (light, plane).  The host tabulates
+// tbl[l][p] = sP (point light) or -(d.n) (sun), zeroed when it is within 1e-4 |n| x (scene scale) of zero; the test below needs
+// sX once per plane (not per light) and per light only a sign comparison.  bit l of the result = "run the exact plane tests
+// for light l" (set for every light when there are more than 32 of them or no table).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned plane_side_prepass(const SceneView &sv, vec3 x) {
+  if (!sv.pl_tbl || sv.n_lights > 32u) return 0xffffffffu;
+  unsigned maybe = 0;
+#pragma unroll 1
+  for (uint32_t p = 0; p < sv.n_planes; p++) {
+    const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + p);
+    const float4 a = __ldg(pp), b = __ldg(pp + 1);
+    const float sx = vdot(mk3(b.x, b.y, b.z), vsub(mk3(a.x, a.y, a.z), x));
+    // "clearly off the plane": far above the rounding error of sx, which grows with |n| (|point| + |x|)
+    const float2 e = __ldg(reinterpret_cast<const float2 *>(sv.pl_eps) + p);
+    const bool clear = fabsf(sx) > fmaf(e.y, fabsf(x.x) + fabsf(x.y) + fabsf(x.z), e.x);
+    const float *row = sv.pl_tbl + p * sv.n_lights;
+#pragma unroll 1
+    for (uint32_t l = 0; l < sv.n_lights; l++) {
+      const float t = __ldg(row + l);
+      // same side, and not so lopsided that t0 = L / (1 - sP/sX) could round below the light distance
+      const bool same_side = clear && t != 0.f && !((__float_as_uint(sx) ^ __float_as_uint(t)) >> 31) && fabsf(sx) < 1e5f * fabsf(t);
+      if (!same_side) maybe |= 1u << l;
+    }
+  }
+  return maybe;
+}
+
+// -------------------------------------------------------------------------------------------------
 // Shadow-ray packets.  All shadow rays of one shaded hit start at the same point (inc/shading.hpp:80),
 // so up to K of them (one per light) walk the BVH together: one stack, one node fetch, the
 // (plane - origin) subtractions and the ray-independent parts of Cramer's rule (a, b, d = p2 - o)
@@ -346,12 +379,13 @@ __device__ __forceinline__ bool any_hit(const SceneView &sv, const float4 *nodes
 template <int MODE, int K, bool BRUTE>
 __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const float4 *__restrict__ nodes,
                                                    const float4 *__restrict__ prims, vec3 o, const vec3 (&d)[K],
-                                                   const float (&max_t)[K], unsigned act) {
+                                                   const float (&max_t)[K], unsigned act, bool test_planes_too = true) {
   const float min_t = (float)(0.0 + 1e-3);   // shadow_intensity: last_hit + 1e-3 with last_hit = 0
   unsigned occ = 0;
-  // planes: (point - o).n is shared by the packet
+  // planes: (point - o).n is shared by the packet.  Skipped when the caller's side test (plane_side_prepass) has already
+  // shown that no plane can lie between the origin and these lights.
 #pragma unroll 1
-  for (uint32_t p = 0; p < sv.n_planes; p++) {
+  for (uint32_t p = 0; test_planes_too && p < sv.n_planes; p++) {
     const float4 *pp = reinterpret_cast<const float4 *>(sv.planes + p);
     const float4 a = __ldg(pp), b = __ldg(pp + 1);
     const vec3 n = mk3(b.x, b.y, b.z);
