@@ -303,6 +303,13 @@ class Bench:
         self.stream = torch.cuda.Stream(device=self.local_rank, priority=-1)
         torch.cuda.set_stream(self.stream)
         self.lib = ct._lib.load()
+        # the per-frame "all tiles stored" barrier + max-depth reduction of the fused exchanges: shared host memory instead of an
+        # NCCL all-reduce (--nccl-frame-barrier restores the latter)
+        self.host_barrier = None
+        if self.world > 1 and not args.nccl_frame_barrier:
+            from cutrace_b200.distributed import HostBarrier
+
+            self.host_barrier = HostBarrier(self.rank, self.world, self.local_rank)
 
     def barrier(self):
         if self.world > 1:
@@ -321,7 +328,7 @@ class Bench:
 
         torch, args = self.torch, self.args
         tsr = TileShardedRenderer(scene, rank=self.rank, world=self.world, device=self.local_rank, flags=args.flags, stream=self.stream.cuda_stream,
-                                  exchange=args.exchange)
+                                  exchange=args.exchange, host_barrier=self.host_barrier)
 
         host = {"render": 0.0, "gather": 0.0}
 
@@ -463,7 +470,7 @@ class Bench:
                 self.barrier()
                 t0 = time.perf_counter()
                 tr = TileShardedRenderer(scene, rank=self.rank, world=self.world, device=self.local_rank, flags=args.flags, stream=self.stream.cuda_stream,
-                                         exchange="host", host_frame=frame)
+                                         exchange="host", host_frame=frame, host_barrier=self.host_barrier)
                 st = tr.render()                      # returns when this rank's tiles are in the host frame
                 tr.max_depth(st["max_depth"])         # 1-float all-reduce (kernel.hpp:120-125); doubles as the "frame complete" barrier
                 if i >= 2:
@@ -516,6 +523,7 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--verbose", action="store_true", help="per-rank timing lines on stderr")
+    ap.add_argument("--nccl-frame-barrier", action="store_true", help="N > 1: end every frame with the NCCL max-depth all-reduce instead of the shared-memory barrier")
     ap.add_argument("--exchange", default="peer", choices=["peer", "gather"],
                     help="N > 1, device-resident frames: peer = kernels store into rank 0's frame over NVLink (CUDA IPC), gather = NCCL gather + un-tile")
     args = ap.parse_args()
@@ -590,7 +598,8 @@ def main():
             "config": config_of(scene, wl),
             "details": {"parallelism": f"tiles{b.world}/{main_res['exchange']}" if b.world > 1 else "single", "scheduler": main_res["scheduler"],
                         "timed": "K frames between two CUDA events on the launching stream" + (
-                            "" if b.world == 1 else ", incl. the rank barrier (tiles are stored into rank 0's frame over NVLink by the kernels)"
+                            "" if b.world == 1 else ", incl. the per-frame rank barrier + max-depth reduction (" + ("shared host memory" if b.host_barrier is not None else "NCCL all-reduce") +
+                            "; tiles are stored into rank 0's frame over NVLink by the kernels)"
                             if main_res["exchange"] == "peer" else ", incl. NCCL gather + un-tile"),
                         "render_device_ms": main_res["render_device_ms"], "rays_counted": int(rays)},
             "clocks": clocks,

@@ -144,6 +144,68 @@ class SharedHostFrame:
                 pass
 
 
+class HostBarrier:
+    """Barrier + max-reduce of one float between the rank processes of one box through a few cache lines of shared host memory
+    (memfd opened through /proc/<pid>/fd, like SharedHostFrame).  The exchanges that are fused into the kernels (peer frame, host
+    frame) need exactly this per frame — "every rank's kernel has finished" and the frame-wide max depth (kernel.hpp:120-125).
+    Each rank's cutrace_render returns after its stream is idle, so a host-side barrier is sufficient; it takes ~2 us where the
+    NCCL all-reduce + the read-back of its result took 90 us — 6 % of a 1.4 ms frame at N = 8 (profiles/r02_scaling.md).
+    x86-64 keeps stores in order, so a rank's value is visible before its sequence number."""
+
+    LINE = 16   # 128-byte slots (float64 view)
+
+    def __init__(self, rank, world, device=None):
+        import mmap
+        import os
+
+        import torch
+        import torch.distributed as dist
+
+        self.rank, self.world, self.seq = rank, world, 0
+        nbytes = 8 * self.LINE * max(world, 1)
+        path = [None]
+        if rank == 0:
+            self._fd = os.memfd_create("cutrace_b200_barrier")
+            os.ftruncate(self._fd, nbytes)
+            path[0] = f"/proc/{os.getpid()}/fd/{self._fd}"
+        if world > 1:
+            dist.broadcast_object_list(path, src=0, **({"device": torch.device("cuda", device)} if device is not None else {}))
+        if rank != 0:
+            self._fd = os.open(path[0], os.O_RDWR)
+        self._map = mmap.mmap(self._fd, nbytes)
+        self.slots = np.frombuffer(self._map, dtype=np.float64).reshape(max(world, 1), self.LINE)
+        if world > 1:
+            dist.barrier()
+
+    def max(self, value, timeout_s=60.0):
+        """Collective: returns the max of ``value`` over the ranks once every rank has called it."""
+        import time
+
+        self.seq += 1
+        col = 1 + (self.seq & 1)            # values of even / odd rounds live in different words: a rank that is already in round
+        mine = self.slots[self.rank]        # k+1 (it cannot be further ahead) never overwrites what a slower rank still reads for k
+        mine[col] = float(value)
+        mine[0] = float(self.seq)           # published last
+        seqs = self.slots[:, 0]
+        t0 = time.perf_counter()
+        while float(seqs.min()) < self.seq:
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError("HostBarrier: a rank did not arrive")
+        return float(self.slots[:, col].max())
+
+    def close(self):
+        import os
+
+        self.slots = None
+        try:
+            self._map.close()
+        except (BufferError, AttributeError):
+            pass
+        if getattr(self, "_fd", None) is not None:
+            os.close(self._fd)
+            self._fd = None
+
+
 class _DevArray:
     """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it (no copy)."""
 
@@ -164,9 +226,10 @@ class TileShardedRenderer:
     to rank 0 followed by the device un-tile kernel.
     """
 
-    def __init__(self, scene, rank, world, device, exchange="peer", host_frame=None, **kw):
+    def __init__(self, scene, rank, world, device, exchange="peer", host_frame=None, host_barrier=None, **kw):
         import torch
 
+        self.host_barrier = host_barrier    # a HostBarrier shared by the ranks: replaces the NCCL all-reduce that ends a frame
         self.torch = torch
         self.rank, self.world = rank, world
         self.scene = scene
@@ -244,8 +307,11 @@ class TileShardedRenderer:
         if self.world == 1:
             return
         if self.exchange in ("peer", "host"):
-            # the only collective of these exchanges: the 1-float max-depth all-reduce (kernel.hpp:120-125), which is also the
+            # the only collective of these exchanges: the 1-float max-depth reduction (kernel.hpp:120-125), which is also the
             # "every rank's tiles are stored" barrier (each rank's cutrace_render returned before it joined)
+            if self.host_barrier is not None:
+                self.frame_max_depth = self.host_barrier.max(self.r.stats()["max_depth"])
+                return
             if not hasattr(self, "_md"):
                 self._md = torch.zeros(1, dtype=torch.float32, device=self.device)
             self._md.fill_(float(self.r.stats()["max_depth"]))
@@ -267,6 +333,8 @@ class TileShardedRenderer:
         """max over ranks of the largest finite depth (kernel.hpp:120-125) — a 1-float all-reduce."""
         import torch.distributed as dist
 
+        if self.host_barrier is not None and self.world > 1:
+            return self.host_barrier.max(local_max)
         t = self.torch.tensor([local_max], dtype=self.torch.float32, device=self.device)
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -130,3 +130,34 @@ def test_world2_shared_host_frame(tmp_path, oracle):
     ref = oracle.oracle_render(load_golden_scene("sphere_plane").with_resolution(w, h))
     for k in ("depth", "normal", "color", "hit_id"):
         assert np.array_equal(got[k].reshape(-1).view(np.uint32), ref[k].reshape(-1).view(np.uint32)), k
+
+
+def _barrier_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    import time
+
+    import torch.distributed as dist
+
+    from cutrace_b200.distributed import HostBarrier
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    hb = HostBarrier(rank, world)
+    got = []
+    for k in range(200):
+        if rank == k % world:
+            time.sleep(0.0005)           # a different straggler every round
+        got.append(hb.max(float(k * 10 + rank)))
+    hb.close()
+    if rank == 0:
+        np.save(out_path, np.asarray(got))
+    dist.destroy_process_group()
+
+
+def test_host_barrier_max_world3(tmp_path):
+    """HostBarrier: 200 rounds with a rotating straggler; every round returns the max over the ranks of THAT round."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "hb.npy")
+    mp.spawn(_barrier_worker, args=(3, _free_port(), out), nprocs=3, join=True)
+    got = np.load(out)
+    assert np.array_equal(got, np.arange(200) * 10.0 + 2.0)
