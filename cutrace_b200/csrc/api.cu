@@ -656,7 +656,8 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   sv.n_lights = s->n_lights; sv.n_materials = s->n_materials; sv.n_objects = s->n_objects;
   sv.root = c->bvh.root;
   sv.all_opaque = all_opaque ? 1u : 0u;
-  sv.brute_force = (o.flags & CUTRACE_FLAG_BRUTE_FORCE) ? 1u : 0u;
+  // a handful of primitives is looped over directly: no node loads, no stack (sphere_plane.json 1080p 0.56 -> 0.51 ms, same image)
+  sv.brute_force = ((o.flags & CUTRACE_FLAG_BRUTE_FORCE) || c->bvh.n_prims <= 8u) ? 1u : 0u;
   sv.fudge = o.fudge;
   sv.scene_mag = 0.f;
   for (int a = 0; a < 3; a++) sv.scene_mag = fmaxf(sv.scene_mag, fmaxf(fabsf(c->bvh.lo[a]), fabsf(c->bvh.hi[a])));

@@ -16,17 +16,19 @@
 // weights: own Phong term w*(1-t), reflected child w*(1-t)*r, transmitted child w*t; at the last
 // level (bounces exhausted) the blend is skipped exactly like `if constexpr(bounces != 0)`.
 //
-// Two schedulers drive the same device functions (trace_chunk / shade_chunk):
+// Three schedulers drive the same per-ray device functions:
 //
-//   frame_kernel   (default) ONE persistent cooperative kernel per frame: the level loop runs on the device.  Phase p
+//   pixel_kernel   (default) ONE persistent kernel per frame: a thread walks a pixel's whole path — the recursion of ray_color
+//                  as a loop with an explicit stack — and warps claim pixels from a global cursor.  No queues at all.
+//   frame_kernel   the wavefront as ONE persistent cooperative kernel per frame: the level loop runs on the device.  Phase p
 //                  = trace(p); a warp that runs out of trace(p) work arrives at the phase barrier and, instead of
 //                  spinning, shades records of the levels < p until the barrier opens (all warps arrived), so the
 //                  tail of every trace level is filled with shading.  After the last phase: ordered per-pixel sum of
 //                  the level images, G-buffer / colour stores to wherever the frame lives (own HBM, a peer GPU over
 //                  NVLink, pinned host memory), counters published to mapped host memory and cleared for the next
 //                  frame.  The scene is staged into shared memory once per CTA and frame (cp.async.bulk + mbarrier).
-//   trace_kernel / shade_kernel   one launch per level and kind (CUTRACE_FLAG_SERIALIZE: per-kernel timings; also the
-//                  fallback when a cooperative launch is not possible).
+//   trace_kernel / shade_kernel   the wavefront as one launch per level and kind (CUTRACE_FLAG_LAUNCHES; CUTRACE_FLAG_SERIALIZE:
+//                  per-kernel timings; also the fallback when a cooperative launch is not possible).
 //
 // All kernels are persistent: each warp claims work from a global cursor (guided chunk sizes).
 #include <cstddef>
@@ -542,12 +544,9 @@ __device__ __forceinline__ void shade_chunk(const SceneView &sv, const float4 *n
         lp[0] = weight * final.x; lp[1] = weight * final.y; lp[2] = weight * final.z;
         continue;
       }
+      // a material reflects AND transmits: several hits of one pixel can sit in one level -> float atomics into the local accumulator
       float *cp = fb.color + 3 * (size_t)pix;
-      if (atomic_accumulate) {
-        atomicAdd(cp, weight * final.x); atomicAdd(cp + 1, weight * final.y); atomicAdd(cp + 2, weight * final.z);
-      } else {
-        cp[0] += weight * final.x; cp[1] += weight * final.y; cp[2] += weight * final.z;
-      }
+      atomicAdd(cp, weight * final.x); atomicAdd(cp + 1, weight * final.y); atomicAdd(cp + 2, weight * final.z);
     }
   }
 }

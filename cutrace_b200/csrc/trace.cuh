@@ -409,7 +409,8 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
 #pragma unroll
       for (int k = 0; k < K; k++) {
         if (act & (1u << k)) {
-          RayCtx r; make_ray(r, o, d[k], sv.scene_mag);
+          RayCtx r;
+          r.o = o; r.d = d[k];   // test_prim only reads origin and direction (the slab data is for the BVH walk)
           Hit h; hit_reset(h);
           test_prim<MODE>(sv, prims, i, r, min_t, h);
           if (h.t < max_t[k]) { occ |= 1u << k; act &= ~(1u << k); }
