@@ -469,7 +469,7 @@ void cutrace_free(cutrace_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_frame(c);
   LAP("free: frame + graph");
-  dfree(c->bvh.nodes, c->stream); dfree(c->bvh.prims, c->stream);
+  dfree(c->bvh.nodes, c->stream); dfree(c->bvh.nodes4, c->stream); dfree(c->bvh.prims, c->stream);
   dfree(c->planes, c->stream); dfree(c->materials, c->stream); dfree(c->lights, c->stream); dfree(c->obj_material, c->stream);
   dfree(c->obj_bounds, c->stream); dfree(c->pl_tbl, c->stream); dfree(c->pl_eps, c->stream);
   dfree(c->d_ctr, c->stream);
@@ -655,6 +655,10 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   sv.n_prims = c->bvh.n_prims; sv.n_nodes = c->bvh.n_nodes; sv.n_planes = (uint32_t)s->n_planes;
   sv.n_lights = s->n_lights; sv.n_materials = s->n_materials; sv.n_objects = s->n_objects;
   sv.root = c->bvh.root;
+  if (CTB_BVH4 && c->bvh.nodes4) {   // the kernels of this build walk the 4-wide tree (node 0 is its root, too)
+    sv.nodes = reinterpret_cast<const Node *>(c->bvh.nodes4);
+    sv.n_nodes = c->bvh.n_nodes4;
+  }
   sv.all_opaque = all_opaque ? 1u : 0u;
   // a handful of primitives is looped over directly: no node loads, no stack (sphere_plane.json 1080p 0.56 -> 0.51 ms, same image)
   sv.brute_force = ((o.flags & CUTRACE_FLAG_BRUTE_FORCE) || c->bvh.n_prims <= 8u) ? 1u : 0u;
@@ -676,8 +680,8 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
     // shared-memory plan: everything (nodes + primitives) if it fits next to the SM, else the top of the tree
     int smem_optin = 0;
     CUF(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t whole = (size_t)sv.n_nodes * sizeof(Node) + (size_t)sv.n_prims * sizeof(PrimRec);
-    const bool allow = !(o.flags & CUTRACE_FLAG_NO_SMEM_TOP) && !sv.brute_force;
+    const size_t whole = (size_t)sv.n_nodes * CTB_NODE_BYTES + (size_t)sv.n_prims * sizeof(PrimRec);
+    const bool allow = !(o.flags & CUTRACE_FLAG_NO_SMEM_TOP) && !sv.brute_force && !CTB_BVH4;
     sv.smem_nodes = 0;
     if (allow && whole + 1024 > (size_t)smem_optin && sv.root == 0 && sv.n_nodes > 0) {
       uint32_t want = CTB_SMEM_TOP_NODES, n_top = 0;

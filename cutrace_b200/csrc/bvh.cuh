@@ -21,6 +21,8 @@ struct BvhInput {
 };
 
 struct BvhResult {
+  Node4 *nodes4 = nullptr;    // CTB_BVH4 builds only: n_nodes4 nodes of the 4-wide tree; node 0 is the root when root >= 0
+  uint32_t n_nodes4 = 0;
   Node *nodes = nullptr;      // n_nodes compacted live nodes; node 0 is the root when root >= 0
   PrimRec *prims = nullptr;   // n_prims records in leaf order
   uint32_t n_nodes = 0, n_prims = 0;

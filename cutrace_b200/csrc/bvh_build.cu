@@ -500,6 +500,279 @@ __global__ void emit_kernel(int n_internal, const int2 *__restrict__ children, c
   nodes[compact[i]] = nd;
 }
 
+// ---- SAH treelets -------------------------------------------------------------------------------------------------------
+// Karras' hierarchy splits a node where its Morton prefix ends — a spatial-median split on a fixed axis cycle.  Its lower
+// levels decide most of a ray's cost (every ray that reaches a mesh walks them), and there a sweep-SAH tree is ~20 % cheaper
+// (expected cost of bunny.json's 1000 triangles: 29.2 -> 23.3, profiles/r02_tuning.md).  So every maximal subtree of at most
+// SAH_T primitives (a "treelet": the whole tree of the reference scenes, one mesh instance of the 10 M-triangle hall) gets
+// its TOPOLOGY rebuilt by one CTA: full-sweep SAH over the three centroid orders, top down, level by level, one primitive
+// per thread.  The treelet keeps its root index and its primitive range [lo, hi] in the sorted order; the primitives are
+// permuted inside that range (leaves of the new tree, left to right) and the internal nodes lo+1 .. hi-1 (Karras numbering:
+// the indices inside a subtree are its range minus the two endpoints, plus the root) are re-linked.  Everything downstream
+// (gather, refit, leaf collapse, emit) works on the Karras arrays as before.
+#ifndef CTB_SAH_TREELETS
+#define CTB_SAH_TREELETS 1
+#endif
+#define SAH_T 1024
+struct SahShared {
+  float blo[3][SAH_T], bhi[3][SAH_T];   // primitive boxes by local id
+  float key[SAH_T];                     // sort keys / scratch
+  unsigned short ord[3][SAH_T];         // local ids per axis, partitioned by segment
+  unsigned short tmp[SAH_T];
+  unsigned short sa[SAH_T], sb[SAH_T];  // segment [sa, sb) a position belongs to
+  short pg[SAH_T];                      // parent gap of that segment (-1: the treelet root)
+  unsigned char side[SAH_T];            // which child of the parent the segment is
+  unsigned char left[SAH_T];            // by local id: goes to the left child in this level
+  float parea[SAH_T], sarea[SAH_T];     // prefix / suffix box areas in the current axis order
+  float scan[6][SAH_T];                 // scan workspace
+  int cnt[SAH_T];
+  unsigned long long best[SAH_T];       // by segment start: min over (cost, axis, position)
+  uint32_t vals_in[SAH_T];
+  int open;                             // segments with more than one primitive
+  int g_root;                           // gap (split position - 1) of the treelet root
+};
+
+__device__ __forceinline__ float box_area6(const float b[6]) {
+  const float dx = fmaxf(b[3] - b[0], 0.f), dy = fmaxf(b[4] - b[1], 0.f), dz = fmaxf(b[5] - b[2], 0.f);
+  return dx * dy + dy * dz + dz * dx;
+}
+
+// roots of the treelets: internal nodes of at most SAH_T (and more than leaf_size) primitives whose parent is bigger
+__global__ void sah_roots_kernel(int n_internal, const int2 *__restrict__ range, const int *__restrict__ parent_node, uint32_t leaf_size,
+                                 uint32_t *__restrict__ roots, uint32_t *__restrict__ n_roots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal) return;
+  const int2 r = range[i];
+  const uint32_t cnt = (uint32_t)(r.y - r.x + 1);
+  if (cnt > SAH_T || cnt <= leaf_size || cnt < 3) return;
+  const int p = parent_node[i];
+  if (p >= 0) { const int2 pr = range[p]; if ((uint32_t)(pr.y - pr.x + 1) <= SAH_T) return; }
+  roots[atomicAdd(n_roots, 1u)] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(SAH_T, 1)
+sah_treelet_kernel(const uint32_t *__restrict__ roots, const float4 *__restrict__ g_lo, const float4 *__restrict__ g_hi,
+                   uint32_t *__restrict__ vals, int2 *__restrict__ children, int2 *__restrict__ range, int *__restrict__ parent_node,
+                   int *__restrict__ parent_leaf) {
+  extern __shared__ unsigned char sah_raw[];
+  SahShared &S = *reinterpret_cast<SahShared *>(sah_raw);
+  const int r = (int)roots[blockIdx.x];
+  const int2 rr = range[r];
+  const int lo = rr.x, m = rr.y - rr.x + 1;
+  const int t = threadIdx.x;
+  const bool on = t < m;
+  // internal node index of a gap of this treelet (see the header comment); the root keeps r
+  auto node_of_gap = [&](int g) -> int { return g == S.g_root ? r : lo + 1 + (g < S.g_root ? g : g - 1); };
+
+  // ---- load ----
+  if (on) {
+    const uint32_t id = vals[lo + t];
+    S.vals_in[t] = id;
+    const float4 l = g_lo[id], h = g_hi[id];
+    S.blo[0][t] = l.x; S.blo[1][t] = l.y; S.blo[2][t] = l.z; S.bhi[0][t] = h.x; S.bhi[1][t] = h.y; S.bhi[2][t] = h.z;
+    S.sa[t] = 0; S.sb[t] = (unsigned short)m; S.pg[t] = -1; S.side[t] = 0;
+  }
+  if (t == 0) { S.open = 1; S.g_root = -1; }
+  __syncthreads();
+  // ---- three centroid orders: bitonic sort of (key, id) over the next power of two ----
+  int P = 1;
+  while (P < m) P <<= 1;
+  for (int ax = 0; ax < 3; ax++) {
+    S.key[t] = on ? S.blo[ax][t] + S.bhi[ax][t] : INFINITY;
+    S.tmp[t] = (unsigned short)t;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const int x = t ^ j;
+        if (t < P && x > t) {
+          const bool up = (t & k) == 0;
+          const float a = S.key[t], b = S.key[x];
+          const unsigned short ia = S.tmp[t], ib = S.tmp[x];
+          const bool gt = a > b || (a == b && ia > ib);
+          if (gt == up) { S.key[t] = b; S.key[x] = a; S.tmp[t] = ib; S.tmp[x] = ia; }
+        }
+        __syncthreads();
+      }
+    if (on) S.ord[ax][t] = S.tmp[t];
+    __syncthreads();
+  }
+
+  // ---- top down, one level per iteration ----
+  for (int level = 0; level < SAH_T && S.open > 0; level++) {
+    const int a = on ? S.sa[t] : 0, b = on ? S.sb[t] : 0;
+    const bool live = on && b - a > 1;
+    if (on && t == a) S.best[a] = ~0ull;
+    __syncthreads();
+    for (int ax = 0; ax < 3; ax++) {
+      // segmented inclusive prefix / suffix box scans in this axis' order (Hillis-Steele, one element per thread)
+      for (int dir = 0; dir < 2; dir++) {
+        float bx[6];
+        if (on) {
+          const int id = S.ord[ax][t];
+          bx[0] = S.blo[0][id]; bx[1] = S.blo[1][id]; bx[2] = S.blo[2][id]; bx[3] = S.bhi[0][id]; bx[4] = S.bhi[1][id]; bx[5] = S.bhi[2][id];
+#pragma unroll
+          for (int c = 0; c < 6; c++) S.scan[c][t] = bx[c];
+        }
+        __syncthreads();
+        for (int d = 1; d < m; d <<= 1) {
+          const int o = dir == 0 ? t - d : t + d;
+          const bool take = on && (dir == 0 ? o >= a : o < b);
+          float nb[6];
+          if (take) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) nb[c] = S.scan[c][o];
+          }
+          __syncthreads();
+          if (take) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { bx[c] = fminf(bx[c], nb[c]); bx[c + 3] = fmaxf(bx[c + 3], nb[c + 3]); }
+#pragma unroll
+            for (int c = 0; c < 6; c++) S.scan[c][t] = bx[c];
+          }
+          __syncthreads();
+        }
+        if (on) { if (dir == 0) S.parea[t] = box_area6(bx); else S.sarea[t] = box_area6(bx); }
+        __syncthreads();
+      }
+      // cost of splitting after position t (left = [a, t], right = [t+1, b))
+      if (live && t < b - 1) {
+        const float c = S.parea[t] * (float)(t - a + 1) + S.sarea[t + 1] * (float)(b - t - 1);
+        const unsigned long long packed = ((unsigned long long)__float_as_uint(fmaxf(c, 0.f)) << 32) | ((unsigned long long)ax << 16) | (unsigned long long)t;
+        atomicMin(&S.best[a], packed);
+      }
+      __syncthreads();
+    }
+    // ---- the split of my segment ----
+    int ax_s = 0, nleft = 0;
+    if (live) {
+      const unsigned long long bst = S.best[a];
+      ax_s = (int)((bst >> 16) & 3ull);
+      nleft = (int)(bst & 0xffffull) - a + 1;
+      S.left[S.ord[ax_s][t]] = (t - a) < nleft ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- stable partition of the three orders by the side flags ----
+    for (int ax = 0; ax < 3; ax++) {
+      int f = 0;
+      if (live) f = S.left[S.ord[ax][t]];
+      S.cnt[t] = f;
+      __syncthreads();
+      int run = f;   // segmented inclusive scan of the flags
+      for (int d = 1; d < m; d <<= 1) {
+        int add = 0;
+        if (live && t - d >= a) add = S.cnt[t - d];
+        __syncthreads();
+        if (live) { run += add; S.cnt[t] = run; }
+        __syncthreads();
+      }
+      if (live) {
+        const int before = run - f;
+        const int np = f ? a + before : a + nleft + (t - a - before);
+        S.tmp[np] = S.ord[ax][t];
+      }
+      __syncthreads();
+      if (live) S.ord[ax][t] = S.tmp[t];
+      __syncthreads();
+    }
+    // ---- link the new node, hand the two halves down ----
+    if (t == 0) S.open = 0;
+    __syncthreads();
+    if (live) {
+      const int g = a + nleft - 1;                 // gap of this node
+      if (t == a) {
+        if (S.pg[t] < 0) S.g_root = g;
+      }
+    }
+    __syncthreads();
+    if (live) {
+      const int g = a + nleft - 1;
+      const int me = node_of_gap(g);
+      if (t == a) {
+        range[me] = make_int2(lo + a, lo + b - 1);
+        const int pgap = S.pg[t];
+        if (pgap >= 0) {
+          const int par = node_of_gap(pgap);
+          if (S.side[t] == 0) children[par].x = me; else children[par].y = me;
+          parent_node[me] = par;
+        }
+      }
+      // my new segment
+      const bool is_left = (t - a) < nleft;
+      const int na = is_left ? a : a + nleft, nbd = is_left ? a + nleft : b;
+      S.sa[t] = (unsigned short)na; S.sb[t] = (unsigned short)nbd; S.pg[t] = (short)g; S.side[t] = is_left ? 0 : 1;
+      if (nbd - na == 1) {                         // a single primitive: a leaf of the tree
+        if (is_left) children[me].x = ~(lo + t); else children[me].y = ~(lo + t);
+        parent_leaf[lo + t] = me;
+      } else if (t == na) {
+        atomicAdd(&S.open, 1);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- the new left-to-right order of the primitives ----
+  if (on) vals[lo + t] = S.vals_in[S.ord[0][t]];
+}
+
+// ---- 4-wide collapse (CTB_BVH4) ----------------------------------------------------------------------------------------
+// A live internal node of the binary tree is KEPT when its depth is even; a kept node adopts the children of its live
+// internal children (odd depth), so it ends up with 2..4 slots: leaves (single primitives or collapsed subtrees) and kept
+// grandchildren.  Every ancestor of a live node is live, so the depth is the length of the parent chain.
+__global__ void kept_kernel(int n_internal, const int2 *__restrict__ range, const int *__restrict__ parent_node, uint32_t leaf_size,
+                            uint32_t *__restrict__ kept) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal) return;
+  int2 r = range[i];
+  unsigned int d = 0;
+  if ((uint32_t)(r.y - r.x + 1) > leaf_size)
+    for (int p = parent_node[i]; p >= 0; p = parent_node[p]) d++;
+  else
+    d = 1;   // not live
+  kept[i] = (d & 1u) ? 0u : 1u;
+}
+
+__global__ void emit4_kernel(int n_internal, const int2 *__restrict__ children, const int2 *__restrict__ range, const uint32_t *__restrict__ kept,
+                             const uint32_t *__restrict__ idx4, uint32_t leaf_size, const float4 *__restrict__ leaf_lo,
+                             const float4 *__restrict__ leaf_hi, const float4 *__restrict__ node_lo, const float4 *__restrict__ node_hi,
+                             float eps, Node4 *__restrict__ nodes4) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal || !kept[i]) return;
+  int ref[4] = {CTB_SENTINEL, CTB_SENTINEL, CTB_SENTINEL, CTB_SENTINEL};
+  float lo[4][3], hi[4][3];
+  for (int s = 0; s < 4; s++)
+    for (int a = 0; a < 3; a++) { lo[s][a] = INFINITY; hi[s][a] = -INFINITY; }
+  int n = 0;
+  auto add = [&](int r_, float4 l, float4 h) {
+    ref[n] = r_;
+    lo[n][0] = l.x - eps; lo[n][1] = l.y - eps; lo[n][2] = l.z - eps;
+    hi[n][0] = h.x + eps; hi[n][1] = h.y + eps; hi[n][2] = h.z + eps;
+    n++;
+  };
+  // one child of a binary node as a slot: leaf, collapsed subtree, or (expand == false) a kept node
+  auto visit = [&](int ch, bool may_expand, auto &&self) -> void {
+    if (ch < 0) { add(leaf_encode((uint32_t)~ch, 1u), leaf_lo[~ch], leaf_hi[~ch]); return; }
+    int2 cr = range[ch];
+    uint32_t cnt = (uint32_t)(cr.y - cr.x + 1);
+    if (cnt <= leaf_size) { add(leaf_encode((uint32_t)cr.x, cnt), node_lo[ch], node_hi[ch]); return; }
+    if (may_expand) {   // live internal child at odd depth: adopt its two children
+      int2 g = children[ch];
+      self(g.x, false, self);
+      self(g.y, false, self);
+    } else {            // live internal grandchild at even depth: a kept node
+      add((int)idx4[ch], node_lo[ch], node_hi[ch]);
+    }
+  };
+  int2 c = children[i];
+  visit(c.x, true, visit);
+  visit(c.y, true, visit);
+  Node4 nd;
+  nd.lox = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]); nd.hix = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+  nd.loy = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]); nd.hiy = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+  nd.loz = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]); nd.hiz = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+  nd.ref = make_int4(ref[0], ref[1], ref[2], ref[3]);
+  nd.pad = make_int4(range[i].x, range[i].y, n, 0);
+  nodes4[idx4[i]] = nd;
+}
+
 __global__ void depth_kernel(int n_internal, const int2 *__restrict__ range, const int *__restrict__ parent_node,
                              uint32_t leaf_size, unsigned int *max_depth) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -843,11 +1116,10 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
     rc = radix_sort_pairs(keys, vals, n, st, err);
     if (rc) goto done;
     BLAP("morton + sort");
-    gather_kernel<<<nb, T, 0, st>>>(vals, n, in.d_p1, in.d_p2, in.d_p3, in.d_tri_obj, in.n_tri, in.d_sph_center,
-                                    in.d_sph_radius, in.d_sph_obj, lo, hi, out.prims, leaf_lo, leaf_hi);
-    CK(cudaGetLastError());
-
     if (n <= leaf_size) {  // the whole scene is one leaf
+      gather_kernel<<<nb, T, 0, st>>>(vals, n, in.d_p1, in.d_p2, in.d_p3, in.d_tri_obj, in.n_tri, in.d_sph_center,
+                                      in.d_sph_radius, in.d_sph_obj, lo, hi, out.prims, leaf_lo, leaf_hi);
+      CK(cudaGetLastError());
       out.root = leaf_encode(0u, n);
       out.n_nodes = 0;
       out.depth = 0;
@@ -875,6 +1147,24 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
     BLAP("gather + alloc 2");
     const uint32_t nbi = (ni + T - 1) / T;
     karras_kernel<<<nbi, T, 0, st>>>(keys, (int)n, children, range, parent_node, parent_leaf);
+    if (CTB_SAH_TREELETS && !getenv("CUTRACE_DEBUG_NO_SAH")) {
+      // rebuild the topology of every subtree of at most SAH_T primitives with sweep SAH (`live` is free until live_kernel: treelet roots)
+      uint32_t n_roots = 0;
+      CK(cudaMemsetAsync(d_total, 0, 4, st));
+      sah_roots_kernel<<<nbi, T, 0, st>>>(ni, range, parent_node, leaf_size, live, d_total);
+      CK(cudaMemcpyAsync(&n_roots, d_total, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (n_roots) {
+        CK(cudaFuncSetAttribute(sah_treelet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SahShared)));
+        sah_treelet_kernel<<<n_roots, SAH_T, sizeof(SahShared), st>>>(live, lo, hi, vals, children, range, parent_node, parent_leaf);
+        CK(cudaGetLastError());
+      }
+      BLAP("sah treelets");
+    }
+    // primitives in their final order (the treelets permute `vals` inside their ranges)
+    gather_kernel<<<nb, T, 0, st>>>(vals, n, in.d_p1, in.d_p2, in.d_p3, in.d_tri_obj, in.n_tri, in.d_sph_center,
+                                    in.d_sph_radius, in.d_sph_obj, lo, hi, out.prims, leaf_lo, leaf_hi);
+    CK(cudaGetLastError());
     refit_kernel<<<nb, T, 0, st>>>((int)n, children, parent_node, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags);
     live_kernel<<<nbi, T, 0, st>>>(ni, range, leaf_size, live);
     exclusive_scan_u32(live, live, (uint32_t)ni, tile_sums, d_total, st);
@@ -886,6 +1176,17 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
     out.n_nodes = n_live;
     CK(dmalloc(&out.nodes, sizeof(Node) * n_live, st));
     emit_kernel<<<nbi, T, 0, st>>>(ni, children, range, live, leaf_size, leaf_lo, leaf_hi, node_lo, node_hi, eps, out.nodes);
+    if (CTB_BVH4) {   // `live` (the compact indices of the binary nodes) is not needed any more: reuse it for the kept flags / indices
+      kept_kernel<<<nbi, T, 0, st>>>(ni, range, parent_node, leaf_size, live);
+      exclusive_scan_u32(live, vals, (uint32_t)ni, tile_sums, d_total, st);   // vals (sort payload) is free by now: 4-wide indices
+      uint32_t n4 = 0;
+      CK(cudaMemcpyAsync(&n4, d_total, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (n4 == 0) { err = "internal: 4-wide collapse kept no node"; rc = CUTRACE_ERR_INTERNAL; goto done; }
+      out.n_nodes4 = n4;
+      CK(dmalloc(&out.nodes4, sizeof(Node4) * n4, st));
+      emit4_kernel<<<nbi, T, 0, st>>>(ni, children, range, live, vals, leaf_size, leaf_lo, leaf_hi, node_lo, node_hi, eps, out.nodes4);
+    }
     depth_kernel<<<nbi, T, 0, st>>>(ni, range, parent_node, leaf_size, d_depth);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&out.depth, d_depth, 4, cudaMemcpyDeviceToHost, st));
@@ -903,7 +1204,7 @@ done:
   dfree(node_lo, st); dfree(node_hi, st); dfree(children, st); dfree(range, st); dfree(parent_node, st); dfree(parent_leaf, st);
   dfree(flags, st); dfree(live, st); dfree(tile_sums, st); dfree(d_total, st); dfree(d_depth, st);
   if (rc != CUTRACE_OK) {
-    dfree(out.prims, st); dfree(out.nodes, st);
+    dfree(out.prims, st); dfree(out.nodes, st); dfree(out.nodes4, st); out.nodes4 = nullptr;
     out.prims = nullptr; out.nodes = nullptr;
   }
   return rc;

@@ -119,6 +119,21 @@ struct __align__(16) Node {
   int4 meta;
 };
 static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
+
+// -DCTB_BVH4=1: the kernels walk a 4-wide tree instead — every second level of the binary LBVH collapsed into its parent
+// (bvh_build.cu: collapse4).  128-byte node, structure of arrays over the four children so that one float4 holds one box plane
+// of all of them; an empty slot has an inverted box (never hit) and the reference CTB_SENTINEL.
+struct __align__(16) Node4 {
+  float4 lox, hix, loy, hiy, loz, hiz;
+  int4 ref;     // child >= 0: Node4 index; child < 0: leaf code (as in Node); CTB_SENTINEL: empty slot
+  int4 pad;
+};
+static_assert(sizeof(Node4) == 128, "Node4 must be 128 bytes");
+#ifndef CTB_BVH4
+#define CTB_BVH4 0
+#endif
+#define CTB_NODE_F4 (CTB_BVH4 ? 8u : 4u)          // float4 words per node of the tree the kernels walk
+#define CTB_NODE_BYTES (16u * CTB_NODE_F4)
 #define CTB_SENTINEL 0x7fffffff
 #define CTB_STACK 64
 #define CTB_MAX_LEAF 8

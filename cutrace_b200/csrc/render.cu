@@ -156,11 +156,11 @@ __device__ __forceinline__ void stage_scene(const SceneView &sv, float4 *smem, c
   const float4 *gn = reinterpret_cast<const float4 *>(sv.nodes);
   const float4 *gp = reinterpret_cast<const float4 *>(sv.prims);
   if (MODE == 1) {
-    const uint32_t nb = sv.n_nodes * (uint32_t)sizeof(Node), pb = sv.n_prims * (uint32_t)sizeof(PrimRec);
+    const uint32_t nb = sv.n_nodes * CTB_NODE_BYTES, pb = sv.n_prims * (uint32_t)sizeof(PrimRec);
     uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(smem) + nb + pb);   // 16-byte aligned: both sizes are multiples of 16
     bulk_stage(smem, gn, nb, gp, pb, bar);
     nodes = smem;
-    prims = smem + sv.n_nodes * 4u;
+    prims = smem + sv.n_nodes * CTB_NODE_F4;
   } else {
     if (MODE == 2) {   // top of the BVH (first smem_nodes nodes, breadth-first) -> shared memory
       const uint32_t nb = sv.smem_nodes * (uint32_t)sizeof(Node);
@@ -596,7 +596,7 @@ __device__ __forceinline__ void scene_ptrs(const SceneView &sv, const float4 *&n
   extern __shared__ float4 ctb_dyn_smem[];
   if (MODE == 1) {
     nodes = ctb_dyn_smem;
-    prims = ctb_dyn_smem + sv.n_nodes * 4u;
+    prims = ctb_dyn_smem + sv.n_nodes * CTB_NODE_F4;
   } else {
     nodes = reinterpret_cast<const float4 *>(sv.nodes);
     prims = reinterpret_cast<const float4 *>(sv.prims);
@@ -1147,7 +1147,7 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev)) != cudaSuccess) return e;
-  size_t need = (size_t)sv.n_nodes * sizeof(Node) + (size_t)sv.n_prims * sizeof(PrimRec);
+  size_t need = (size_t)sv.n_nodes * CTB_NODE_BYTES + (size_t)sv.n_prims * sizeof(PrimRec);
   cfg->mode = 0;
   cfg->smem_bytes = 0;
   if (allow_smem && !sv.brute_force && sv.n_prims > 0 && need + 1024 <= (size_t)smem_optin) {

@@ -207,6 +207,57 @@ __device__ __forceinline__ void test_prim(const SceneView &sv, const float4 *__r
   }
 }
 
+#if CTB_BVH4
+// The same walk over the 4-wide tree (Node4): one iteration loads six float4 box planes + four references and tests four
+// boxes; of the children that are hit the nearest (closest hit) or any one (any hit) is entered, the others are pushed.
+#define CTB_NONE 0x7ffffffe
+template <int MODE, bool ANY>
+__device__ __forceinline__ bool traverse4(const SceneView &sv, const float4 *__restrict__ nodes, const float4 *__restrict__ prims,
+                                          const RayCtx &r, float min_t, float max_t, Hit &h) {
+  int stack[CTB_STACK];
+  stack[0] = CTB_SENTINEL;
+  int sp = 1;
+  int cur = sv.root;
+  const float slack = 1.0f + 4.0f * 1.1920929e-7f;
+  while (cur != CTB_SENTINEL) {
+#pragma unroll 1
+    while ((unsigned)cur < (unsigned)CTB_SENTINEL) {   // internal node
+      const float4 *np = nodes + 8 * (size_t)cur;
+      const float4 lox = ld16<MODE>(np), hix = ld16<MODE>(np + 1), loy = ld16<MODE>(np + 2), hiy = ld16<MODE>(np + 3);
+      const float4 loz = ld16<MODE>(np + 4), hiz = ld16<MODE>(np + 5), rf = ld16<MODE>(np + 6);
+      const float limit = ANY ? fminf(max_t, h.t) : h.t;
+      int nxt = CTB_NONE;
+      float tnxt = INFINITY;
+#define CTB_CHILD(C)                                                                                                                  \
+      {                                                                                                                               \
+        const float ax = fmaf(lox.C, r.inv.x, -r.oi.x), bx = fmaf(hix.C, r.inv.x, -r.oi.x);                                          \
+        const float ay = fmaf(loy.C, r.inv.y, -r.oi.y), by = fmaf(hiy.C, r.inv.y, -r.oi.y);                                          \
+        const float az = fmaf(loz.C, r.inv.z, -r.oi.z), bz = fmaf(hiz.C, r.inv.z, -r.oi.z);                                          \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), min_t));                                     \
+        const float tf = fmaf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), limit)), slack, r.eabs);                \
+        const int rc = __float_as_int(rf.C);                                                                                          \
+        if (tn <= tf && rc != CTB_SENTINEL) {   /* (an empty slot's inverted box passes the symmetric slab test) */                   \
+          if (ANY || tn < tnxt) { if (nxt != CTB_NONE) stack[sp++] = nxt; nxt = rc; tnxt = tn; }                                      \
+          else stack[sp++] = rc;                                                                                                      \
+        }                                                                                                                             \
+      }
+      CTB_CHILD(x) CTB_CHILD(y) CTB_CHILD(z) CTB_CHILD(w)
+#undef CTB_CHILD
+      cur = nxt != CTB_NONE ? nxt : stack[--sp];
+    }
+    if (cur == CTB_SENTINEL) break;
+    {   // leaf
+      const uint32_t first = leaf_first(cur), count = leaf_count(cur);
+#pragma unroll 1
+      for (uint32_t k = first; k < first + count; k++) test_prim<MODE>(sv, prims, k, r, min_t, h);
+      if (ANY && h.t < max_t) return true;
+      cur = stack[--sp];
+    }
+  }
+  return false;
+}
+#endif
+
 // Closest hit over the BVH primitives (planes are handled by the caller).  `h` carries the best hit
 // so far in and out.  ANY: stop at the first accepted hit with t < max_t (shadow rays in scenes
 // without translucent materials) and return true.  while-while traversal: the inner loop walks
@@ -223,6 +274,9 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
     }
     return false;
   }
+#if CTB_BVH4
+  return traverse4<MODE, ANY>(sv, nodes, prims, r, min_t, max_t, h);
+#else
   int stack[CTB_STACK];
   stack[0] = CTB_SENTINEL;
   int sp = 1;
@@ -288,6 +342,7 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
     }
   }
   return false;
+#endif
 }
 
 // planes: unbounded, kept out of the BVH and always tested (the reference tests them like any other
@@ -420,6 +475,17 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
     return occ;
   }
 
+#if CTB_BVH4
+  {
+    static_assert(K == 1, "the 4-wide walk has no packet form: build with SHADOW_PACKET=1");
+    RayCtx r4;
+    make_ray(r4, o, d[0], sv.scene_mag);
+    Hit h4;
+    hit_reset(h4);
+    if (traverse4<MODE, true>(sv, nodes, prims, r4, min_t, max_t[0], h4)) occ |= act & 1u;
+    return occ;
+  }
+#endif
   RayCtx rc[K];
 #pragma unroll
   for (int k = 0; k < K; k++) make_ray(rc[k], o, d[k], sv.scene_mag);
