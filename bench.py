@@ -425,13 +425,14 @@ class Bench:
                 "note": "per-kernel times of the WAVEFRONT scheduler (CUTRACE_FLAG_SERIALIZE: one launch per level and kind on one stream), for comparison; the timed frames run the scheduler named in details.scheduler"}
 
     # ---- end to end: host scene in, host frame out, every step ----
-    def e2e(self, scene, steps, check_parity=False):
+    def e2e(self, scene, steps, check_parity=False, flags=None):
         import ctypes as C
 
         from cutrace_b200.distributed import SharedHostFrame, TileShardedRenderer
         from cutrace_b200.scene import _ARRAY_FIELDS
 
         ct, lib, args = self.ct, self.lib, self.args
+        flags = args.flags if flags is None else flags
         n_px = scene.width * scene.height
         scene_bytes = sum(getattr(scene, k).nbytes for k, _, _ in _ARRAY_FIELDS if k != "obj_kind") + 64
         ms, parity = [], None
@@ -450,7 +451,7 @@ class Bench:
             for i in range(2 + steps):
                 self.barrier()
                 t0 = time.perf_counter()
-                r = ct.Renderer(scene, device=self.local_rank, flags=args.flags, stream=self.stream.cuda_stream)
+                r = ct.Renderer(scene, device=self.local_rank, flags=flags, stream=self.stream.cuda_stream)
                 md = C.c_float()
                 ct._lib.check(lib.cutrace_render_download(r._ctx, pinned["depth"].ctypes.data, pinned["normal"].ctypes.data, pinned["color"].ctypes.data,
                                                           None, C.byref(md), None))
@@ -461,7 +462,7 @@ class Bench:
             del pinned
             for p in ptrs:
                 lib.cutrace_host_free(p)
-            what = ("cutrace_upload_scene (H2D + LBVH build) + cutrace_render_download (render; depth/normal D2H under the bounce levels, colour D2H at "
+            what = ("cutrace_upload_scene (H2D + BVH build: LBVH + SAH treelets) + cutrace_render_download (render; depth/normal D2H under the bounce levels, colour D2H at "
                     "the end) into pinned host buffers + cutrace_free, every frame")
             d2h = 28 * n_px
         else:
@@ -469,7 +470,7 @@ class Bench:
             for i in range(2 + steps):
                 self.barrier()
                 t0 = time.perf_counter()
-                tr = TileShardedRenderer(scene, rank=self.rank, world=self.world, device=self.local_rank, flags=args.flags, stream=self.stream.cuda_stream,
+                tr = TileShardedRenderer(scene, rank=self.rank, world=self.world, device=self.local_rank, flags=flags, stream=self.stream.cuda_stream,
                                          exchange="host", host_frame=frame, host_barrier=self.host_barrier)
                 st = tr.render()                      # returns when this rank's tiles are in the host frame
                 tr.max_depth(st["max_depth"])         # 1-float all-reduce (kernel.hpp:120-125); doubles as the "frame complete" barrier
@@ -480,7 +481,7 @@ class Bench:
                 tr.close()
                 self.barrier()
             frame.close()
-            what = ("per rank: cutrace_upload_scene (H2D + LBVH build) + cutrace_frame_attach(shared pinned host frame) + cutrace_render — every rank's "
+            what = ("per rank: cutrace_upload_scene (H2D + BVH build: LBVH + SAH treelets) + cutrace_frame_attach(shared pinned host frame) + cutrace_render — every rank's "
                     "kernels store their tiles (G-buffer under the bounce levels, colour at the end) straight into ONE host frame over their own PCIe link — "
                     "+ max-depth all-reduce, every frame (cutrace_free of the frame's ctx follows outside the bracket)")
             d2h = 32 * n_px
@@ -540,6 +541,8 @@ def main():
     main_res = b.resident(scene, args.steps, args.warmup, sampler=True)
     kms = b.kernel_ms(scene)
     e2e = b.e2e(scene, max(5, min(args.steps, 20)), check_parity=not args.no_parity_check)
+    # the same call with CUTRACE_FLAG_FAST_BUILD (LBVH only): what a one-frame-per-upload caller of a primitive-heavy scene would set
+    e2e["fast_build_ms_per_frame"] = b.e2e(scene, 5, flags=args.flags | b.ct.FLAG_FAST_BUILD)["ms_per_frame"]
     rays, ms_step = main_res["rays"], main_res["ms_per_step"]
 
     extra = {}
@@ -551,9 +554,11 @@ def main():
             big = name == "synthetic10m"
             r2 = b.resident(s2, 5 if big else 10, 3)
             e2 = b.e2e(s2, 3 if big else 5, check_parity=(big and not args.no_parity_check))
+            e2f = b.e2e(s2, 3 if big else 5, flags=args.flags | b.ct.FLAG_FAST_BUILD)
             extra[name] = {"workload": w2["label"], "ms_per_frame": r2["ms_per_step"], "value": r2["rays"] / r2["ms_per_step"] / 1e3, "unit": "Mrays/s",
                            "rays_per_frame": int(r2["rays"]), "scheduler": r2["scheduler"], "render_device_ms": r2["render_device_ms"],
-                           "e2e_ms_per_frame": e2["ms_per_frame"], "e2e_value": r2["rays"] / e2["ms_per_frame"] / 1e3}
+                           "e2e_ms_per_frame": e2["ms_per_frame"], "e2e_value": r2["rays"] / e2["ms_per_frame"] / 1e3,
+                           "e2e_fast_build_ms_per_frame": e2f["ms_per_frame"]}
             if "parity_check" in r2:
                 extra[name]["parity_check"] = r2["parity_check"]
             if "parity_check" in e2:

@@ -19,12 +19,12 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import (CutraceError, FLAG_BRUTE_FORCE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, FLAG_NO_SMEM_TOP, FLAG_PIXEL_KERNEL, FLAG_SERIALIZE, FLAG_VALIDATE_BVH,
+from ._lib import (CutraceError, FLAG_BRUTE_FORCE, FLAG_FAST_BUILD, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, FLAG_NO_SMEM_TOP, FLAG_PIXEL_KERNEL, FLAG_SERIALIZE, FLAG_VALIDATE_BVH,
                    cutrace_opts, cutrace_stats)
 from .scene import FlatScene, SceneError, load_scene_json, look_at
 
 __all__ = ["Renderer", "render", "FlatScene", "SceneError", "CutraceError", "load_scene_json", "look_at",
-           "FLAG_BRUTE_FORCE", "FLAG_NO_SMEM_TOP", "FLAG_VALIDATE_BVH", "FLAG_SERIALIZE", "FLAG_FRAME_KERNEL", "FLAG_LAUNCHES", "FLAG_PIXEL_KERNEL"]
+           "FLAG_BRUTE_FORCE", "FLAG_NO_SMEM_TOP", "FLAG_VALIDATE_BVH", "FLAG_SERIALIZE", "FLAG_FRAME_KERNEL", "FLAG_LAUNCHES", "FLAG_PIXEL_KERNEL", "FLAG_FAST_BUILD"]
 
 
 class Renderer:

@@ -21,7 +21,8 @@ SYMBOLS = (
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version", "cutrace_tile_size",
 )
 
-FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, FLAG_PIXEL_KERNEL = 1, 2, 4, 8, 16, 32, 64
+FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, \
+    FLAG_PIXEL_KERNEL, FLAG_FAST_BUILD = 1, 2, 4, 8, 16, 32, 64, 128
 IPC_HANDLE_BYTES = 80
 
 

@@ -634,6 +634,7 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
   bi.d_sph_center = d_sc; bi.d_sph_radius = d_sr; bi.d_sph_obj = d_so; bi.n_sph = (uint32_t)ns;
   bi.n_objects = s->n_objects;
   bi.leaf_size = o.leaf_size; bi.stream = c->stream;
+  bi.sah_treelets = !(o.flags & CUTRACE_FLAG_FAST_BUILD);
   CUT(cudaEventRecord(c->events[0], c->stream));
   std::string berr;
   rc = build_bvh(bi, c->bvh, berr);

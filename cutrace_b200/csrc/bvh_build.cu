@@ -524,8 +524,9 @@ struct SahShared {
   unsigned char side[SAH_T];            // which child of the parent the segment is
   unsigned char left[SAH_T];            // by local id: goes to the left child in this level
   float parea[SAH_T], sarea[SAH_T];     // prefix / suffix box areas in the current axis order
-  float scan[6][SAH_T];                 // scan workspace
-  int cnt[SAH_T];
+  float scan[6][32];                    // warp aggregates of a box scan
+  int cnt[32];                          // ... of a count scan
+  unsigned char side2[32];              // ... their "a head lies in the window" flags
   unsigned long long best[SAH_T];       // by segment start: min over (cost, axis, position)
   uint32_t vals_in[SAH_T];
   int open;                             // segments with more than one primitive
@@ -548,6 +549,86 @@ __global__ void sah_roots_kernel(int n_internal, const int2 *__restrict__ range,
   const int p = parent_node[i];
   if (p >= 0) { const int2 pr = range[p]; if ((uint32_t)(pr.y - pr.x + 1) <= SAH_T) return; }
   roots[atomicAdd(n_roots, 1u)] = (uint32_t)i;
+}
+
+// Block-wide segmented inclusive scans (1024 threads, one element each, index order): a warp scan with shuffles over
+// (value, "a segment head lies in my window") pairs, the 32 warp aggregates scanned by warp 0, one fix-up — three barriers
+// per scan.  The first version used Hillis-Steele steps through shared memory: twenty barriers per scan, six box scans and
+// three count scans per level, ~0.6 ms per treelet — 25 ms on the 10,112 treelets of the hall.
+struct SahBox { float v[6]; };
+__device__ __forceinline__ void sah_box_merge(SahBox &into, const SahBox &o) {   // into = o (+) into
+#pragma unroll
+  for (int c = 0; c < 3; c++) { into.v[c] = fminf(into.v[c], o.v[c]); into.v[c + 3] = fmaxf(into.v[c + 3], o.v[c + 3]); }
+}
+__device__ __forceinline__ SahBox sah_seg_scan_box(SahBox x, bool head, float (*wagg)[32], unsigned char *wflag) {
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  bool f = head;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    SahBox nb;
+#pragma unroll
+    for (int c = 0; c < 6; c++) nb.v[c] = __shfl_up_sync(0xffffffffu, x.v[c], d);
+    const bool nf = __shfl_up_sync(0xffffffffu, f, d);
+    if (lane >= (unsigned)d && !f) { sah_box_merge(x, nb); f = nf; }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) wagg[c][w] = x.v[c];
+    wflag[w] = f ? 1 : 0;
+  }
+  __syncthreads();
+  if (w == 0) {   // scan of the warp aggregates
+    SahBox a;
+#pragma unroll
+    for (int c = 0; c < 6; c++) a.v[c] = wagg[c][lane];
+    bool af = wflag[lane] != 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      SahBox nb;
+#pragma unroll
+      for (int c = 0; c < 6; c++) nb.v[c] = __shfl_up_sync(0xffffffffu, a.v[c], d);
+      const bool nf = __shfl_up_sync(0xffffffffu, af, d);
+      if (lane >= (unsigned)d && !af) { sah_box_merge(a, nb); af = nf; }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) wagg[c][lane] = a.v[c];
+  }
+  __syncthreads();
+  if (w > 0 && !f) {   // no head between the start of my warp and me: the carry of the warps before applies
+    SahBox cbox;
+#pragma unroll
+    for (int c = 0; c < 6; c++) cbox.v[c] = wagg[c][w - 1];
+    sah_box_merge(x, cbox);
+  }
+  __syncthreads();
+  return x;
+}
+__device__ __forceinline__ int sah_seg_scan_int(int x, bool head, int *wsum, unsigned char *wflag) {
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  bool f = head;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int nb = __shfl_up_sync(0xffffffffu, x, d);
+    const bool nf = __shfl_up_sync(0xffffffffu, f, d);
+    if (lane >= (unsigned)d && !f) { x += nb; f = nf; }
+  }
+  if (lane == 31) { wsum[w] = x; wflag[w] = f ? 1 : 0; }
+  __syncthreads();
+  if (w == 0) {
+    int a = wsum[lane];
+    bool af = wflag[lane] != 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int nb = __shfl_up_sync(0xffffffffu, a, d);
+      const bool nf = __shfl_up_sync(0xffffffffu, af, d);
+      if (lane >= (unsigned)d && !af) { a += nb; af = nf; }
+    }
+    wsum[lane] = a;
+  }
+  __syncthreads();
+  if (w > 0 && !f) x += wsum[w - 1];
+  __syncthreads();
+  return x;
 }
 
 __global__ void __launch_bounds__(SAH_T, 1)
@@ -598,42 +679,30 @@ sah_treelet_kernel(const uint32_t *__restrict__ roots, const float4 *__restrict_
   }
 
   // ---- top down, one level per iteration ----
+  const int q = m - 1 - t;   // the position this thread handles in the suffix (reversed) scans
   for (int level = 0; level < SAH_T && S.open > 0; level++) {
     const int a = on ? S.sa[t] : 0, b = on ? S.sb[t] : 0;
     const bool live = on && b - a > 1;
     if (on && t == a) S.best[a] = ~0ull;
     __syncthreads();
     for (int ax = 0; ax < 3; ax++) {
-      // segmented inclusive prefix / suffix box scans in this axis' order (Hillis-Steele, one element per thread)
-      for (int dir = 0; dir < 2; dir++) {
-        float bx[6];
-        if (on) {
-          const int id = S.ord[ax][t];
-          bx[0] = S.blo[0][id]; bx[1] = S.blo[1][id]; bx[2] = S.blo[2][id]; bx[3] = S.bhi[0][id]; bx[4] = S.bhi[1][id]; bx[5] = S.bhi[2][id];
+      SahBox x;
+      {   // prefix boxes in this axis' order
+        const int id = on ? S.ord[ax][t] : 0;
 #pragma unroll
-          for (int c = 0; c < 6; c++) S.scan[c][t] = bx[c];
-        }
-        __syncthreads();
-        for (int d = 1; d < m; d <<= 1) {
-          const int o = dir == 0 ? t - d : t + d;
-          const bool take = on && (dir == 0 ? o >= a : o < b);
-          float nb[6];
-          if (take) {
-#pragma unroll
-            for (int c = 0; c < 6; c++) nb[c] = S.scan[c][o];
-          }
-          __syncthreads();
-          if (take) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { bx[c] = fminf(bx[c], nb[c]); bx[c + 3] = fmaxf(bx[c + 3], nb[c + 3]); }
-#pragma unroll
-            for (int c = 0; c < 6; c++) S.scan[c][t] = bx[c];
-          }
-          __syncthreads();
-        }
-        if (on) { if (dir == 0) S.parea[t] = box_area6(bx); else S.sarea[t] = box_area6(bx); }
-        __syncthreads();
+        for (int c = 0; c < 3; c++) { x.v[c] = on ? S.blo[c][id] : INFINITY; x.v[c + 3] = on ? S.bhi[c][id] : -INFINITY; }
+        x = sah_seg_scan_box(x, !on || t == a, S.scan, S.side2);
+        if (on) S.parea[t] = box_area6(x.v);
       }
+      {   // suffix boxes: the same scan over the reversed positions
+        const bool qon = q >= 0;
+        const int id = qon ? S.ord[ax][q] : 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { x.v[c] = qon ? S.blo[c][id] : INFINITY; x.v[c + 3] = qon ? S.bhi[c][id] : -INFINITY; }
+        x = sah_seg_scan_box(x, !qon || q == (int)S.sb[q] - 1, S.scan, S.side2);
+        if (qon) S.sarea[q] = box_area6(x.v);
+      }
+      __syncthreads();
       // cost of splitting after position t (left = [a, t], right = [t+1, b))
       if (live && t < b - 1) {
         const float c = S.parea[t] * (float)(t - a + 1) + S.sarea[t + 1] * (float)(b - t - 1);
@@ -653,18 +722,8 @@ sah_treelet_kernel(const uint32_t *__restrict__ roots, const float4 *__restrict_
     __syncthreads();
     // ---- stable partition of the three orders by the side flags ----
     for (int ax = 0; ax < 3; ax++) {
-      int f = 0;
-      if (live) f = S.left[S.ord[ax][t]];
-      S.cnt[t] = f;
-      __syncthreads();
-      int run = f;   // segmented inclusive scan of the flags
-      for (int d = 1; d < m; d <<= 1) {
-        int add = 0;
-        if (live && t - d >= a) add = S.cnt[t - d];
-        __syncthreads();
-        if (live) { run += add; S.cnt[t] = run; }
-        __syncthreads();
-      }
+      const int f = live ? (int)S.left[S.ord[ax][t]] : 0;
+      const int run = sah_seg_scan_int(f, !on || t == a, S.cnt, S.side2);
       if (live) {
         const int before = run - f;
         const int np = f ? a + before : a + nleft + (t - a - before);
@@ -676,16 +735,10 @@ sah_treelet_kernel(const uint32_t *__restrict__ roots, const float4 *__restrict_
     }
     // ---- link the new node, hand the two halves down ----
     if (t == 0) S.open = 0;
+    if (live && t == a && S.pg[t] < 0) S.g_root = a + nleft - 1;
     __syncthreads();
     if (live) {
       const int g = a + nleft - 1;                 // gap of this node
-      if (t == a) {
-        if (S.pg[t] < 0) S.g_root = g;
-      }
-    }
-    __syncthreads();
-    if (live) {
-      const int g = a + nleft - 1;
       const int me = node_of_gap(g);
       if (t == a) {
         range[me] = make_int2(lo + a, lo + b - 1);
@@ -696,7 +749,11 @@ sah_treelet_kernel(const uint32_t *__restrict__ roots, const float4 *__restrict_
           parent_node[me] = par;
         }
       }
-      // my new segment
+    }
+    __syncthreads();   // (every leader has read its parent gap before the segments are renamed)
+    if (live) {
+      const int g = a + nleft - 1;
+      const int me = node_of_gap(g);
       const bool is_left = (t - a) < nleft;
       const int na = is_left ? a : a + nleft, nbd = is_left ? a + nleft : b;
       S.sa[t] = (unsigned short)na; S.sb[t] = (unsigned short)nbd; S.pg[t] = (short)g; S.side[t] = is_left ? 0 : 1;
@@ -1147,7 +1204,7 @@ int build_bvh(const BvhInput &in, BvhResult &out, std::string &err) {
     BLAP("gather + alloc 2");
     const uint32_t nbi = (ni + T - 1) / T;
     karras_kernel<<<nbi, T, 0, st>>>(keys, (int)n, children, range, parent_node, parent_leaf);
-    if (CTB_SAH_TREELETS && !getenv("CUTRACE_DEBUG_NO_SAH")) {
+    if (CTB_SAH_TREELETS && in.sah_treelets && !getenv("CUTRACE_DEBUG_NO_SAH")) {
       // rebuild the topology of every subtree of at most SAH_T primitives with sweep SAH (`live` is free until live_kernel: treelet roots)
       uint32_t n_roots = 0;
       CK(cudaMemsetAsync(d_total, 0, 4, st));

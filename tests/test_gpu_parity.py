@@ -485,6 +485,20 @@ def test_bvh_validates_on_a_large_scene(ct):
             assert st["bvh_depth"] < 62 and st["bvh_nodes"] > 0
 
 
+def test_fast_build_renders_the_same_frame_as_the_sah_treelet_build(ct):
+    """CUTRACE_FLAG_FAST_BUILD keeps the LBVH topology, the default rebuilds every <=1024-primitive subtree with sweep SAH: two
+    different trees over the same primitives — closest hits (ties broken by primitive id) and any-hit shadow results cannot differ,
+    so the frames are bit-identical; the SAH tree must be the shallower-to-trace one (fewer nodes is not required, a valid tree is)."""
+    from cutrace_b200 import synth
+
+    meshes = synth.meshes_from_scenes(load_golden_scene("bunny"), load_golden_scene("mirror"))[:2]
+    for s in (load_golden_scene("bunny").with_resolution(480, 270), synth.grid_scene(meshes, grid=6, width=320, height=180)):
+        a, sa = gpu_render(ct, s)
+        b, sb = gpu_render(ct, s, flags=ct.FLAG_FAST_BUILD)
+        assert_same_frame(a, b, "sah treelets vs lbvh")
+        assert sa["rays_total"] == sb["rays_total"]
+
+
 def test_synthetic_grid_subset_vs_oracle(ct, oracle):
     """config 5 in small: instanced grid with mirror planes; a seeded pixel subset against the C oracle
     (brute force over every triangle is only affordable on a subset)."""
