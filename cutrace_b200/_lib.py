@@ -18,7 +18,7 @@ SYMBOLS = (
     "cutrace_frame_ipc_export", "cutrace_frame_ipc_import", "cutrace_frame_attach", "cutrace_enable_peer_access",
     "cutrace_set_frame_max_depth",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free", "cutrace_host_register", "cutrace_host_unregister", "cutrace_trim_memory",
-    "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_abi_version", "cutrace_tile_size",
+    "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_debug_phong_pow", "cutrace_abi_version", "cutrace_tile_size",
 )
 
 FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, \
@@ -101,6 +101,7 @@ def load():
     lib.cutrace_host_free.restype = None
     lib.cutrace_validate_bvh.argtypes = [P]
     lib.cutrace_debug_radix_sort.argtypes = [P, P, C.c_uint32, C.c_int]
+    lib.cutrace_debug_phong_pow.argtypes = [P, P, P, P, C.c_uint32, C.c_int]
     lib.cutrace_abi_version.restype = C.c_uint32
     lib.cutrace_tile_size.restype = C.c_uint32
     _lib = lib

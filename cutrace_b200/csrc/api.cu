@@ -442,6 +442,13 @@ void set_cam(cutrace_ctx *c, const float pos[3], const float up[3], const float 
   cam.ambient = ambient;
 }
 
+__global__ void phong_pow_debug_kernel(const float *x, const float *e, float *out_powf, float *out_fast, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out_powf[i] = powf(x[i], e[i]);
+  out_fast[i] = phong_pow(x[i], e[i], phong_pow_floor(e[i]));
+}
+
 }  // namespace
 
 extern "C" {
@@ -1032,6 +1039,13 @@ int cutrace_get_phase_ms(cutrace_ctx *c, float *out, uint32_t capacity, uint32_t
   return CUTRACE_OK;
 }
 
+#ifdef CTB_PIXEL_STAMPS
+int cutrace_debug_pixel_stamps(cutrace_ctx *c, unsigned long long *out) {   // tuning builds: the seven %globaltimer stamps of the last frame
+  for (int i = 0; i < 7; i++) out[i] = c->h_ctr->phase_ns[i];
+  return 0;
+}
+#endif
+
 int cutrace_get_stats(cutrace_ctx *c, cutrace_stats *stats) {
   if (!c || !stats) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
   *stats = c->stats;
@@ -1277,6 +1291,28 @@ void *cutrace_host_alloc(size_t bytes) {
 
 void cutrace_host_free(void *p) {
   if (p) cudaFreeHost(p);
+}
+
+int cutrace_debug_phong_pow(const float *x, const float *e, float *out_powf, float *out_fast, uint32_t n, int device) {
+  if (n && (!x || !e || !out_powf || !out_fast)) return fail(CUTRACE_ERR_INVALID_ARG, "NULL argument");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(CUTRACE_ERR_NO_DEVICE, "no CUDA device");
+  if (device < 0) CU(cudaGetDevice(&device));
+  DeviceGuard g(device);
+  if (n == 0) return CUTRACE_OK;
+  float *d = nullptr;   // x | e | powf | fast
+  CU(cudaMalloc(&d, sizeof(float) * 4 * (size_t)n));
+  int rc = CUTRACE_OK;
+  if (cudaMemcpy(d, x, sizeof(float) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d + n, e, sizeof(float) * n, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(CUTRACE_ERR_CUDA, "H2D copy failed");
+  if (!rc) {
+    phong_pow_debug_kernel<<<(n + 255) / 256, 256>>>(d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, n);
+    if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(CUTRACE_ERR_CUDA, "phong_pow_debug_kernel failed");
+  }
+  if (!rc && (cudaMemcpy(out_powf, d + 2 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost) != cudaSuccess ||
+              cudaMemcpy(out_fast, d + 3 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost) != cudaSuccess)) rc = fail(CUTRACE_ERR_CUDA, "D2H copy failed");
+  cudaFree(d);
+  return rc;
 }
 
 int cutrace_debug_radix_sort(uint64_t *keys, uint32_t *values, uint32_t n, int device) {

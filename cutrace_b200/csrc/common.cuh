@@ -56,6 +56,13 @@ __host__ __device__ __forceinline__ float vdot(vec3 a, vec3 b) { return CTB_FMA(
 __host__ __device__ __forceinline__ vec3 vcross(vec3 a, vec3 o) {                                                                       // :65-71
   return mk3(CTB_FMA(a.y, o.z, -CTB_MUL(a.z, o.y)), CTB_FMA(a.z, o.x, -CTB_MUL(a.x, o.z)), CTB_FMA(a.x, o.y, -CTB_MUL(a.y, o.x)));
 }
+// The specular term pow(max(0, n.h), e) (inc/shading.hpp:91): below x0 = 2^(-152 / e) the true power is under 2^-152, less than half
+// the smallest denormal, and powf returns +0 (it is accurate to a few ulp and correctly rounded-to-zero there;
+// tests/test_gpu_parity.py::test_phong_pow_floor checks the device function against this claim).  0.98 covers the 2-ulp MUFU.EX2
+// behind exp2f: (0.98 x0)^e <= 0.98 * 2^-152.  Phong highlights are narrow (e = 200 / 500 in bunny.json: x0 = 0.59 / 0.81), so most
+// warps skip the ~70-instruction powf — it was 4.9 % of the frame's instructions.  e < 1 or not finite: no floor, powf always runs.
+__device__ __forceinline__ float phong_pow_floor(float e) { return (e >= 1.0f && e <= 3.0e38f) ? 0.98f * exp2f(-152.0f / e) : -1.0f; }
+__device__ __forceinline__ float phong_pow(float x, float e, float floor_x) { return x < floor_x ? 0.0f : powf(x, e); }
 __host__ __device__ __forceinline__ float vnorm(vec3 a) { return CTB_SQRT(vdot(a, a)); }                                                // :85-92
 __host__ __device__ __forceinline__ vec3 vnormalized(vec3 a) { return vscale(a, CTB_DIV(1.0f, vnorm(a))); }                              // :77-79
 __host__ __device__ __forceinline__ vec3 vreflect(vec3 incoming, vec3 normal) {                                                         // :204-206

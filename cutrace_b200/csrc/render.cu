@@ -31,6 +31,7 @@
 //                  per-kernel timings; also the fallback when a cooperative launch is not possible).
 //
 // All kernels are persistent: each warp claims work from a global cursor (guided chunk sizes).
+#include <cstdio>
 #include <cstddef>
 #include <cstdlib>
 #include "render.cuh"
@@ -440,7 +441,7 @@ __device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *
   const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
   const vec3 diffuse = mk3(m0.x, m0.y, m0.z);
   const vec3 specular = vscale(diffuse, m0.w);        // *spec = specular * color
-  const float phong_exp = m1.y;
+  const float phong_exp = m1.y, pow_floor = phong_pow_floor(phong_exp);
   vec3 final = vscale(diffuse, sv.cam.ambient);
   const vec3 nn = vnormalized(normal);
   const vec3 in_n = vscale(vnormalized(in_dir), -1.0f);
@@ -485,7 +486,7 @@ __device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *
           float fd = fmaxf(0.0f, vdot(nn, nd));
           vec3 ld = vmul(diffuse, lcol[k]);
           vec3 hv = vnormalized(vadd(in_n, nd));
-          float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+          float fs = phong_pow(fmaxf(0.0f, vdot(nn, hv)), phong_exp, pow_floor);
           vec3 ls = vmul(specular, lcol[k]);
           phong_add(final, ld, fd, ls, fs, 1.0f);
         }
@@ -514,7 +515,7 @@ __device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *
         float fd = fmaxf(0.0f, vdot(nn, nd));
         vec3 ld = vmul(diffuse, color);
         vec3 hv = vnormalized(vadd(in_n, nd));
-        float fs = powf(fmaxf(0.0f, vdot(nn, hv)), phong_exp);
+        float fs = phong_pow(fmaxf(0.0f, vdot(nn, hv)), phong_exp, pow_floor);
         vec3 ls = vmul(specular, color);
         phong_add(final, ld, fd, ls, fs, 1 - shadow_fac);
       }
@@ -949,13 +950,24 @@ __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(co
 // inc/shading.hpp:123), path weights replace the nested blend, and the colour is summed in depth-first order — for
 // non-branching scenes exactly the level order of the wavefront's ordered sum.  Counters arrive in mapped host memory and
 // are cleared by the last block, like in the frame kernel: the frame is ONE launch, no memset, no copy.
+#ifdef CTB_PIXEL_STAMPS   // tuning builds: %globaltimer at eight points of the kernel, taken by one thread in the middle of a 20 x 20 frame
+#define CTB_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 200) s_stamp[i] = globaltimer_ns(); } while (0)
+#else
+#define CTB_STAMP(i) do { } while (0)
+#endif
+
 template <int MODE, bool BRUTE, bool OPAQUE>
 __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel_kernel(const __grid_constant__ PixelArgs a) {
   extern __shared__ float4 smem[];
+#ifdef CTB_PIXEL_STAMPS
+  __shared__ unsigned long long s_stamp[10];
+#endif
+  CTB_STAMP(0);
   const SceneView &sv = a.sv;
   const float4 *nodes, *prims;
   stage_scene<MODE>(sv, smem, nodes, prims);
   const unsigned lane = threadIdx.x & 31u;
+  CTB_STAMP(1);
   TraceAcc acc;
   trace_acc_reset(acc);
   unsigned casts = 0;
@@ -984,6 +996,7 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
       for (;;) {
         Hit h;
         closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
+        if (level == 0) CTB_STAMP(2);
         const bool hit = h.kind >= 0;
         vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
         if (hit) hit_surface<MODE>(sv, prims, h, o, d, point, nrm);
@@ -1006,6 +1019,7 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
           const bool do_refl = deeper && (double)reflect >= 1e-6, do_trans = deeper && (double)transp >= 1e-6;
           const float w_own = do_trans ? w * (1.0f - transp) : w;
           const vec3 final = phong_record<MODE, BRUTE, OPAQUE>(sv, nodes, prims, point, nrm, d, mat, casts);
+          if (level == 0) CTB_STAMP(3);
           acc.n_shaded++;
           // product and sum rounded separately, like the wavefront's level image + ordered sum
           r = __fadd_rn(r, __fmul_rn(w_own, final.x)); g = __fadd_rn(g, __fmul_rn(w_own, final.y)); b = __fadd_rn(b, __fmul_rn(w_own, final.z));
@@ -1031,8 +1045,10 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
       float *cp = a.out.color + 3 * gi;
       cp[0] = r; cp[1] = g; cp[2] = b;
       if (a.out2.color) { float *c2 = a.out2.color + 3 * g2; c2[0] = r; c2[1] = g; c2[2] = b; }
+      CTB_STAMP(4);
     }
   }
+  CTB_STAMP(5);
   // ---- tallies: warp -> block -> frame statistics; the last block publishes them and clears the counters ----
   __shared__ unsigned long long s_t[4];
   __shared__ unsigned s_md, s_last;
@@ -1057,6 +1073,28 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
   }
   __syncthreads();
   FrameCounters *ctr = a.ctr;
+  if (gridDim.x == 1) {
+    // a frame of at most 512 pixels (triangle.json is 20 x 20): the block's tallies ARE the frame's.  The general path below
+    // is a chain of dependent round trips — counters -> fence -> `finished` -> re-read -> host — about 3 us of an 11 us kernel.
+    __shared__ FrameStats s_fs;
+    constexpr unsigned SN1 = sizeof(FrameStats) / 4;
+    if (threadIdx.x < SN1) reinterpret_cast<unsigned *>(&s_fs)[threadIdx.x] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_fs.rays_reflect = s_t[0]; s_fs.rays_transmit = s_t[1]; s_fs.shade_records = s_t[2]; s_fs.shadow_casts = s_t[3];
+      s_fs.max_depth_bits = s_md;
+      ctr->work_trace[0].v = 0u;   // (only a debug grid override makes one block claim dynamically)
+    }
+    __syncthreads();
+    volatile unsigned *dst1 = reinterpret_cast<volatile unsigned *>(a.host_stats);
+    if (dst1 && threadIdx.x < SN1) dst1[threadIdx.x] = reinterpret_cast<const unsigned *>(&s_fs)[threadIdx.x];
+#ifdef CTB_PIXEL_STAMPS
+    CTB_STAMP(6);
+    __syncthreads();
+    if (threadIdx.x < 7 && a.host_stats) reinterpret_cast<volatile unsigned long long *>(a.host_stats->phase_ns)[threadIdx.x] = s_stamp[threadIdx.x];
+#endif
+    return;
+  }
   if (threadIdx.x == 0) {
     if (s_t[0]) atomicAdd(&ctr->st.rays_reflect, s_t[0]);
     if (s_t[1]) atomicAdd(&ctr->st.rays_transmit, s_t[1]);
@@ -1067,10 +1105,19 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
     s_last = atomicAdd(&ctr->finished.v, 1u) == gridDim.x - 1u;
   }
   __syncthreads();
+#ifdef CTB_PIXEL_STAMPS
+  CTB_STAMP(6);
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < 7 && a.host_stats) reinterpret_cast<volatile unsigned long long *>(a.host_stats->phase_ns)[threadIdx.x] = s_stamp[threadIdx.x];
+#endif
   if (s_last) {
     __threadfence();
     unsigned *src = reinterpret_cast<unsigned *>(ctr);
+#ifdef CTB_PIXEL_STAMPS
+    constexpr unsigned S0 = offsetof(FrameCounters, st) / 4, SN = 10;   // (leaves phase_ns to the stamps)
+#else
     constexpr unsigned S0 = offsetof(FrameCounters, st) / 4, SN = sizeof(FrameStats) / 4;
+#endif
     volatile unsigned *dst = reinterpret_cast<volatile unsigned *>(a.host_stats);
     if (threadIdx.x < SN) {
       const unsigned v = __ldcg(src + S0 + threadIdx.x);

@@ -305,6 +305,10 @@ int cutrace_validate_bvh(cutrace_ctx *ctx);
  * sorted in place by key (device round trip inside). */
 int cutrace_debug_radix_sort(uint64_t *keys, uint32_t *values, uint32_t n, int device);
 
+/* test hook: out_powf[i] = powf(x[i], e[i]) and out_fast[i] = the specular power as the shading code computes it (powf skipped
+ * below the underflow floor of e[i]), both on the device; the two arrays must be bit-identical. */
+int cutrace_debug_phong_pow(const float *x, const float *e, float *out_powf, float *out_fast, uint32_t n, int device);
+
 uint32_t cutrace_abi_version(void);
 /* edge of the screen tiles the sharding works in (CUTRACE_TILE of the library that is loaded) */
 uint32_t cutrace_tile_size(void);

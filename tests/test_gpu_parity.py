@@ -473,6 +473,31 @@ def test_radix_sort_is_a_stable_sort(ct, n):
     assert np.array_equal(v2, vals[order])
 
 
+def test_phong_pow_floor(ct):
+    """The shading code skips powf(x, e) for x below 0.98 * 2^(-152/e) (the power underflows to +0 there): the device's own powf must
+    agree bit for bit on both sides of the floor, for Phong exponents from 1 to FLT_MAX and for the exponents that get no floor."""
+    lib = ct._lib.load()
+    rng = np.random.default_rng(5)
+    es = np.array([1.0, 1.0000001, 1.5, 2, 3, 10, 32, 50, 151, 152, 153, 200, 500, 1e3, 1e4, 1e6, 1e12, 1e30, 3e38, 3.4e38,
+                   0.0, 0.5, 0.999, -1.0, -200.0, np.inf, -np.inf, np.nan], dtype=np.float32)
+    xs, ee = [], []
+    for e in es:
+        with np.errstate(all="ignore"):
+            fl = np.float32(0.98) * np.exp2(np.float32(-152.0) / np.float32(e)).astype(np.float32)
+        fl = np.float32(fl) if np.isfinite(fl) else np.float32(1.0)
+        around = [np.nextafter(fl, np.float32(0)), fl, np.nextafter(fl, np.float32(2)), fl * np.float32(0.999), fl * np.float32(1.001), fl * np.float32(0.5),
+                  fl * np.float32(1.03), np.float32(0), np.float32(1), np.float32(1e-45), np.float32(1e-30), np.float32(0.5), np.float32(0.999999)]
+        pts = np.concatenate([np.array(around, dtype=np.float32), rng.random(4000, dtype=np.float32),
+                              (fl * (np.float32(0.9) + np.float32(0.15) * rng.random(4000, dtype=np.float32))).astype(np.float32)])
+        xs.append(pts); ee.append(np.full(pts.shape, e, dtype=np.float32))
+    x, e = np.concatenate(xs), np.concatenate(ee)
+    a, b = np.empty_like(x), np.empty_like(x)
+    ct._lib.check(lib.cutrace_debug_phong_pow(x.ctypes.data, e.ctypes.data, a.ctypes.data, b.ctypes.data, x.size, 0))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{int((a.view(np.uint32) != b.view(np.uint32)).sum())} of {x.size} differ"
+    skipped = (x < (np.float32(0.98) * np.exp2(np.float32(-152.0) / e))) & (e >= 1) & (e <= np.float32(3e38))
+    assert skipped.sum() > 10_000 and not a[skipped].any()       # the shortcut was exercised, and powf is +0 there
+
+
 def test_bvh_validates_on_a_large_scene(ct):
     from cutrace_b200 import synth
 

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import bench
 import cutrace_b200 as ct
-for name in ("bunny4k", "synthetic10m"):
+for name in (sys.argv[1:] or ("bunny4k", "synthetic10m")):
     s, _ = bench.load_workload(name)
     for sah in (1, 0):
         os.environ.pop("CUTRACE_DEBUG_NO_SAH", None)
