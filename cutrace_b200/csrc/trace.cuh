@@ -73,12 +73,31 @@ __device__ __forceinline__ bool tri_test(vec3 p1, vec3 p2, vec3 p3, vec3 o, vec3
   return isfinite(t0) && min_t <= t0 && t0 > min_t;
 }
 
-// sphere::intersect, inc/default_schema.hpp:226-243 (out of line: rare next to triangles)
+// sphere::intersect, inc/default_schema.hpp:226-243.  `d` is the NORMALISED direction (the reference normalises inside, :228); the
+// brute-force loops over the <= 8 primitives of a scene like sphere_plane.json normalise once per ray instead of once per sphere.
+// A negative (or NaN) discriminant leaves early: sqrt gives NaN, both roots are NaN, neither is finite — the reference returns
+// false through the same values, only after two IEEE square roots (on their slow path: the argument is out of range) and two
+// divisions.  Misses are the common case: in sphere_plane.json those four operations were a quarter of the frame's instructions.
+__device__ __noinline__ bool sphere_test_n(float cx, float cy, float cz, float R, vec3 e, vec3 d, float min_t, float *tout) {
+  vec3 c = mk3(cx, cy, cz);
+  float dec = -vdot(d, vsub(e, c));
+  // dec^2 - (d.d) * ((e-c).(e-c) - R^2), inc/default_schema.hpp:231
+  float sub = CTB_FMA(dec, dec, -CTB_MUL(vdot(d, d), CTB_FMA(-R, R, vdot(vsub(e, c), vsub(e, c)))));
+  if (!(sub >= 0.0f)) return false;
+  float t0 = CTB_DIV(CTB_SUB(dec, CTB_SQRT(sub)), vdot(d, d)), t1 = CTB_DIV(CTB_ADD(dec, CTB_SQRT(sub)), vdot(d, d));
+  bool t0v = isfinite(t0) && min_t <= t0, t1v = isfinite(t1) && min_t <= t1;
+  if (!t0v && !t1v) return false;
+  float t = (t0v && t1v) ? fminf(t0, t1) : (t0v ? t0 : t1);
+  *tout = t;
+  return t > min_t;
+}
+// The same test for the BVH walks, which meet a sphere rarely and keep nothing per ray: the direction is normalised here.  No early
+// return on a negative discriminant in this copy: with it ptxas allocates the (sphere-free) bunny.json kernel differently —
+// 8 more bytes of spills, 8.0 -> 8.2 ms per 4K frame — and the reference scenes have no BVH with spheres in it to pay that back.
 __device__ __noinline__ bool sphere_test(float cx, float cy, float cz, float R, vec3 e, vec3 dir, float min_t, float *tout) {
   vec3 c = mk3(cx, cy, cz);
   vec3 d = vnormalized(dir);
   float dec = -vdot(d, vsub(e, c));
-  // dec^2 - (d.d) * ((e-c).(e-c) - R^2), inc/default_schema.hpp:231
   float sub = CTB_FMA(dec, dec, -CTB_MUL(vdot(d, d), CTB_FMA(-R, R, vdot(vsub(e, c), vsub(e, c)))));
   float t0 = CTB_DIV(CTB_SUB(dec, CTB_SQRT(sub)), vdot(d, d)), t1 = CTB_DIV(CTB_ADD(dec, CTB_SQRT(sub)), vdot(d, d));
   bool t0v = isfinite(t0) && min_t <= t0, t1v = isfinite(t1) && min_t <= t1;
@@ -191,13 +210,19 @@ __device__ __forceinline__ NodeData load_node(const SceneView &sv, const float4 
   return n;
 }
 
+struct DirCache { vec3 dn; bool have; };   // the normalised direction of a ray, computed when the first sphere is met
 template <int MODE>
-__device__ __forceinline__ void test_prim(const SceneView &sv, const float4 *__restrict__ prims, uint32_t k, const RayCtx &r, float min_t, Hit &h) {
+__device__ __forceinline__ void test_prim(const SceneView &sv, const float4 *__restrict__ prims, uint32_t k, const RayCtx &r, float min_t, Hit &h,
+                                          DirCache *dc = nullptr) {
   const float4 *pp = prims + 3 * (size_t)k;
   const float4 q0 = ld16<MODE>(pp), q1 = ld16<MODE>(pp + 1), q2 = ld16<MODE>(pp + 2);
   float t;
   bool ok;
   if (__float_as_uint(q2.w) == CTB_PRIM_TRI) ok = tri_test(mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), r.o, r.d, min_t, t);
+  else if (dc) {
+    if (!dc->have) { dc->dn = vnormalized(r.d); dc->have = true; }
+    ok = sphere_test_n(q0.x, q0.y, q0.z, q1.x, r.o, dc->dn, min_t, &t);
+  }
   else ok = sphere_test(q0.x, q0.y, q0.z, q1.x, r.o, r.d, min_t, &t);
   if (ok) {
     const uint32_t obj = __float_as_uint(q0.w), idx = __float_as_uint(q1.w);
@@ -267,9 +292,11 @@ template <int MODE, bool ANY, bool BRUTE>
 __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__restrict__ nodes, const float4 *__restrict__ prims,
                                          const RayCtx &r, float min_t, float max_t, Hit &h) {
   if (BRUTE) {
+    DirCache dc;
+    dc.have = false;
 #pragma unroll 1
     for (uint32_t k = 0; k < sv.n_prims; k++) {
-      test_prim<MODE>(sv, prims, k, r, min_t, h);
+      test_prim<MODE>(sv, prims, k, r, min_t, h, &dc);
       if (ANY && h.t < max_t) return true;
     }
     return false;
@@ -459,6 +486,9 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
   if (!act) return occ;
 
   if (BRUTE) {
+    DirCache dc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) dc[k].have = false;
 #pragma unroll 1
     for (uint32_t i = 0; i < sv.n_prims && act; i++) {
 #pragma unroll
@@ -467,7 +497,7 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
           RayCtx r;
           r.o = o; r.d = d[k];   // test_prim only reads origin and direction (the slab data is for the BVH walk)
           Hit h; hit_reset(h);
-          test_prim<MODE>(sv, prims, i, r, min_t, h);
+          test_prim<MODE>(sv, prims, i, r, min_t, h, &dc[k]);
           if (h.t < max_t[k]) { occ |= 1u << k; act &= ~(1u << k); }
         }
       }
