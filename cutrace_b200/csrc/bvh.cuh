@@ -16,7 +16,7 @@ struct BvhInput {
   const uint32_t *d_sph_obj = nullptr;
   uint32_t n_sph = 0;
   uint32_t n_objects = 0;     // object indices of the primitives are range-checked on the device
-  uint32_t leaf_size = 4;
+  uint32_t leaf_size = 3;
   bool sah_treelets = true;   // false: CUTRACE_FLAG_FAST_BUILD, the LBVH topology is kept
   cudaStream_t stream = nullptr;
 };

@@ -395,6 +395,10 @@ __device__ __forceinline__ void tallies_flush(FrameCounters *ctr, unsigned lane,
 }
 
 // shadow_intensity, inc/shading.hpp:22-45
+#ifndef CTB_LIGHTS_IN_ONE_WALK
+#define CTB_LIGHTS_IN_ONE_WALK 0   // 1: big scenes (MODE 0 / 2) walk all shadow rays of a hit in one traversal loop (any_hit_lights, trace.cuh);
+                                   // measured on the 10 M-triangle hall: 70.7 -> 85.0 ms per frame (profiles/r02_tuning.md), off
+#endif
 #ifndef SHADOW_PACKET
 #define SHADOW_PACKET 1   // shadow rays of one hit that traverse together
 #endif
@@ -445,7 +449,46 @@ __device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *
   vec3 final = vscale(diffuse, sv.cam.ambient);
   const vec3 nn = vnormalized(normal);
   const vec3 in_n = vscale(vnormalized(in_dir), -1.0f);
-  if (OPAQUE) {
+  if (OPAQUE && CTB_LIGHTS_IN_ONE_WALK && MODE != 1 && !BRUTE && SHADOW_PACKET == 1 && !CTB_BVH4 && sv.n_lights <= (uint32_t)CTB_MULTI_LIGHTS) {
+    // big scenes: the shadow rays of this hit share one traversal loop, a lane moves on to its next light as soon as its
+    // ray has ended (any_hit_lights, trace.cuh).  Ray set-up and the Phong sums run before / after it with all lanes.
+    float dx[CTB_MULTI_LIGHTS], dy[CTB_MULTI_LIGHTS], dz[CTB_MULTI_LIGHTS], len[CTB_MULTI_LIGHTS];
+    unsigned todo = 0;
+#pragma unroll 1
+    for (uint32_t l = 0; l < sv.n_lights; l++) {
+      const float4 l0v = __ldg(reinterpret_cast<const float4 *>(sv.lights + l));
+      vec3 direction;
+      float distance;
+      if (__float_as_uint(l0v.w) == CUTRACE_LIGHT_SUN) {     // inc/default_schema.hpp:280-283
+        direction = vscale(mk3(l0v.x, l0v.y, l0v.z), -1.0f);
+        distance = INFINITY;
+      } else {                                               // inc/default_schema.hpp:305-308
+        vec3 P = mk3(l0v.x, l0v.y, l0v.z);
+        direction = vnormalized(vsub(P, hit));
+        distance = vnorm(vsub(P, hit));
+      }
+      const vec3 sdir = vnormalized(direction);
+      const float md = distance * vnorm(direction);
+      dx[l] = sdir.x; dy[l] = sdir.y; dz[l] = sdir.z; len[l] = md;
+      if (!planes_occlude(sv, hit, sdir, md)) todo |= 1u << l;
+    }
+    casts += sv.n_lights;
+    const unsigned lit = todo & ~any_hit_lights<MODE>(sv, nodes, prims, hit, dx, dy, dz, len, todo);
+#pragma unroll 1
+    for (uint32_t l = 0; l < sv.n_lights; l++) {
+      if (lit & (1u << l)) {        // shadow_fac = 0 < 1
+        const float4 l1v = __ldg(reinterpret_cast<const float4 *>(sv.lights + l) + 1);
+        const vec3 lcol = mk3(l1v.x, l1v.y, l1v.z);
+        const vec3 nd = mk3(dx[l], dy[l], dz[l]);
+        float fd = fmaxf(0.0f, vdot(nn, nd));
+        vec3 ld = vmul(diffuse, lcol);
+        vec3 hv = vnormalized(vadd(in_n, nd));
+        float fs = phong_pow(fmaxf(0.0f, vdot(nn, hv)), phong_exp, pow_floor);
+        vec3 ls = vmul(specular, lcol);
+        phong_add(final, ld, fd, ls, fs, 1.0f);
+      }
+    }
+  } else if (OPAQUE) {
     // every material is opaque: the shadow march saturates on its first step, so the K shadow rays
     // of this hit are any-hit queries and walk the BVH as one packet
     const unsigned plane_maybe = CTB_PLANE_PREPASS ? plane_side_prepass(sv, hit) : 0xffffffffu;

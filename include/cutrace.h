@@ -151,7 +151,7 @@ typedef struct cutrace_opts {
    * row-major tile order. */
   uint32_t tile_rank, tile_world;
   void *stream;         /* cudaStream_t to launch on; NULL = a stream owned by the ctx         */
-  uint32_t leaf_size;   /* max primitives per BVH leaf (1..8); 0 = default (4)                 */
+  uint32_t leaf_size;   /* max primitives per BVH leaf (1..8); 0 = default (3)                 */
   uint32_t reserved[7];
 } cutrace_opts;
 
