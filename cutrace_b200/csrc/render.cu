@@ -1117,8 +1117,8 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
   __syncthreads();
   FrameCounters *ctr = a.ctr;
   if (gridDim.x == 1) {
-    // a frame of at most 512 pixels (triangle.json is 20 x 20): the block's tallies ARE the frame's.  The general path below
-    // is a chain of dependent round trips — counters -> fence -> `finished` -> re-read -> host — about 3 us of an 11 us kernel.
+    // a frame of at most 1024 tile-padded pixels (triangle.json: 20 x 20 = four 16 x 16 tiles): the block's tallies ARE the frame's.  The general path below
+    // is a chain of dependent round trips — counters -> fence -> `finished` -> re-read -> host — about 1 us of an 11 us kernel.
     __shared__ FrameStats s_fs;
     constexpr unsigned SN1 = sizeof(FrameStats) / 4;
     if (threadIdx.x < SN1) reinterpret_cast<unsigned *>(&s_fs)[threadIdx.x] = 0u;

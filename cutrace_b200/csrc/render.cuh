@@ -47,13 +47,15 @@ struct LaunchCfg {
   int grid_frame;               // co-resident CTAs of the cooperative frame kernel (0: not available on this device)
   int grid_pixel;               // persistent grid of the pixel kernel
 };
-// pixel kernel: 512 threads x 2 CTAs per SM (64 registers) measured best on bunny.json 4K — 9.01 ms against 9.44 (256 x 3),
-// 10.3 (256 x 4, where 71 KB of staged scene per CTA caps the SM at 3 CTAs) and 10.7 (256 x 2, 128 registers); profiles/r02_tuning.md
+// pixel kernel: ONE CTA of 1024 threads per SM (64 registers).  Measured on bunny.json 4K (profiles/r02_tuning.md): 256 x 4 10.3 ms
+// (71 KB of staged scene per CTA caps the SM at 3 CTAs), 256 x 3 9.44, 256 x 2 (128 registers) 10.7, 512 x 2 9.01; and on the
+// final build 512 x 2 7.83, 768 x 1 (80 registers) 8.03, 640 x 1 (96 registers) 8.58, 1024 x 1 7.70 — the scene is staged once
+// per SM, and more registers per thread do not pay for the warps they cost.
 #ifndef CTB_PIXEL_THREADS
-#define CTB_PIXEL_THREADS 512
+#define CTB_PIXEL_THREADS 1024
 #endif
 #ifndef CTB_PIXEL_MIN_BLOCKS
-#define CTB_PIXEL_MIN_BLOCKS 2
+#define CTB_PIXEL_MIN_BLOCKS 1
 #endif
 
 #ifndef CTB_FILL_CHUNK_MAX
