@@ -864,7 +864,8 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     }
     PixelArgs pa{};
     pa.sv = c->sv; pa.tm = c->tm; pa.bounces = bounces; pa.px_base = (uint32_t)base; pa.n_px = n_px;
-    pa.ctr = c->d_ctr; pa.host_stats = c->h_ctr_dev; pa.out = out;
+    static const bool dbg_no_host_stats = getenv("CUTRACE_DEBUG_NO_HOST_STATS") != nullptr;   // timing experiment: the statistics stay on the device
+    pa.ctr = c->d_ctr; pa.host_stats = dbg_no_host_stats ? nullptr : c->h_ctr_dev; pa.out = out;
     if (c->dl_direct_on) { pa.out2 = c->dl_direct; pa.tm.wide_warps = 1u; }   // 16 x 2 warps: whole tile rows per store over PCIe
     c->ctr_dirty = true;   // until the kernel has run to its end
     if ((e = launch_pixel(c->cfg, pa, st)) != cudaSuccess) return e;

@@ -116,6 +116,40 @@ __device__ __forceinline__ bool claim_work(unsigned *cursor, unsigned n_work, un
   return base < n_work;
 }
 
+// The pixel kernel's lane refill (pixel_kernel<.., REFILL>) claims for the `asked` free lanes of a warp, not for a whole warp: the
+// same static first slot and the same guided sizes while there is plenty of work, but never rounded to 32 and never less than
+// `asked` — at the end of a frame a warp takes exactly the pixels its free lanes can start at once (a 32-pixel claim for one free
+// lane would be walked one pixel at a time while other warps have nothing left).
+__device__ __forceinline__ bool claim_pixels(unsigned *cursor, unsigned n_work, unsigned lane, unsigned max_chunk, bool first, unsigned asked,
+                                             unsigned &base, unsigned &end) {
+  const unsigned warps = gridDim.x * (blockDim.x >> 5);
+  const unsigned c0 = guided_chunk(n_work, warps, max_chunk);
+  if (first) {
+    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    base = gw * c0;
+    end = base + c0 < n_work ? base + c0 : n_work;
+    return base < n_work;
+  }
+  const unsigned dyn0 = warps * c0;
+  if (dyn0 >= n_work) return false;
+  unsigned b = 0, chunk = 0;
+  if (lane == 0) {
+    const unsigned cur = dyn0 + *reinterpret_cast<volatile unsigned *>(cursor);
+    if (cur < n_work) {
+      chunk = (n_work - cur) / (2u * warps);
+      chunk = chunk > max_chunk ? max_chunk : chunk;
+      chunk = chunk < asked ? asked : chunk;
+      b = dyn0 + atomicAdd(cursor, chunk);
+    } else {
+      b = n_work;
+    }
+  }
+  base = __shfl_sync(CTB_FULL, b, 0);
+  chunk = __shfl_sync(CTB_FULL, chunk, 0);
+  end = base + chunk < n_work ? base + chunk : n_work;
+  return base < n_work;
+}
+
 // ---- scene staging (MODE 1: whole BVH + primitive store, MODE 2: top of the BVH) ------------------------------------------
 // One thread arms an mbarrier with the byte count and issues bulk asynchronous copies global -> shared (cp.async.bulk,
 // SASS UBLKCP): the copy engine of the SM moves the 71 KB of bunny.json's BVH while no thread spends issue slots on
@@ -999,7 +1033,103 @@ __global__ void __launch_bounds__(TRACE_THREADS, CTB_MIN_BLOCKS) frame_kernel(co
 #define CTB_STAMP(i) do { } while (0)
 #endif
 
+// One pixel's walk through the recursion of ray_color: the ray in flight, its path weight and level, the colour summed so far and the
+// deferred children (at most one per level: the transmitted ray of a material that also reflects).
+struct PendingRay { vec3 o, d; float w; uint32_t level; };
+struct PixelPath {
+  vec3 o, d;
+  float w;
+  uint32_t level;
+  float r, g, b;
+  size_t gi, g2;   // the pixel's index in a.out (its layout) and in a.out2 (row-major)
+  int sp;
+  PendingRay stack[16];
+};
+
+__device__ __forceinline__ void path_begin(const PixelArgs &a, uint32_t gx, uint32_t gy, uint32_t pix, PixelPath &p) {
+  camera_ray(a.sv.cam, gx, gy, p.o, p.d);
+  p.w = 1.0f;
+  p.level = 0;
+  p.r = p.g = p.b = 0.f;
+  p.sp = 0;
+  p.gi = a.out.row_major ? (size_t)gy * a.tm.width + gx : (size_t)pix;
+  p.g2 = (size_t)gy * a.tm.width + gx;
+}
+
+// casts the path's current ray, shades its hit and moves on to the next ray of the pixel; false when the pixel is finished
 template <int MODE, bool BRUTE, bool OPAQUE>
+__device__ __forceinline__ bool path_step(const PixelArgs &a, const float4 *nodes, const float4 *prims, PixelPath &p, TraceAcc &acc, unsigned &casts) {
+  const SceneView &sv = a.sv;
+  Hit h;
+  closest_hit<MODE, BRUTE>(sv, nodes, prims, p.o, p.d, sv.fudge, h);
+  const bool hit = h.kind >= 0;
+  vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
+  if (hit) hit_surface<MODE>(sv, prims, h, p.o, p.d, point, nrm);
+  if (p.level == 0) {   // G-buffer, inc/kernel.hpp:52-56
+    const size_t gi = p.gi, g2 = p.g2;
+    a.out.depth[gi] = h.t;
+    a.out.normal[3 * gi] = nrm.x; a.out.normal[3 * gi + 1] = nrm.y; a.out.normal[3 * gi + 2] = nrm.z;
+    a.out.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
+    if (a.out2.depth) a.out2.depth[g2] = h.t;
+    if (a.out2.normal) { a.out2.normal[3 * g2] = nrm.x; a.out2.normal[3 * g2 + 1] = nrm.y; a.out2.normal[3 * g2 + 2] = nrm.z; }
+    if (a.out2.hit_id) a.out2.hit_id[g2] = hit ? h.obj : CUTRACE_NO_HIT;
+    if (hit && isfinite(h.t)) acc.max_depth = fmaxf(acc.max_depth, h.t);
+  }
+  bool next = false;
+  if (hit) {
+    const uint32_t mat = __ldg(sv.obj_material + h.obj);
+    const float4 m1 = __ldg(reinterpret_cast<const float4 *>(sv.materials + mat) + 1);
+    const float reflect = m1.x, transp = m1.z;
+    // inc/shading.hpp:126-149
+    const bool deeper = p.level < a.bounces;
+    const bool do_refl = deeper && (double)reflect >= 1e-6, do_trans = deeper && (double)transp >= 1e-6;
+    const float w_own = do_trans ? p.w * (1.0f - transp) : p.w;
+    const vec3 final = phong_record<MODE, BRUTE, OPAQUE>(sv, nodes, prims, point, nrm, p.d, mat, casts);
+    acc.n_shaded++;
+    // product and sum rounded separately, like the wavefront's level image + ordered sum
+    p.r = __fadd_rn(p.r, __fmul_rn(w_own, final.x)); p.g = __fadd_rn(p.g, __fmul_rn(w_own, final.y)); p.b = __fadd_rn(p.b, __fmul_rn(w_own, final.z));
+    const vec3 origin = vmad(p.o, p.d, h.t);   // incoming->start + distance * incoming->dir
+    if (do_trans) {
+      acc.n_trans++;
+      if (do_refl) { PendingRay &q = p.stack[p.sp++]; q.o = origin; q.d = p.d; q.w = p.w * transp; q.level = p.level + 1; }
+      else { p.o = origin; p.w = p.w * transp; p.level++; next = true; }
+    }
+    if (do_refl) {
+      acc.n_refl++;
+      const vec3 nd = vnormalized(p.d), nn = vnormalized(nrm);
+      p.d = vreflect(nd, nn);
+      p.o = origin; p.w = w_own * reflect; p.level++; next = true;
+    }
+  }
+  if (!next) {
+    if (p.sp == 0) return false;
+    const PendingRay &q = p.stack[--p.sp];
+    p.o = q.o; p.d = q.d; p.w = q.w; p.level = q.level;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void path_store_color(const PixelArgs &a, const PixelPath &p) {
+  float *cp = a.out.color + 3 * p.gi;
+  cp[0] = p.r; cp[1] = p.g; cp[2] = p.b;
+  if (a.out2.color) { float *c2 = a.out2.color + 3 * p.g2; c2[0] = p.r; c2[1] = p.g; c2[2] = p.b; }
+}
+
+// REFILL (-DCTB_PIXEL_REFILL=1 builds + CUTRACE_PIXEL_REFILL=1): a LANE whose pixel is finished takes the next pixel of its warp's
+// claim at once, instead of idling until the longest path of its 32 pixels has ended.  In the 10 M-triangle hall a mesh pixel is one
+// level deep, a floor pixel two to six: 16 x 2 pixel groups mix them, and a warp runs at 11.6 of 32 lanes
+// (profiles/r02_pixel_kernel_synthetic10m.md).  Every step of the loop is: hand unassigned work of the claim to the free lanes
+// (ballot + popc ranks; a new claim from the global cursor when the current one is used up), then ONE path step for every lane that
+// holds a pixel.  A pixel's arithmetic does not depend on the lane or the step it runs in: the frames are bit-identical (same md5
+// on all five workloads, full frames and 1/8 shards).
+// NEGATIVE RESULT (profiles/r02_tuning.md 7): the hall got 32 % SLOWER (70.1 -> 92.7 ms, 1/8 shard 9.45 -> 12.03 ms), bunny.json 4 %,
+// mirror.json 16 %.  Lanes that sit at different bounce levels of different pixels share no nodes: what the warp gains in active
+// lanes it loses in L1 sectors per node visit and in walks that leave the node loop out of phase — the same finding as
+// any_hit_lights (trace.cuh).  Compiled out by default.
+#ifndef CTB_PIXEL_REFILL
+#define CTB_PIXEL_REFILL 0
+#endif
+template <int MODE, bool BRUTE, bool OPAQUE, bool REFILL>
 __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel_kernel(const __grid_constant__ PixelArgs a) {
   extern __shared__ float4 smem[];
 #ifdef CTB_PIXEL_STAMPS
@@ -1019,76 +1149,111 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
   const unsigned warps_total = gridDim.x * (blockDim.x >> 5);
   unsigned max_chunk = (a.n_px / (warps_total * 16u)) & ~31u;
   max_chunk = max_chunk < 32u ? 32u : (max_chunk > 128u ? 128u : max_chunk);
-  for (bool first = true;; first = false) {
-    unsigned base, end;
-    if (!claim_work(&a.ctr->work_trace[0].v, a.n_px, lane, max_chunk, true, first, base, end)) { if (first) continue; break; }
-#pragma unroll 1
-    for (unsigned off = 0; base + off < end; off += 32) {
-      const uint32_t i = base + off + lane;
-      uint32_t gx = 0, gy = 0, pix = 0;
-      if (!(i < a.n_px && work_to_pixel(a.tm, a.px_base + i, gx, gy, pix))) continue;
-      struct Pending { vec3 o, d; float w; uint32_t level; } stack[16];
-      int sp = 0;
-      vec3 o, d;
-      camera_ray(sv.cam, gx, gy, o, d);
-      float w = 1.0f;
-      uint32_t level = 0;
-      float r = 0.f, g = 0.f, b = 0.f;
-      const size_t gi = a.out.row_major ? (size_t)gy * a.tm.width + gx : (size_t)pix;
-      const size_t g2 = (size_t)gy * a.tm.width + gx;
-      for (;;) {
-        Hit h;
-        closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
-        if (level == 0) CTB_STAMP(2);
-        const bool hit = h.kind >= 0;
-        vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
-        if (hit) hit_surface<MODE>(sv, prims, h, o, d, point, nrm);
-        if (level == 0) {   // G-buffer, inc/kernel.hpp:52-56
-          a.out.depth[gi] = h.t;
-          a.out.normal[3 * gi] = nrm.x; a.out.normal[3 * gi + 1] = nrm.y; a.out.normal[3 * gi + 2] = nrm.z;
-          a.out.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
-          if (a.out2.depth) a.out2.depth[g2] = h.t;
-          if (a.out2.normal) { a.out2.normal[3 * g2] = nrm.x; a.out2.normal[3 * g2 + 1] = nrm.y; a.out2.normal[3 * g2 + 2] = nrm.z; }
-          if (a.out2.hit_id) a.out2.hit_id[g2] = hit ? h.obj : CUTRACE_NO_HIT;
-          if (hit && isfinite(h.t)) acc.max_depth = fmaxf(acc.max_depth, h.t);
+  if (REFILL) {
+    PixelPath p;
+    bool have = false;                 // this lane holds a pixel
+    unsigned nxt = 0, end = 0;         // warp-uniform: the unassigned work items of the current claim
+    bool more = true, first = true;    // warp-uniform: the cursor may have work left / the static first claim is still to come
+    for (;;) {
+      unsigned need = __ballot_sync(CTB_FULL, !have);
+      while (need) {
+        if (nxt >= end) {
+          if (!more) break;
+          unsigned b, e;
+          const bool got = claim_pixels(&a.ctr->work_trace[0].v, a.n_px, lane, max_chunk, first, __popc(need), b, e);
+          if (!got && !first) { more = false; break; }
+          first = false;
+          if (!got) continue;
+          nxt = b; end = e;
         }
-        bool next = false;
-        if (hit) {
-          const uint32_t mat = __ldg(sv.obj_material + h.obj);
-          const float4 m1 = __ldg(reinterpret_cast<const float4 *>(sv.materials + mat) + 1);
-          const float reflect = m1.x, transp = m1.z;
-          // inc/shading.hpp:126-149
-          const bool deeper = level < a.bounces;
-          const bool do_refl = deeper && (double)reflect >= 1e-6, do_trans = deeper && (double)transp >= 1e-6;
-          const float w_own = do_trans ? w * (1.0f - transp) : w;
-          const vec3 final = phong_record<MODE, BRUTE, OPAQUE>(sv, nodes, prims, point, nrm, d, mat, casts);
-          if (level == 0) CTB_STAMP(3);
-          acc.n_shaded++;
-          // product and sum rounded separately, like the wavefront's level image + ordered sum
-          r = __fadd_rn(r, __fmul_rn(w_own, final.x)); g = __fadd_rn(g, __fmul_rn(w_own, final.y)); b = __fadd_rn(b, __fmul_rn(w_own, final.z));
-          const vec3 origin = vmad(o, d, h.t);   // incoming->start + distance * incoming->dir
-          if (do_trans) {
-            acc.n_trans++;
-            if (do_refl) { stack[sp].o = origin; stack[sp].d = d; stack[sp].w = w * transp; stack[sp].level = level + 1; sp++; }
-            else { o = origin; w = w * transp; level++; next = true; }
-          }
-          if (do_refl) {
-            acc.n_refl++;
-            const vec3 nd = vnormalized(d), nn = vnormalized(nrm);
-            d = vreflect(nd, nn);
-            o = origin; w = w_own * reflect; level++; next = true;
-          }
+        const unsigned avail = end - nxt, asked = __popc(need);
+        const unsigned rank = __popc(need & lanemask_lt());
+        if (!have && rank < avail) {
+          const uint32_t i = nxt + rank;
+          uint32_t gx = 0, gy = 0, pix = 0;
+          if (i < a.n_px && work_to_pixel(a.tm, a.px_base + i, gx, gy, pix)) { path_begin(a, gx, gy, pix, p); have = true; }
         }
-        if (!next) {
-          if (sp == 0) break;
-          sp--;
-          o = stack[sp].o; d = stack[sp].d; w = stack[sp].w; level = stack[sp].level;
-        }
+        nxt += asked < avail ? asked : avail;
+        need = __ballot_sync(CTB_FULL, !have);   // out-of-image slots of the tile padding: ask again
       }
-      float *cp = a.out.color + 3 * gi;
-      cp[0] = r; cp[1] = g; cp[2] = b;
-      if (a.out2.color) { float *c2 = a.out2.color + 3 * g2; c2[0] = r; c2[1] = g; c2[2] = b; }
-      CTB_STAMP(4);
+      if (!__any_sync(CTB_FULL, have)) break;
+      if (have && !path_step<MODE, BRUTE, OPAQUE>(a, nodes, prims, p, acc, casts)) {
+        path_store_color(a, p);
+        have = false;
+      }
+    }
+  } else {
+    for (bool first = true;; first = false) {
+      unsigned base, end;
+      if (!claim_work(&a.ctr->work_trace[0].v, a.n_px, lane, max_chunk, true, first, base, end)) { if (first) continue; break; }
+#pragma unroll 1
+      for (unsigned off = 0; base + off < end; off += 32) {
+        const uint32_t i = base + off + lane;
+        uint32_t gx = 0, gy = 0, pix = 0;
+        if (!(i < a.n_px && work_to_pixel(a.tm, a.px_base + i, gx, gy, pix))) continue;
+        struct Pending { vec3 o, d; float w; uint32_t level; } stack[16];
+        int sp = 0;
+        vec3 o, d;
+        camera_ray(sv.cam, gx, gy, o, d);
+        float w = 1.0f;
+        uint32_t level = 0;
+        float r = 0.f, g = 0.f, b = 0.f;
+        const size_t gi = a.out.row_major ? (size_t)gy * a.tm.width + gx : (size_t)pix;
+        const size_t g2 = (size_t)gy * a.tm.width + gx;
+        for (;;) {
+          Hit h;
+          closest_hit<MODE, BRUTE>(sv, nodes, prims, o, d, sv.fudge, h);
+          if (level == 0) CTB_STAMP(2);
+          const bool hit = h.kind >= 0;
+          vec3 point = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
+          if (hit) hit_surface<MODE>(sv, prims, h, o, d, point, nrm);
+          if (level == 0) {   // G-buffer, inc/kernel.hpp:52-56
+            a.out.depth[gi] = h.t;
+            a.out.normal[3 * gi] = nrm.x; a.out.normal[3 * gi + 1] = nrm.y; a.out.normal[3 * gi + 2] = nrm.z;
+            a.out.hit_id[gi] = hit ? h.obj : CUTRACE_NO_HIT;
+            if (a.out2.depth) a.out2.depth[g2] = h.t;
+            if (a.out2.normal) { a.out2.normal[3 * g2] = nrm.x; a.out2.normal[3 * g2 + 1] = nrm.y; a.out2.normal[3 * g2 + 2] = nrm.z; }
+            if (a.out2.hit_id) a.out2.hit_id[g2] = hit ? h.obj : CUTRACE_NO_HIT;
+            if (hit && isfinite(h.t)) acc.max_depth = fmaxf(acc.max_depth, h.t);
+          }
+          bool next = false;
+          if (hit) {
+            const uint32_t mat = __ldg(sv.obj_material + h.obj);
+            const float4 m1 = __ldg(reinterpret_cast<const float4 *>(sv.materials + mat) + 1);
+            const float reflect = m1.x, transp = m1.z;
+            // inc/shading.hpp:126-149
+            const bool deeper = level < a.bounces;
+            const bool do_refl = deeper && (double)reflect >= 1e-6, do_trans = deeper && (double)transp >= 1e-6;
+            const float w_own = do_trans ? w * (1.0f - transp) : w;
+            const vec3 final = phong_record<MODE, BRUTE, OPAQUE>(sv, nodes, prims, point, nrm, d, mat, casts);
+            if (level == 0) CTB_STAMP(3);
+            acc.n_shaded++;
+            // product and sum rounded separately, like the wavefront's level image + ordered sum
+            r = __fadd_rn(r, __fmul_rn(w_own, final.x)); g = __fadd_rn(g, __fmul_rn(w_own, final.y)); b = __fadd_rn(b, __fmul_rn(w_own, final.z));
+            const vec3 origin = vmad(o, d, h.t);   // incoming->start + distance * incoming->dir
+            if (do_trans) {
+              acc.n_trans++;
+              if (do_refl) { stack[sp].o = origin; stack[sp].d = d; stack[sp].w = w * transp; stack[sp].level = level + 1; sp++; }
+              else { o = origin; w = w * transp; level++; next = true; }
+            }
+            if (do_refl) {
+              acc.n_refl++;
+              const vec3 nd = vnormalized(d), nn = vnormalized(nrm);
+              d = vreflect(nd, nn);
+              o = origin; w = w_own * reflect; level++; next = true;
+            }
+          }
+          if (!next) {
+            if (sp == 0) break;
+            sp--;
+            o = stack[sp].o; d = stack[sp].d; w = stack[sp].w; level = stack[sp].level;
+          }
+        }
+        float *cp = a.out.color + 3 * gi;
+        cp[0] = r; cp[1] = g; cp[2] = b;
+        if (a.out2.color) { float *c2 = a.out2.color + 3 * g2; c2[0] = r; c2[1] = g; c2[2] = b; }
+        CTB_STAMP(4);
+      }
     }
   }
   CTB_STAMP(5);
@@ -1224,10 +1389,18 @@ static frame_fn pick_frame(int mode, bool brute, bool opaque) {
 }
 
 typedef void (*pixel_fn)(const PixelArgs);
-static pixel_fn pick_pixel(int mode, bool brute, bool opaque) {
-  if (brute) return opaque ? pixel_kernel<0, true, true> : pixel_kernel<0, true, false>;
-  if (mode == 1) return opaque ? pixel_kernel<1, false, true> : pixel_kernel<1, false, false>;
-  return opaque ? pixel_kernel<0, false, true> : pixel_kernel<0, false, false>;
+template <bool REFILL>
+static pixel_fn pick_pixel_r(int mode, bool brute, bool opaque) {
+  if (brute) return opaque ? pixel_kernel<0, true, true, REFILL> : pixel_kernel<0, true, false, REFILL>;
+  if (mode == 1) return opaque ? pixel_kernel<1, false, true, REFILL> : pixel_kernel<1, false, false, REFILL>;
+  return opaque ? pixel_kernel<0, false, true, REFILL> : pixel_kernel<0, false, false, REFILL>;
+}
+static pixel_fn pick_pixel(int mode, bool brute, bool opaque, bool refill) {
+#if CTB_PIXEL_REFILL
+  if (refill) return pick_pixel_r<true>(mode, brute, opaque);
+#endif
+  (void)refill;
+  return pick_pixel_r<false>(mode, brute, opaque);
 }
 
 cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
@@ -1266,7 +1439,9 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
   cfg->grid_frame = occ_f >= 1 && coop ? sms * occ_f : 0;   // 0: no cooperative launch on this device -> multi-launch path
   {
     const int pmode = cfg->mode == 1 ? 1 : 0;
-    pixel_fn pf = pick_pixel(pmode, sv.brute_force != 0, sv.all_opaque != 0);
+    cfg->pixel_refill = 0;   // lane refill (pixel_kernel<.., REFILL>): a tuning build's experiment, see render.cu
+    if (CTB_PIXEL_REFILL) { if (const char *e = getenv("CUTRACE_PIXEL_REFILL")) cfg->pixel_refill = atoi(e) != 0; }
+    pixel_fn pf = pick_pixel(pmode, sv.brute_force != 0, sv.all_opaque != 0, cfg->pixel_refill != 0);
     const size_t psmem = pmode == 1 ? cfg->smem_bytes : 0;
     int occ_p = 1;
     if (pmode == 1 && (e = cudaFuncSetAttribute(pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)) != cudaSuccess) return e;
@@ -1304,11 +1479,16 @@ cudaError_t launch_pixel(const LaunchCfg &cfg, const PixelArgs &args, cudaStream
   // frames of a few thousand pixels read the scene through L1: staging it per CTA (mbarrier round trip) costs more than it saves
   const int mode = cfg.mode == 1 && args.n_px >= (1u << 16) ? 1 : 0;
   const size_t smem = mode == 1 ? cfg.smem_bytes : 0;
-  uint64_t need = ((uint64_t)args.n_px + CTB_PIXEL_THREADS - 1) / CTB_PIXEL_THREADS;
+  // tuning experiments (read once per process: a 20 x 20 frame is a few microseconds, two walks over environ[] are not free)
+  static const int dbg_threads = [] { const char *e = getenv("CUTRACE_DEBUG_PIXEL_THREADS"); return e ? atoi(e) : 0; }();
+  static const int dbg_grid = [] { const char *e = getenv("CUTRACE_DEBUG_PIXEL_GRID"); return e ? atoi(e) : 0; }();
+  int threads = CTB_PIXEL_THREADS;
+  if (dbg_threads >= 32 && dbg_threads <= CTB_PIXEL_THREADS && dbg_threads % 32 == 0) threads = dbg_threads;
+  uint64_t need = ((uint64_t)args.n_px + threads - 1) / threads;
   int grid = (int)(need < (uint64_t)cfg.grid_pixel ? need : (uint64_t)cfg.grid_pixel);
-  if (const char *e = getenv("CUTRACE_DEBUG_PIXEL_GRID")) { int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // tuning experiments
+  if (dbg_grid > 0 && dbg_grid < grid) grid = dbg_grid;
   if (grid < 1) grid = 1;
-  pick_pixel(mode, args.sv.brute_force != 0, args.sv.all_opaque != 0)<<<grid, CTB_PIXEL_THREADS, smem, st>>>(args);
+  pick_pixel(mode, args.sv.brute_force != 0, args.sv.all_opaque != 0, cfg.pixel_refill != 0)<<<grid, threads, smem, st>>>(args);
   return cudaGetLastError();
 }
 
