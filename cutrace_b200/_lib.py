@@ -19,6 +19,7 @@ SYMBOLS = (
     "cutrace_set_frame_max_depth",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free", "cutrace_host_register", "cutrace_host_unregister", "cutrace_trim_memory",
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_debug_phong_pow", "cutrace_abi_version", "cutrace_tile_size",
+    "cutrace_debug_tile_of_slot", "cutrace_debug_slot_of_tile",
 )
 
 FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, \
@@ -104,6 +105,9 @@ def load():
     lib.cutrace_debug_phong_pow.argtypes = [P, P, P, P, C.c_uint32, C.c_int]
     lib.cutrace_abi_version.restype = C.c_uint32
     lib.cutrace_tile_size.restype = C.c_uint32
+    lib.cutrace_debug_tile_of_slot.argtypes = [C.c_uint32] * 5 + [P, P]
+    lib.cutrace_debug_slot_of_tile.argtypes = [C.c_uint32] * 6
+    lib.cutrace_debug_slot_of_tile.restype = C.c_uint32
     _lib = lib
     return lib
 

@@ -279,6 +279,8 @@ int alloc_frame(cutrace_ctx *c, uint32_t width, uint32_t height) {
   tm.n_local_tiles = (total_tiles + tm.world - 1) / tm.world;
   tm.n_tiles = total_tiles;
   tile_permutation(total_tiles, tm.world, &tm.perm_a, &tm.perm_ainv);
+  tm.curve = 1u;   // super-tile order (common.cuh: TileMap); CUTRACE_TILE_CURVE=0: round 1's multiplicative scatter (tuning comparisons)
+  if (const char *e = getenv("CUTRACE_TILE_CURVE")) tm.curve = atoi(e) != 0 ? 1u : 0u;
   tm.wide_warps = 0u;   // set by cutrace_frame_attach for a frame in host memory   // a sharded ctx usually stores into a remote frame: 16 x 2 warps give 64 / 192-byte row segments
   c->tm = tm;
   c->n_local_px = (uint64_t)tm.n_local_tiles * CUTRACE_TILE_PIXELS;
@@ -456,6 +458,31 @@ extern "C" {
 uint32_t cutrace_abi_version(void) { return CUTRACE_ABI_VERSION; }
 
 uint32_t cutrace_tile_size(void) { return CUTRACE_TILE; }
+
+static TileMap debug_tile_map(uint32_t width, uint32_t height, uint32_t world, uint32_t curve) {
+  TileMap tm{};
+  tm.width = width; tm.height = height;
+  tm.tiles_x = (width + CUTRACE_TILE - 1) / CUTRACE_TILE;
+  tm.tiles_y = (height + CUTRACE_TILE - 1) / CUTRACE_TILE;
+  tm.world = world > 1 ? world : 1;
+  tm.n_tiles = tm.tiles_x * tm.tiles_y;
+  tm.n_local_tiles = (tm.n_tiles + tm.world - 1) / tm.world;
+  tile_permutation(tm.n_tiles, tm.world, &tm.perm_a, &tm.perm_ainv);
+  tm.curve = curve ? 1u : 0u;
+  return tm;
+}
+int cutrace_debug_tile_of_slot(uint32_t width, uint32_t height, uint32_t tile_world, uint32_t curve, uint32_t slot, uint32_t *tx, uint32_t *ty) {
+  const TileMap tm = debug_tile_map(width, height, tile_world, curve);
+  uint32_t x = 0, y = 0;
+  const bool ok = tile_of_slot(tm, slot, x, y);
+  if (tx) *tx = x;
+  if (ty) *ty = y;
+  return ok ? 1 : 0;
+}
+uint32_t cutrace_debug_slot_of_tile(uint32_t width, uint32_t height, uint32_t tile_world, uint32_t curve, uint32_t tx, uint32_t ty) {
+  const TileMap tm = debug_tile_map(width, height, tile_world, curve);
+  return slot_of_tile(tm, ty * tm.tiles_x + tx);
+}
 
 const char *cutrace_last_error(void) { return g_err.c_str(); }
 

@@ -188,6 +188,7 @@ static_assert(sizeof(RayRec) == 32 && sizeof(ShadeRec) == 48, "queue record size
 // Words that many warps hit with atomics at the same time each sit on their own 128-byte line: same-address atomics
 // retire at ~0.67 ns each on B200 whatever the SM count, and atomics to ONE line from every warp of the grid (cursor,
 // queue tails, barrier) had made a nearly empty bounce level cost 40 us (profiles/r02_tuning.md).
+#define CTB_MAX_SEGS 320   // CTAs of the pixel kernel's persistent grid that can have a work cursor of their own (148 SMs x 1 or 2)
 struct __align__(128) HotWord { unsigned int v; unsigned int pad_[31]; };
 struct FrameStats {               // what the host reads after a frame
   unsigned long long rays_reflect, rays_transmit, shadow_casts, shade_records;
@@ -203,6 +204,7 @@ struct FrameCounters {
   HotWord arrive[19];       // frame kernel: CTAs that have finished trace(p)   (arrive[levels]: all shading done)
   HotWord work_export;      // cursor of the G-buffer export (peer / host frame)
   HotWord finished;         // CTAs that have left the frame kernel: the last one publishes the stats and clears everything
+  HotWord seg[CTB_MAX_SEGS];   // pixel kernel: one work cursor per CTA (render.cu: claim_segment)
   FrameStats st;
 };
 
@@ -236,10 +238,17 @@ struct SceneView {
 };
 
 // Screen-space tiling.  The frame is cut into CUTRACE_TILE x CUTRACE_TILE tiles; tile "slots" 0..n_tiles-1 are dealt round-robin to the
-// ranks (slot s belongs to rank s % world, local tile s / world) and slot s shows screen tile (s * perm_a) % n_tiles.
-// The multiplicative permutation (perm_a coprime to n_tiles, ~0.618 n) scatters every rank's tiles over the whole
-// image: with plain interleaving a rank owned vertical stripes and the 8-way shards of bunny.json differed by 20 % in
-// cost (profiles/r01_tuning.md).  One rank: perm_a = 1 (natural order).
+// ranks (slot s belongs to rank s % world, local tile s / world).  Which screen tile a slot shows:
+//   curve = 1 (default)  slots walk the frame super-tile by super-tile (CTB_SUPER_W x CTB_SUPER_H tiles, row-major inside and across):
+//             tiles that are processed at the same time — by the warps of one CTA, and by one rank — lie next to each other on the
+//             screen and walk the same part of the BVH.  The super-tile is 9 tiles wide so that inside it slot % world runs along
+//             DIAGONALS for world = 2, 4, 8 ((iy * 9 + ix) % 8 = (ix + iy) % 8): every rank samples the whole image at tile
+//             granularity (plain interleaving of rows gave a rank vertical stripes, and the 8-way shards of bunny.json differed by
+//             20 % in cost, profiles/r01_tuning.md), and a rank's consecutive local tiles are at most a few tiles apart.
+//   curve = 0            round 1's scatter: slot s shows screen tile (s * perm_a) % n_tiles, perm_a coprime to n_tiles, ~0.618 n
+//             (one rank: perm_a = 1, natural order) — balanced, but a rank's consecutive tiles are 0.6 frames apart.
+#define CTB_SUPER_W 9u
+#define CTB_SUPER_H 8u
 struct TileMap {
   uint32_t width, height;
   uint32_t tiles_x, tiles_y;
@@ -248,11 +257,24 @@ struct TileMap {
   uint32_t n_tiles, perm_a, perm_ainv;
   uint32_t wide_warps;        // 0: the 32 pixels of a warp form an 8 x 4 block (most coherent primary rays); 1: a 16 x 2 block — whole
                               // tile rows, so that per-pixel stores into a remote frame (peer GPU, pinned host memory) are 64 / 192-byte segments
+  uint32_t curve;             // slot order, see above
 };
 
 // slot -> screen tile coordinates; false for the padding slots of the last local tile
 __host__ __device__ __forceinline__ bool tile_of_slot(const TileMap &tm, uint32_t slot, uint32_t &tx, uint32_t &ty) {
   if (slot >= tm.n_tiles) return false;
+  if (tm.curve) {
+    const uint32_t row_tiles = tm.tiles_x * CTB_SUPER_H;                 // tiles of a full row of super-tiles
+    const uint32_t sr = slot / row_tiles, rem = slot - sr * row_tiles;
+    const uint32_t left_y = tm.tiles_y - sr * CTB_SUPER_H, h = left_y < CTB_SUPER_H ? left_y : CTB_SUPER_H;
+    const uint32_t col_tiles = CTB_SUPER_W * h;                          // tiles of a full-width super-tile in this row
+    const uint32_t sc = rem / col_tiles, rem2 = rem - sc * col_tiles;
+    const uint32_t left_x = tm.tiles_x - sc * CTB_SUPER_W, w = left_x < CTB_SUPER_W ? left_x : CTB_SUPER_W;
+    const uint32_t iy = rem2 / w, ix = rem2 - iy * w;
+    tx = sc * CTB_SUPER_W + ix;
+    ty = sr * CTB_SUPER_H + iy;
+    return true;
+  }
   const uint32_t t = (uint32_t)(((unsigned long long)slot * tm.perm_a) % tm.n_tiles);
   tx = t % tm.tiles_x;
   ty = t / tm.tiles_x;
@@ -260,6 +282,13 @@ __host__ __device__ __forceinline__ bool tile_of_slot(const TileMap &tm, uint32_
 }
 // screen tile index (ty * tiles_x + tx) -> slot
 __host__ __device__ __forceinline__ uint32_t slot_of_tile(const TileMap &tm, uint32_t t) {
+  if (tm.curve) {
+    const uint32_t tx = t % tm.tiles_x, ty = t / tm.tiles_x;
+    const uint32_t sr = ty / CTB_SUPER_H, sc = tx / CTB_SUPER_W;
+    const uint32_t left_y = tm.tiles_y - sr * CTB_SUPER_H, h = left_y < CTB_SUPER_H ? left_y : CTB_SUPER_H;
+    const uint32_t left_x = tm.tiles_x - sc * CTB_SUPER_W, w = left_x < CTB_SUPER_W ? left_x : CTB_SUPER_W;
+    return sr * tm.tiles_x * CTB_SUPER_H + sc * CTB_SUPER_W * h + (ty - sr * CTB_SUPER_H) * w + (tx - sc * CTB_SUPER_W);
+  }
   return (uint32_t)(((unsigned long long)t * tm.perm_ainv) % tm.n_tiles);
 }
 // local pixel index (tile-major, row-major inside the tile) -> pixel; false outside the image

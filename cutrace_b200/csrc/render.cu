@@ -150,6 +150,76 @@ __device__ __forceinline__ bool claim_pixels(unsigned *cursor, unsigned n_work, 
   return base < n_work;
 }
 
+// ---- pixel kernel: one work cursor per CTA ----------------------------------------------------------------------------------
+// With ONE cursor for the whole grid, consecutive claims go to whichever warps ask next: the 32 warps of an SM work on 32 unrelated
+// places of the frame and share nothing in L1 but the top of the BVH (10 M-triangle hall: L1 hit rate 74 %, long-scoreboard stalls
+// 4.3 warp-cycles per issue, profiles/r02_pixel_kernel_synthetic10m.md).  Here the frame's work items are cut into chunks of
+// CTB_SEG_CHUNK (4096 pixels = 16 tiles = one 128-pixel claim for each of a CTA's 32 warps) that are dealt to the CTAs
+// round-robin — CTA k owns chunks k, k + G, k + 2G, ..: every CTA samples the whole frame, so the CTAs finish within a few per
+// cent of each other — and the warps of a CTA claim from THEIR cursor: at any moment an SM works on one or two 16-tile chunks.
+// A warp whose CTA has run dry steals 32 pixels at a time from the CTA with the most work left (the warp reads all cursors, one
+// per lane and round).  `o` below is an offset in a CTA's own index space [0, seg_len(k)).
+#define CTB_SEG_CHUNK 4096u
+__device__ __forceinline__ unsigned seg_len(unsigned n_work, unsigned k, unsigned G) {
+  const unsigned nc = (n_work + CTB_SEG_CHUNK - 1u) / CTB_SEG_CHUNK;   // chunks of the frame (the last one may be partial)
+  if (k >= nc) return 0u;
+  const unsigned mine = (nc - 1u - k) / G + 1u;
+  const unsigned len = mine * CTB_SEG_CHUNK;
+  return ((nc - 1u) % G == k) ? len - (nc * CTB_SEG_CHUNK - n_work) : len;   // the owner of the last chunk
+}
+__device__ __forceinline__ unsigned seg_to_work(unsigned o, unsigned k, unsigned G) {
+  return ((o / CTB_SEG_CHUNK) * G + k) * CTB_SEG_CHUNK + (o % CTB_SEG_CHUNK);
+}
+// claims [base, end) in the index space of CTA `owner` (warp-uniform results); false: the frame has no unclaimed work left
+__device__ __forceinline__ bool claim_segment(FrameCounters *ctr, unsigned n_work, unsigned lane, unsigned max_chunk, bool first, unsigned &owner,
+                                              unsigned &base, unsigned &end) {
+  const unsigned G = gridDim.x, wpc = blockDim.x >> 5, k = blockIdx.x;
+  const unsigned len = seg_len(n_work, k, G);
+  const unsigned c0 = guided_chunk(len, wpc, max_chunk);
+  owner = k;
+  if (first) {   // static first slot: no atomic (see claim_work)
+    base = (threadIdx.x >> 5) * c0;
+    end = base + c0 < len ? base + c0 : len;
+    return base < len;
+  }
+  const unsigned dyn0 = wpc * c0;
+  unsigned b = 0xffffffffu, chunk = 0;
+  if (dyn0 < len) {
+    if (lane == 0) {
+      const unsigned cur = dyn0 + *reinterpret_cast<volatile unsigned *>(&ctr->seg[k].v);
+      if (cur < len) {
+        chunk = guided_chunk(len - cur, wpc, max_chunk);
+        b = dyn0 + atomicAdd(&ctr->seg[k].v, chunk);
+      }
+    }
+    b = __shfl_sync(CTB_FULL, b, 0);
+    chunk = __shfl_sync(CTB_FULL, chunk, 0);
+    if (b < len) { base = b; end = b + chunk < len ? b + chunk : len; return true; }
+  }
+  // own segment used up: steal from the CTA with the most work left
+  for (;;) {
+    unsigned best_rem = 0, best_v = 0;
+    for (unsigned v = lane; v < G; v += 32) {
+      const unsigned lv = seg_len(n_work, v, G);
+      const unsigned d0 = wpc * guided_chunk(lv, wpc, max_chunk);
+      const unsigned cur = d0 + *reinterpret_cast<volatile unsigned *>(&ctr->seg[v].v);
+      const unsigned rem = cur < lv ? lv - cur : 0u;
+      if (rem > best_rem) { best_rem = rem; best_v = v; }
+    }
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      const unsigned r2 = __shfl_xor_sync(CTB_FULL, best_rem, sft), v2 = __shfl_xor_sync(CTB_FULL, best_v, sft);
+      if (r2 > best_rem || (r2 == best_rem && v2 < best_v)) { best_rem = r2; best_v = v2; }
+    }
+    if (best_rem == 0) return false;
+    const unsigned lv = seg_len(n_work, best_v, G);
+    const unsigned d0 = wpc * guided_chunk(lv, wpc, max_chunk);
+    unsigned sb = 0;
+    if (lane == 0) sb = d0 + atomicAdd(&ctr->seg[best_v].v, 32u);
+    sb = __shfl_sync(CTB_FULL, sb, 0);
+    if (sb < lv) { owner = best_v; base = sb; end = sb + 32u < lv ? sb + 32u : lv; return true; }
+  }
+}
+
 // ---- scene staging (MODE 1: whole BVH + primitive store, MODE 2: top of the BVH) ------------------------------------------
 // One thread arms an mbarrier with the byte count and issues bulk asynchronous copies global -> shared (cp.async.bulk,
 // SASS UBLKCP): the copy engine of the SM moves the 71 KB of bunny.json's BVH while no thread spends issue slots on
@@ -1129,7 +1199,7 @@ __device__ __forceinline__ void path_store_color(const PixelArgs &a, const Pixel
 #ifndef CTB_PIXEL_REFILL
 #define CTB_PIXEL_REFILL 0
 #endif
-template <int MODE, bool BRUTE, bool OPAQUE, bool REFILL>
+template <int MODE, bool BRUTE, bool OPAQUE, bool REFILL, bool SEG>
 __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel_kernel(const __grid_constant__ PixelArgs a) {
   extern __shared__ float4 smem[];
 #ifdef CTB_PIXEL_STAMPS
@@ -1184,11 +1254,15 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
     }
   } else {
     for (bool first = true;; first = false) {
-      unsigned base, end;
-      if (!claim_work(&a.ctr->work_trace[0].v, a.n_px, lane, max_chunk, true, first, base, end)) { if (first) continue; break; }
+      unsigned base, end, owner = 0;
+      if (SEG) {
+        if (!claim_segment(a.ctr, a.n_px, lane, max_chunk, first, owner, base, end)) { if (first) continue; break; }
+      } else {
+        if (!claim_work(&a.ctr->work_trace[0].v, a.n_px, lane, max_chunk, true, first, base, end)) { if (first) continue; break; }
+      }
 #pragma unroll 1
       for (unsigned off = 0; base + off < end; off += 32) {
-        const uint32_t i = base + off + lane;
+        const uint32_t i = SEG ? seg_to_work(base + off, owner, gridDim.x) + lane : base + off + lane;
         uint32_t gx = 0, gy = 0, pix = 0;
         if (!(i < a.n_px && work_to_pixel(a.tm, a.px_base + i, gx, gy, pix))) continue;
         struct Pending { vec3 o, d; float w; uint32_t level; } stack[16];
@@ -1291,7 +1365,7 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
     if (threadIdx.x == 0) {
       s_fs.rays_reflect = s_t[0]; s_fs.rays_transmit = s_t[1]; s_fs.shade_records = s_t[2]; s_fs.shadow_casts = s_t[3];
       s_fs.max_depth_bits = s_md;
-      ctr->work_trace[0].v = 0u;   // (only a debug grid override makes one block claim dynamically)
+      ctr->work_trace[0].v = 0u; ctr->seg[0].v = 0u;   // (only a debug grid override makes one block claim dynamically)
     }
     __syncthreads();
     volatile unsigned *dst1 = reinterpret_cast<volatile unsigned *>(a.host_stats);
@@ -1333,6 +1407,7 @@ __global__ void __launch_bounds__(CTB_PIXEL_THREADS, CTB_PIXEL_MIN_BLOCKS) pixel
       src[S0 + threadIdx.x] = 0u;
     }
     if (threadIdx.x == 0) { ctr->finished.v = 0u; ctr->work_trace[0].v = 0u; }
+    if (SEG) for (unsigned k = threadIdx.x; k < gridDim.x; k += blockDim.x) ctr->seg[k].v = 0u;
     // (no system fence: the stores to the mapped host block are complete when the kernel is, and nobody reads them earlier)
   }
 }
@@ -1389,18 +1464,18 @@ static frame_fn pick_frame(int mode, bool brute, bool opaque) {
 }
 
 typedef void (*pixel_fn)(const PixelArgs);
-template <bool REFILL>
+template <bool REFILL, bool SEG>
 static pixel_fn pick_pixel_r(int mode, bool brute, bool opaque) {
-  if (brute) return opaque ? pixel_kernel<0, true, true, REFILL> : pixel_kernel<0, true, false, REFILL>;
-  if (mode == 1) return opaque ? pixel_kernel<1, false, true, REFILL> : pixel_kernel<1, false, false, REFILL>;
-  return opaque ? pixel_kernel<0, false, true, REFILL> : pixel_kernel<0, false, false, REFILL>;
+  if (brute) return opaque ? pixel_kernel<0, true, true, REFILL, SEG> : pixel_kernel<0, true, false, REFILL, SEG>;
+  if (mode == 1) return opaque ? pixel_kernel<1, false, true, REFILL, SEG> : pixel_kernel<1, false, false, REFILL, SEG>;
+  return opaque ? pixel_kernel<0, false, true, REFILL, SEG> : pixel_kernel<0, false, false, REFILL, SEG>;
 }
-static pixel_fn pick_pixel(int mode, bool brute, bool opaque, bool refill) {
+static pixel_fn pick_pixel(int mode, bool brute, bool opaque, bool refill, bool seg) {
 #if CTB_PIXEL_REFILL
-  if (refill) return pick_pixel_r<true>(mode, brute, opaque);
+  if (refill) return pick_pixel_r<true, false>(mode, brute, opaque);
 #endif
   (void)refill;
-  return pick_pixel_r<false>(mode, brute, opaque);
+  return seg ? pick_pixel_r<false, true>(mode, brute, opaque) : pick_pixel_r<false, false>(mode, brute, opaque);
 }
 
 cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
@@ -1441,10 +1516,14 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
     const int pmode = cfg->mode == 1 ? 1 : 0;
     cfg->pixel_refill = 0;   // lane refill (pixel_kernel<.., REFILL>): a tuning build's experiment, see render.cu
     if (CTB_PIXEL_REFILL) { if (const char *e = getenv("CUTRACE_PIXEL_REFILL")) cfg->pixel_refill = atoi(e) != 0; }
-    pixel_fn pf = pick_pixel(pmode, sv.brute_force != 0, sv.all_opaque != 0, cfg->pixel_refill != 0);
+    cfg->pixel_seg = 1;      // one work cursor per CTA (claim_segment); CUTRACE_PIXEL_SEG=0: the single global cursor
+    if (const char *e = getenv("CUTRACE_PIXEL_SEG")) cfg->pixel_seg = atoi(e) != 0;
+    pixel_fn pf = pick_pixel(pmode, sv.brute_force != 0, sv.all_opaque != 0, cfg->pixel_refill != 0, cfg->pixel_seg != 0);
     const size_t psmem = pmode == 1 ? cfg->smem_bytes : 0;
     int occ_p = 1;
-    if (pmode == 1 && (e = cudaFuncSetAttribute(pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)) != cudaSuccess) return e;
+    for (int sg = 0; sg < 2 && pmode == 1; sg++)   // launch_pixel may pick either cursor variant
+      if ((e = cudaFuncSetAttribute(pick_pixel(pmode, sv.brute_force != 0, sv.all_opaque != 0, cfg->pixel_refill != 0, sg != 0),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pf, CTB_PIXEL_THREADS, psmem)) != cudaSuccess) return e;
     cfg->grid_pixel = sms * (occ_p < 1 ? 1 : occ_p);
   }
@@ -1488,7 +1567,8 @@ cudaError_t launch_pixel(const LaunchCfg &cfg, const PixelArgs &args, cudaStream
   int grid = (int)(need < (uint64_t)cfg.grid_pixel ? need : (uint64_t)cfg.grid_pixel);
   if (dbg_grid > 0 && dbg_grid < grid) grid = dbg_grid;
   if (grid < 1) grid = 1;
-  pick_pixel(mode, args.sv.brute_force != 0, args.sv.all_opaque != 0, cfg.pixel_refill != 0)<<<grid, threads, smem, st>>>(args);
+  const bool seg = cfg.pixel_seg != 0 && grid <= (int)CTB_MAX_SEGS;
+  pick_pixel(mode, args.sv.brute_force != 0, args.sv.all_opaque != 0, cfg.pixel_refill != 0, seg)<<<grid, threads, smem, st>>>(args);
   return cudaGetLastError();
 }
 

@@ -47,6 +47,7 @@ struct LaunchCfg {
   int grid_frame;               // co-resident CTAs of the cooperative frame kernel (0: not available on this device)
   int grid_pixel;               // persistent grid of the pixel kernel
   int pixel_refill;             // pixel kernel: a lane takes its next pixel as soon as its path has ended (render.cu)
+  int pixel_seg;                // pixel kernel: one work cursor per CTA instead of one for the grid (render.cu: claim_segment)
 };
 // pixel kernel: ONE CTA of 1024 threads per SM (64 registers).  Measured on bunny.json 4K (profiles/r02_tuning.md): 256 x 4 10.3 ms
 // (71 KB of staged scene per CTA caps the SM at 3 CTAs), 256 x 3 9.44, 256 x 2 (128 registers) 10.7, 512 x 2 9.01; and on the

@@ -309,6 +309,12 @@ int cutrace_debug_radix_sort(uint64_t *keys, uint32_t *values, uint32_t n, int d
  * below the underflow floor of e[i]), both on the device; the two arrays must be bit-identical. */
 int cutrace_debug_phong_pow(const float *x, const float *e, float *out_powf, float *out_fast, uint32_t n, int device);
 
+/* test hook (host only, no device needed): the screen tile (tx, ty) that tile slot `slot` of a width x height frame shows for
+ * tile_world ranks, as the kernels compute it (curve: 1 = super-tile order, 0 = round 1's multiplicative scatter), and the inverse.
+ * cutrace_debug_tile_of_slot returns 0 for a padding slot (slot >= number of tiles), 1 otherwise. */
+int cutrace_debug_tile_of_slot(uint32_t width, uint32_t height, uint32_t tile_world, uint32_t curve, uint32_t slot, uint32_t *tx, uint32_t *ty);
+uint32_t cutrace_debug_slot_of_tile(uint32_t width, uint32_t height, uint32_t tile_world, uint32_t curve, uint32_t tx, uint32_t ty);
+
 uint32_t cutrace_abi_version(void);
 /* edge of the screen tiles the sharding works in (CUTRACE_TILE of the library that is loaded) */
 uint32_t cutrace_tile_size(void);

@@ -106,3 +106,37 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"(from|import)\s+oracle|pyoracle|cutrace_oracle|libcutrace_ref", txt):
                     bad.append(fn)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("curve", [1, 0])
+@pytest.mark.parametrize("dims", [(20, 20), (1920, 1080), (300, 2), (1021, 577), (16 * 9 * 3 + 5, 16 * 8 * 2 + 1)])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_tile_slot_mapping_is_a_bijection_and_balanced(lib, curve, dims, world):
+    """Host-only hook over the kernels' own tile_of_slot / slot_of_tile (csrc/common.cuh): every screen tile has exactly one slot,
+    the two functions invert each other, padding slots are reported, and (super-tile order) every rank's tiles cover the frame at
+    tile granularity: every 8 x 8-tile window of an 8-rank frame holds every rank in nearly equal shares, and consecutive local tiles of a rank stay close."""
+    from cutrace_b200.scene import TILE
+
+    w, h = dims
+    tiles_x, tiles_y = (w + TILE - 1) // TILE, (h + TILE - 1) // TILE
+    n = tiles_x * tiles_y
+    tx, ty = C.c_uint32(), C.c_uint32()
+    owner = np.full((tiles_y, tiles_x), -1, np.int64)
+    pos = []
+    for slot in range(n):
+        assert lib.cutrace_debug_tile_of_slot(w, h, world, curve, slot, C.byref(tx), C.byref(ty)) == 1
+        assert tx.value < tiles_x and ty.value < tiles_y
+        assert owner[ty.value, tx.value] == -1, "two slots show the same tile"
+        owner[ty.value, tx.value] = slot % world
+        assert lib.cutrace_debug_slot_of_tile(w, h, world, curve, tx.value, ty.value) == slot
+        pos.append((tx.value, ty.value))
+    assert (owner >= 0).all()
+    assert lib.cutrace_debug_tile_of_slot(w, h, world, curve, n, C.byref(tx), C.byref(ty)) == 0
+    if curve and world == 8 and tiles_x >= 32 and tiles_y >= 32:
+        for y0 in range(0, tiles_y - 8, 5):          # every 8 x 8-tile window holds every rank, in nearly equal shares
+            for x0 in range(0, tiles_x - 8, 7):
+                counts = np.bincount(owner[y0:y0 + 8, x0:x0 + 8].ravel(), minlength=8)
+                assert counts.min() >= 5 and counts.max() <= 11, (x0, y0, counts)
+        p = np.asarray(pos[0::8], np.int64)            # rank 0's tiles in its own order
+        step = np.abs(np.diff(p, axis=0)).max(axis=1)
+        assert np.percentile(step, 90) <= 9, "a rank's consecutive tiles are neighbours inside a super-tile"
