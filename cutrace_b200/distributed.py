@@ -2,7 +2,8 @@
 
 This is the only place the render path shards: pixels are independent
 (/root/reference/inc/kernel.hpp:37-59 has no inter-thread communication), so rank r renders the
-16x16 tiles whose slot s (screen tile (s * a) % n_tiles, a multiplicative permutation) has s % world == r.
+16x16 tiles whose slot s has s % world == r; slots walk the frame super-tile by super-tile (9 x 8 tiles, TileMap in
+csrc/common.cuh), so a rank's tiles are a diagonal lattice over the whole image and its consecutive tiles are neighbours.
 ONE exchange step follows.  Default ("peer"): every rank's kernels store their tiles straight into rank 0's
 row-major frame over NVLink (CUDA IPC), so the exchange is fused into the producing kernels and only a
 barrier remains.  Fallback ("gather"): tile-major local buffers, an NCCL gather of the float framebuffers
@@ -24,39 +25,49 @@ def local_tile_count(width, height, world):
     return (n_tiles(width, height) + world - 1) // world
 
 
-def tile_permutation(n, world):
-    """(a, a^-1 mod n) of the multiplicative tile permutation (TileMap in csrc/common.cuh): slot s shows screen tile
-    (s * a) % n; slots are dealt round-robin to the ranks.  One rank: identity."""
-    import math
+SUPER_W, SUPER_H = 9, 8   # CTB_SUPER_W / CTB_SUPER_H of csrc/common.cuh
 
-    if world <= 1 or n < 3:
-        return 1, 1
-    a = (n * 618 // 1000) | 1
-    while a < n and math.gcd(a, n) != 1:
-        a += 2
-    if a >= n:
-        return 1, 1
-    return a, pow(a, -1, n)
+
+def tile_of_slot(slot, width, height):
+    """Screen tile (tx, ty) that tile slot ``slot`` shows — the Python mirror of tile_of_slot(curve = 1) in csrc/common.cuh
+    (tests/test_abi.py checks it against the library's own function): super-tiles of SUPER_W x SUPER_H tiles in row-major order,
+    row-major inside; the super-tiles of the last row / column are cut to what the frame has."""
+    tiles_x, tiles_y = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+    sr, rem = divmod(slot, tiles_x * SUPER_H)
+    h = min(SUPER_H, tiles_y - sr * SUPER_H)
+    sc, rem2 = divmod(rem, SUPER_W * h)
+    w = min(SUPER_W, tiles_x - sc * SUPER_W)
+    iy, ix = divmod(rem2, w)
+    return sc * SUPER_W + ix, sr * SUPER_H + iy
+
+
+def slot_of_tile(tx, ty, width, height):
+    """Inverse of tile_of_slot."""
+    tiles_x, tiles_y = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+    sr, sc = ty // SUPER_H, tx // SUPER_W
+    h = min(SUPER_H, tiles_y - sr * SUPER_H)
+    w = min(SUPER_W, tiles_x - sc * SUPER_W)
+    return sr * tiles_x * SUPER_H + sc * SUPER_W * h + (ty - sr * SUPER_H) * w + (tx - sc * SUPER_W)
 
 
 def tiles_of_rank(width, height, rank, world):
     """Screen tile indices (row-major tile order) owned by ``rank``, in local-tile order."""
-    n = n_tiles(width, height)
-    a, _ = tile_permutation(n, world)
-    return [(s * a) % n for s in range(rank, n, world)]
+    tiles_x = (width + TILE - 1) // TILE
+    out = []
+    for s in range(rank, n_tiles(width, height), world):
+        tx, ty = tile_of_slot(s, width, height)
+        out.append(ty * tiles_x + tx)
+    return out
 
 
 def untile_host(parts, width, height, channels):
     """CPU reference of the un-tile step (used by the gloo tests): ``parts[r]`` is rank r's tile-major
     buffer of shape (n_local_tiles*TILE*TILE, channels)."""
     world = len(parts)
-    tx = (width + TILE - 1) // TILE
-    n = n_tiles(width, height)
-    _, ainv = tile_permutation(n, world)
     out = np.zeros((height, width, channels), parts[0].dtype)
     for y in range(height):
         for x0 in range(0, width, TILE):
-            slot = (((y // TILE) * tx + x0 // TILE) * ainv) % n
+            slot = slot_of_tile(x0 // TILE, y // TILE, width, height)
             r, lt = slot % world, slot // world
             cnt = min(TILE, width - x0)
             src = lt * TILE * TILE + (y % TILE) * TILE

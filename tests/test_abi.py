@@ -115,6 +115,7 @@ def test_tile_slot_mapping_is_a_bijection_and_balanced(lib, curve, dims, world):
     """Host-only hook over the kernels' own tile_of_slot / slot_of_tile (csrc/common.cuh): every screen tile has exactly one slot,
     the two functions invert each other, padding slots are reported, and (super-tile order) every rank's tiles cover the frame at
     tile granularity: every 8 x 8-tile window of an 8-rank frame holds every rank in nearly equal shares, and consecutive local tiles of a rank stay close."""
+    from cutrace_b200 import distributed as dist_py
     from cutrace_b200.scene import TILE
 
     w, h = dims
@@ -129,6 +130,8 @@ def test_tile_slot_mapping_is_a_bijection_and_balanced(lib, curve, dims, world):
         assert owner[ty.value, tx.value] == -1, "two slots show the same tile"
         owner[ty.value, tx.value] = slot % world
         assert lib.cutrace_debug_slot_of_tile(w, h, world, curve, tx.value, ty.value) == slot
+        if curve:   # the Python mirror the gloo tests and untile_host use
+            assert dist_py.tile_of_slot(slot, w, h) == (tx.value, ty.value) and dist_py.slot_of_tile(tx.value, ty.value, w, h) == slot
         pos.append((tx.value, ty.value))
     assert (owner >= 0).all()
     assert lib.cutrace_debug_tile_of_slot(w, h, world, curve, n, C.byref(tx), C.byref(ty)) == 0

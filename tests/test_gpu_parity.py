@@ -779,20 +779,22 @@ def test_render_download_with_the_frame_kernel(ct, monkeypatch):
         assert_same_frame(a, c, "two fused frames")
 
 
-def test_render_download_straight_into_pinned_host_memory(ct):
+@pytest.mark.parametrize("width,height,skew", [(1000, 562, 0), (1001, 563, 0), (1000, 562, 4), (1920, 1080, 0)])
+def test_render_download_straight_into_pinned_host_memory(ct, width, height, skew):
     """cutrace_render_download with pinned + mapped destinations (cutrace_host_alloc): the pixel kernel stores every finished pixel
     into the ctx's frame AND into the caller's images over PCIe — no copy afterwards.  Same bits as render + download, the
-    device frame stays valid, NULL destinations are skipped, pageable destinations take the copy path."""
+    device frame stays valid, NULL destinations are skipped, pageable destinations take the copy path.  Odd sizes (partial tiles
+    at both edges), a width that is no multiple of 4, destinations that start 4 bytes into the pinned block, and BASELINE's 1080p."""
     import ctypes as C
 
     lib = ct._lib.load()
-    s = load_golden_scene("bunny").with_resolution(1000, 562)     # odd sizes: partial tiles at both edges
+    s = load_golden_scene("bunny").with_resolution(width, height)     # odd sizes: partial tiles at both edges
     n = s.width * s.height
     ptrs, pinned = [], {}
     for k, m, dt in (("depth", 1, np.float32), ("normal", 3, np.float32), ("color", 3, np.float32), ("hit_id", 1, np.uint32)):
-        p = lib.cutrace_host_alloc(n * m * 4)
+        p = lib.cutrace_host_alloc(n * m * 4 + 16)
         ptrs.append(p)
-        pinned[k] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float if dt is np.float32 else C.c_uint32)), shape=(n * m,))
+        pinned[k] = np.ctypeslib.as_array(C.cast(p + skew, C.POINTER(C.c_float if dt is np.float32 else C.c_uint32)), shape=(n * m,))
         pinned[k][:] = 0
     with ct.Renderer(s) as r:
         md, st = C.c_float(), ct.cutrace_stats()

@@ -1,35 +1,50 @@
-// Event -> launch -> event on an idle stream: what a tiny frame pays outside its kernel body.  Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a
-// -o build/launch_floor tools/launch_floor.cu.  Prints the median microseconds of 200 launches per case.
+// Event -> launch -> event on an idle stream: what a tiny frame pays outside its kernel body, as a function of the kernel's parameter
+// bytes and of a final store to mapped host memory.  Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/launch_floor.bin
+// tools/launch_floor.cu.  The cases are interleaved round-robin (clock ramps and drift hit all of them alike); median of 300 each.
 #include <algorithm>
 #include <cstdio>
+#include <functional>
+#include <string>
 #include <vector>
 #include <cuda_runtime.h>
-struct Small { int x[4]; };
-struct Big { int x[176]; };   // 704 bytes, about sizeof(PixelArgs)
-__global__ void k_small(Small a, int *out) { if (a.x[0] == 12345) out[0] = 1; }
-__global__ void __launch_bounds__(1024, 1) k_big(const __grid_constant__ Big a, int *out) { if (a.x[threadIdx.x % 176] == 12345) out[0] = 1; }
-__global__ void __launch_bounds__(1024, 1) k_big_host(const __grid_constant__ Big a, volatile int *host) { if (threadIdx.x < 20) host[threadIdx.x] = a.x[threadIdx.x]; }
-__global__ void __launch_bounds__(1024, 1) k_big_dev(const __grid_constant__ Big a, volatile int *dev) { if (threadIdx.x < 20) dev[threadIdx.x] = a.x[threadIdx.x]; }
-template <typename F> static float median_us(F launch) {
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  std::vector<float> v;
-  for (int i = 0; i < 220; i++) {
-    cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
-    float ms; cudaEventElapsedTime(&ms, e0, e1); if (i >= 20) v.push_back(ms * 1e3f);
-  }
-  std::sort(v.begin(), v.end());
-  return v[v.size() / 2];
+template <int N> struct P { int x[N]; };
+template <int N> __global__ void __launch_bounds__(1024, 1) k_dev(const __grid_constant__ P<N> a, volatile int *out) {
+  if (a.x[threadIdx.x % N] == 12345) out[0] = 1;
 }
+template <int N> __global__ void __launch_bounds__(1024, 1) k_host(const __grid_constant__ P<N> a, volatile int *host) {
+  if (threadIdx.x < 20) host[threadIdx.x] = a.x[threadIdx.x % N];
+}
+__constant__ P<176> g_args;
+__global__ void __launch_bounds__(1024, 1) k_sym(volatile int *out) { if (g_args.x[threadIdx.x % 176] == 12345) out[0] = 1; }
 int main() {
   int *d; cudaMalloc(&d, 4096);
   int *h; cudaHostAlloc(&h, 4096, cudaHostAllocMapped); int *hd; cudaHostGetDevicePointer(&hd, h, 0);
-  Small s{}; Big b{};
-  printf("empty, 16-byte params, 1 x 32 threads        %6.2f us\n", median_us([&] { k_small<<<1, 32>>>(s, d); }));
-  printf("empty, 16-byte params, 2 x 256 threads       %6.2f us\n", median_us([&] { k_small<<<2, 256>>>(s, d); }));
-  printf("empty, 704-byte params, 1 x 1024 threads     %6.2f us\n", median_us([&] { k_big<<<1, 1024>>>(b, d); }));
-  printf("empty, 704-byte params, 4 x 256 threads      %6.2f us\n", median_us([&] { k_big<<<4, 256>>>(b, d); }));
-  printf("80 B to device memory, 1 x 1024              %6.2f us\n", median_us([&] { k_big_dev<<<1, 1024>>>(b, d); }));
-  printf("80 B to mapped host memory, 1 x 1024         %6.2f us\n", median_us([&] { k_big_host<<<1, 1024>>>(b, hd); }));
-  printf("no kernel (event, event)                     %6.2f us\n", median_us([&] {}));
+  static P<4> p4{}; static P<16> p16{}; static P<32> p32{}; static P<64> p64{}; static P<96> p96{}; static P<128> p128{}; static P<176> p176{};
+  std::vector<std::pair<std::string, std::function<void()>>> cases = {
+      {"   16 B params, 1 x 1024", [&] { k_dev<4><<<1, 1024>>>(p4, d); }},
+      {"   64 B params", [&] { k_dev<16><<<1, 1024>>>(p16, d); }},
+      {"  128 B params", [&] { k_dev<32><<<1, 1024>>>(p32, d); }},
+      {"  256 B params", [&] { k_dev<64><<<1, 1024>>>(p64, d); }},
+      {"  384 B params", [&] { k_dev<96><<<1, 1024>>>(p96, d); }},
+      {"  512 B params", [&] { k_dev<128><<<1, 1024>>>(p128, d); }},
+      {"  704 B params", [&] { k_dev<176><<<1, 1024>>>(p176, d); }},
+      {"  704 B params, 2 x 256", [&] { k_dev<176><<<2, 256>>>(p176, d); }},
+      {"   16 B params + 80 B to mapped host memory", [&] { k_host<4><<<1, 1024>>>(p4, hd); }},
+      {"  704 B params + 80 B to mapped host memory", [&] { k_host<176><<<1, 1024>>>(p176, hd); }},
+      {"  704 B in a __constant__ symbol (8 B params)", [&] { k_sym<<<1, 1024>>>(d); }},
+      {"  no kernel (event, event)", [&] {}},
+  };
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  std::vector<std::vector<float>> v(cases.size());
+  for (int it = 0; it < 330; it++)
+    for (size_t c = 0; c < cases.size(); c++) {
+      cudaEventRecord(e0); cases[c].second(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (it >= 30) v[c].push_back(ms * 1e3f);
+    }
+  for (size_t c = 0; c < cases.size(); c++) {
+    std::sort(v[c].begin(), v[c].end());
+    printf("%-48s median %6.2f us   min %6.2f us\n", cases[c].first.c_str(), v[c][v[c].size() / 2], v[c][0]);
+  }
   return 0;
 }
