@@ -540,6 +540,23 @@ __device__ __forceinline__ void phong_add(vec3 &final, vec3 ld, float fd, vec3 l
   final.z = __fmaf_rn(keep, __fmaf_rn(fd, ld.z, __fmul_rn(fs, ls.z)), final.z);
 }
 
+// A light whose diffuse AND specular factors are exactly zero at this hit adds keep * (0 * ld + 0 * ls) = +0 to the sum whatever
+// its shadow ray finds (inc/shading.hpp:95: `final` stays bit for bit what it was): the ray is not traced.  fd = max(0, n.l) is
+// zero for every light behind the surface; fs = pow(max(0, n.h), phong) is then zero unless the half vector still leans towards
+// the normal by more than the underflow floor of the exponent (phong_pow).  Roughly half of a closed mesh faces away from any
+// given light.  The query still counts in shadow_casts (the statistics describe the reference's rays, not this path's shortcuts).
+// All-opaque scenes only: a march through translucent surfaces is several casts in the reference's count, and mirror.json (lights
+// behind many of its surfaces, low exponents: the test runs but rarely skips) got 19 % slower with it (profiles/r02_tuning.md 8).
+#ifndef CTB_SKIP_DARK_LIGHTS
+#define CTB_SKIP_DARK_LIGHTS 1
+#endif
+__device__ __forceinline__ bool light_is_dark(vec3 nn, vec3 in_n, vec3 nd, float phong_exp, float pow_floor) {
+  if (!CTB_SKIP_DARK_LIGHTS) return false;
+  if (fmaxf(0.0f, vdot(nn, nd)) != 0.0f) return false;
+  const vec3 hv = vnormalized(vadd(in_n, nd));
+  return phong_pow(fmaxf(0.0f, vdot(nn, hv)), phong_exp, pow_floor) == 0.0f;
+}
+
 // phong (inc/shading.hpp:64-99) of one shaded hit: all its shadow rays (shadow_intensity, :22-45) and the sum over the lights
 template <int MODE, bool BRUTE, bool OPAQUE>
 __device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *nodes, const float4 *prims, vec3 hit, vec3 normal, vec3 in_dir,
@@ -624,6 +641,7 @@ __device__ __forceinline__ vec3 phong_record(const SceneView &sv, const float4 *
         }
       }
       casts += __popc(valid);
+      if (SHADOW_PACKET == 1 && valid && light_is_dark(nn, in_n, sd[0], phong_exp, pow_floor)) continue;
       const unsigned occ = any_hit_packet<MODE, SHADOW_PACKET, BRUTE>(sv, nodes, prims, hit, sd, md, valid,
                                                                       SHADOW_PACKET > 1 || l0 >= 32u || ((plane_maybe >> l0) & 1u));
 #pragma unroll

@@ -27,6 +27,10 @@
 #define CTB_PREFETCH_FAR 1   // prefetch the pushed (far) child node into L1: -0.5..1 % on the 10 M-triangle hall
 #endif
 
+#ifndef CTB_PREFETCH_CHILDREN
+#define CTB_PREFETCH_CHILDREN 0   // 1 / 2: when a node arrives, prefetch the records of BOTH its children into L1 (one / two 32-byte sectors each; leaves: their first primitive)
+#endif
+
 namespace ctb {
 
 #define CTB_KIND_TRI 0
@@ -204,6 +208,18 @@ __device__ __forceinline__ float4 ld16(const float4 *p) {
 
 struct NodeData { float4 n0, n1, nz, mf; };
 
+// The node loop's critical path is load node -> slab tests -> pick a child -> load ITS node: on the 10 M-triangle hall the first
+// FFMA after the loads collects 20 % of all stall samples (profiles/r02_tuning.md 8).  The children's indices arrive with the node:
+// their records can be on the way while the slab tests run.
+template <int MODE>
+__device__ __forceinline__ void prefetch_child(const float4 *__restrict__ nodes, const float4 *__restrict__ prims, int c) {
+  if (MODE == 1 || !CTB_PREFETCH_CHILDREN) return;
+  const char *p = c >= 0 ? reinterpret_cast<const char *>(nodes + 4 * (size_t)c) : reinterpret_cast<const char *>(prims + 3 * (size_t)leaf_first(c));
+  if (c == CTB_SENTINEL) return;
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  if (CTB_PREFETCH_CHILDREN >= 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
+}
+
 template <int MODE>
 __device__ __forceinline__ NodeData load_node(const SceneView &sv, const float4 *__restrict__ nodes, int cur) {
   NodeData n;
@@ -328,6 +344,8 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
       const NodeData nd = load_node<MODE>(sv, nodes, cur);
       const float4 n0 = nd.n0, n1 = nd.n1, nz = nd.nz;
       const int c0 = __float_as_int(nd.mf.x), c1 = __float_as_int(nd.mf.y);
+      prefetch_child<MODE>(nodes, prims, c0);
+      prefetch_child<MODE>(nodes, prims, c1);
       const float limit = ANY ? fminf(max_t, h.t) : h.t;
       // slabs: one FFMA per box plane (error budget: see RayCtx)
       const float c0lox = fmaf(n0.x, r.inv.x, -r.oi.x), c0hix = fmaf(n0.y, r.inv.x, -r.oi.x);
@@ -540,6 +558,8 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
       const NodeData nd = load_node<MODE>(sv, nodes, cur);
       const float4 n0 = nd.n0, n1 = nd.n1, nz = nd.nz;
       const int c0 = __float_as_int(nd.mf.x), c1 = __float_as_int(nd.mf.y);
+      prefetch_child<MODE>(nodes, prims, c0);
+      prefetch_child<MODE>(nodes, prims, c1);
       bool h0 = false, h1 = false;
 #pragma unroll
       for (int k = 0; k < K; k++) {

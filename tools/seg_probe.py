@@ -18,7 +18,11 @@ for wl in sys.argv[1:] or ["synthetic10m"]:
     scene, _ = bench.load_workload(wl)
     for world in [int(x) for x in os.environ.get("PROBE_WORLDS", "1,8").split(",")]:
         for combo in os.environ.get("PROBE_COMBOS", "00,01,10,11").split(","):
-            os.environ["CUTRACE_PIXEL_SEG"], os.environ["CUTRACE_TILE_CURVE"] = combo[0], combo[1]
+            for key, v in (("CUTRACE_PIXEL_SEG", combo[0]), ("CUTRACE_TILE_CURVE", combo[1])):   # "d": the library's default
+                if v == "d":
+                    os.environ.pop(key, None)
+                else:
+                    os.environ[key] = v
             with ct.Renderer(scene, tile_rank=0, tile_world=world) as r:
                 ms = [r.render()["render_ms"] for _ in range(5 if wl == "synthetic10m" else 9)]
                 st = r.render()
