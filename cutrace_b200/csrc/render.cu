@@ -160,6 +160,7 @@ __device__ __forceinline__ bool claim_pixels(unsigned *cursor, unsigned n_work, 
 // A warp whose CTA has run dry steals 32 pixels at a time from the CTA with the most work left (the warp reads all cursors, one
 // per lane and round).  `o` below is an offset in a CTA's own index space [0, seg_len(k)).
 #define CTB_SEG_CHUNK 4096u
+#define CTB_SEG_MIN_PX (1u << 20)   // frames below this keep the single cursor (see plan_launch)
 __device__ __forceinline__ unsigned seg_len(unsigned n_work, unsigned k, unsigned G) {
   const unsigned nc = (n_work + CTB_SEG_CHUNK - 1u) / CTB_SEG_CHUNK;   // chunks of the frame (the last one may be partial)
   if (k >= nc) return 0u;
@@ -1534,8 +1535,12 @@ cudaError_t plan_launch(const SceneView &sv, bool allow_smem, LaunchCfg *cfg) {
     const int pmode = cfg->mode == 1 ? 1 : 0;
     cfg->pixel_refill = 0;   // lane refill (pixel_kernel<.., REFILL>): a tuning build's experiment, see render.cu
     if (CTB_PIXEL_REFILL) { if (const char *e = getenv("CUTRACE_PIXEL_REFILL")) cfg->pixel_refill = atoi(e) != 0; }
-    cfg->pixel_seg = 1;      // one work cursor per CTA (claim_segment); CUTRACE_PIXEL_SEG=0: the single global cursor
-    if (const char *e = getenv("CUTRACE_PIXEL_SEG")) cfg->pixel_seg = atoi(e) != 0;
+    // one work cursor per CTA (claim_segment) for scenes that are walked through L1 / L2, on frames of at least CTB_SEG_MIN_PX
+    // pixels (launch_pixel): hall 8K 70.2 -> 68.7 ms, its 1/8 shard 9.36 -> 8.89; the staged scenes gain nothing (their BVH is in
+    // shared memory) and small frames lose to the chunk granularity (mirror.json 1080p 0.26 -> 0.31 ms), profiles/r02_tuning.md 7.
+    // CUTRACE_PIXEL_SEG=0|1 (developer override): never / whenever the grid allows.
+    cfg->pixel_seg = pmode == 0 && !sv.brute_force ? 1 : 0;
+    if (const char *e = getenv("CUTRACE_PIXEL_SEG")) cfg->pixel_seg = atoi(e) != 0 ? 2 : 0;
     pixel_fn pf = pick_pixel(pmode, sv.brute_force != 0, sv.all_opaque != 0, cfg->pixel_refill != 0, cfg->pixel_seg != 0);
     const size_t psmem = pmode == 1 ? cfg->smem_bytes : 0;
     int occ_p = 1;
@@ -1585,7 +1590,7 @@ cudaError_t launch_pixel(const LaunchCfg &cfg, const PixelArgs &args, cudaStream
   int grid = (int)(need < (uint64_t)cfg.grid_pixel ? need : (uint64_t)cfg.grid_pixel);
   if (dbg_grid > 0 && dbg_grid < grid) grid = dbg_grid;
   if (grid < 1) grid = 1;
-  const bool seg = cfg.pixel_seg != 0 && grid <= (int)CTB_MAX_SEGS;
+  const bool seg = (cfg.pixel_seg == 2 || (cfg.pixel_seg == 1 && args.n_px >= CTB_SEG_MIN_PX)) && grid <= (int)CTB_MAX_SEGS;
   pick_pixel(mode, args.sv.brute_force != 0, args.sv.all_opaque != 0, cfg.pixel_refill != 0, seg)<<<grid, threads, smem, st>>>(args);
   return cudaGetLastError();
 }
