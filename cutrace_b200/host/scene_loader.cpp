@@ -120,7 +120,7 @@ bool read_stl(const std::string &path, std::vector<float> &p1, std::vector<float
   return true;
 }
 
-// ---- Wavefront OBJ (mesh import breadth) ---------------------------------------------------------
+// ---- Wavefront OBJ (mesh import breadth; PLY and OFF follow below) --------------------------------
 // The reference accepts whatever Assimp reads (inc/default_schema.hpp:516-545: aiProcess_Triangulate, faces in file
 // order, positions only).  Here: `v x y z` and `f a b c ...` with a/b/c, a//c, a/b forms and negative (relative)
 // indices; polygons are split as a fan from their first vertex; everything else (vt, vn, o, g, s, usemtl) is ignored.
@@ -166,11 +166,219 @@ bool read_obj(const std::string &path, std::vector<float> &p1, std::vector<float
   return true;
 }
 
+// fan triangulation of one polygon (indices into the flat xyz array `v`) in face order, like read_obj
+static void emit_fan(const std::vector<float> &v, const std::vector<long> &idx, std::vector<float> &p1, std::vector<float> &p2,
+                     std::vector<float> &p3, size_t &faces) {
+  for (size_t k = 1; k + 1 < idx.size(); k++) {
+    p1.insert(p1.end(), &v[3 * idx[0]], &v[3 * idx[0]] + 3);
+    p2.insert(p2.end(), &v[3 * idx[k]], &v[3 * idx[k]] + 3);
+    p3.insert(p3.end(), &v[3 * idx[k + 1]], &v[3 * idx[k + 1]] + 3);
+    faces++;
+  }
+}
+
+// ---- Stanford PLY (ASCII, binary little / big endian) ---------------------------------------------------------------------
+// header: `element <name> <count>` blocks with `property <type> <name>` / `property list <count type> <item type> <name>` lines.
+// Read: x, y, z of element `vertex` (any scalar type, converted to float) and the list property vertex_indices / vertex_index of
+// element `face`; every other property and element is parsed only to be skipped.  Polygons are fan-triangulated in face order.
+namespace {
+struct PlyProp { bool list = false; int type = 0, count_type = 0; std::string name; };
+struct PlyElem { std::string name; size_t count = 0; std::vector<PlyProp> props; };
+// type codes: 1 int8 2 uint8 3 int16 4 uint16 5 int32 6 uint32 7 float32 8 float64
+int ply_type(const std::string &t) {
+  static const char *names[][2] = {{"char", "int8"}, {"uchar", "uint8"}, {"short", "int16"}, {"ushort", "uint16"},
+                                   {"int", "int32"}, {"uint", "uint32"}, {"float", "float32"}, {"double", "float64"}};
+  for (int i = 0; i < 8; i++) if (t == names[i][0] || t == names[i][1]) return i + 1;
+  return 0;
+}
+const size_t ply_size[9] = {0, 1, 1, 2, 2, 4, 4, 4, 8};
+bool ply_binary_scalar(const std::string &d, size_t &at, int type, bool big, double &out) {
+  const size_t n = ply_size[type];
+  if (at + n > d.size()) return false;
+  unsigned char b[8];
+  for (size_t i = 0; i < n; i++) b[i] = (unsigned char)d[at + (big ? n - 1 - i : i)];   // to little endian
+  at += n;
+  switch (type) {
+    case 1: { int8_t x; memcpy(&x, b, 1); out = x; break; }
+    case 2: { uint8_t x; memcpy(&x, b, 1); out = x; break; }
+    case 3: { int16_t x; memcpy(&x, b, 2); out = x; break; }
+    case 4: { uint16_t x; memcpy(&x, b, 2); out = x; break; }
+    case 5: { int32_t x; memcpy(&x, b, 4); out = x; break; }
+    case 6: { uint32_t x; memcpy(&x, b, 4); out = x; break; }
+    case 7: { float x; memcpy(&x, b, 4); out = x; break; }
+    default: { double x; memcpy(&x, b, 8); out = x; break; }
+  }
+  return true;
+}
+}  // namespace
+
+bool read_ply(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { err = "cannot open mesh file '" + path + "'"; return false; }
+  const std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  // ---- header: lines up to end_header
+  size_t at = 0;
+  auto next_line = [&](std::string &line) {
+    if (at >= data.size()) return false;
+    size_t e = data.find('\n', at);
+    if (e == std::string::npos) e = data.size();
+    line = data.substr(at, e - at);
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    at = e + 1;
+    return true;
+  };
+  std::string line;
+  if (!next_line(line) || line != "ply") { err = "not a PLY file: '" + path + "'"; return false; }
+  int format = -1;   // 0 ascii, 1 little endian, 2 big endian
+  std::vector<PlyElem> elems;
+  bool ended = false;
+  while (next_line(line)) {
+    std::istringstream in(line);
+    std::string tag;
+    if (!(in >> tag) || tag == "comment" || tag == "obj_info") continue;
+    if (tag == "end_header") { ended = true; break; }
+    if (tag == "format") {
+      std::string kind;
+      in >> kind;
+      format = kind == "ascii" ? 0 : kind == "binary_little_endian" ? 1 : kind == "binary_big_endian" ? 2 : -1;
+    } else if (tag == "element") {
+      PlyElem e;
+      long long n = -1;
+      if (!(in >> e.name >> n) || n < 0) { err = "bad element line in PLY '" + path + "'"; return false; }
+      e.count = (size_t)n;
+      elems.push_back(e);
+    } else if (tag == "property") {
+      if (elems.empty()) { err = "property before any element in PLY '" + path + "'"; return false; }
+      PlyProp pr;
+      std::string t;
+      in >> t;
+      if (t == "list") {
+        std::string ct, it;
+        in >> ct >> it >> pr.name;
+        pr.list = true; pr.count_type = ply_type(ct); pr.type = ply_type(it);
+        if (!pr.count_type || pr.count_type >= 7) { err = "bad list count type in PLY '" + path + "'"; return false; }
+      } else {
+        pr.type = ply_type(t);
+        in >> pr.name;
+      }
+      if (!pr.type || pr.name.empty()) { err = "bad property line in PLY '" + path + "'"; return false; }
+      elems.back().props.push_back(pr);
+    }
+  }
+  if (!ended || format < 0) { err = "bad PLY header in '" + path + "'"; return false; }
+  // ---- body
+  std::istringstream body;   // ASCII: one token stream
+  if (format == 0) body.str(data.substr(at < data.size() ? at : data.size()));
+  auto scalar = [&](int type, double &out) {
+    if (format == 0) {
+      std::string tok;
+      return (bool)(body >> tok) && parse_number(tok, out);
+    }
+    return ply_binary_scalar(data, at, type, format == 2, out);
+  };
+  std::vector<float> v;
+  size_t faces = 0;
+  bool saw_vertex = false;
+  for (const PlyElem &e : elems) {
+    const bool is_vertex = e.name == "vertex", is_face = e.name == "face";
+    int ix = -1, iy = -1, iz = -1, il = -1;
+    for (size_t k = 0; k < e.props.size(); k++) {
+      const PlyProp &pr = e.props[k];
+      if (is_vertex && !pr.list) { if (pr.name == "x") ix = (int)k; else if (pr.name == "y") iy = (int)k; else if (pr.name == "z") iz = (int)k; }
+      if (is_face && pr.list && (pr.name == "vertex_indices" || pr.name == "vertex_index")) il = (int)k;
+    }
+    if (is_vertex && (ix < 0 || iy < 0 || iz < 0)) { err = "PLY vertex element without x / y / z in '" + path + "'"; return false; }
+    if (is_face && il < 0) { err = "PLY face element without vertex_indices in '" + path + "'"; return false; }
+    if (is_face && !saw_vertex) { err = "PLY face element before the vertex element in '" + path + "'"; return false; }
+    saw_vertex = saw_vertex || is_vertex;
+    for (size_t r = 0; r < e.count; r++) {
+      double xyz[3] = {0, 0, 0};
+      std::vector<long> idx;
+      for (size_t k = 0; k < e.props.size(); k++) {
+        const PlyProp &pr = e.props[k];
+        double x;
+        if (!pr.list) {
+          if (!scalar(pr.type, x)) { err = "truncated or malformed PLY body in '" + path + "'"; return false; }
+          if ((int)k == ix) xyz[0] = x; else if ((int)k == iy) xyz[1] = x; else if ((int)k == iz) xyz[2] = x;
+          continue;
+        }
+        double cnt;
+        if (!scalar(pr.count_type, cnt) || cnt < 0 || cnt > 1e6 || cnt != (double)(long)cnt) { err = "bad list length in PLY '" + path + "'"; return false; }
+        for (long j = 0; j < (long)cnt; j++) {
+          if (!scalar(pr.type, x)) { err = "truncated or malformed PLY body in '" + path + "'"; return false; }
+          if ((int)k == il) {
+            const long nv = (long)(v.size() / 3);
+            if (x != (double)(long)x || x < 0 || (long)x >= nv) { err = "face index out of range in PLY '" + path + "'"; return false; }
+            idx.push_back((long)x);
+          }
+        }
+      }
+      if (is_vertex) { v.push_back((float)xyz[0]); v.push_back((float)xyz[1]); v.push_back((float)xyz[2]); }
+      if (is_face) emit_fan(v, idx, p1, p2, p3, faces);
+    }
+  }
+  if (!faces) { err = "no faces in PLY file '" + path + "'"; return false; }
+  return true;
+}
+
+// ---- Object File Format (OFF) ---------------------------------------------------------------------------------------------
+// `OFF`, then `nv nf ne`, nv lines `x y z`, nf lines `n i0 .. i(n-1) [colour]`; `#` starts a comment; counts may share the OFF line.
+bool read_off(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err) {
+  std::ifstream f(path);
+  if (!f) { err = "cannot open mesh file '" + path + "'"; return false; }
+  std::vector<std::vector<std::string>> lines;   // the non-empty, comment-free lines as tokens
+  std::string line;
+  while (std::getline(f, line)) {
+    const size_t h = line.find('#');
+    if (h != std::string::npos) line.resize(h);
+    std::istringstream in(line);
+    std::vector<std::string> toks;
+    std::string t;
+    while (in >> t) toks.push_back(t);
+    if (!toks.empty()) lines.push_back(toks);
+  }
+  if (lines.empty() || lines[0][0] != "OFF") { err = "not an OFF file: '" + path + "'"; return false; }
+  size_t row = 0;
+  std::vector<std::string> head(lines[0].begin() + 1, lines[0].end());
+  if (head.empty()) { if (lines.size() < 2) { err = "truncated OFF file '" + path + "'"; return false; } head = lines[1]; row = 2; } else row = 1;
+  double nv = -1, nf = -1;
+  if (head.size() < 2 || !parse_number(head[0], nv) || !parse_number(head[1], nf) || nv < 0 || nf < 0 || nv != (double)(long)nv || nf != (double)(long)nf) {
+    err = "bad counts in OFF file '" + path + "'";
+    return false;
+  }
+  if (lines.size() < row + (size_t)nv + (size_t)nf) { err = "truncated OFF file '" + path + "'"; return false; }
+  std::vector<float> v;
+  for (size_t i = 0; i < (size_t)nv; i++, row++) {
+    double c[3];
+    if (lines[row].size() < 3 || !parse_number(lines[row][0], c[0]) || !parse_number(lines[row][1], c[1]) || !parse_number(lines[row][2], c[2])) {
+      err = "bad vertex in OFF '" + path + "'";
+      return false;
+    }
+    v.push_back((float)c[0]); v.push_back((float)c[1]); v.push_back((float)c[2]);
+  }
+  size_t faces = 0;
+  for (size_t i = 0; i < (size_t)nf; i++, row++) {
+    double n;
+    if (!parse_number(lines[row][0], n) || n < 0 || n != (double)(long)n || lines[row].size() < 1 + (size_t)n) { err = "bad face in OFF '" + path + "'"; return false; }
+    std::vector<long> idx;
+    for (size_t k = 0; k < (size_t)n; k++) {
+      double x;
+      if (!parse_number(lines[row][1 + k], x) || x != (double)(long)x || x < 0 || x >= nv) { err = "face index out of range in OFF '" + path + "'"; return false; }
+      idx.push_back((long)x);
+    }
+    emit_fan(v, idx, p1, p2, p3, faces);
+  }
+  if (!faces) { err = "no faces in OFF file '" + path + "'"; return false; }
+  return true;
+}
+
 static bool read_mesh(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err) {
   const size_t dot = path.rfind('.');
   std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
   for (auto &ch : ext) ch = (char)tolower((unsigned char)ch);
   if (ext == "obj") return read_obj(path, p1, p2, p3, err);
+  if (ext == "ply") return read_ply(path, p1, p2, p3, err);
+  if (ext == "off") return read_off(path, p1, p2, p3, err);
   return read_stl(path, p1, p2, p3, err);
 }
 

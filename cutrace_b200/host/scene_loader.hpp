@@ -46,6 +46,8 @@ bool load_scene_file(const std::string &path, const LoadOptions &opt, FlatScene 
 bool load_scene_text(const std::string &json_text, const LoadOptions &opt, FlatScene &out, std::vector<std::string> &errors);
 bool read_stl(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err);
 bool read_obj(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err);
+bool read_ply(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err);
+bool read_off(const std::string &path, std::vector<float> &p1, std::vector<float> &p2, std::vector<float> &p3, std::string &err);
 
 // cam::look_at in float arithmetic (inc/default_schema.hpp:370-374)
 void look_at(const float pos[3], const float up_in[3], const float look[3], float forward[3], float right[3], float up[3]);

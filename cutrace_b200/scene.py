@@ -163,8 +163,191 @@ def read_obj(path):
     return np.asarray(tris, dtype=np.float64).astype(np.float32)
 
 
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2", "uint16": "u2",
+              "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
+
+
+def read_ply(path):
+    """Stanford PLY (ascii / binary_little_endian / binary_big_endian) -> (n,3,3) float32: x, y, z of element `vertex`, the list
+    property vertex_indices / vertex_index of element `face`, polygons fan-triangulated in face order; every other property and
+    element is parsed and skipped (mirror of cutrace_b200/host/scene_loader.cpp read_ply)."""
+    try:
+        with open(path, "rb") as f:
+            data = f.read()
+    except OSError as e:
+        raise SceneError(f"cannot open mesh file {path!r}") from e
+    at = 0
+
+    def next_line():
+        nonlocal at
+        if at >= len(data):
+            return None
+        e = data.find(b"\n", at)
+        if e < 0:
+            e = len(data)
+        line = data[at:e]
+        at = e + 1
+        return line[:-1] if line.endswith(b"\r") else line
+
+    if next_line() != b"ply":
+        raise SceneError(f"not a PLY file: {path!r}")
+    fmt, elems, ended = None, [], False
+    while (line := next_line()) is not None:
+        p = line.split()
+        if not p or p[0] in (b"comment", b"obj_info"):
+            continue
+        if p[0] == b"end_header":
+            ended = True
+            break
+        if p[0] == b"format":
+            fmt = {b"ascii": 0, b"binary_little_endian": 1, b"binary_big_endian": 2}.get(p[1] if len(p) > 1 else b"")
+        elif p[0] == b"element":
+            if len(p) < 3 or not _INDEX.match(p[2]) or int(p[2]) < 0:
+                raise SceneError(f"bad element line in PLY {path!r}")
+            elems.append((p[1].decode("latin-1"), int(p[2]), []))
+        elif p[0] == b"property":
+            if not elems:
+                raise SceneError(f"property before any element in PLY {path!r}")
+            t = [x.decode("latin-1") for x in p[1:]]
+            if t and t[0] == "list":
+                if len(t) < 4 or t[1] not in _PLY_TYPES or _PLY_TYPES[t[1]][0] == "f" or t[2] not in _PLY_TYPES:
+                    raise SceneError(f"bad list count type in PLY {path!r}" if len(t) >= 4 and t[2] in _PLY_TYPES else f"bad property line in PLY {path!r}")
+                elems[-1][2].append((True, _PLY_TYPES[t[2]], _PLY_TYPES[t[1]], t[3]))
+            else:
+                if len(t) < 2 or t[0] not in _PLY_TYPES:
+                    raise SceneError(f"bad property line in PLY {path!r}")
+                elems[-1][2].append((False, _PLY_TYPES[t[0]], None, t[1]))
+    if not ended or fmt is None:
+        raise SceneError(f"bad PLY header in {path!r}")
+    toks = data[at:].split() if fmt == 0 else None
+    tk = 0
+
+    def scalar(ty):
+        nonlocal at, tk
+        if fmt == 0:
+            if tk >= len(toks):
+                raise SceneError(f"truncated or malformed PLY body in {path!r}")
+            try:
+                x = _mesh_number(toks[tk])
+            except ValueError as e:
+                raise SceneError(f"truncated or malformed PLY body in {path!r}") from e
+            tk += 1
+            return x
+        n = int(ty[1])
+        if at + n > len(data):
+            raise SceneError(f"truncated or malformed PLY body in {path!r}")
+        x = np.frombuffer(data, dtype=(">" if fmt == 2 else "<") + ty, count=1, offset=at)[0]
+        at += n
+        return float(x)
+
+    v, tris, saw_vertex = [], [], False
+    for name, count, props in elems:
+        is_vertex, is_face = name == "vertex", name == "face"
+        names = [pr[3] for pr in props]
+        if is_vertex and not all(any(n == c and not pr[0] for n, pr in zip(names, props)) for c in "xyz"):
+            raise SceneError(f"PLY vertex element without x / y / z in {path!r}")
+        il = next((k for k, pr in enumerate(props) if pr[0] and pr[3] in ("vertex_indices", "vertex_index")), -1) if is_face else -1
+        if is_face and il < 0:
+            raise SceneError(f"PLY face element without vertex_indices in {path!r}")
+        if is_face and not saw_vertex:
+            raise SceneError(f"PLY face element before the vertex element in {path!r}")
+        saw_vertex = saw_vertex or is_vertex
+        ix, iy, iz = (next(k for k, pr in enumerate(props) if pr[3] == c and not pr[0]) for c in "xyz") if is_vertex else (-1, -1, -1)
+        for _ in range(count):
+            xyz, idx = [0.0, 0.0, 0.0], []
+            for k, (is_list, ty, cty, _n) in enumerate(props):
+                if not is_list:
+                    x = scalar(ty)
+                    if k == ix:
+                        xyz[0] = x
+                    elif k == iy:
+                        xyz[1] = x
+                    elif k == iz:
+                        xyz[2] = x
+                    continue
+                cnt = scalar(cty)
+                if cnt < 0 or cnt > 1e6 or cnt != int(cnt):
+                    raise SceneError(f"bad list length in PLY {path!r}")
+                for _j in range(int(cnt)):
+                    x = scalar(ty)
+                    if k == il:
+                        if x != int(x) or x < 0 or int(x) >= len(v):
+                            raise SceneError(f"face index out of range in PLY {path!r}")
+                        idx.append(int(x))
+            if is_vertex:
+                v.append(xyz)
+            if is_face:
+                for k in range(1, len(idx) - 1):
+                    tris.append([v[idx[0]], v[idx[k]], v[idx[k + 1]]])
+    if not tris:
+        raise SceneError(f"no faces in PLY file {path!r}")
+    return np.asarray(tris, dtype=np.float64).astype(np.float32)
+
+
+def read_off(path):
+    """Object File Format: `OFF`, `nv nf ne` (possibly on the OFF line), nv vertex lines, nf face lines `n i0 .. [colour]`, `#` comments;
+    polygons fan-triangulated in face order (mirror of cutrace_b200/host/scene_loader.cpp read_off)."""
+    try:
+        with open(path, "rb") as f:
+            raw = f.read().split(b"\n")
+    except OSError as e:
+        raise SceneError(f"cannot open mesh file {path!r}") from e
+    lines = [t for t in (ln.split(b"#")[0].split() for ln in raw) if t]
+    if not lines or lines[0][0] != b"OFF":
+        raise SceneError(f"not an OFF file: {path!r}")
+    head, row = lines[0][1:], 1
+    if not head:
+        if len(lines) < 2:
+            raise SceneError(f"truncated OFF file {path!r}")
+        head, row = lines[1], 2
+    try:
+        nv, nf = _mesh_number(head[0]), _mesh_number(head[1])
+        if nv < 0 or nf < 0 or nv != int(nv) or nf != int(nf):
+            raise ValueError(head)
+    except (IndexError, ValueError) as e:
+        raise SceneError(f"bad counts in OFF file {path!r}") from e
+    nv, nf = int(nv), int(nf)
+    if len(lines) < row + nv + nf:
+        raise SceneError(f"truncated OFF file {path!r}")
+    v, tris = [], []
+    for ln in lines[row:row + nv]:
+        try:
+            v.append([_mesh_number(ln[0]), _mesh_number(ln[1]), _mesh_number(ln[2])])
+        except (IndexError, ValueError) as e:
+            raise SceneError(f"bad vertex in OFF {path!r}") from e
+    for ln in lines[row + nv:row + nv + nf]:
+        try:
+            n = _mesh_number(ln[0])
+            if n < 0 or n != int(n) or len(ln) < 1 + int(n):
+                raise ValueError(ln)
+        except ValueError as e:
+            raise SceneError(f"bad face in OFF {path!r}") from e
+        idx = []
+        for tok in ln[1:1 + int(n)]:
+            try:
+                x = _mesh_number(tok)
+            except ValueError:
+                x = -1.0
+            if x != int(x) or x < 0 or x >= nv:
+                raise SceneError(f"face index out of range in OFF {path!r}")
+            idx.append(int(x))
+        for k in range(1, len(idx) - 1):
+            tris.append([v[idx[0]], v[idx[k]], v[idx[k + 1]]])
+    if not tris:
+        raise SceneError(f"no faces in OFF file {path!r}")
+    return np.asarray(tris, dtype=np.float64).astype(np.float32)
+
+
 def read_mesh(path):
-    return read_obj(path) if path.lower().endswith(".obj") else read_stl(path)
+    """Mesh import by file extension: .obj, .ply, .off, everything else as STL (binary or ASCII)."""
+    low = path.lower()
+    if low.endswith(".obj"):
+        return read_obj(path)
+    if low.endswith(".ply"):
+        return read_ply(path)
+    if low.endswith(".off"):
+        return read_off(path)
+    return read_stl(path)
 
 
 class cutrace_scene_desc(C.Structure):

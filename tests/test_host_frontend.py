@@ -246,3 +246,79 @@ def test_mesh_tokens_must_be_whole_numbers(host, tmp_path):
     assert both("idx.obj", obj[:face] + b"1x " + obj[face:]) == [None, None]
     assert both("nul.obj", obj[:face + 1] + b"\x00" + obj[face + 1:]) == [None, None]
     assert both("cr.obj", obj.replace(b"\n", b"\r\n")) == [12, 12]                             # CR is white space
+
+
+def _ply_bytes(verts, faces, fmt):
+    """A PLY file with extra vertex properties, an extra list property per face and a trailing extra element — everything a reader
+    has to skip.  fmt: "ascii" | "binary_little_endian" | "binary_big_endian"."""
+    import struct
+
+    head = ["ply", f"format {fmt} 1.0", "comment written by the test", f"element vertex {len(verts)}", "property double x", "property float y",
+            "property float z", "property uchar red", "property short flag", f"element face {len(faces)}", "property uchar kind",
+            "property list uchar int vertex_indices", "property list ushort float weights", "element edge 2", "property int a", "property int b",
+            "end_header"]
+    out = ("\n".join(head) + "\n").encode()
+    if fmt == "ascii":
+        body = [f"{x!r} {y!r} {z!r} 200 -3" for x, y, z in verts]
+        body += [f"7 {len(f)} " + " ".join(map(str, f)) + " 2 0.5 0.25" for f in faces]
+        body += ["0 1", "1 2"]
+        return out + ("\n".join(body) + "\n").encode()
+    e = "<" if fmt == "binary_little_endian" else ">"
+    for x, y, z in verts:
+        out += struct.pack(e + "dffBh", x, y, z, 200, -3)
+    for f in faces:
+        out += struct.pack(e + "BB" + "i" * len(f), 7, len(f), *f) + struct.pack(e + "Hff", 2, 0.5, 0.25)
+    return out + struct.pack(e + "iiii", 0, 1, 1, 2)
+
+
+def test_ply_and_off_mesh_import(host, tmp_path):
+    """Mesh import breadth (the reference reads whatever Assimp reads, inc/default_schema.hpp:516-545): Stanford PLY
+    in its three encodings and OFF, polygons fan-triangulated in face order.  The C++ loader, the Python mirror and the expected
+    triangles agree bit for bit; malformed files are errors in both."""
+    from cutrace_b200.scene import SceneError, load_scene_json, read_mesh
+
+    verts = [(-0.5, -0.5, -0.5), (0.5, -0.5, -0.5), (0.5, 0.5, -0.5), (-0.5, 0.5, -0.5), (-0.5, -0.5, 0.5), (0.5, -0.5, 0.5),
+             (0.5, 0.5, 0.5), (-0.5, 0.5, 0.5), (0.1, 1.25, 0.3)]
+    faces = [(0, 3, 2, 1), (4, 5, 6, 7), (0, 1, 5, 4), (2, 3, 7, 6), (1, 2, 6, 5), (0, 4, 7, 3), (3, 8, 2), (7, 6, 2, 8, 3)]
+    v = np.asarray(verts, np.float64).astype(np.float32)
+    want = np.asarray([[v[f[0]], v[f[k]], v[f[k + 1]]] for f in faces for k in range(1, len(f) - 1)], np.float32)
+    files = {}
+    for fmt in ("ascii", "binary_little_endian", "binary_big_endian"):
+        files[fmt] = tmp_path / f"solid_{fmt}.ply"
+        files[fmt].write_bytes(_ply_bytes(verts, faces, fmt))
+    off = ["OFF  # a comment", f"{len(verts)} {len(faces)} 0", ""] + [f"{x!r} {y!r} {z!r}" for x, y, z in verts]
+    off += ["# faces", *(f"{len(f)} " + " ".join(map(str, f)) + "  0.5 0.5 0.5" for f in faces)]
+    files["off"] = tmp_path / "solid.off"
+    files["off"].write_text("\n".join(off) + "\n")
+    for name, path in files.items():
+        got = read_mesh(str(path))
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32)), name
+    cam = {"near_plane": 0.1, "far_plane": 100.0, "eye": [0.5, 1.2, -4.5], "up": [0, 1, 0], "look": [0, 0, 0], "width": 64, "height": 40, "ambient": 0.03}
+    doc = {"camera": cam, "materials": [{"type": "solid", "color": [0.8, 0.3, 0.2]}], "lights": [{"type": "sun", "direction": [0, -1, 0.5]}],
+           "objects": [{"type": "mesh", "file": p.name, "material": 0} for p in files.values()]}
+    scene = tmp_path / "solids_ply_off.json"
+    scene.write_text(json.dumps(doc))
+    a = host.load_scene(str(scene), base_dir=str(tmp_path))
+    b = load_scene_json(str(scene), base_dir=str(tmp_path))
+    assert _same(a, b) == []
+    assert a.n_triangles == 4 * len(want) and a.obj_kind.tolist() == [1, 1, 1, 1]
+    for k in range(4):
+        sel = slice(k * len(want), (k + 1) * len(want))
+        assert np.array_equal(np.stack([a.tri_p1[sel], a.tri_p2[sel], a.tri_p3[sel]], axis=1), want)
+    # malformed inputs: errors in both front-ends
+    bad = {
+        "truncated.ply": _ply_bytes(verts, faces, "binary_little_endian")[:-40],
+        "index.ply": _ply_bytes(verts, [(0, 1, 99)], "ascii"),
+        "noface.ply": b"ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\nproperty float y\nproperty float z\nend_header\n0 0 0\n",
+        "header.ply": b"ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\n",
+        "index.off": b"OFF\n3 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 3\n",
+        "short.off": b"OFF\n3 2 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n",
+    }
+    for name, blob in bad.items():
+        (tmp_path / name).write_bytes(blob)
+        doc["objects"] = [{"type": "mesh", "file": name, "material": 0}]
+        scene.write_text(json.dumps(doc))
+        with pytest.raises(SceneError):
+            load_scene_json(str(scene), base_dir=str(tmp_path))
+        with pytest.raises(SceneError):
+            host.load_scene(str(scene), base_dir=str(tmp_path))
