@@ -112,8 +112,13 @@ __device__ __noinline__ bool sphere_test(float cx, float cy, float cz, float R, 
 }
 
 // plane::intersect, inc/default_schema.hpp:189-192
+// A ray that starts ON the plane (a bounce or shadow ray leaving a wall) has a numerator of exactly 0 for axis-aligned planes: the
+// quotient is +-0 or NaN, never accepted with min_t >= 0 — and a zero operand sends the IEEE division through its ~30-instruction
+// slow path (2.3 % of the bunny.json frame, profiles/r02_tuning.md 8).  Left before dividing; same decisions.
 __device__ __forceinline__ bool plane_test(vec3 point, vec3 n, vec3 o, vec3 dir, float min_t, float &t) {
-  float t0 = CTB_DIV(vdot(n, vsub(point, o)), vdot(dir, n));
+  const float num = vdot(n, vsub(point, o));
+  if (num == 0.0f && min_t >= 0.0f) { t = 0.0f; return false; }
+  float t0 = CTB_DIV(num, vdot(dir, n));
   t = t0;
   return isfinite(t0) && min_t <= t0 && t0 > min_t;
 }
@@ -504,7 +509,8 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
     for (int k = 0; k < K; k++) {
       const float den = vdot(d[k], n);
       // t0 > 1e-3 needs num and den of equal sign; then the exact IEEE quotient decides (plane::intersect)
-      if (!((__float_as_uint(num) ^ __float_as_uint(den)) >> 31) && fabsf(num) < CTB_MUL(CTB_MUL(max_t[k], fabsf(den)), 1.0001f)) {
+      // (num == 0: the ray starts on the plane, t0 = +-0 or NaN < min_t — and a zero operand is the division's slow path, see plane_test)
+      if (!((__float_as_uint(num) ^ __float_as_uint(den)) >> 31) && num != 0.0f && fabsf(num) < CTB_MUL(CTB_MUL(max_t[k], fabsf(den)), 1.0001f)) {
         const float t0 = CTB_DIV(num, den);
         if (isfinite(t0) && min_t <= t0 && t0 > min_t && t0 < max_t[k]) occ |= (act & (1u << k));
       }
@@ -740,7 +746,7 @@ __device__ __forceinline__ bool planes_occlude(const SceneView &sv, vec3 o, vec3
     const vec3 n = mk3(b.x, b.y, b.z);
     const float num = vdot(n, vsub(mk3(a.x, a.y, a.z), o));
     const float den = vdot(d, n);
-    if (!((__float_as_uint(num) ^ __float_as_uint(den)) >> 31) && fabsf(num) < CTB_MUL(CTB_MUL(max_t, fabsf(den)), 1.0001f)) {
+    if (!((__float_as_uint(num) ^ __float_as_uint(den)) >> 31) && num != 0.0f && fabsf(num) < CTB_MUL(CTB_MUL(max_t, fabsf(den)), 1.0001f)) {
       const float t0 = CTB_DIV(num, den);
       if (isfinite(t0) && min_t <= t0 && t0 > min_t && t0 < max_t) occ = true;
     }
