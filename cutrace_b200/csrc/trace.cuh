@@ -27,6 +27,10 @@
 #define CTB_PREFETCH_FAR 1   // prefetch the pushed (far) child node into L1: -0.5..1 % on the 10 M-triangle hall
 #endif
 
+#ifndef CTB_BRANCHFREE_STACK
+#define CTB_BRANCHFREE_STACK 1   // walks through L1 / L2 (MODE != 1): the node loops push speculatively (store always, move the pointer by "both children
+                                 // hit") instead of branching three ways — hall 60.6 -> 60.0 ms; the staged scenes keep the branches (bunny.json 6.65 vs 6.69)
+#endif
 #ifndef CTB_PREFETCH_CHILDREN
 #define CTB_PREFETCH_CHILDREN 0   // 1 / 2: when a node arrives, prefetch the records of BOTH its children into L1 (one / two 32-byte sectors each; leaves: their first primitive)
 #endif
@@ -364,7 +368,13 @@ __device__ __forceinline__ bool traverse(const SceneView &sv, const float4 *__re
       const float tn1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), min_t));
       const float tf1 = fmaf(fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), limit)), slack, r.eabs);
       const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
-      if (h0 && h1) {
+      if (CTB_BRANCHFREE_STACK && MODE != 1) {
+        const bool swap = h1 && (!h0 || tn1 < tn0);   // enter c1 first: it is the only child hit, or the nearer of two
+        stack[sp] = swap ? c0 : c1;                   // speculative push of the other child (above the top: harmless when not kept)
+        sp += (h0 && h1) ? 1 : 0;
+        cur = swap ? c1 : c0;
+        if (!(h0 || h1)) cur = stack[--sp];
+      } else if (h0 && h1) {
         const bool swap = tn1 < tn0;
         const int far = swap ? c0 : c1;
         stack[sp++] = far;
@@ -584,7 +594,12 @@ __device__ __forceinline__ unsigned any_hit_packet(const SceneView &sv, const fl
         h0 = h0 || (on && tn <= tf);
         h1 = h1 || (on && tn1 <= tf1);
       }
-      if (h0 && h1) { stack[sp++] = c1; cur = c0; }
+      if (CTB_BRANCHFREE_STACK && MODE != 1) {
+        stack[sp] = c1;
+        sp += (h0 && h1) ? 1 : 0;
+        cur = h0 ? c0 : c1;
+        if (!(h0 || h1)) cur = stack[--sp];
+      } else if (h0 && h1) { stack[sp++] = c1; cur = c0; }
       else if (h0 || h1) cur = h0 ? c0 : c1;
       else cur = stack[--sp];
     }
