@@ -555,6 +555,9 @@ def main():
             r2 = b.resident(s2, 5 if big else 10, 3)
             e2 = b.e2e(s2, 3 if big else 5, check_parity=(big and not args.no_parity_check))
             e2f = b.e2e(s2, 3 if big else 5, flags=args.flags | b.ct.FLAG_FAST_BUILD)
+            # ms_per_frame: K frames between two CUDA events, i.e. including cutrace_render's per-frame host synchronisation (what a caller
+            # sees per frame; on a 20 x 20 frame that round trip is longer than the kernel).  render_device_ms: events around each frame's
+            # kernel — the quantity the reference arm reports for its kernel (one event pair per launch, oracle/ref_gpu.cu).
             extra[name] = {"workload": w2["label"], "ms_per_frame": r2["ms_per_step"], "value": r2["rays"] / r2["ms_per_step"] / 1e3, "unit": "Mrays/s",
                            "rays_per_frame": int(r2["rays"]), "scheduler": r2["scheduler"], "render_device_ms": r2["render_device_ms"],
                            "e2e_ms_per_frame": e2["ms_per_frame"], "e2e_value": r2["rays"] / e2["ms_per_frame"] / 1e3,
