@@ -896,6 +896,8 @@ int cutrace_render(cutrace_ctx *c, cutrace_stats *stats) {
     static const bool dbg_no_host_stats = getenv("CUTRACE_DEBUG_NO_HOST_STATS") != nullptr;   // timing experiment: the statistics stay on the device
     pa.ctr = c->d_ctr; pa.host_stats = dbg_no_host_stats ? nullptr : c->h_ctr_dev; pa.out = out;
     if (c->dl_direct_on) { pa.out2 = c->dl_direct; pa.tm.wide_warps = 1u; }   // 16 x 2 warps: whole tile rows per store over PCIe
+    static const int dbg_wide = [] { const char *e = getenv("CUTRACE_DEBUG_WIDE_WARPS"); return e ? atoi(e) : -1; }();   // tuning experiments
+    if (dbg_wide >= 0) pa.tm.wide_warps = dbg_wide ? 1u : 0u;
     c->ctr_dirty = true;   // until the kernel has run to its end
     if ((e = launch_pixel(c->cfg, pa, st)) != cudaSuccess) return e;
     if (early_event) {   // cutrace_render_download: the G-buffer is complete when the kernel is
