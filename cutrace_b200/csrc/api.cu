@@ -380,12 +380,12 @@ int alloc_queues(cutrace_ctx *c) {
 }
 
 template <typename T>
-int upload(T **dst, const std::vector<T> &src, cudaStream_t st) {
+int upload(T **dst, const std::vector<T> &src, cudaStream_t st, bool sync = true) {
   *dst = nullptr;
   if (src.empty()) return CUTRACE_OK;
   CU(dmalloc(dst, sizeof(T) * src.size(), st));
   CU(cudaMemcpyAsync(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, st));
-  CU(cudaStreamSynchronize(st));   // src is a temporary host vector
+  if (sync) CU(cudaStreamSynchronize(st));   // src may be a temporary host vector; sync = false: the caller keeps it alive until it has synchronised the stream
   return CUTRACE_OK;
 }
 
@@ -624,12 +624,14 @@ int cutrace_upload_scene(const cutrace_scene_desc *s, const cutrace_opts *opts, 
     }
   }
   std::vector<uint32_t> omat(s->obj_material, s->obj_material + s->n_objects);
-  UP(upload(&c->planes, planes, c->stream));
-  UP(upload(&c->materials, mats, c->stream));
-  UP(upload(&c->lights, lights, c->stream));
-  UP(upload(&c->obj_material, omat, c->stream));
-  UP(upload(&c->pl_tbl, pl_tbl, c->stream));
-  UP(upload(&c->pl_eps, pl_eps, c->stream));
+  // (no stream synchronisation per array — six round trips were 0.04 ms of every upload: the vectors live until this function
+  // returns, and the stream is synchronised after the primitive copies below)
+  UP(upload(&c->planes, planes, c->stream, false));
+  UP(upload(&c->materials, mats, c->stream, false));
+  UP(upload(&c->lights, lights, c->stream, false));
+  UP(upload(&c->obj_material, omat, c->stream, false));
+  UP(upload(&c->pl_tbl, pl_tbl, c->stream, false));
+  UP(upload(&c->pl_eps, pl_eps, c->stream, false));
   LAP("small record uploads");
 
   // ---- primitives + LBVH ----
