@@ -243,8 +243,13 @@ bool read_ply(const std::string &path, std::vector<float> &p1, std::vector<float
       format = kind == "ascii" ? 0 : kind == "binary_little_endian" ? 1 : kind == "binary_big_endian" ? 2 : -1;
     } else if (tag == "element") {
       PlyElem e;
-      long long n = -1;
-      if (!(in >> e.name >> n) || n < 0) { err = "bad element line in PLY '" + path + "'"; return false; }
+      std::string cnt;   // a whole token of digits (an optional sign like the Python mirror's int grammar), not "9abc"
+      if (!(in >> e.name >> cnt)) { err = "bad element line in PLY '" + path + "'"; return false; }
+      size_t k = (cnt[0] == '+' || cnt[0] == '-') ? 1 : 0;
+      bool digits = k < cnt.size() && cnt.size() - k <= 18;
+      for (size_t j = k; j < cnt.size(); j++) digits = digits && isdigit((unsigned char)cnt[j]);
+      const long long n = digits ? strtoll(cnt.c_str(), nullptr, 10) : -1;
+      if (n < 0) { err = "bad element line in PLY '" + path + "'"; return false; }
       e.count = (size_t)n;
       elems.push_back(e);
     } else if (tag == "property") {
@@ -291,6 +296,7 @@ bool read_ply(const std::string &path, std::vector<float> &p1, std::vector<float
     if (is_face && il < 0) { err = "PLY face element without vertex_indices in '" + path + "'"; return false; }
     if (is_face && !saw_vertex) { err = "PLY face element before the vertex element in '" + path + "'"; return false; }
     saw_vertex = saw_vertex || is_vertex;
+    if (e.props.empty()) continue;   // rows without properties hold nothing (and a huge count must not spin here)
     for (size_t r = 0; r < e.count; r++) {
       double xyz[3] = {0, 0, 0};
       std::vector<long> idx;

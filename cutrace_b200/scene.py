@@ -253,6 +253,8 @@ def read_ply(path):
             raise SceneError(f"PLY face element before the vertex element in {path!r}")
         saw_vertex = saw_vertex or is_vertex
         ix, iy, iz = (next(k for k, pr in enumerate(props) if pr[3] == c and not pr[0]) for c in "xyz") if is_vertex else (-1, -1, -1)
+        if not props:
+            continue      # rows without properties hold nothing (and a huge count must not spin here)
         for _ in range(count):
             xyz, idx = [0.0, 0.0, 0.0], []
             for k, (is_list, ty, cty, _n) in enumerate(props):
