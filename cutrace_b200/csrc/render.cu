@@ -18,8 +18,10 @@
 //
 // Three schedulers drive the same per-ray device functions:
 //
-//   pixel_kernel   (default) ONE persistent kernel per frame: a thread walks a pixel's whole path — the recursion of ray_color
-//                  as a loop with an explicit stack — and warps claim pixels from a global cursor.  No queues at all.
+//   pixel_kernel   (default) ONE persistent kernel per frame, one 1024-thread CTA per SM: a thread walks a pixel's whole path — the
+//                  recursion of ray_color as a loop with an explicit stack — and warps claim 32..128 pixels at a time from a global
+//                  cursor, or (scenes walked through L1 / L2, big frames) from their CTA's own cursor over round-robin 16-tile
+//                  chunks with stealing (claim_segment).  No queues at all.
 //   frame_kernel   the wavefront as ONE persistent cooperative kernel per frame: the level loop runs on the device.  Phase p
 //                  = trace(p); a warp that runs out of trace(p) work arrives at the phase barrier and, instead of
 //                  spinning, shades records of the levels < p until the barrier opens (all warps arrived), so the
