@@ -19,7 +19,7 @@ SYMBOLS = (
     "cutrace_set_frame_max_depth",
     "cutrace_untile_device", "cutrace_encode_bytes_device", "cutrace_host_alloc", "cutrace_host_free", "cutrace_host_register", "cutrace_host_unregister", "cutrace_trim_memory",
     "cutrace_validate_bvh", "cutrace_debug_radix_sort", "cutrace_debug_phong_pow", "cutrace_abi_version", "cutrace_tile_size",
-    "cutrace_debug_tile_of_slot", "cutrace_debug_slot_of_tile",
+    "cutrace_debug_tile_of_slot", "cutrace_debug_slot_of_tile", "cutrace_debug_segment_length", "cutrace_debug_segment_work",
 )
 
 FLAG_NO_SMEM_TOP, FLAG_VALIDATE_BVH, FLAG_BRUTE_FORCE, FLAG_SERIALIZE, FLAG_FRAME_KERNEL, FLAG_LAUNCHES, \
@@ -108,6 +108,9 @@ def load():
     lib.cutrace_debug_tile_of_slot.argtypes = [C.c_uint32] * 5 + [P, P]
     lib.cutrace_debug_slot_of_tile.argtypes = [C.c_uint32] * 6
     lib.cutrace_debug_slot_of_tile.restype = C.c_uint32
+    for fn in (lib.cutrace_debug_segment_length, lib.cutrace_debug_segment_work):
+        fn.argtypes = [C.c_uint32] * 3
+        fn.restype = C.c_uint32
     _lib = lib
     return lib
 

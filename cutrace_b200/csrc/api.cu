@@ -461,6 +461,9 @@ uint32_t cutrace_abi_version(void) { return CUTRACE_ABI_VERSION; }
 
 uint32_t cutrace_tile_size(void) { return CUTRACE_TILE; }
 
+uint32_t cutrace_debug_segment_length(uint32_t n_work, uint32_t k, uint32_t G) { return G ? seg_len(n_work, k, G) : 0u; }
+uint32_t cutrace_debug_segment_work(uint32_t o, uint32_t k, uint32_t G) { return G ? seg_to_work(o, k, G) : 0u; }
+
 static TileMap debug_tile_map(uint32_t width, uint32_t height, uint32_t world, uint32_t curve) {
   TileMap tm{};
   tm.width = width; tm.height = height;

@@ -208,6 +208,21 @@ struct FrameCounters {
   FrameStats st;
 };
 
+// Index arithmetic of the pixel kernel's per-CTA work cursors (render.cu: claim_segment; host-callable for tests/test_abi.py):
+// the frame's work items in chunks of CTB_SEG_CHUNK, chunk j owned by CTA j % G; `o` is an offset in a CTA's own index space.
+#define CTB_SEG_CHUNK 4096u
+#define CTB_SEG_MIN_PX (1u << 20)   // frames below this keep the single cursor (see plan_launch)
+__host__ __device__ __forceinline__ unsigned seg_len(unsigned n_work, unsigned k, unsigned G) {
+  const unsigned nc = (n_work + CTB_SEG_CHUNK - 1u) / CTB_SEG_CHUNK;   // chunks of the frame (the last one may be partial)
+  if (k >= nc) return 0u;
+  const unsigned mine = (nc - 1u - k) / G + 1u;
+  const unsigned len = mine * CTB_SEG_CHUNK;
+  return ((nc - 1u) % G == k) ? len - (nc * CTB_SEG_CHUNK - n_work) : len;   // the owner of the last chunk
+}
+__host__ __device__ __forceinline__ unsigned seg_to_work(unsigned o, unsigned k, unsigned G) {
+  return ((o / CTB_SEG_CHUNK) * G + k) * CTB_SEG_CHUNK + (o % CTB_SEG_CHUNK);
+}
+
 // Per-object data for the reference's mesh pre-test (inc/default_schema.hpp:99-114): the AABB cutrace computes on the host
 // for every mesh (inc/default_schema.hpp:573-586) and whether the object is a mesh at all.
 struct __align__(16) ObjBound {

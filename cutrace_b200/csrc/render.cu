@@ -161,18 +161,6 @@ __device__ __forceinline__ bool claim_pixels(unsigned *cursor, unsigned n_work, 
 // cent of each other — and the warps of a CTA claim from THEIR cursor: at any moment an SM works on one or two 16-tile chunks.
 // A warp whose CTA has run dry steals 32 pixels at a time from the CTA with the most work left (the warp reads all cursors, one
 // per lane and round).  `o` below is an offset in a CTA's own index space [0, seg_len(k)).
-#define CTB_SEG_CHUNK 4096u
-#define CTB_SEG_MIN_PX (1u << 20)   // frames below this keep the single cursor (see plan_launch)
-__device__ __forceinline__ unsigned seg_len(unsigned n_work, unsigned k, unsigned G) {
-  const unsigned nc = (n_work + CTB_SEG_CHUNK - 1u) / CTB_SEG_CHUNK;   // chunks of the frame (the last one may be partial)
-  if (k >= nc) return 0u;
-  const unsigned mine = (nc - 1u - k) / G + 1u;
-  const unsigned len = mine * CTB_SEG_CHUNK;
-  return ((nc - 1u) % G == k) ? len - (nc * CTB_SEG_CHUNK - n_work) : len;   // the owner of the last chunk
-}
-__device__ __forceinline__ unsigned seg_to_work(unsigned o, unsigned k, unsigned G) {
-  return ((o / CTB_SEG_CHUNK) * G + k) * CTB_SEG_CHUNK + (o % CTB_SEG_CHUNK);
-}
 // claims [base, end) in the index space of CTA `owner` (warp-uniform results); false: the frame has no unclaimed work left
 __device__ __forceinline__ bool claim_segment(FrameCounters *ctr, unsigned n_work, unsigned lane, unsigned max_chunk, bool first, unsigned &owner,
                                               unsigned &base, unsigned &end) {

@@ -315,6 +315,12 @@ int cutrace_debug_phong_pow(const float *x, const float *e, float *out_powf, flo
 int cutrace_debug_tile_of_slot(uint32_t width, uint32_t height, uint32_t tile_world, uint32_t curve, uint32_t slot, uint32_t *tx, uint32_t *ty);
 uint32_t cutrace_debug_slot_of_tile(uint32_t width, uint32_t height, uint32_t tile_world, uint32_t curve, uint32_t tx, uint32_t ty);
 
+/* test hook (host only): the pixel kernel's per-CTA work cursors.  cutrace_debug_segment_length = number of work items CTA k of a
+ * grid of G CTAs owns in a frame of n_work items; cutrace_debug_segment_work = the frame work item behind offset o of CTA k's own
+ * index space (o < that length). */
+uint32_t cutrace_debug_segment_length(uint32_t n_work, uint32_t k, uint32_t G);
+uint32_t cutrace_debug_segment_work(uint32_t o, uint32_t k, uint32_t G);
+
 uint32_t cutrace_abi_version(void);
 /* edge of the screen tiles the sharding works in (CUTRACE_TILE of the library that is loaded) */
 uint32_t cutrace_tile_size(void);

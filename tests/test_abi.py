@@ -143,3 +143,25 @@ def test_tile_slot_mapping_is_a_bijection_and_balanced(lib, curve, dims, world):
         p = np.asarray(pos[0::8], np.int64)            # rank 0's tiles in its own order
         step = np.abs(np.diff(p, axis=0)).max(axis=1)
         assert np.percentile(step, 90) <= 9, "a rank's consecutive tiles are neighbours inside a super-tile"
+
+
+@pytest.mark.parametrize("n_work,G", [(1024, 1), (4096, 148), (4096 * 148, 148), (4096 * 148 + 256, 148), (1_048_576 + 768, 148), (33_177_600 // 8 + 256, 148),
+                                      (300_032, 7), (256, 320)])
+def test_per_cta_work_segments_cover_the_frame_once(lib, n_work, G):
+    """The pixel kernel's per-CTA cursors (csrc/common.cuh: seg_len / seg_to_work, render.cu: claim_segment): the CTAs' own index
+    spaces map onto the frame's work items exactly once, 32-item warp blocks never straddle a chunk, and the segments are balanced
+    to one 4096-item chunk."""
+    seen = np.zeros(n_work, np.uint8)
+    lens = []
+    for k in range(G):
+        ln = lib.cutrace_debug_segment_length(n_work, k, G)
+        lens.append(ln)
+        assert ln % 32 == 0 or n_work % 32
+        for o in range(0, ln, 32):                      # a warp iteration: offsets o .. o + 31 of CTA k
+            w0 = lib.cutrace_debug_segment_work(o, k, G)
+            assert w0 + min(32, ln - o) <= n_work, (k, o, w0)
+            assert w0 // 4096 == (w0 + min(32, ln - o) - 1) // 4096        # one chunk
+            assert (w0 // 4096) % G == k                                     # ... of this CTA
+            seen[w0:w0 + min(32, ln - o)] += 1
+    assert sum(lens) == n_work and (seen == 1).all()
+    assert max(lens) - min(lens) <= 4096
