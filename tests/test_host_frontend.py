@@ -322,3 +322,15 @@ def test_ply_and_off_mesh_import(host, tmp_path):
             load_scene_json(str(scene), base_dir=str(tmp_path))
         with pytest.raises(SceneError):
             host.load_scene(str(scene), base_dir=str(tmp_path))
+
+
+def test_mesh_front_ends_agree_on_mutated_files(host):
+    """A short, seeded run of tools/fuzz_mesh_frontends.py (mutated STL / OBJ / PLY / OFF files): the C++ loader and the Python mirror
+    accept or reject the same files with the same triangle count, and neither crashes."""
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_mesh_frontends.py"), "11", "400"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    last = r.stdout.strip().splitlines()[-1]
+    assert last.endswith("front-end disagreements 0"), r.stdout[-2000:]
+    assert int(last.split()[1]) > 10 and int(last.split()[3]) > 100      # both outcomes occur
