@@ -671,12 +671,50 @@ def scene_from_dict(doc, base_dir=".", accept_aliases=False):
     )
 
 
+_JSON_STRICT_NUMBER = re.compile(r"-?(0|[1-9][0-9]*)(\.[0-9]+)?([eE][+-]?[0-9]+)?\Z")
+_STRTOD_NUMBER = re.compile(r"[+-]?([0-9]+\.?[0-9]*|\.[0-9]+)([eE][+-]?[0-9]+)?\Z")
+
+
+def _picojson_numbers(text):
+    """The reference parses its scenes with picojson, whose number rule is laxer than strict JSON: a number starts at a digit or
+    '-', is the longest run of [0-9+-.eE], and strtod must consume all of it — "041", "0." and "1.e5" are numbers, "1e" and "1-2"
+    are errors (cutrace_b200/host/json.hpp restates the same rule).  This pass rewrites the runs strict JSON would reject into
+    their value, outside string literals, so that json.loads accepts exactly what the C++ front-end accepts."""
+    out, i, n, in_str = [], 0, len(text), False
+    while i < n:
+        c = text[i]
+        if in_str:
+            if c == "\\" and i + 1 < n:
+                out.append(text[i:i + 2])
+                i += 2
+                continue
+            in_str = c != '"'
+        elif c == '"':
+            in_str = True
+        elif c == "-" or "0" <= c <= "9":
+            q = i
+            while q < n and text[q] in "0123456789+-.eE":
+                q += 1
+            run = text[i:q]
+            if not _JSON_STRICT_NUMBER.match(run):
+                if not _STRTOD_NUMBER.match(run):
+                    raise SceneError("JSON parse error: bad number")
+                v = float(run)
+                run = repr(v) if v == v and abs(v) != float("inf") else ("-1e999" if v < 0 else "1e999")
+            out.append(run)
+            i = q
+            continue
+        out.append(c)
+        i += 1
+    return "".join(out)
+
+
 def load_scene_json(path, base_dir=None, accept_aliases=False):
     """``default_schema::load_file`` equivalent. Mesh paths are relative to the CWD in the
     reference (schema.md:73-74); pass ``base_dir`` to resolve them elsewhere."""
     with open(path, "r") as f:
         try:
-            doc = json.load(f)
+            doc = json.loads(_picojson_numbers(f.read()))
         except json.JSONDecodeError as e:
             raise SceneError(f"JSON parse error: {e}") from e
     if not isinstance(doc, dict):

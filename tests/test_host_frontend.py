@@ -334,3 +334,20 @@ def test_mesh_front_ends_agree_on_mutated_files(host):
     last = r.stdout.strip().splitlines()[-1]
     assert last.endswith("front-end disagreements 0"), r.stdout[-2000:]
     assert int(last.split()[1]) > 10 and int(last.split()[3]) > 100      # both outcomes occur
+
+
+def test_json_front_ends_agree_on_mutated_scenes(host):
+    """A short, seeded run of tools/fuzz_json_frontends.py: mutated scene files are accepted or rejected by both front-ends, with
+    identical arrays when accepted — including picojson's lax numbers ("041", "0.", "1.e5"), which the Python mirror rewrites
+    before json.loads (scene.py: _picojson_numbers) and the C++ parser reads with the same rule (host/json.hpp)."""
+    import sys
+
+    from cutrace_b200.scene import SceneError, _picojson_numbers
+
+    assert json.loads(_picojson_numbers('{"a": 0., "b": "0. \\\\\\" 041", "c": 041, "d": -1.e5, "e": [1, 2.5]}')) == {"a": 0.0, "b": '0. \\" 041', "c": 41.0, "d": -1e5, "e": [1, 2.5]}
+    for bad in ('{"a": 1e}', '{"a": 1-2}', '{"a": -}', '{"a": 1.2.3}'):
+        with pytest.raises(SceneError):
+            _picojson_numbers(bad)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_json_frontends.py"), "3", "400"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().splitlines()[-1] == "agree 400 disagree 0", r.stdout[-2000:]
