@@ -561,7 +561,9 @@ def main():
             extra[name] = {"workload": w2["label"], "ms_per_frame": r2["ms_per_step"], "value": r2["rays"] / r2["ms_per_step"] / 1e3, "unit": "Mrays/s",
                            "rays_per_frame": int(r2["rays"]), "scheduler": r2["scheduler"], "render_device_ms": r2["render_device_ms"],
                            "e2e_ms_per_frame": e2["ms_per_frame"], "e2e_value": r2["rays"] / e2["ms_per_frame"] / 1e3,
-                           "e2e_fast_build_ms_per_frame": e2f["ms_per_frame"]}
+                           "e2e_fast_build_ms_per_frame": e2f["ms_per_frame"],
+                           "timed": "ms_per_frame: K frames between two CUDA events incl. cutrace_render's per-frame host synchronisation (and the rank "
+                                    "barrier at N > 1); render_device_ms: events around each frame's kernel, the reference arm's per-launch quantity"}
             if "parity_check" in r2:
                 extra[name]["parity_check"] = r2["parity_check"]
             if "parity_check" in e2:
