@@ -929,3 +929,31 @@ def test_integration_binding_against_the_reference_operator(ct):
         assert m["normal_max_abs"] <= 1e-5 and m["depth_max_rel"] <= 1e-6, m
     assert m["color_max_abs"] < 5e-2, m
     assert m["max_ref"] == m["max_new"]
+
+
+def test_cta_work_cursors_render_the_same_frame_as_the_global_cursor(ct, monkeypatch):
+    """The pixel kernel's per-CTA work cursors (render.cu: claim_segment — the default for scenes walked through L1 / L2 on frames of
+    at least 2^20 pixels) against its single global cursor (CUTRACE_PIXEL_SEG=0), on a frame whose size is no multiple of a tile
+    or a chunk: bit-identical, unsharded and as the three shards of a world-3 render stored into one frame."""
+    s = load_golden_scene("mirror").with_resolution(1283, 1021)          # 1.31 M pixels, partial tiles at both edges
+    flags = ct.FLAG_NO_SMEM_TOP | ct.FLAG_PIXEL_KERNEL                  # walk the BVH through L1 / L2: the mode that uses the cursors
+    monkeypatch.setenv("CUTRACE_PIXEL_SEG", "0")
+    want, st0 = gpu_render(ct, s, flags=flags)
+    monkeypatch.delenv("CUTRACE_PIXEL_SEG")
+    got, st1 = gpu_render(ct, s, flags=flags)
+    assert st1["scheduler"] == 2 and st1["rays_total"] == st0["rays_total"]
+    for k in ("depth", "normal", "color", "hit_id"):
+        assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), k
+    monkeypatch.setenv("CUTRACE_PIXEL_SEG", "1")                          # force them on the shards too (0.44 M pixels each)
+    rs = [ct.Renderer(s, tile_rank=r, tile_world=3, flags=flags) for r in range(3)]
+    rs[0].frame_ipc_export()
+    block = rs[0].frame_device()[0]
+    for r in rs[1:]:
+        r.frame_attach(block)
+    rays = sum(r.render()["rays_total"] for r in rs)
+    out = rs[0].download()
+    for r in rs:
+        r.close()
+    assert rays == st0["rays_total"]
+    for k in ("depth", "normal", "color", "hit_id"):
+        assert np.array_equal(out[k].view(np.uint32), want[k].view(np.uint32)), ("world 3", k)
